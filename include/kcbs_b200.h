@@ -1,0 +1,166 @@
+/*
+ * kcbs_b200.h -- C ABI of the B200-native K-CBS low-level hot path (libkcbs_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, integer status
+ * returns, never throws.  Each entry point names the reference interface it replaces
+ * (file:line relative to the K-CBS-Demos tree).  The host-side mirror of the reference's OMPL
+ * plugin classes (k-cbs-demos_b200/includes/*.h) is written on top of these calls.
+ *
+ * Conventions
+ *   state  s = (x, y, v, phi, theta)   OMPL "reals" order, StatePropagatorDatabase.h:46
+ *   control u = (a, phidot)            StatePropagatorDatabase.h:47, ControlSpaceDatabase.h:43-54
+ *   All batches are structure-of-arrays float32 "planes": plane c of a batch of n starts at
+ *   base + c * n.  Entry points without suffix take HOST pointers and copy through the context's
+ *   device workspace; `_dev` entry points take DEVICE pointers on the context's device and are
+ *   asynchronous on `stream` (a cudaStream_t passed as void*, NULL = context stream).
+ *   There is no CPU fallback: every compute call runs sm_100a kernels or returns an error.
+ */
+#ifndef KCBS_B200_H
+#define KCBS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define KCBS_API
+#else
+#define KCBS_API __attribute__((visibility("default")))
+#endif
+
+#define KCBS_ABI_VERSION 1
+#define KCBS_MAX_OBSTACLES 64 /* Congested10x10 uses 9 (demo_Congested10x10_7robots...:82-90) */
+#define KCBS_MAX_ROBOTS 64    /* largest demo has 30 (demo_Benchmark_Empty32x32_30robots...)   */
+#define KCBS_MAX_STEPS 32     /* setMinMaxControlDuration(1, 10), demo_*.cpp:118               */
+
+typedef enum kcbs_status {
+    KCBS_OK = 0,
+    KCBS_ERR_INVALID_ARGUMENT = 1, /* null pointer, negative size, index out of range          */
+    KCBS_ERR_CUDA = 2,             /* CUDA runtime/driver failure; see kcbs_last_error         */
+    KCBS_ERR_NO_DEVICE = 3,        /* no sm_100-class device: there is no CPU fallback         */
+    KCBS_ERR_OUT_OF_MEMORY = 4,
+    KCBS_ERR_UNKNOWN_ROBOT = 5     /* mirrors unordered_map::at throwing,                       *
+                                    * StateValidityCheckerDatabase.h:111                        */
+} kcbs_status;
+
+/* Immutable scene description, copied by kcbs_create (mirrors the by-value copies of the robot
+ * map and obstacle set in homogeneous2ndOrderCarSystemSVC's constructor,
+ * StateValidityCheckerDatabase.h:47-49). */
+typedef struct kcbs_world {
+    double lo[4];            /* StateSpaceDatabase.h:51-58 lower bounds of (x, y, v, phi)       */
+    double hi[4];            /* upper bounds                                                    */
+    double step_size;        /* si->setPropagationStepSize(0.1), demo_*.cpp:115                 */
+    double integration_step; /* ODEBasicSolver intStep (1e-2), call site demo_*.cpp:111         */
+    double car_length;       /* StatePropagatorDatabase.h:53 (0.5)                              */
+    int32_t n_obstacles;
+    int32_t n_robots;
+    const double *obstacles;  /* n_obstacles x (x, y, length, width): RectangularObstacle ctor,  *
+                               * Obstacle.h:82                                                   */
+    const double *robot_dims; /* n_robots x (length, width): RectangularRobot ctor, Robot.h:82   */
+} kcbs_world;
+
+/* First conflict of one plan; replaces the result of KCBS::findConflicts (call sites
+ * demo_*.cpp:155,168, Benchmark.h:151-158). r1 = -1 when the plan is conflict free. */
+typedef struct kcbs_conflict {
+    int32_t r1, r2;  /* robot indices in addIndividual order, r1 < r2                           */
+    int32_t k_start; /* earliest colliding time index                                           */
+    int32_t k_end;   /* last consecutive colliding index of the same pair                       */
+} kcbs_conflict;
+
+typedef struct kcbs_ctx kcbs_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+
+KCBS_API int kcbs_abi_version(void);
+KCBS_API const char *kcbs_status_string(int status);
+
+/* Fills *w with the constants every demo uses: bounds of createBounded2ndOrderCarStateSpace
+ * (StateSpaceDatabase.h:42-62) for x_max, y_max; step 0.1, integration step 0.01, car length 0.5. */
+KCBS_API void kcbs_world_defaults(kcbs_world *w, double x_max, double y_max);
+
+/* Creates a context on CUDA device `device`.  Fails with KCBS_ERR_NO_DEVICE when the device is
+ * absent or not compute capability 10.x. */
+KCBS_API int kcbs_create(const kcbs_world *world, int device, kcbs_ctx **out);
+KCBS_API void kcbs_destroy(kcbs_ctx *ctx);
+/* Last error text of this context (or of the failed kcbs_create when ctx == NULL). */
+KCBS_API const char *kcbs_last_error(const kcbs_ctx *ctx);
+/* Blocks until all work queued on the context stream has finished. */
+KCBS_API int kcbs_sync(kcbs_ctx *ctx);
+/* Pinned host memory for callers that want full-rate transfers through the host entry points. */
+KCBS_API int kcbs_host_alloc(kcbs_ctx *ctx, size_t bytes, void **out);
+KCBS_API int kcbs_host_free(kcbs_ctx *ctx, void *p);
+
+/* ---- (1) batched tree expansion ------------------------------------------------------------
+ * Replaces n calls of oc::SpaceInformation::propagateWhileValid(state, control, steps, result)
+ * with the propagator of demo_*.cpp:111-112 (SecondOrderCarODE + RK4 + theta wrap,
+ * StatePropagatorDatabase.h:44-74) and the validity checker of
+ * StateValidityCheckerDatabase.h:54-75, for robot `robot`.
+ *
+ *   parents     5 planes of n_parents floats.
+ *   parent_idx  n indices into parents, or NULL: then n_parents must be 1 (one shared parent,
+ *               a tree-node expansion) or n (sample i starts at parent i).
+ *   controls    2 planes of n floats (a, phidot).
+ *   steps       n requested step counts in [0, max_steps], or NULL for max_steps everywhere.
+ *   seg_out     [5][max_steps][n] floats: seg_out[(c*max_steps + j)*n + i] is component c of
+ *               sample i after j+1 steps, written for j < valid_steps[i] only.  May be NULL.
+ *   final_out   [5][n] floats, last valid state (the parent when 0 steps are valid). May be NULL.
+ *   valid_steps n ints: the propagateWhileValid return value.
+ */
+KCBS_API int kcbs_propagate_batch(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents, const float *parents,
+                                  const int32_t *parent_idx, const float *controls, const int32_t *steps,
+                                  int max_steps, float *seg_out, float *final_out, int32_t *valid_steps);
+KCBS_API int kcbs_propagate_batch_dev(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents,
+                                      const float *parents, const int32_t *parent_idx, const float *controls,
+                                      const int32_t *steps, int max_steps, float *seg_out, float *final_out,
+                                      int32_t *valid_steps, void *stream);
+
+/* ---- (2) batched state validity ------------------------------------------------------------
+ * Replaces n calls of homogeneous2ndOrderCarSystemSVC::isValid
+ * (StateValidityCheckerDatabase.h:54-75) for robot `robot`.
+ *   states   5 planes of n floats.
+ *   bitmask  (n + 31) / 32 words; bit (i & 31) of word i >> 5 is 1 when state i is valid.
+ */
+KCBS_API int kcbs_validity_batch(kcbs_ctx *ctx, int robot, int64_t n, const float *states, uint32_t *bitmask);
+KCBS_API int kcbs_validity_batch_dev(kcbs_ctx *ctx, int robot, int64_t n, const float *states, uint32_t *bitmask,
+                                     void *stream);
+
+/* ---- (3) plan validation ---------------------------------------------------------------------
+ * Replaces KCBS::findConflicts' scan over homogeneous2ndOrderCarSystemSVC::areStatesValid
+ * (StateValidityCheckerDatabase.h:78-125) for n_plans candidate plans at once.
+ *   traj     [n_plans][R][3][T] floats: per robot the x, y and theta planes, one state per
+ *            propagation step (already interpolated).
+ *   lengths  [n_plans][R] path lengths (1..T), shorter paths are padded with their last state;
+ *            NULL when every path has T states.
+ *   out      n_plans results: the earliest (k, r1, r2) in lexicographic order, extended to k_end.
+ * R is the number of robots of the world given to kcbs_create (robot_dims rows are used by index).
+ */
+KCBS_API int kcbs_first_conflict(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj,
+                                 const int32_t *lengths, kcbs_conflict *out);
+KCBS_API int kcbs_first_conflict_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj,
+                                     const int32_t *lengths, kcbs_conflict *out, void *stream);
+
+/* Partial scan for sharding one plan set across GPUs: only time indices [k_lo, k_hi) are
+ * examined and the result is the packed key (k << 16 | r1 << 8 | r2), UINT64_MAX when none;
+ * the minimum over all shards is the first conflict.  keys = n_plans device words. */
+KCBS_API int kcbs_conflict_keys_dev(kcbs_ctx *ctx, int n_plans, int R, int T, int k_lo, int k_hi,
+                                    const float *traj, const int32_t *lengths, uint64_t *keys, void *stream);
+/* Turns reduced keys into kcbs_conflict records (runs the k_end extension). */
+KCBS_API int kcbs_conflict_finish_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj,
+                                      const int32_t *lengths, const uint64_t *keys, kcbs_conflict *out,
+                                      void *stream);
+
+/* ---- measurement support ------------------------------------------------------------------- */
+
+/* Runs an FFMA-saturating kernel and reports the device's sustained FP32 rate in TFLOP/s
+ * (2 flops per FMA); the denominator of the propagation roofline. */
+KCBS_API int kcbs_measure_fp32_peak(kcbs_ctx *ctx, double *tflops);
+/* Number of kernels this context has launched since creation. */
+KCBS_API int64_t kcbs_launch_count(const kcbs_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KCBS_B200_H */

@@ -1,0 +1,276 @@
+"""ctypes binding of include/kcbs_b200.h.  No compute happens in Python and there is no fallback:
+if libkcbs_b200.so is missing or a context cannot be created, the call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB: Optional[C.CDLL] = None
+
+KCBS_MAX_OBSTACLES = 64
+KCBS_MAX_ROBOTS = 64
+KCBS_MAX_STEPS = 32
+NO_CONFLICT_KEY = 0xFFFFFFFFFFFFFFFF
+
+
+class KcbsError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"kcbs status {status}: {message}")
+        self.status = status
+
+
+class _CWorld(C.Structure):
+    _fields_ = [
+        ("lo", C.c_double * 4),
+        ("hi", C.c_double * 4),
+        ("step_size", C.c_double),
+        ("integration_step", C.c_double),
+        ("car_length", C.c_double),
+        ("n_obstacles", C.c_int32),
+        ("n_robots", C.c_int32),
+        ("obstacles", C.POINTER(C.c_double)),
+        ("robot_dims", C.POINTER(C.c_double)),
+    ]
+
+
+class Conflict(C.Structure):
+    """kcbs_conflict: first conflict of a plan (r1 = -1 when conflict free)."""
+
+    _fields_ = [("r1", C.c_int32), ("r2", C.c_int32), ("k_start", C.c_int32), ("k_end", C.c_int32)]
+
+    def as_tuple(self):
+        return (self.r1, self.r2, self.k_start, self.k_end)
+
+
+CONFLICT_DTYPE = np.dtype([("r1", "<i4"), ("r2", "<i4"), ("k_start", "<i4"), ("k_end", "<i4")])
+
+EXPORTS = [
+    "kcbs_abi_version", "kcbs_status_string", "kcbs_world_defaults", "kcbs_create", "kcbs_destroy",
+    "kcbs_last_error", "kcbs_sync", "kcbs_host_alloc", "kcbs_host_free", "kcbs_propagate_batch",
+    "kcbs_propagate_batch_dev", "kcbs_validity_batch", "kcbs_validity_batch_dev", "kcbs_first_conflict",
+    "kcbs_first_conflict_dev", "kcbs_conflict_keys_dev", "kcbs_conflict_finish_dev",
+    "kcbs_measure_fp32_peak", "kcbs_launch_count",
+]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libkcbs_b200.so")
+
+
+def load_library() -> C.CDLL:
+    """Loads libkcbs_b200.so (built in-tree by __graft_entry__.build()); raises if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no Python/CPU fallback)")
+    lib = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    lib.kcbs_abi_version.restype = C.c_int
+    lib.kcbs_status_string.restype = C.c_char_p
+    lib.kcbs_status_string.argtypes = [C.c_int]
+    lib.kcbs_world_defaults.restype = None
+    lib.kcbs_world_defaults.argtypes = [C.POINTER(_CWorld), C.c_double, C.c_double]
+    lib.kcbs_create.argtypes = [C.POINTER(_CWorld), i32, C.POINTER(vp)]
+    lib.kcbs_destroy.restype = None
+    lib.kcbs_destroy.argtypes = [vp]
+    lib.kcbs_last_error.restype = C.c_char_p
+    lib.kcbs_last_error.argtypes = [vp]
+    lib.kcbs_sync.argtypes = [vp]
+    lib.kcbs_host_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    lib.kcbs_host_free.argtypes = [vp, vp]
+    prop = [vp, i32, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.kcbs_propagate_batch.argtypes = prop
+    lib.kcbs_propagate_batch_dev.argtypes = prop + [vp]
+    lib.kcbs_validity_batch.argtypes = [vp, i32, i64, vp, vp]
+    lib.kcbs_validity_batch_dev.argtypes = [vp, i32, i64, vp, vp, vp]
+    lib.kcbs_first_conflict.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+    lib.kcbs_first_conflict_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.kcbs_conflict_keys_dev.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.kcbs_conflict_finish_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.kcbs_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.kcbs_launch_count.restype = i64
+    lib.kcbs_launch_count.argtypes = [vp]
+    _LIB = lib
+    return lib
+
+
+@dataclass
+class World:
+    """Scene description (kcbs_world).  obstacles: rows (x, y, length, width) as given to
+    RectangularObstacle (Obstacle.h:82); robot_dims: rows (length, width) as given to
+    RectangularRobot (Robot.h:82), in addIndividual order."""
+
+    x_max: float
+    y_max: float
+    robot_dims: Sequence[Sequence[float]]
+    obstacles: Sequence[Sequence[float]] = field(default_factory=list)
+    lo: Optional[Sequence[float]] = None
+    hi: Optional[Sequence[float]] = None
+    step_size: float = 0.1
+    integration_step: float = 1e-2
+    car_length: float = 0.5
+
+    def bounds(self):
+        lo = list(self.lo) if self.lo is not None else [0.0, 0.0, -1.0, -np.pi / 3]
+        hi = list(self.hi) if self.hi is not None else [float(self.x_max), float(self.y_max), 1.0, np.pi / 3]
+        return lo, hi
+
+
+def _ptr(a) -> Optional[int]:
+    """Host pointer of a C-contiguous numpy array, device pointer of a torch tensor, or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous(), "tensor must be contiguous"
+        return a.data_ptr()
+    if isinstance(a, int):
+        return a
+    raise TypeError(type(a))
+
+
+class Context:
+    """kcbs_ctx.  Host-array methods mirror the reference-facing host entry points; *_dev methods
+    take torch CUDA tensors (or raw device pointers) and are asynchronous on `stream`."""
+
+    def __init__(self, world: World, device: int = 0):
+        self._lib = load_library()
+        self.world = world
+        lo, hi = world.bounds()
+        self._obs = np.ascontiguousarray(np.asarray(world.obstacles, dtype=np.float64).reshape(-1, 4))
+        self._dims = np.ascontiguousarray(np.asarray(world.robot_dims, dtype=np.float64).reshape(-1, 2))
+        cw = _CWorld()
+        cw.lo[:] = lo
+        cw.hi[:] = hi
+        cw.step_size, cw.integration_step, cw.car_length = world.step_size, world.integration_step, world.car_length
+        cw.n_obstacles, cw.n_robots = len(self._obs), len(self._dims)
+        cw.obstacles = self._obs.ctypes.data_as(C.POINTER(C.c_double)) if len(self._obs) else None
+        cw.robot_dims = self._dims.ctypes.data_as(C.POINTER(C.c_double))
+        h = C.c_void_p()
+        st = self._lib.kcbs_create(C.byref(cw), device, C.byref(h))
+        if st != 0:
+            raise KcbsError(st, self._lib.kcbs_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    # -- plumbing -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kcbs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, st: int):
+        if st != 0:
+            raise KcbsError(st, self._lib.kcbs_last_error(self._h).decode())
+
+    def sync(self):
+        self._check(self._lib.kcbs_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.kcbs_launch_count(self._h))
+
+    def measure_fp32_peak(self) -> float:
+        v = C.c_double()
+        self._check(self._lib.kcbs_measure_fp32_peak(self._h, C.byref(v)))
+        return v.value
+
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        """numpy array over pinned host memory from kcbs_host_alloc (freed with the context)."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._check(self._lib.kcbs_host_alloc(self._h, nbytes, C.byref(p)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        return arr
+
+    # -- (1) propagation ------------------------------------------------------------------
+    def propagate_batch(self, robot, parents, controls, steps=None, parent_idx=None, max_steps=10,
+                        want_seg=True, want_final=True, out=None):
+        """Host entry point kcbs_propagate_batch.  parents [5, n_parents], controls [2, n] float32.
+        Returns (seg [5, max_steps, n] or None, final [5, n] or None, valid_steps [n])."""
+        parents = np.ascontiguousarray(parents, dtype=np.float32)
+        controls = np.ascontiguousarray(controls, dtype=np.float32)
+        n, n_parents = controls.shape[1], parents.shape[1]
+        steps = None if steps is None else np.ascontiguousarray(steps, dtype=np.int32)
+        parent_idx = None if parent_idx is None else np.ascontiguousarray(parent_idx, dtype=np.int32)
+        if out is not None:
+            seg, fin, valid = out
+        else:
+            seg = np.zeros((5, max_steps, n), np.float32) if want_seg else None
+            fin = np.zeros((5, n), np.float32) if want_final else None
+            valid = np.zeros(n, np.int32)
+        self._check(self._lib.kcbs_propagate_batch(self._h, robot, n, n_parents, _ptr(parents), _ptr(parent_idx),
+                                                   _ptr(controls), _ptr(steps), max_steps, _ptr(seg), _ptr(fin),
+                                                   _ptr(valid)))
+        return seg, fin, valid
+
+    def propagate_batch_dev(self, robot, n, n_parents, parents, controls, steps, parent_idx, max_steps, seg, fin,
+                            valid, stream=None):
+        self._check(self._lib.kcbs_propagate_batch_dev(self._h, robot, n, n_parents, _ptr(parents), _ptr(parent_idx),
+                                                       _ptr(controls), _ptr(steps), max_steps, _ptr(seg), _ptr(fin),
+                                                       _ptr(valid), stream))
+
+    # -- (2) validity ---------------------------------------------------------------------
+    def validity_batch(self, robot, states, out=None):
+        """Host entry point kcbs_validity_batch.  states [5, n] float32 -> packed uint32 bitmask."""
+        states = np.ascontiguousarray(states, dtype=np.float32)
+        n = states.shape[1]
+        mask = out if out is not None else np.zeros((n + 31) // 32, np.uint32)
+        self._check(self._lib.kcbs_validity_batch(self._h, robot, n, _ptr(states), _ptr(mask)))
+        return mask
+
+    def validity_batch_dev(self, robot, n, states, bitmask, stream=None):
+        self._check(self._lib.kcbs_validity_batch_dev(self._h, robot, n, _ptr(states), _ptr(bitmask), stream))
+
+    @staticmethod
+    def unpack_mask(mask: np.ndarray, n: int) -> np.ndarray:
+        bits = np.unpackbits(mask.view(np.uint8), bitorder="little")
+        return bits[:n].astype(bool)
+
+    # -- (3) plan validation --------------------------------------------------------------
+    def first_conflict(self, traj, lengths=None, out=None):
+        """Host entry point kcbs_first_conflict.  traj [P, R, 3, T] float32 (or [R, 3, T])."""
+        traj = np.ascontiguousarray(traj, dtype=np.float32)
+        if traj.ndim == 3:
+            traj = traj[None]
+        P, R, _, T = traj.shape
+        lengths = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int32).reshape(P, R)
+        res = out if out is not None else np.zeros(P, CONFLICT_DTYPE)
+        self._check(self._lib.kcbs_first_conflict(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(res)))
+        return res
+
+    def first_conflict_dev(self, P, R, T, traj, lengths, out, stream=None):
+        self._check(self._lib.kcbs_first_conflict_dev(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(out), stream))
+
+    def conflict_keys_dev(self, P, R, T, k_lo, k_hi, traj, lengths, keys, stream=None):
+        self._check(self._lib.kcbs_conflict_keys_dev(self._h, P, R, T, k_lo, k_hi, _ptr(traj), _ptr(lengths),
+                                                     _ptr(keys), stream))
+
+    def conflict_finish_dev(self, P, R, T, traj, lengths, keys, out, stream=None):
+        self._check(self._lib.kcbs_conflict_finish_dev(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(keys),
+                                                       _ptr(out), stream))

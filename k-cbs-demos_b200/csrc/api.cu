@@ -1,0 +1,493 @@
+// api.cu -- the C ABI of include/kcbs_b200.h: context life cycle, scene upload, host-buffer and
+// device-pointer entry points.  No CPU fallback anywhere: a context cannot be created without an
+// sm_100-class device and every compute entry point launches the kernels of this library.
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "kcbs_device.cuh"
+#include "kernels.h"
+
+using namespace kcbs;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct kcbs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevWorld world;
+    int n_robots = 0;
+    long long launches = 0;
+    std::string err;
+    // grow-only device workspaces for the host-buffer entry points
+    DevBuf in0, in1, in2, in3, out0, out1, out2, keys;
+};
+
+namespace {
+
+int fail(kcbs_ctx *ctx, int status, const char *what, cudaError_t e = cudaSuccess)
+{
+    std::string msg = what;
+    if (e != cudaSuccess) {
+        msg += ": ";
+        msg += cudaGetErrorString(e);
+    }
+    if (ctx)
+        ctx->err = msg;
+    else
+        g_create_error = msg;
+    return status;
+}
+
+#define KCBS_CUDA(ctx, call)                                              \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? KCBS_ERR_OUT_OF_MEMORY : KCBS_ERR_CUDA, #call, e_); \
+    } while (0)
+
+int reserve(kcbs_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return KCBS_OK;
+    if (b.p) {
+        KCBS_CUDA(ctx, cudaDeviceSynchronize());  // callers may still use it on their own stream
+        KCBS_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    const size_t want = bytes + bytes / 4 + 256;
+    KCBS_CUDA(ctx, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return KCBS_OK;
+}
+
+// Largest float f with ((double)f - eps <= hi)  /  smallest float f with ((double)f + eps >= lo):
+// the float image of OMPL's RealVectorStateSpace::satisfiesBounds test.
+float hi_threshold(double hi, double eps)
+{
+    float f = (float)hi;
+    while ((double)f - eps > hi) f = nextafterf(f, -INFINITY);
+    while ((double)nextafterf(f, INFINITY) - eps <= hi) f = nextafterf(f, INFINITY);
+    return f;
+}
+float lo_threshold(double lo, double eps)
+{
+    float f = (float)lo;
+    while ((double)f + eps < lo) f = nextafterf(f, INFINITY);
+    while ((double)nextafterf(f, -INFINITY) + eps >= lo) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
+// Number of h-steps odeint::integrate_const takes over [0, duration] (ODEBasicSolver::solve).
+int count_substeps(double duration, double h)
+{
+    double time = 0.0;
+    int step = 0;
+    while (((time + h) - duration) <= DBL_EPSILON && step < 1000000) {
+        ++step;
+        time = 0.0 + (double)step * h;
+    }
+    return step;
+}
+
+int build_world(const kcbs_world *src, DevWorld &w)
+{
+    if (!src) return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "world is null");
+    if (src->n_obstacles < 0 || src->n_obstacles > KCBS_MAX_OBSTACLES)
+        return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "n_obstacles out of range");
+    if (src->n_robots < 1 || src->n_robots > KCBS_MAX_ROBOTS)
+        return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "n_robots out of range");
+    if ((src->n_obstacles > 0 && !src->obstacles) || !src->robot_dims)
+        return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "obstacles / robot_dims is null");
+    if (!(src->step_size > 0) || !(src->integration_step > 0) || !(src->car_length > 0))
+        return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "step_size, integration_step and car_length must be > 0");
+    std::memset(&w, 0, sizeof w);
+    for (int i = 0; i < 4; ++i) {
+        if (!(src->lo[i] <= src->hi[i])) return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "lo > hi");
+        w.lo_t[i] = lo_threshold(src->lo[i], DBL_EPSILON);
+        w.hi_t[i] = hi_threshold(src->hi[i], DBL_EPSILON);
+    }
+    // SO2StateSpace::satisfiesBounds is strict: value < pi + eps && value > -pi - eps
+    {
+        const double hi = M_PI + DBL_EPSILON, lo = -M_PI - DBL_EPSILON;
+        float f = (float)hi;
+        while (!((double)f < hi)) f = nextafterf(f, -INFINITY);
+        w.th_hi_t = f;
+        f = (float)lo;
+        while (!((double)f > lo)) f = nextafterf(f, INFINITY);
+        w.th_lo_t = f;
+    }
+    w.h = (float)src->integration_step;
+    w.step = (float)src->step_size;
+    w.inv_len = (float)(1.0 / src->car_length);
+    w.n_sub = count_substeps(src->step_size, src->integration_step);
+    w.n_obs = src->n_obstacles;
+    w.n_robots = src->n_robots;
+    for (int o = 0; o < src->n_obstacles; ++o) {
+        const double *ob = src->obstacles + 4 * o;  // Obstacle.h:82-99
+        if (!(ob[2] >= 0) || !(ob[3] >= 0)) return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "negative obstacle size");
+        w.obs_cx[o] = (float)(ob[0] + ob[2] / 2);
+        w.obs_cy[o] = (float)(ob[1] + ob[3] / 2);
+        w.obs_hx[o] = (float)(ob[2] / 2);
+        w.obs_hy[o] = (float)(ob[3] / 2);
+    }
+    float max_rad = 0.0f;
+    for (int r = 0; r < src->n_robots; ++r) {
+        const double *d = src->robot_dims + 2 * r;  // Robot.h:82-99
+        if (!(d[0] > 0) || !(d[1] > 0)) return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "robot size must be > 0");
+        w.rob_hl[r] = (float)(d[0] / 2);
+        w.rob_hw[r] = (float)(d[1] / 2);
+        w.rob_rad[r] = (float)std::sqrt(d[0] * d[0] / 4 + d[1] * d[1] / 4);
+        // the cull radii must never be smaller than the true radius
+        if ((double)w.rob_rad[r] < std::sqrt(d[0] * d[0] / 4 + d[1] * d[1] / 4)) w.rob_rad[r] = nextafterf(w.rob_rad[r], INFINITY);
+        max_rad = fmaxf(max_rad, w.rob_rad[r]);
+    }
+    w.max_rad = max_rad;
+    return KCBS_OK;
+}
+
+cudaStream_t pick(kcbs_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+int check_robot(kcbs_ctx *ctx, int robot)
+{
+    if (robot < 0 || robot >= ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "robot index out of range");
+    return KCBS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kcbs_abi_version(void) { return KCBS_ABI_VERSION; }
+
+const char *kcbs_status_string(int status)
+{
+    switch (status) {
+        case KCBS_OK: return "ok";
+        case KCBS_ERR_INVALID_ARGUMENT: return "invalid argument";
+        case KCBS_ERR_CUDA: return "CUDA error";
+        case KCBS_ERR_NO_DEVICE: return "no sm_100 device (no CPU fallback)";
+        case KCBS_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case KCBS_ERR_UNKNOWN_ROBOT: return "unknown robot";
+        default: return "unknown status";
+    }
+}
+
+void kcbs_world_defaults(kcbs_world *w, double x_max, double y_max)
+{
+    if (!w) return;
+    std::memset(w, 0, sizeof *w);
+    // StateSpaceDatabase.h:49-59
+    w->lo[0] = 0.0;          w->hi[0] = x_max;
+    w->lo[1] = 0.0;          w->hi[1] = y_max;
+    w->lo[2] = -1.0;         w->hi[2] = 1.0;
+    w->lo[3] = -M_PI / 3;    w->hi[3] = M_PI / 3;
+    w->step_size = 0.1;          // demo_*.cpp:115
+    w->integration_step = 1e-2;  // ODEBasicSolver default
+    w->car_length = 0.5;         // StatePropagatorDatabase.h:53
+}
+
+int kcbs_create(const kcbs_world *world, int device, kcbs_ctx **out)
+{
+    if (!out) return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    DevWorld w;
+    int st = build_world(world, w);
+    if (st != KCBS_OK) return st;
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(nullptr, KCBS_ERR_NO_DEVICE, "no CUDA device available (this library has no CPU fallback)", e);
+    if (device < 0 || device >= count) return fail(nullptr, KCBS_ERR_NO_DEVICE, "device index out of range");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, KCBS_ERR_CUDA, "cudaGetDeviceProperties", e);
+    if (prop.major != 10)
+        return fail(nullptr, KCBS_ERR_NO_DEVICE, "device is not compute capability 10.x (kernels are sm_100a only)");
+
+    kcbs_ctx *ctx = new (std::nothrow) kcbs_ctx();
+    if (!ctx) return fail(nullptr, KCBS_ERR_OUT_OF_MEMORY, "host allocation failed");
+    ctx->device = device;
+    ctx->world = w;
+    ctx->n_robots = world->n_robots;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = init_conflict_kernels()) != cudaSuccess) {
+        fail(nullptr, KCBS_ERR_CUDA, "context setup", e);
+        kcbs_destroy(ctx);
+        return KCBS_ERR_CUDA;
+    }
+    *out = ctx;
+    return KCBS_OK;
+}
+
+void kcbs_destroy(kcbs_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->in0, &ctx->in1, &ctx->in2, &ctx->in3, &ctx->out0, &ctx->out1, &ctx->out2, &ctx->keys};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *kcbs_last_error(const kcbs_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int kcbs_sync(kcbs_ctx *ctx)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    KCBS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KCBS_OK;
+}
+
+int kcbs_host_alloc(kcbs_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return KCBS_ERR_INVALID_ARGUMENT;
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCBS_CUDA(ctx, cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return KCBS_OK;
+}
+
+int kcbs_host_free(kcbs_ctx *ctx, void *p)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    if (p) KCBS_CUDA(ctx, cudaFreeHost(p));
+    return KCBS_OK;
+}
+
+/* ---- (1) propagation -------------------------------------------------------------------- */
+
+int kcbs_propagate_batch_dev(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents, const float *parents,
+                             const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,
+                             float *seg_out, float *final_out, int32_t *valid_steps, void *stream)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    int st = check_robot(ctx, robot);
+    if (st != KCBS_OK) return st;
+    if (n < 0 || n_parents < 1 || max_steps < 0 || max_steps > KCBS_MAX_STEPS)
+        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n, n_parents or max_steps out of range");
+    if (n == 0) return KCBS_OK;
+    if (!parents || !controls) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "parents / controls is null");
+    if (!parent_idx && n_parents != 1 && n_parents != n)
+        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "without parent_idx, n_parents must be 1 or n");
+    if (n > (int64_t)0x7fffffff * 256) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n too large");
+    PropArgs a;
+    a.n = n; a.n_parents = n_parents; a.parents = parents; a.parent_idx = parent_idx; a.controls = controls;
+    a.steps = steps; a.seg = seg_out; a.fin = final_out; a.valid_steps = valid_steps; a.max_steps = max_steps;
+    a.robot = robot;
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCBS_CUDA(ctx, launch_propagate(ctx->world, a, pick(ctx, stream)));
+    ctx->launches += 1;
+    return KCBS_OK;
+}
+
+int kcbs_propagate_batch(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents, const float *parents,
+                         const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,
+                         float *seg_out, float *final_out, int32_t *valid_steps)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    if (n < 0 || n_parents < 1 || max_steps < 0 || max_steps > KCBS_MAX_STEPS)
+        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n, n_parents or max_steps out of range");
+    if (n == 0) return KCBS_OK;
+    if (!parents || !controls) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "parents / controls is null");
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t b_par = sizeof(float) * 5 * (size_t)n_parents, b_ctl = sizeof(float) * 2 * (size_t)n;
+    const size_t b_idx = sizeof(int32_t) * (size_t)n;
+    const size_t b_seg = sizeof(float) * 5 * (size_t)max_steps * (size_t)n, b_fin = sizeof(float) * 5 * (size_t)n;
+    int st;
+    if ((st = reserve(ctx, ctx->in0, b_par)) || (st = reserve(ctx, ctx->in1, b_ctl)) ||
+        (st = reserve(ctx, ctx->in2, parent_idx ? b_idx : 0)) || (st = reserve(ctx, ctx->in3, steps ? b_idx : 0)) ||
+        (st = reserve(ctx, ctx->out0, seg_out ? b_seg : 0)) || (st = reserve(ctx, ctx->out1, final_out ? b_fin : 0)) ||
+        (st = reserve(ctx, ctx->out2, b_idx)))
+        return st;
+    KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in0.p, parents, b_par, cudaMemcpyHostToDevice, s));
+    KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in1.p, controls, b_ctl, cudaMemcpyHostToDevice, s));
+    if (parent_idx) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in2.p, parent_idx, b_idx, cudaMemcpyHostToDevice, s));
+    if (steps) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in3.p, steps, b_idx, cudaMemcpyHostToDevice, s));
+    // unwritten tail states of a segment read back as zero rather than stale workspace contents
+    if (seg_out) KCBS_CUDA(ctx, cudaMemsetAsync(ctx->out0.p, 0, b_seg, s));
+    st = kcbs_propagate_batch_dev(ctx, robot, n, n_parents, (const float *)ctx->in0.p,
+                                  parent_idx ? (const int32_t *)ctx->in2.p : nullptr, (const float *)ctx->in1.p,
+                                  steps ? (const int32_t *)ctx->in3.p : nullptr, max_steps,
+                                  seg_out ? (float *)ctx->out0.p : nullptr, final_out ? (float *)ctx->out1.p : nullptr,
+                                  (int32_t *)ctx->out2.p, s);
+    if (st != KCBS_OK) return st;
+    if (seg_out) KCBS_CUDA(ctx, cudaMemcpyAsync(seg_out, ctx->out0.p, b_seg, cudaMemcpyDeviceToHost, s));
+    if (final_out) KCBS_CUDA(ctx, cudaMemcpyAsync(final_out, ctx->out1.p, b_fin, cudaMemcpyDeviceToHost, s));
+    if (valid_steps) KCBS_CUDA(ctx, cudaMemcpyAsync(valid_steps, ctx->out2.p, b_idx, cudaMemcpyDeviceToHost, s));
+    KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+    return KCBS_OK;
+}
+
+/* ---- (2) validity -------------------------------------------------------------------------- */
+
+int kcbs_validity_batch_dev(kcbs_ctx *ctx, int robot, int64_t n, const float *states, uint32_t *bitmask, void *stream)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    int st = check_robot(ctx, robot);
+    if (st != KCBS_OK) return st;
+    if (n < 0) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n is negative");
+    if (n == 0) return KCBS_OK;
+    if (!states || !bitmask) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "states / bitmask is null");
+    ValidArgs a;
+    a.n = n; a.states = states; a.bitmask = bitmask; a.robot = robot;
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCBS_CUDA(ctx, launch_validity(ctx->world, a, pick(ctx, stream)));
+    ctx->launches += 1;
+    return KCBS_OK;
+}
+
+int kcbs_validity_batch(kcbs_ctx *ctx, int robot, int64_t n, const float *states, uint32_t *bitmask)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    if (n < 0) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n is negative");
+    if (n == 0) return KCBS_OK;
+    if (!states || !bitmask) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "states / bitmask is null");
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t b_in = sizeof(float) * 5 * (size_t)n, b_out = sizeof(uint32_t) * (size_t)((n + 31) / 32);
+    int st;
+    if ((st = reserve(ctx, ctx->in0, b_in)) || (st = reserve(ctx, ctx->out0, b_out))) return st;
+    KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in0.p, states, b_in, cudaMemcpyHostToDevice, s));
+    st = kcbs_validity_batch_dev(ctx, robot, n, (const float *)ctx->in0.p, (uint32_t *)ctx->out0.p, s);
+    if (st != KCBS_OK) return st;
+    KCBS_CUDA(ctx, cudaMemcpyAsync(bitmask, ctx->out0.p, b_out, cudaMemcpyDeviceToHost, s));
+    KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+    return KCBS_OK;
+}
+
+/* ---- (3) plan validation --------------------------------------------------------------------- */
+
+static int check_plan_args(kcbs_ctx *ctx, int n_plans, int R, int T)
+{
+    if (n_plans < 0 || T < 0) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n_plans or T is negative");
+    if (R < 1 || R > ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "R exceeds the robots of this world");
+    if ((long long)T >= (1ll << 31)) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "T too large");
+    return KCBS_OK;
+}
+
+int kcbs_conflict_keys_dev(kcbs_ctx *ctx, int n_plans, int R, int T, int k_lo, int k_hi, const float *traj,
+                           const int32_t *lengths, uint64_t *keys, void *stream)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    int st = check_plan_args(ctx, n_plans, R, T);
+    if (st != KCBS_OK) return st;
+    if (n_plans == 0) return KCBS_OK;
+    if (!keys || (T > 0 && !traj)) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "traj / keys is null");
+    k_lo = k_lo < 0 ? 0 : k_lo;
+    k_hi = k_hi > T ? T : k_hi;
+    cudaStream_t s = pick(ctx, stream);
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCBS_CUDA(ctx, launch_fill_keys((unsigned long long *)keys, n_plans, s));
+    ctx->launches += 1;
+    if (k_hi > k_lo) {
+        ConflictArgs a;
+        a.traj = traj; a.lengths = lengths; a.keys = (unsigned long long *)keys; a.P = n_plans; a.R = R; a.T = T;
+        a.k_lo = k_lo; a.k_hi = k_hi;
+        KCBS_CUDA(ctx, launch_conflict_keys(ctx->world, a, s));
+        ctx->launches += conflict_keys_launches();
+    }
+    return KCBS_OK;
+}
+
+int kcbs_conflict_finish_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
+                             const uint64_t *keys, kcbs_conflict *out, void *stream)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    int st = check_plan_args(ctx, n_plans, R, T);
+    if (st != KCBS_OK) return st;
+    if (n_plans == 0) return KCBS_OK;
+    if (!keys || !out || (T > 0 && !traj)) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "traj / keys / out is null");
+    FinishArgs a;
+    a.traj = traj; a.lengths = lengths; a.keys = (const unsigned long long *)keys; a.out = out; a.P = n_plans;
+    a.R = R; a.T = T;
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCBS_CUDA(ctx, launch_conflict_finish(ctx->world, a, pick(ctx, stream)));
+    ctx->launches += 1;
+    return KCBS_OK;
+}
+
+int kcbs_first_conflict_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
+                            kcbs_conflict *out, void *stream)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    int st = check_plan_args(ctx, n_plans, R, T);
+    if (st != KCBS_OK) return st;
+    if (n_plans == 0) return KCBS_OK;
+    if ((st = reserve(ctx, ctx->keys, sizeof(uint64_t) * (size_t)n_plans))) return st;
+    if ((st = kcbs_conflict_keys_dev(ctx, n_plans, R, T, 0, T, traj, lengths, (uint64_t *)ctx->keys.p, stream))) return st;
+    return kcbs_conflict_finish_dev(ctx, n_plans, R, T, traj, lengths, (const uint64_t *)ctx->keys.p, out, stream);
+}
+
+int kcbs_first_conflict(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
+                        kcbs_conflict *out)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    int st = check_plan_args(ctx, n_plans, R, T);
+    if (st != KCBS_OK) return st;
+    if (n_plans == 0) return KCBS_OK;
+    if (!out || (T > 0 && !traj)) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "traj / out is null");
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t b_traj = sizeof(float) * (size_t)n_plans * R * 3 * (size_t)T;
+    const size_t b_len = sizeof(int32_t) * (size_t)n_plans * R, b_out = sizeof(kcbs_conflict) * (size_t)n_plans;
+    if ((st = reserve(ctx, ctx->in0, b_traj)) || (st = reserve(ctx, ctx->in2, lengths ? b_len : 0)) ||
+        (st = reserve(ctx, ctx->out0, b_out)))
+        return st;
+    if (b_traj) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in0.p, traj, b_traj, cudaMemcpyHostToDevice, s));
+    if (lengths) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in2.p, lengths, b_len, cudaMemcpyHostToDevice, s));
+    st = kcbs_first_conflict_dev(ctx, n_plans, R, T, (const float *)ctx->in0.p,
+                                 lengths ? (const int32_t *)ctx->in2.p : nullptr, (kcbs_conflict *)ctx->out0.p, s);
+    if (st != KCBS_OK) return st;
+    KCBS_CUDA(ctx, cudaMemcpyAsync(out, ctx->out0.p, b_out, cudaMemcpyDeviceToHost, s));
+    KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+    return KCBS_OK;
+}
+
+/* ---- measurement support ------------------------------------------------------------------- */
+
+int kcbs_measure_fp32_peak(kcbs_ctx *ctx, double *tflops)
+{
+    if (!ctx || !tflops) return KCBS_ERR_INVALID_ARGUMENT;
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int st = reserve(ctx, ctx->out2, 256);
+    if (st != KCBS_OK) return st;
+    double flops = 0, best = 0;
+    KCBS_CUDA(ctx, launch_fp32_probe((float *)ctx->out2.p, 64, ctx->stream, &flops));  // warm-up
+    for (int rep = 0; rep < 5; ++rep) {
+        KCBS_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        KCBS_CUDA(ctx, launch_fp32_probe((float *)ctx->out2.p, 2048, ctx->stream, &flops));
+        KCBS_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        KCBS_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        KCBS_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double t = flops / (ms * 1e-3) * 1e-12;
+        if (t > best) best = t;
+    }
+    ctx->launches += 6;
+    *tflops = best;
+    return KCBS_OK;
+}
+
+int64_t kcbs_launch_count(const kcbs_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

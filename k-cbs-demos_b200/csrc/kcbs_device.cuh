@@ -1,0 +1,131 @@
+// kcbs_device.cuh -- device-side scene constants and the geometric predicates shared by the
+// three kernels (propagate / validity / conflict).  sm_100a only.
+//
+// Reference semantics restated here (file:line relative to the K-CBS-Demos tree):
+//   bounds            StateSpaceDatabase.h:49-59 + OMPL RealVectorStateSpace::satisfiesBounds
+//   broad phase       StateValidityCheckerDatabase.h:134-141
+//   robot footprint   StateValidityCheckerDatabase.h:152-155 / :188-191  (rotation by -theta)
+//   narrow phase      boost::geometry::disjoint at :173 / :201 == SAT with touching = collision
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kcbs_b200.h"
+
+namespace kcbs {
+
+// Passed to every kernel as a __grid_constant__ parameter: it lives in the constant bank, so the
+// warp-uniform obstacle loop reads it through the uniform datapath (no LSU traffic).
+struct DevWorld {
+    // Exact float thresholds: a float value f passes the reference's double test
+    // (f - DBL_EPSILON <= hi && f + DBL_EPSILON >= lo) iff lo_t <= f <= hi_t.  Computed on the host.
+    float lo_t[4];
+    float hi_t[4];
+    float th_lo_t, th_hi_t;  // SO2StateSpace::satisfiesBounds thresholds
+    float h;                 // RK4 sub-step (ODEBasicSolver intStep)
+    float step;              // propagation step size
+    float inv_len;           // 1 / car_length
+    int n_sub;               // RK4 sub-steps per propagation step (integrate_const rule)
+    int n_obs;
+    int n_robots;
+    float max_rad;           // largest robot bounding radius
+    float pad0;
+    float obs_cx[KCBS_MAX_OBSTACLES];  // Obstacle.h:85-86 centre
+    float obs_cy[KCBS_MAX_OBSTACLES];
+    float obs_hx[KCBS_MAX_OBSTACLES];  // half extents
+    float obs_hy[KCBS_MAX_OBSTACLES];
+    float rob_hl[KCBS_MAX_ROBOTS];     // Robot.h:85-88 half length / half width
+    float rob_hw[KCBS_MAX_ROBOTS];
+    float rob_rad[KCBS_MAX_ROBOTS];    // Robot.h:99
+};
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kTwoPi = 6.28318530717958647692f;
+
+// SO2StateSpace::enforceBounds restated for float: result in [-pi, pi).
+__device__ __forceinline__ float wrap_angle(float th)
+{
+    if (th >= kPi)
+        th -= kTwoPi;
+    else if (th < -kPi)
+        th += kTwoPi;
+    if (!(th >= -kPi && th < kPi)) {  // more than one turn away: rare general path
+        th = fmodf(th, kTwoPi);
+        if (th < -kPi)
+            th += kTwoPi;
+        else if (th >= kPi)
+            th -= kTwoPi;
+    }
+    return th;
+}
+
+__device__ __forceinline__ bool in_bounds(const DevWorld &w, float x, float y, float v, float phi, float th)
+{
+    bool ok = (x >= w.lo_t[0]) & (x <= w.hi_t[0]);
+    ok &= (y >= w.lo_t[1]) & (y <= w.hi_t[1]);
+    ok &= (v >= w.lo_t[2]) & (v <= w.hi_t[2]);
+    ok &= (phi >= w.lo_t[3]) & (phi <= w.hi_t[3]);
+    ok &= (th >= w.th_lo_t) & (th <= w.th_hi_t);
+    return ok;
+}
+
+// SAT gap, robot rectangle (half extents hl, hw, centre (x, y), axes e1 = (c, -s), e2 = (s, c)) against
+// an axis-aligned rectangle (centre (cx, cy), half extents (hx, hy)).  > 0 separated.
+__device__ __forceinline__ float sat_gap_obstacle(float x, float y, float c, float s, float hl, float hw, float cx,
+                                                  float cy, float hx, float hy)
+{
+    const float dx = cx - x, dy = cy - y;
+    const float ac = fabsf(c), as = fabsf(s);
+    const float g0 = fabsf(dx) - (hx + fmaf(hl, ac, hw * as));              // world x axis
+    const float g1 = fabsf(dy) - (hy + fmaf(hl, as, hw * ac));              // world y axis
+    const float g2 = fabsf(fmaf(dx, c, -dy * s)) - (hl + fmaf(hx, ac, hy * as));  // robot e1
+    const float g3 = fabsf(fmaf(dx, s, dy * c)) - (hw + fmaf(hx, as, hy * ac));   // robot e2
+    return fmaxf(fmaxf(g0, g1), fmaxf(g2, g3));
+}
+
+// SAT gap of two robot rectangles, each rotated by -theta (StateValidityCheckerDatabase.h:152-168).
+__device__ __forceinline__ float sat_gap_robots(float xa, float ya, float ca, float sa, float hla, float hwa, float xb,
+                                                float yb, float cb, float sb, float hlb, float hwb)
+{
+    const float dx = xb - xa, dy = yb - ya;
+    // |a1.b1| = |a2.b2| = |cos(tb - ta)|, |a1.b2| = |a2.b1| = |sin(tb - ta)|
+    const float cd = fabsf(fmaf(ca, cb, sa * sb));
+    const float sd = fabsf(fmaf(ca, sb, -sa * cb));
+    const float g0 = fabsf(fmaf(dx, ca, -dy * sa)) - (hla + fmaf(hlb, cd, hwb * sd));  // a1 = (ca, -sa)
+    const float g1 = fabsf(fmaf(dx, sa, dy * ca)) - (hwa + fmaf(hlb, sd, hwb * cd));   // a2 = (sa, ca)
+    const float g2 = fabsf(fmaf(dx, cb, -dy * sb)) - (hlb + fmaf(hla, cd, hwa * sd));  // b1
+    const float g3 = fabsf(fmaf(dx, sb, dy * cb)) - (hwb + fmaf(hla, sd, hwa * cd));   // b2
+    return fmaxf(fmaxf(g0, g1), fmaxf(g2, g3));
+}
+
+// Obstacle part of isValid (StateValidityCheckerDatabase.h:62-73).
+// The reference's circle test only skips obstacles whose SAT gap is positive anyway, so a cheaper
+// conservative cull (obstacle AABB grown by the robot's bounding radius) followed by the exact SAT
+// gives the same boolean.  cos/sin of the heading are only evaluated when some obstacle is near.
+__device__ __forceinline__ bool obstacles_clear(const DevWorld &w, float x, float y, float th, float hl, float hw,
+                                                float rad)
+{
+    bool ok = true, have = false;
+    float c = 1.0f, s = 0.0f;
+    for (int o = 0; o < w.n_obs; ++o) {
+        const float cx = w.obs_cx[o], cy = w.obs_cy[o], hx = w.obs_hx[o], hy = w.obs_hy[o];
+        if (fabsf(cx - x) <= hx + rad && fabsf(cy - y) <= hy + rad) {
+            if (!have) {
+                sincosf(th, &s, &c);
+                have = true;
+            }
+            ok &= sat_gap_obstacle(x, y, c, s, hl, hw, cx, cy, hx, hy) > 0.0f;
+        }
+    }
+    return ok;
+}
+
+// Packed first-conflict key: lexicographic (k, r1, r2) order == integer order.
+__host__ __device__ __forceinline__ unsigned long long pack_key(int k, int r1, int r2)
+{
+    return ((unsigned long long)(unsigned)k << 16) | ((unsigned long long)r1 << 8) | (unsigned long long)r2;
+}
+constexpr unsigned long long kNoConflict = ~0ull;
+
+}  // namespace kcbs

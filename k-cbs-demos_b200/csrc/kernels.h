@@ -1,0 +1,59 @@
+// kernels.h -- argument blocks and launchers of the three hot-path kernels (internal).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kcbs_b200.h"
+
+namespace kcbs {
+
+struct DevWorld;
+
+struct PropArgs {
+    long long n, n_parents;
+    const float *parents;      // [5][n_parents]
+    const int *parent_idx;     // [n] or null
+    const float *controls;     // [2][n]
+    const int *steps;          // [n] or null
+    float *seg;                // [5][max_steps][n] or null
+    float *fin;                // [5][n] or null
+    int *valid_steps;          // [n] or null
+    int max_steps;
+    int robot;
+};
+
+struct ValidArgs {
+    long long n;
+    const float *states;       // [5][n]
+    uint32_t *bitmask;         // [(n + 31) / 32]
+    int robot;
+};
+
+struct ConflictArgs {
+    const float *traj;         // [P][R][3][T]
+    const int *lengths;        // [P][R] or null
+    unsigned long long *keys;  // [P], pre-set to kNoConflict
+    int P, R, T;
+    int k_lo, k_hi;            // scanned time range
+};
+
+struct FinishArgs {
+    const float *traj;
+    const int *lengths;
+    const unsigned long long *keys;
+    kcbs_conflict *out;
+    int P, R, T;
+};
+
+cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t stream);
+cudaError_t launch_validity(const DevWorld &w, const ValidArgs &a, cudaStream_t stream);
+cudaError_t launch_conflict_keys(const DevWorld &w, const ConflictArgs &a, cudaStream_t stream);
+cudaError_t launch_conflict_finish(const DevWorld &w, const FinishArgs &a, cudaStream_t stream);
+cudaError_t launch_fill_keys(unsigned long long *keys, int n, cudaStream_t stream);
+// FFMA saturation probe: returns flops executed; elapsed time is measured by the caller.
+cudaError_t launch_fp32_probe(float *sink, int iters, cudaStream_t stream, double *flops);
+cudaError_t init_conflict_kernels();  // per-device function attributes; call once per context
+int conflict_keys_launches();  // kernels per launch_conflict_keys call (for launch accounting)
+
+}  // namespace kcbs
