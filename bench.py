@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the K-CBS low-level hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (sm_100a kernels via the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU path (oracle restatement,
+                                                            all host threads) on the same workload
+
+Workload (BASELINE.json configs[1]): Empty32x32, 10 robots, 2nd-order cars, batched propagation with
+65,536 controls per expansion.  One STEP = every robot's low-level planner issuing `--expansions`
+tree expansions (one C-ABI call = one kernel launch = one 64K-control expansion from one tree node),
+each robot on its own CUDA stream.  metric = propagated states/s; one unit = one 0.1 s propagation
+step of one control sample (10 RK4 sub-steps + theta wrap + validity).
+
+Printed JSON (one line, rank 0): the driver contract keys plus `roofline` (dominant kernel:
+k_propagate, FP32-pipe bound), `cpu_baseline`, `e2e` (host buffers through the reference-facing
+host entry point, H2D + D2H inside the timed region), `clocks`, `gpu_launches`, and `secondary`
+(validity and conflict-scan throughput with their HBM rooflines).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as graft  # noqa: E402
+
+SCENE = "Empty32x32_10robots"
+N_CONTROLS = 65536
+MAX_STEPS = 10
+FLOPS_PER_STATE = 980.0      # 860 arithmetic + 120 transcendental FP32 ops per propagated state
+BYTES_PER_STATE = 20.0       # 5 f32 written per propagated state
+BYTES_PER_SAMPLE = 16.0      # 2 f32 controls + 1 i32 steps read + 1 i32 valid count written per sample
+CONFLICT_BYTES_PER_TRAJ_STATE = 12.0   # x, y, theta f32 read once per plan
+VALIDITY_BYTES_PER_STATE = 20.125      # 5 f32 read + 1 bit written
+FP32_NOMINAL_TFLOPS = 74.4   # 148 SM x 128 lanes x 2 x 1.965 GHz
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, torch_device_index: int, period_s: float = 0.005):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.period = period_s
+        self._stop = threading.Event()
+        self._t = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[torch_device_index]) if vis and vis.split(",")[0].isdigit() else torch_device_index
+                h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.h = h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # NVML unavailable: clocks are reported as unknown
+            self.nv = None
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for b, name in self.REASONS.items():
+                    if bits & b:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t is not None:
+            self._stop.set()
+            self._t.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
+                    "note": getattr(self, "err", "no samples")}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+
+
+# ---------------------------------------------------------------------------------------------
+def make_expansions(workloads, rank: int, n_robots: int, n_exp: int, fixed_steps=None):
+    """Inputs of one step for this rank: per robot `n_exp` expansions, each from its own tree node
+    (one shared parent) with N_CONTROLS sampled controls and durations."""
+    per_robot = []
+    for r in range(n_robots):
+        exps = []
+        for e in range(n_exp):
+            seed = 1 + 1000003 * rank + 1009 * r + e
+            parents, controls, steps = workloads.expansion_batch(SCENE, N_CONTROLS, seed=seed, shared_parent=True,
+                                                                 interior=1.5, fixed_steps=fixed_steps)
+            exps.append((parents, controls, steps))
+        per_robot.append(exps)
+    return per_robot
+
+
+def cpu_baseline_leg(args, pkg, orc, workloads, budget_s: float, n_threads: int):
+    """Oracle (port of the reference's CPU path) on a bounded sample of the same workload."""
+    world = pkg.scenes.world(SCENE)
+    oracle = orc.Oracle(world)
+    units, t_used, n_exp = 0, 0.0, 0
+    t_end = time.perf_counter() + budget_s
+    while True:
+        parents, controls, steps = workloads.expansion_batch(SCENE, N_CONTROLS, seed=77 + n_exp, shared_parent=True,
+                                                             interior=1.5)
+        t0 = time.perf_counter()
+        _, _, _, calls = oracle.propagate_batch(0, parents, controls, steps, want_seg=True, n_threads=n_threads)
+        t_used += time.perf_counter() - t0
+        units += calls
+        n_exp += 1
+        if time.perf_counter() >= t_end or n_exp >= 64:
+            break
+    return {"value": units / t_used, "unit": "states/s", "cores": n_threads, "kind": "port",
+            "sample": f"{n_exp} expansions x {N_CONTROLS} controls ({units} propagated states, {t_used:.1f} s)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be
+    built here (OMPL K-CBS fork + Boost absent), so this is the oracle port with every host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = graft.load_package()
+    orc = graft.load_oracle()
+    orc.build()
+    from kcbs_b200 import workloads
+    world = pkg.scenes.world(SCENE)
+    oracle = orc.Oracle(world)
+    n_threads = os.cpu_count() or 1
+    sample = 4  # expansions of 64K controls per step (bounded sample of the 10 x --expansions GPU step)
+
+    def one_step(seed0):
+        units, t = 0, 0.0
+        for e in range(sample):
+            parents, controls, steps = workloads.expansion_batch(SCENE, N_CONTROLS, seed=seed0 + e, shared_parent=True,
+                                                                 interior=1.5)
+            t0 = time.perf_counter()
+            _, _, _, calls = oracle.propagate_batch(0, parents, controls, steps, want_seg=True, n_threads=n_threads)
+            t += time.perf_counter() - t0
+            units += calls
+        return units, t
+
+    for w in range(args.warmup):
+        one_step(9000 + 10 * w)
+    units, t = 0, 0.0
+    for k in range(args.steps):
+        u, dt = one_step(100 + 10 * k)
+        units += u
+        t += dt
+    value = units / t
+    line = {
+        "impl": "reference", "metric": "propagated states/s", "value": value, "unit": "states/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Empty32x32 10 robots, batched propagation 64K controls/expansion",
+                   "scene": SCENE, "controls_per_expansion": N_CONTROLS, "max_steps": MAX_STEPS,
+                   "step_sample": f"{sample} expansions per step"},
+        "cpu_baseline": {"value": value, "unit": "states/s", "cores": n_threads, "kind": "port",
+                         "sample": f"{sample} expansions x {N_CONTROLS} controls per step, {args.steps} steps"},
+        "e2e": {"value": value, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = CPU oracle port (OMPL K-CBS fork + Boost are not installable here); the reference is "
+                "single-threaded, this arm uses every host thread",
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--expansions", type=int, default=25, help="expansions per robot per step")
+    ap.add_argument("--fixed-steps", type=int, default=None, help="use a fixed duration instead of U{1..10}")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world_size == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world_size == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    pkg = graft.load_package()
+    from kcbs_b200 import workloads
+    world = pkg.scenes.world(SCENE)
+    n_robots = len(world.robot_dims)
+    n_exp = args.expansions
+    hbm_peak, peak_src = read_peaks()
+
+    # one context (= one stream) per robot planner
+    ctxs = [pkg.Context(world, device=local_rank) for _ in range(n_robots)]
+    streams = [torch.cuda.Stream() for _ in range(n_robots)]
+    main_stream = torch.cuda.current_stream()
+
+    # ---- inputs resident in HBM ---------------------------------------------------------------
+    host_in = make_expansions(workloads, rank, n_robots, n_exp, args.fixed_steps)
+    dev_in = [[(torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(s).cuda()) for p, c, s in exps]
+              for exps in host_in]
+    # outputs: every expansion of a step has its own segment buffer (13.1 MB each), so one step writes
+    # n_robots * n_exp * 13.1 MB (3.3 GB by default) >> 126 MB L2: no L2 flush needed between steps
+    seg = torch.empty((n_robots, n_exp, 5, MAX_STEPS, N_CONTROLS), dtype=torch.float32, device="cuda")
+    fin = torch.empty((n_robots, n_exp, 5, N_CONTROLS), dtype=torch.float32, device="cuda")
+    valid = torch.zeros((n_robots, n_exp, N_CONTROLS), dtype=torch.int32, device="cuda")
+
+    def gpu_step():
+        ev = torch.cuda.Event()
+        ev.record(main_stream)
+        for r in range(n_robots):
+            streams[r].wait_event(ev)
+            sp = streams[r].cuda_stream
+            for e in range(n_exp):
+                p, c, s = dev_in[r][e]
+                ctxs[r].propagate_batch_dev(r, N_CONTROLS, 1, p, c, s, None, MAX_STEPS, seg[r, e], fin[r, e], valid[r, e], sp)
+        for r in range(n_robots):
+            done = torch.cuda.Event()
+            done.record(streams[r])
+            main_stream.wait_event(done)
+
+    fp32_peak_before = ctxs[0].measure_fp32_peak()
+
+    for _ in range(max(args.warmup, 1)):
+        gpu_step()
+    barrier()
+    # units of one step: propagate() calls the reference would have made = min(steps, valid + 1)
+    steps_all = torch.stack([torch.stack([s for _, _, s in exps]) for exps in dev_in])
+    units_step = float(torch.minimum(steps_all, valid + 1).sum().item())
+    samples_step = n_robots * n_exp * N_CONTROLS
+    written_step = float(valid.sum().item())
+
+    sampler = ClockSampler(local_rank)
+    launches0 = sum(c.launch_count() for c in ctxs)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main_stream)
+    for _ in range(args.steps):
+        gpu_step()
+    e1.record(main_stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = sum(c.launch_count() for c in ctxs) - launches0
+    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
+    total_units = sum_over_ranks(units_step) * args.steps
+    value = total_units / (elapsed_ms * 1e-3)
+    fp32_peak_after = ctxs[0].measure_fp32_peak()
+    fp32_peak = max(fp32_peak_before, fp32_peak_after)
+
+    # kernel-level roofline (this rank): all launches of the timed region are k_propagate
+    kern_ms = e0.elapsed_time(e1) / max(launches, 1)      # average launch duration (streams overlap: busy time / launches)
+    ach_tflops = FLOPS_PER_STATE * units_step * args.steps / (e0.elapsed_time(e1) * 1e-3) * 1e-12
+    ach_gbs = (BYTES_PER_STATE * written_step + BYTES_PER_SAMPLE * samples_step) * args.steps / (e0.elapsed_time(e1) * 1e-3) * 1e-9
+    roofline = {
+        "kernel": "k_propagate", "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": ach_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+        "peak_source": "FFMA saturation probe run in this process (kcbs_measure_fp32_peak); nominal 74.4",
+        "frac_of_nominal": ach_tflops / FP32_NOMINAL_TFLOPS,
+        "algorithmic_flops_per_state": FLOPS_PER_STATE, "avg_launch_ms": kern_ms,
+        "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src},
+    }
+
+    # ---- e2e: host buffers through the reference-facing host entry point --------------------------
+    e2e_exp = min(n_exp, 4)
+    ctx0 = ctxs[0]
+    pin = []
+    for r in range(n_robots):
+        row = []
+        for e in range(e2e_exp):
+            p, c, s = host_in[r][e]
+            pp, pc, ps = ctx0.pinned_empty(p.shape, np.float32), ctx0.pinned_empty(c.shape, np.float32), ctx0.pinned_empty(s.shape, np.int32)
+            pp[...], pc[...], ps[...] = p, c, s
+            row.append((pp, pc, ps))
+        pin.append(row)
+    out_seg = ctx0.pinned_empty((5, MAX_STEPS, N_CONTROLS), np.float32)
+    out_fin = ctx0.pinned_empty((5, N_CONTROLS), np.float32)
+    out_valid = ctx0.pinned_empty((N_CONTROLS,), np.int32)
+
+    def e2e_step():
+        for r in range(n_robots):
+            for e in range(e2e_exp):
+                pp, pc, ps = pin[r][e]
+                ctxs[r].propagate_batch(r, pp, pc, ps, max_steps=MAX_STEPS, out=(out_seg, out_fin, out_valid))
+
+    e2e_steps = max(2, min(args.steps, 10))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_units = float(torch.minimum(steps_all[:, :e2e_exp], valid[:, :e2e_exp] + 1).sum().item())
+    e2e_value = sum_over_ranks(e2e_units) * e2e_steps / e2e_s
+    calls = n_robots * e2e_exp
+    e2e = {"value": e2e_value, "unit": "states/s",
+           "h2d_bytes_per_step": calls * (5 * 4 + N_CONTROLS * 12),
+           "d2h_bytes_per_step": calls * (N_CONTROLS * (5 * MAX_STEPS * 4 + 5 * 4 + 4)),
+           "calls_per_step": calls, "steps": e2e_steps,
+           "note": "kcbs_propagate_batch with pinned host buffers; whole segments + final states + counts copied back"}
+
+    # ---- secondary metrics: validity (K2) and conflict scan (K3), device resident ------------------
+    secondary = {}
+    if not args.no_secondary:
+        secondary = run_secondary(pkg, workloads, local_rank, hbm_peak, peak_src, max_over_ranks, sum_over_ranks, barrier, rank)
+
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu:
+        orc = graft.load_oracle()
+        orc.build()
+        cpu = cpu_baseline_leg(args, pkg, orc, workloads, args.cpu_budget, os.cpu_count() or 1)
+
+    if rank == 0:
+        line = {
+            "metric": "propagated states/s", "value": value, "unit": "states/s", "n_gpus": world_size,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Empty32x32 10 robots, batched propagation 64K controls/expansion",
+                       "scene": SCENE, "robots": n_robots, "controls_per_expansion": N_CONTROLS,
+                       "expansions_per_robot_per_step": n_exp, "max_steps": MAX_STEPS,
+                       "durations": "U{1..10}" if args.fixed_steps is None else f"fixed {args.fixed_steps}",
+                       "parents": "one shared tree node per expansion", "streams": n_robots,
+                       "states_per_step_per_gpu": units_step,
+                       "l2": f"each step writes {samples_step * 200 / 1e6:.0f} MB of distinct segment buffers per GPU (> 126 MB L2); no flush needed",
+                       "parallelism": f"{world_size} x independent per-robot replans, no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
+            "secondary": secondary,
+        }
+        print(json.dumps(line))
+    for c in ctxs:
+        c.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_over_ranks, barrier, rank):
+    import torch
+    out = {}
+    # ---- validity: Congested10x10, 2^24 states ------------------------------
+    scene = "Congested10x10_7robots"
+    n = 1 << 24
+    with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
+        sets = [torch.from_numpy(workloads.validity_states(scene, n, seed=1 + s + 100 * rank)).cuda() for s in range(2)]
+        mask = torch.empty((n + 31) // 32, dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for i in range(3):
+            ctx.validity_batch_dev(0, n, sets[i % 2], mask, st)
+        barrier()
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            ctx.validity_batch_dev(0, n, sets[i % 2], mask, st)   # 2 x 336 MB inputs alternate: > L2
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        rate = sum_over_ranks(float(n)) * reps / (ms * 1e-3)
+        gbs = VALIDITY_BYTES_PER_STATE * n * reps / (e0.elapsed_time(e1) * 1e-3) * 1e-9
+        out["validity"] = {"metric": "validity-checked states/s", "value": rate, "scene": scene, "states": n,
+                           "roofline": {"kernel": "k_validity", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                                        "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src}}
+        del sets, mask
+    # ---- conflict scan: Empty32x32 30 robots, 435 pairs x 10K steps, 256 plans (config 5) --------------
+    scene = "Benchmark_Empty32x32_30robots"
+    P, R, T = 256, 30, 10000
+    with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
+        traj = workloads.cell_plans(scene, P, T, seed=1 + rank, xp=torch)     # 922 MB >> L2, conflict free
+        res = torch.empty((P, 4), dtype=torch.int32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(3):
+            ctx.first_conflict_dev(P, R, T, traj, None, res, st)
+        barrier()
+        assert int((res[:, 0] >= 0).sum().item()) == 0, "throughput plans must be conflict free (full scan)"
+        reps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ctx.first_conflict_dev(P, R, T, traj, None, res, st)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        pairs = P * (R * (R - 1) // 2) * T
+        rate = sum_over_ranks(float(pairs)) * reps / (ms * 1e-3)
+        gbs = CONFLICT_BYTES_PER_TRAJ_STATE * P * R * T * reps / (e0.elapsed_time(e1) * 1e-3) * 1e-9
+        # single-plan latency (435 pairs x 10K steps, L2 resident)
+        one = traj[:1].contiguous()
+        for _ in range(3):
+            ctx.first_conflict_dev(1, R, T, one, None, res[:1], st)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(50):
+            ctx.first_conflict_dev(1, R, T, one, None, res[:1], st)
+        e1.record()
+        torch.cuda.synchronize()
+        out["conflict"] = {"metric": "conflict-checked state-pairs/s", "value": rate, "scene": scene, "plans": P,
+                           "pairs": R * (R - 1) // 2, "timesteps": T, "single_plan_latency_us": 1e3 * e0.elapsed_time(e1) / 50,
+                           "roofline": {"kernel": "k_conflict_keys", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                                        "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src}}
+    return out
+
+
+if __name__ == "__main__":
+    main()

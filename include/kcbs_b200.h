@@ -12,7 +12,8 @@
  *   All batches are structure-of-arrays float32 "planes": plane c of a batch of n starts at
  *   base + c * n.  Entry points without suffix take HOST pointers and copy through the context's
  *   device workspace; `_dev` entry points take DEVICE pointers on the context's device and are
- *   asynchronous on `stream` (a cudaStream_t passed as void*, NULL = context stream).
+ *   asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the context's own stream, pass
+ *   cudaStreamLegacy for the legacy default stream).
  *   There is no CPU fallback: every compute call runs sm_100a kernels or returns an error.
  */
 #ifndef KCBS_B200_H

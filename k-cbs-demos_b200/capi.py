@@ -124,6 +124,16 @@ class World:
         return lo, hi
 
 
+def _stream(s) -> Optional[int]:
+    """cudaStream_t for the *_dev calls.  None -> the context's own stream.  torch reports its default
+    stream as handle 0, which the C ABI would read as "context stream"; map it to cudaStreamLegacy."""
+    if s is None:
+        return None
+    if hasattr(s, "cuda_stream"):
+        s = s.cuda_stream
+    return 1 if int(s) == 0 else int(s)
+
+
 def _ptr(a) -> Optional[int]:
     """Host pointer of a C-contiguous numpy array, device pointer of a torch tensor, or None."""
     if a is None:
@@ -166,6 +176,9 @@ class Context:
     # -- plumbing -------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
+            for p in getattr(self, "_pinned", []):
+                self._lib.kcbs_host_free(self._h, p)
+            self._pinned = []
             self._lib.kcbs_destroy(self._h)
             self._h = None
 
@@ -233,7 +246,7 @@ class Context:
                             valid, stream=None):
         self._check(self._lib.kcbs_propagate_batch_dev(self._h, robot, n, n_parents, _ptr(parents), _ptr(parent_idx),
                                                        _ptr(controls), _ptr(steps), max_steps, _ptr(seg), _ptr(fin),
-                                                       _ptr(valid), stream))
+                                                       _ptr(valid), _stream(stream)))
 
     # -- (2) validity ---------------------------------------------------------------------
     def validity_batch(self, robot, states, out=None):
@@ -245,7 +258,7 @@ class Context:
         return mask
 
     def validity_batch_dev(self, robot, n, states, bitmask, stream=None):
-        self._check(self._lib.kcbs_validity_batch_dev(self._h, robot, n, _ptr(states), _ptr(bitmask), stream))
+        self._check(self._lib.kcbs_validity_batch_dev(self._h, robot, n, _ptr(states), _ptr(bitmask), _stream(stream)))
 
     @staticmethod
     def unpack_mask(mask: np.ndarray, n: int) -> np.ndarray:
@@ -265,12 +278,12 @@ class Context:
         return res
 
     def first_conflict_dev(self, P, R, T, traj, lengths, out, stream=None):
-        self._check(self._lib.kcbs_first_conflict_dev(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(out), stream))
+        self._check(self._lib.kcbs_first_conflict_dev(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(out), _stream(stream)))
 
     def conflict_keys_dev(self, P, R, T, k_lo, k_hi, traj, lengths, keys, stream=None):
         self._check(self._lib.kcbs_conflict_keys_dev(self._h, P, R, T, k_lo, k_hi, _ptr(traj), _ptr(lengths),
-                                                     _ptr(keys), stream))
+                                                     _ptr(keys), _stream(stream)))
 
     def conflict_finish_dev(self, P, R, T, traj, lengths, keys, out, stream=None):
         self._check(self._lib.kcbs_conflict_finish_dev(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(keys),
-                                                       _ptr(out), stream))
+                                                       _ptr(out), _stream(stream)))

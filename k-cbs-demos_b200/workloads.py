@@ -52,10 +52,11 @@ def validity_states(scene: str, n: int, seed: int = 1) -> np.ndarray:
     return st
 
 
-def cell_plans(scene: str, P: int, T: int, seed: int = 1, margin: float = 0.36, xp=np) -> "np.ndarray":
+def cell_plans(scene: str, P: int, T: int, seed: int = 1, margin: float = 0.435, xp=np) -> "np.ndarray":
     """[P, R, 3, T] conflict-free synthetic plans for full-scan throughput: robot r wanders smoothly
-    inside its own cell of a square grid over the workspace, keeping `margin` from the cell edge, so
-    centres of neighbours come within the bounding circles (broad phase fires) without overlap.
+    inside its own cell of a square grid over the workspace, keeping `margin` from the cell edge.  The
+    default margin exceeds the 0.7 x 0.5 robots' bounding radius (0.4301), which guarantees that no two
+    footprints can touch; smaller margins give near misses (and occasional real conflicts).
     xp = numpy or torch (torch generates on the current CUDA device)."""
     s = scenes.SCENES[scene]
     R = len(s["robots"])
