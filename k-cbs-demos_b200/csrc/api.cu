@@ -4,10 +4,12 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "kcbs_device.cuh"
 #include "kernels.h"
@@ -35,6 +37,10 @@ struct kcbs_ctx {
     std::string err;
     // grow-only device workspaces for the host-buffer entry points
     DevBuf in0, in1, in2, in3, out0, out1, out2, keys;
+    int key_plans = 0;      // plans the keys/tickets workspace was laid out for
+    void *scene = nullptr;  // cull grid + obstacle table in device memory
+    std::vector<unsigned long long> h_grid;
+    std::vector<float> h_obs4;
 };
 
 namespace {
@@ -159,6 +165,39 @@ int build_world(const kcbs_world *src, DevWorld &w)
     return KCBS_OK;
 }
 
+// Conservative obstacle cull grid: bit o of cell (ix, iy) is set when obstacle o, grown by the largest robot
+// bounding radius (plus slack for the float cell lookup), overlaps the cell.
+void build_grid(const kcbs_world *src, DevWorld &w, std::vector<unsigned long long> &grid, std::vector<float> &obs4)
+{
+    const int G = kGridDim;
+    const double x0 = src->lo[0], y0 = src->lo[1];
+    const double sx = std::max(src->hi[0] - src->lo[0], 1e-9), sy = std::max(src->hi[1] - src->lo[1], 1e-9);
+    const double cw = sx / G, ch = sy / G;
+    w.gdim = G;
+    w.gx0 = (float)x0;
+    w.gy0 = (float)y0;
+    w.ginvx = (float)(G / sx);
+    w.ginvy = (float)(G / sy);
+    grid.assign((size_t)G * G, 0ull);
+    obs4.assign((size_t)4 * KCBS_MAX_OBSTACLES, 0.0f);
+    for (int o = 0; o < src->n_obstacles; ++o) {
+        const double *ob = src->obstacles + 4 * o;
+        obs4[4 * o + 0] = w.obs_cx[o];
+        obs4[4 * o + 1] = w.obs_cy[o];
+        obs4[4 * o + 2] = w.obs_hx[o];
+        obs4[4 * o + 3] = w.obs_hy[o];
+        const double grow = (double)w.max_rad * (1.0 + 1e-5) + 1e-4 * std::max(cw, ch) + 1e-5;
+        const double ax = ob[0] - grow, bx = ob[0] + ob[2] + grow, ay = ob[1] - grow, by = ob[1] + ob[3] + grow;
+        int ix0 = (int)std::floor((ax - x0) / cw), ix1 = (int)std::floor((bx - x0) / cw);
+        int iy0 = (int)std::floor((ay - y0) / ch), iy1 = (int)std::floor((by - y0) / ch);
+        // (`grow` already holds 1e-4 of a cell of slack for the float cell lookup on the device)
+        ix0 = std::max(ix0, 0); iy0 = std::max(iy0, 0);
+        ix1 = std::min(ix1, G - 1); iy1 = std::min(iy1, G - 1);
+        for (int iy = iy0; iy <= iy1; ++iy)
+            for (int ix = ix0; ix <= ix1; ++ix) grid[(size_t)iy * G + ix] |= 1ull << o;
+    }
+}
+
 cudaStream_t pick(kcbs_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
 
 int check_robot(kcbs_ctx *ctx, int robot)
@@ -222,14 +261,27 @@ int kcbs_create(const kcbs_world *world, int device, kcbs_ctx **out)
     kcbs_ctx *ctx = new (std::nothrow) kcbs_ctx();
     if (!ctx) return fail(nullptr, KCBS_ERR_OUT_OF_MEMORY, "host allocation failed");
     ctx->device = device;
+    build_grid(world, w, ctx->h_grid, ctx->h_obs4);
     ctx->world = w;
     ctx->n_robots = world->n_robots;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
-        (e = init_conflict_kernels()) != cudaSuccess) {
+        (e = init_conflict_kernels()) != cudaSuccess || (e = init_propagate_kernels()) != cudaSuccess) {
         fail(nullptr, KCBS_ERR_CUDA, "context setup", e);
         kcbs_destroy(ctx);
         return KCBS_ERR_CUDA;
+    }
+    {
+        const size_t b_grid = sizeof(unsigned long long) * ctx->h_grid.size(), b_obs = sizeof(float) * ctx->h_obs4.size();
+        if ((e = cudaMalloc(&ctx->scene, b_grid + b_obs)) != cudaSuccess ||
+            (e = cudaMemcpy(ctx->scene, ctx->h_grid.data(), b_grid, cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy((char *)ctx->scene + b_grid, ctx->h_obs4.data(), b_obs, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            fail(nullptr, KCBS_ERR_CUDA, "scene upload", e);
+            kcbs_destroy(ctx);
+            return KCBS_ERR_CUDA;
+        }
+        ctx->world.grid = (const unsigned long long *)ctx->scene;
+        ctx->world.obs4 = (const float4 *)((char *)ctx->scene + b_grid);
     }
     *out = ctx;
     return KCBS_OK;
@@ -243,6 +295,7 @@ void kcbs_destroy(kcbs_ctx *ctx)
     DevBuf *bufs[] = {&ctx->in0, &ctx->in1, &ctx->in2, &ctx->in3, &ctx->out0, &ctx->out1, &ctx->out2, &ctx->keys};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    if (ctx->scene) cudaFree(ctx->scene);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -397,14 +450,14 @@ int kcbs_conflict_keys_dev(kcbs_ctx *ctx, int n_plans, int R, int T, int k_lo, i
     k_hi = k_hi > T ? T : k_hi;
     cudaStream_t s = pick(ctx, stream);
     KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
-    KCBS_CUDA(ctx, launch_fill_keys((unsigned long long *)keys, n_plans, s));
+    KCBS_CUDA(ctx, launch_fill_keys((unsigned long long *)keys, nullptr, n_plans, s));
     ctx->launches += 1;
     if (k_hi > k_lo) {
         ConflictArgs a;
-        a.traj = traj; a.lengths = lengths; a.keys = (unsigned long long *)keys; a.P = n_plans; a.R = R; a.T = T;
-        a.k_lo = k_lo; a.k_hi = k_hi;
+        a.traj = traj; a.lengths = lengths; a.keys = (unsigned long long *)keys; a.tickets = nullptr; a.out = nullptr;
+        a.P = n_plans; a.R = R; a.T = T; a.k_lo = k_lo; a.k_hi = k_hi;
         KCBS_CUDA(ctx, launch_conflict_keys(ctx->world, a, s));
-        ctx->launches += conflict_keys_launches();
+        ctx->launches += 1;
     }
     return KCBS_OK;
 }
@@ -433,9 +486,34 @@ int kcbs_first_conflict_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const floa
     int st = check_plan_args(ctx, n_plans, R, T);
     if (st != KCBS_OK) return st;
     if (n_plans == 0) return KCBS_OK;
-    if ((st = reserve(ctx, ctx->keys, sizeof(uint64_t) * (size_t)n_plans))) return st;
-    if ((st = kcbs_conflict_keys_dev(ctx, n_plans, R, T, 0, T, traj, lengths, (uint64_t *)ctx->keys.p, stream))) return st;
-    return kcbs_conflict_finish_dev(ctx, n_plans, R, T, traj, lengths, (const uint64_t *)ctx->keys.p, out, stream);
+    if (!out || (T > 0 && !traj)) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "traj / out is null");
+    cudaStream_t s = pick(ctx, stream);
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    // keys + tickets live in the context; the kernel leaves them clean, so they are filled only when (re)allocated
+    const size_t need = (sizeof(uint64_t) + sizeof(int)) * (size_t)n_plans;
+    if (need > ctx->keys.cap) {
+        const int cap_plans = n_plans + n_plans / 4 + 64;
+        if ((st = reserve(ctx, ctx->keys, (sizeof(uint64_t) + sizeof(int)) * (size_t)cap_plans))) return st;
+        ctx->key_plans = cap_plans;
+        KCBS_CUDA(ctx, launch_fill_keys((unsigned long long *)ctx->keys.p, (int *)((uint64_t *)ctx->keys.p + cap_plans),
+                                        cap_plans, s));
+        ctx->launches += 1;
+    }
+    if (T == 0) {   // nothing to scan: every plan is conflict free
+        FinishArgs f;
+        f.traj = traj; f.lengths = lengths; f.keys = (const unsigned long long *)ctx->keys.p; f.out = out; f.P = n_plans;
+        f.R = R; f.T = T;
+        KCBS_CUDA(ctx, launch_conflict_finish(ctx->world, f, s));
+        ctx->launches += 1;
+        return KCBS_OK;
+    }
+    ConflictArgs a;
+    a.traj = traj; a.lengths = lengths; a.keys = (unsigned long long *)ctx->keys.p;
+    a.tickets = (int *)((uint64_t *)ctx->keys.p + ctx->key_plans); a.out = out;
+    a.P = n_plans; a.R = R; a.T = T; a.k_lo = 0; a.k_hi = T;
+    KCBS_CUDA(ctx, launch_conflict_keys(ctx->world, a, s));
+    ctx->launches += 1;
+    return KCBS_OK;
 }
 
 int kcbs_first_conflict(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,

@@ -6,14 +6,21 @@
 //   for k ascending, r1 ascending, r2 > r1 ascending: first pair whose rectangles (each rotated by
 //   -theta, :152-168) are not disjoint (:173) is the conflict; it is extended while it persists.
 //
-// Mapping: one CTA = one plan x one tile of kTile time indices; one thread = one time index with
-// every robot's (x, y) of that index parked in a private shared-memory column (coalesced plane
-// reads, no cross-thread sharing, no __syncthreads).  Robots are processed as register tiles of 8
-// ("A") against the remaining robots streamed from shared memory ("B"), tracking only the minimum
-// squared centre distance: the reference's circle test (:134-141) can only clear pairs that the
-// exact test would clear as well, so the rectangle SAT runs only for threads whose minimum falls
-// inside the bounding circles.  Heading planes are read only there.  The lexicographic minimum
-// (k, r1, r2) is a warp shuffle-min followed by one 64-bit atomicMin per warp.
+// Mapping: one CTA = one plan x one tile of kTile time indices; one thread = one time index.
+//   * Staging: the tile's 2R trajectory rows (x and y planes, 512 B each) are fetched by the TMA engine
+//     (cp.async.bulk global -> shared, one instruction per row, completion on an mbarrier), so no
+//     thread holds load registers and the whole tile is one memory round trip.  Tiles that touch the
+//     padding of a short path, or misaligned plans (T % 4 != 0), take a per-element path.
+//   * Broad phase: robots are processed as register tiles of 8 ("A") against the remaining robots
+//     streamed from shared memory ("B").  Only min over pairs of max(|dx|, |dy|) is tracked (2 FADD +
+//     1.5 FMNMX per pair): the reference's circle test (:134-141) can only clear pairs that the exact
+//     test clears as well, and a pair whose centres differ by more than r1 + r2 along an axis is
+//     outside the circle, so the verdict is unchanged.
+//   * Narrow phase (rare): threads whose minimum is inside the bounding circles run the rectangle SAT in
+//     scan order; heading planes are read only here.
+//   * Reduction: the packed key (k, r1, r2) is min-reduced by warp shuffles and one 64-bit atomicMin
+//     per warp; the last CTA of a plan (ticket counter) extends the conflict while the same pair keeps
+//     colliding, writes the record and resets the plan's key and ticket for the next call.
 #include "kcbs_device.cuh"
 #include "kernels.h"
 
@@ -29,99 +36,38 @@ __device__ __forceinline__ int clamp_k(int k, int T, const int *len, int r)
     return max(kk, 0);
 }
 
-__global__ void __launch_bounds__(kTile)
-k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ ConflictArgs a, int tiles_per_plan)
+// ---- mbarrier / bulk-copy helpers (PTX) ------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
 {
-    extern __shared__ float smem[];
-    const int R = a.R, T = a.T;
-    const int plan = blockIdx.x / tiles_per_plan;
-    const int tile = blockIdx.x - plan * tiles_per_plan;
-    const int k0 = a.k_lo + tile * kTile;
-    const int tid = threadIdx.x;
-    const int k = k0 + tid;
-
-    // a conflict already recorded at an earlier time index makes this tile irrelevant
-    const unsigned long long seen = *(volatile const unsigned long long *)(a.keys + plan);
-    if (seen != kNoConflict && (long long)(seen >> 16) < (long long)k0) return;
-
-    const float *base = a.traj + (long long)plan * R * 3 * T;
-    const int *len = a.lengths ? a.lengths + (long long)plan * R : nullptr;
-    float *xs = smem;              // [R][kTile]
-    float *ys = smem + R * kTile;  // [R][kTile]
-    const bool active = k < a.k_hi;
-
-#pragma unroll 4
-    for (int r = 0; r < R; ++r) {
-        const int kk = clamp_k(k, T, len, r);
-        xs[r * kTile + tid] = __ldcs(base + ((long long)r * 3 + 0) * T + kk);
-        ys[r * kTile + tid] = __ldcs(base + ((long long)r * 3 + 1) * T + kk);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
     }
-
-    float m = 3.0e38f;  // min squared centre distance over all pairs at this time index
-    for (int a0 = 0; a0 < R; a0 += kATile) {
-        float xa[kATile], ya[kATile];
-#pragma unroll
-        for (int q = 0; q < kATile; ++q) {
-            const bool in = a0 + q < R;
-            // distinct far-away sentinels for the missing robots of a partial tile
-            xa[q] = in ? xs[(a0 + q) * kTile + tid] : 1.0e18f * (float)(q + 1);
-            ya[q] = in ? ys[(a0 + q) * kTile + tid] : 0.0f;
-        }
-#pragma unroll
-        for (int q = 0; q < kATile; ++q)
-#pragma unroll
-            for (int p = q + 1; p < kATile; ++p) {
-                const float dx = xa[q] - xa[p], dy = ya[q] - ya[p];
-                m = fminf(m, fmaf(dy, dy, dx * dx));
-            }
-        for (int r2 = a0 + kATile; r2 < R; ++r2) {
-            const float xb = xs[r2 * kTile + tid], yb = ys[r2 * kTile + tid];
-#pragma unroll
-            for (int q = 0; q < kATile; ++q) {
-                const float dx = xa[q] - xb, dy = ya[q] - yb;
-                m = fminf(m, fmaf(dy, dy, dx * dx));
-            }
-        }
-    }
-
-    unsigned long long key = kNoConflict;
-    const float lim = 2.0f * w.max_rad;
-    if (active && m <= lim * lim * 1.000001f) {
-        // rare: some pair is inside the bounding circles -> exact rectangle test in scan order
-        for (int r1 = 0; r1 < R && key == kNoConflict; ++r1) {
-            const float x1 = xs[r1 * kTile + tid], y1 = ys[r1 * kTile + tid];
-            bool have1 = false;
-            float c1 = 1.0f, s1 = 0.0f;
-            for (int r2 = r1 + 1; r2 < R; ++r2) {
-                const float x2 = xs[r2 * kTile + tid], y2 = ys[r2 * kTile + tid];
-                const float dx = x2 - x1, dy = y2 - y1;
-                const float rs = w.rob_rad[r1] + w.rob_rad[r2];
-                if (fmaf(dy, dy, dx * dx) <= rs * rs * 1.000001f) {
-                    if (!have1) {
-                        sincosf(base[((long long)r1 * 3 + 2) * T + clamp_k(k, T, len, r1)], &s1, &c1);
-                        have1 = true;
-                    }
-                    float c2, s2;
-                    sincosf(base[((long long)r2 * 3 + 2) * T + clamp_k(k, T, len, r2)], &s2, &c2);
-                    const float gap = sat_gap_robots(x1, y1, c1, s1, w.rob_hl[r1], w.rob_hw[r1], x2, y2, c2, s2,
-                                                     w.rob_hl[r2], w.rob_hw[r2]);
-                    if (gap <= 0.0f) {
-                        key = pack_key(k, r1, r2);
-                        break;
-                    }
-                }
-            }
-        }
-    }
-
-    if (__any_sync(0xffffffffu, key != kNoConflict)) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
-            key = o < key ? o : key;
-        }
-        if ((tid & 31) == 0) atomicMin(a.keys + plan, key);
-    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
 }
 
 // Pair test at one time index, used by the k_end extension.
@@ -141,50 +87,200 @@ __device__ __forceinline__ bool pair_collides(const DevWorld &w, const float *ba
            0.0f;
 }
 
-// One warp per plan: unpack the key and extend the conflict while the same pair keeps colliding.
+// Unpacks a key and extends the conflict while the same pair keeps colliding.  Executed by one full warp.
+__device__ __forceinline__ kcbs_conflict finish_plan(const DevWorld &w, unsigned long long key, const float *base,
+                                                    const int *len, int T, int lane)
+{
+    kcbs_conflict c;
+    if (key == kNoConflict) {
+        c.r1 = c.r2 = c.k_start = c.k_end = -1;
+        return c;
+    }
+    c.k_start = (int)(key >> 16);
+    c.r1 = (int)((key >> 8) & 0xff);
+    c.r2 = (int)(key & 0xff);
+    int k_end = c.k_start;
+    for (int b = c.k_start + 1; b < T; b += 32) {
+        const int k = b + lane;
+        const bool hit = (k < T) && pair_collides(w, base, len, T, c.r1, c.r2, k);
+        const unsigned miss = ~__ballot_sync(0xffffffffu, hit);
+        if (miss) {
+            k_end = b + __ffs(miss) - 2;  // last hit before the first miss
+            break;
+        }
+        k_end = b + 31;
+    }
+    c.k_end = min(k_end, T - 1);
+    return c;
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kTile)
+k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ ConflictArgs a, int tiles_per_plan)
+{
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ int s_last;
+
+    const int R = a.R, T = a.T;
+    const int plan = blockIdx.x / tiles_per_plan;
+    const int tile = blockIdx.x - plan * tiles_per_plan;
+    const int k0 = a.k_lo + tile * kTile;
+    const int tid = threadIdx.x;
+    const int k = k0 + tid;
+    const float *base = a.traj + (long long)plan * R * 3 * T;
+    const int *len = a.lengths ? a.lengths + (long long)plan * R : nullptr;
+    float *xs = smem;              // [R][kTile]
+    float *ys = smem + R * kTile;  // [R][kTile]
+
+    unsigned long long key = kNoConflict;
+
+    // a conflict already recorded at an earlier time index makes this tile irrelevant
+    const unsigned long long seen = *(volatile const unsigned long long *)(a.keys + plan);
+    const bool skip = seen != kNoConflict && (long long)(seen >> 16) < (long long)k0;
+
+    if (!skip) {
+        const int n_k = min(kTile, a.k_hi - k0);   // time indices of this tile
+        // bulk path: rows 16 B aligned, sizes multiples of 16 B, no padding inside the tile
+        bool bulk = ((T & 3) == 0) && ((k0 & 3) == 0) && ((n_k & 3) == 0) && ((((size_t)a.traj) & 15) == 0);
+        if (bulk && len) {
+            for (int r = 0; r < R; ++r) bulk &= len[r] >= k0 + n_k;
+        }
+        if (bulk) {
+            if (tid == 0) {
+                mbar_init(&s_bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            // arrive + expect_tx is one atomic update, so copies may complete before or after it
+            if (tid == 0) mbar_expect_tx(&s_bar, (unsigned)(2 * R * n_k * sizeof(float)));
+            if (tid < 2 * R) {
+                const int r = tid >> 1, c = tid & 1;
+                bulk_g2s((c ? ys : xs) + r * kTile, base + ((long long)r * 3 + c) * T + k0, (unsigned)(n_k * sizeof(float)), &s_bar);
+            }
+            mbar_wait(&s_bar, 0);
+        } else {
+#pragma unroll 4
+            for (int r = 0; r < R; ++r) {
+                const int kk = clamp_k(k, T, len, r);
+                xs[r * kTile + tid] = __ldcs(base + ((long long)r * 3 + 0) * T + kk);
+                ys[r * kTile + tid] = __ldcs(base + ((long long)r * 3 + 1) * T + kk);
+            }
+        }
+        const bool active = tid < n_k;
+
+        // ---- broad phase: min over pairs of the Chebyshev centre distance -----------------------------
+        float m = 3.0e38f;
+        if (active) {
+            for (int a0 = 0; a0 < R; a0 += kATile) {
+                float xa[kATile], ya[kATile];
+#pragma unroll
+                for (int q = 0; q < kATile; ++q) {
+                    const bool in = a0 + q < R;
+                    // distinct far-away sentinels for the missing robots of a partial tile
+                    xa[q] = in ? xs[(a0 + q) * kTile + tid] : 1.0e18f * (float)(q + 1);
+                    ya[q] = in ? ys[(a0 + q) * kTile + tid] : 0.0f;
+                }
+#pragma unroll
+                for (int q = 0; q < kATile; ++q)
+#pragma unroll
+                    for (int p = q + 1; p < kATile; ++p)
+                        m = fminf(m, fmaxf(fabsf(xa[q] - xa[p]), fabsf(ya[q] - ya[p])));
+#pragma unroll 2
+                for (int r2 = a0 + kATile; r2 < R; ++r2) {
+                    const float xb = xs[r2 * kTile + tid], yb = ys[r2 * kTile + tid];
+#pragma unroll
+                    for (int q = 0; q < kATile; ++q) m = fminf(m, fmaxf(fabsf(xa[q] - xb), fabsf(ya[q] - yb)));
+                }
+            }
+        }
+
+        // ---- narrow phase (rare): exact rectangle test in scan order ------------------------------------
+        if (active && m <= 2.0f * w.max_rad * 1.000001f) {
+            for (int r1 = 0; r1 < R && key == kNoConflict; ++r1) {
+                const float x1 = xs[r1 * kTile + tid], y1 = ys[r1 * kTile + tid];
+                bool have1 = false;
+                float c1 = 1.0f, s1 = 0.0f;
+                for (int r2 = r1 + 1; r2 < R; ++r2) {
+                    const float x2 = xs[r2 * kTile + tid], y2 = ys[r2 * kTile + tid];
+                    const float dx = x2 - x1, dy = y2 - y1;
+                    const float rs = w.rob_rad[r1] + w.rob_rad[r2];
+                    if (fmaf(dy, dy, dx * dx) <= rs * rs * 1.000001f) {
+                        if (!have1) {
+                            sincosf(base[((long long)r1 * 3 + 2) * T + clamp_k(k, T, len, r1)], &s1, &c1);
+                            have1 = true;
+                        }
+                        float c2, s2;
+                        sincosf(base[((long long)r2 * 3 + 2) * T + clamp_k(k, T, len, r2)], &s2, &c2);
+                        const float gap = sat_gap_robots(x1, y1, c1, s1, w.rob_hl[r1], w.rob_hw[r1], x2, y2, c2, s2,
+                                                         w.rob_hl[r2], w.rob_hw[r2]);
+                        if (gap <= 0.0f) {
+                            key = pack_key(k, r1, r2);
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+
+        if (__any_sync(0xffffffffu, key != kNoConflict)) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
+                key = o < key ? o : key;
+            }
+            if ((tid & 31) == 0) atomicMin(a.keys + plan, key);
+        }
+    }
+
+    if (FUSED) {
+        // last CTA of the plan finishes it and leaves key + ticket clean for the next call
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const int ticket = atomicAdd(a.tickets + plan, 1);
+            s_last = (ticket == tiles_per_plan - 1);
+        }
+        __syncthreads();
+        if (s_last && tid < 32) {
+            __threadfence();
+            const unsigned long long best = *(volatile const unsigned long long *)(a.keys + plan);
+            const kcbs_conflict c = finish_plan(w, best, base, len, T, tid);
+            if (tid == 0) {
+                a.out[plan] = c;
+                a.keys[plan] = kNoConflict;
+                a.tickets[plan] = 0;
+            }
+        }
+    }
+}
+
+// One warp per plan: unpack the key and extend the conflict (used after a cross-GPU key reduction).
 __global__ void __launch_bounds__(128)
 k_conflict_finish(const __grid_constant__ DevWorld w, const __grid_constant__ FinishArgs a)
 {
     const int plan = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (plan >= a.P) return;
-    const unsigned long long key = a.keys[plan];
-    kcbs_conflict c;
-    if (key == kNoConflict) {
-        c.r1 = c.r2 = c.k_start = c.k_end = -1;
-    } else {
-        const int T = a.T;
-        const float *base = a.traj + (long long)plan * a.R * 3 * T;
-        const int *len = a.lengths ? a.lengths + (long long)plan * a.R : nullptr;
-        c.k_start = (int)(key >> 16);
-        c.r1 = (int)((key >> 8) & 0xff);
-        c.r2 = (int)(key & 0xff);
-        int k_end = c.k_start;
-        for (int b = c.k_start + 1; b < T; b += 32) {
-            const int k = b + lane;
-            const bool hit = (k < T) && pair_collides(w, base, len, T, c.r1, c.r2, k);
-            const unsigned miss = ~__ballot_sync(0xffffffffu, hit);
-            if (miss) {
-                k_end = b + __ffs(miss) - 2;  // last hit before the first miss
-                break;
-            }
-            k_end = b + 31;
-        }
-        c.k_end = min(k_end, T - 1);
-    }
+    const float *base = a.traj + (long long)plan * a.R * 3 * a.T;
+    const int *len = a.lengths ? a.lengths + (long long)plan * a.R : nullptr;
+    const kcbs_conflict c = finish_plan(w, a.keys[plan], base, len, a.T, lane);
     if (lane == 0) a.out[plan] = c;
 }
 
-__global__ void k_fill_keys(unsigned long long *keys, int n)
+__global__ void k_fill_keys(unsigned long long *keys, int *tickets, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = kNoConflict;
+    if (i < n) {
+        keys[i] = kNoConflict;
+        if (tickets) tickets[i] = 0;
+    }
 }
 
-cudaError_t launch_fill_keys(unsigned long long *keys, int n, cudaStream_t stream)
+cudaError_t launch_fill_keys(unsigned long long *keys, int *tickets, int n, cudaStream_t stream)
 {
     if (n <= 0) return cudaSuccess;
-    k_fill_keys<<<(n + 255) / 256, 256, 0, stream>>>(keys, n);
+    k_fill_keys<<<(n + 255) / 256, 256, 0, stream>>>(keys, tickets, n);
     return cudaGetLastError();
 }
 
@@ -193,7 +289,11 @@ cudaError_t launch_conflict_keys(const DevWorld &w, const ConflictArgs &a, cudaS
     if (a.P <= 0 || a.k_hi <= a.k_lo) return cudaSuccess;
     const int tiles = (a.k_hi - a.k_lo + kTile - 1) / kTile;
     const size_t smem = (size_t)2 * a.R * kTile * sizeof(float);
-    k_conflict_keys<<<(unsigned)((long long)tiles * a.P), kTile, smem, stream>>>(w, a, tiles);
+    const unsigned grid = (unsigned)((long long)tiles * a.P);
+    if (a.out)
+        k_conflict_keys<true><<<grid, kTile, smem, stream>>>(w, a, tiles);
+    else
+        k_conflict_keys<false><<<grid, kTile, smem, stream>>>(w, a, tiles);
     return cudaGetLastError();
 }
 
@@ -205,12 +305,12 @@ cudaError_t launch_conflict_finish(const DevWorld &w, const FinishArgs &a, cudaS
     return cudaGetLastError();
 }
 
-int conflict_keys_launches() { return 1; }
-
 cudaError_t init_conflict_kernels()
 {
-    return cudaFuncSetAttribute(k_conflict_keys, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                2 * KCBS_MAX_ROBOTS * kTile * (int)sizeof(float));
+    const int bytes = 2 * KCBS_MAX_ROBOTS * kTile * (int)sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(k_conflict_keys<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_conflict_keys<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 }  // namespace kcbs

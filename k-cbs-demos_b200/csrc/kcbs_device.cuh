@@ -30,7 +30,13 @@ struct DevWorld {
     int n_obs;
     int n_robots;
     float max_rad;           // largest robot bounding radius
-    float pad0;
+    // Obstacle cull grid (built on the host at kcbs_create, lives in device memory): cell (ix, iy) holds a
+    // 64-bit mask of the obstacles whose rectangle, grown by max_rad, overlaps the cell.
+    int gdim;                // cells per side
+    float gx0, gy0;          // grid origin = lower workspace bound
+    float ginvx, ginvy;      // cells per metre
+    const unsigned long long *grid;  // [gdim * gdim]
+    const float4 *obs4;              // [n_obs] (cx, cy, hx, hy), same values as the arrays below
     float obs_cx[KCBS_MAX_OBSTACLES];  // Obstacle.h:85-86 centre
     float obs_cy[KCBS_MAX_OBSTACLES];
     float obs_hx[KCBS_MAX_OBSTACLES];  // half extents
@@ -117,6 +123,37 @@ __device__ __forceinline__ bool obstacles_clear(const DevWorld &w, float x, floa
             }
             ok &= sat_gap_obstacle(x, y, c, s, hl, hw, cx, cy, hx, hy) > 0.0f;
         }
+    }
+    return ok;
+}
+
+constexpr int kGridDim = 32;
+
+// Obstacle part of isValid with the cull grid: only obstacles flagged for the state's cell are tested.
+// `grid` / `obs` may point to shared memory (k_validity stages them) or to global memory (k_propagate).
+__device__ __forceinline__ bool obstacles_clear_grid(const DevWorld &w, const unsigned long long *grid,
+                                                     const float4 *obs, float x, float y, float th, float hl,
+                                                     float hw)
+{
+    const int ix = min(w.gdim - 1, max(0, (int)((x - w.gx0) * w.ginvx)));
+    const int iy = min(w.gdim - 1, max(0, (int)((y - w.gy0) * w.ginvy)));
+    unsigned long long m = grid[iy * w.gdim + ix];
+    if (m == 0ull) return true;
+    float s, c;
+    sincosf(th, &s, &c);
+    const float ac = fabsf(c), as = fabsf(s);
+    const float ex = fmaf(hl, ac, hw * as), ey = fmaf(hl, as, hw * ac);  // robot extent along world x / y
+    bool ok = true;
+    while (m) {
+        const int o = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const float4 ob = obs[o];
+        const float dx = ob.x - x, dy = ob.y - y;
+        // separating axis found <=> SAT gap > 0 (touching counts as collision)
+        const bool sep = (fabsf(dx) > ob.z + ex) | (fabsf(dy) > ob.w + ey) |
+                         (fabsf(fmaf(dx, c, -dy * s)) > hl + fmaf(ob.z, ac, ob.w * as)) |
+                         (fabsf(fmaf(dx, s, dy * c)) > hw + fmaf(ob.z, as, ob.w * ac));
+        ok &= sep;
     }
     return ok;
 }

@@ -34,6 +34,8 @@ struct ConflictArgs {
     const float *traj;         // [P][R][3][T]
     const int *lengths;        // [P][R] or null
     unsigned long long *keys;  // [P], pre-set to kNoConflict
+    int *tickets;              // [P] zeroed CTA tickets (fused finish) or null
+    kcbs_conflict *out;        // [P] results written by the last CTA of each plan (fused finish) or null
     int P, R, T;
     int k_lo, k_hi;            // scanned time range
 };
@@ -50,10 +52,10 @@ cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t 
 cudaError_t launch_validity(const DevWorld &w, const ValidArgs &a, cudaStream_t stream);
 cudaError_t launch_conflict_keys(const DevWorld &w, const ConflictArgs &a, cudaStream_t stream);
 cudaError_t launch_conflict_finish(const DevWorld &w, const FinishArgs &a, cudaStream_t stream);
-cudaError_t launch_fill_keys(unsigned long long *keys, int n, cudaStream_t stream);
+cudaError_t launch_fill_keys(unsigned long long *keys, int *tickets, int n, cudaStream_t stream);
 // FFMA saturation probe: returns flops executed; elapsed time is measured by the caller.
 cudaError_t launch_fp32_probe(float *sink, int iters, cudaStream_t stream, double *flops);
+cudaError_t init_propagate_kernels();
 cudaError_t init_conflict_kernels();  // per-device function attributes; call once per context
-int conflict_keys_launches();  // kernels per launch_conflict_keys call (for launch accounting)
 
 }  // namespace kcbs
