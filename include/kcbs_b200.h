@@ -158,6 +158,8 @@ KCBS_API int kcbs_conflict_finish_dev(kcbs_ctx *ctx, int n_plans, int R, int T, 
 /* Runs an FFMA-saturating kernel and reports the device's sustained FP32 rate in TFLOP/s
  * (2 flops per FMA); the denominator of the propagation roofline. */
 KCBS_API int kcbs_measure_fp32_peak(kcbs_ctx *ctx, double *tflops);
+/* Same probe with the packed fma.rn.f32x2 instruction (two FMAs per lane per instruction). */
+KCBS_API int kcbs_measure_fp32x2_peak(kcbs_ctx *ctx, double *tflops);
 /* Number of kernels this context has launched since creation. */
 KCBS_API int64_t kcbs_launch_count(const kcbs_ctx *ctx);
 

@@ -54,7 +54,7 @@ EXPORTS = [
     "kcbs_last_error", "kcbs_sync", "kcbs_host_alloc", "kcbs_host_free", "kcbs_propagate_batch",
     "kcbs_propagate_batch_dev", "kcbs_validity_batch", "kcbs_validity_batch_dev", "kcbs_first_conflict",
     "kcbs_first_conflict_dev", "kcbs_conflict_keys_dev", "kcbs_conflict_finish_dev",
-    "kcbs_measure_fp32_peak", "kcbs_launch_count",
+    "kcbs_measure_fp32_peak", "kcbs_measure_fp32x2_peak", "kcbs_launch_count",
 ]
 
 
@@ -96,6 +96,7 @@ def load_library() -> C.CDLL:
     lib.kcbs_conflict_keys_dev.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.kcbs_conflict_finish_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.kcbs_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.kcbs_measure_fp32x2_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.kcbs_launch_count.restype = i64
     lib.kcbs_launch_count.argtypes = [vp]
     _LIB = lib
@@ -207,6 +208,11 @@ class Context:
     def measure_fp32_peak(self) -> float:
         v = C.c_double()
         self._check(self._lib.kcbs_measure_fp32_peak(self._h, C.byref(v)))
+        return v.value
+
+    def measure_fp32x2_peak(self) -> float:
+        v = C.c_double()
+        self._check(self._lib.kcbs_measure_fp32x2_peak(self._h, C.byref(v)))
         return v.value
 
     def pinned_empty(self, shape, dtype) -> np.ndarray:

@@ -543,17 +543,18 @@ int kcbs_first_conflict(kcbs_ctx *ctx, int n_plans, int R, int T, const float *t
 
 /* ---- measurement support ------------------------------------------------------------------- */
 
-int kcbs_measure_fp32_peak(kcbs_ctx *ctx, double *tflops)
+static int measure_probe(kcbs_ctx *ctx, double *tflops, bool packed)
 {
     if (!ctx || !tflops) return KCBS_ERR_INVALID_ARGUMENT;
     KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
     int st = reserve(ctx, ctx->out2, 256);
     if (st != KCBS_OK) return st;
+    auto launch = packed ? launch_fp32x2_probe : launch_fp32_probe;
     double flops = 0, best = 0;
-    KCBS_CUDA(ctx, launch_fp32_probe((float *)ctx->out2.p, 64, ctx->stream, &flops));  // warm-up
+    KCBS_CUDA(ctx, launch((float *)ctx->out2.p, 64, ctx->stream, &flops));  // warm-up
     for (int rep = 0; rep < 5; ++rep) {
         KCBS_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-        KCBS_CUDA(ctx, launch_fp32_probe((float *)ctx->out2.p, 2048, ctx->stream, &flops));
+        KCBS_CUDA(ctx, launch((float *)ctx->out2.p, 2048, ctx->stream, &flops));
         KCBS_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
         KCBS_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
         float ms = 0;
@@ -565,6 +566,9 @@ int kcbs_measure_fp32_peak(kcbs_ctx *ctx, double *tflops)
     *tflops = best;
     return KCBS_OK;
 }
+
+int kcbs_measure_fp32_peak(kcbs_ctx *ctx, double *tflops) { return measure_probe(ctx, tflops, false); }
+int kcbs_measure_fp32x2_peak(kcbs_ctx *ctx, double *tflops) { return measure_probe(ctx, tflops, true); }
 
 int64_t kcbs_launch_count(const kcbs_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

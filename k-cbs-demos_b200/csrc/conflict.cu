@@ -114,52 +114,102 @@ __device__ __forceinline__ kcbs_conflict finish_plan(const DevWorld &w, unsigned
     return c;
 }
 
+// Tile descriptor of the persistent loop.
+struct TileInfo {
+    int plan, k0, n_k;
+    bool bulk;
+};
+
+__device__ __forceinline__ TileInfo tile_info(const ConflictArgs &a, int item, int tiles_per_plan)
+{
+    TileInfo t;
+    t.plan = item / tiles_per_plan;
+    t.k0 = a.k_lo + (item - t.plan * tiles_per_plan) * kTile;
+    t.n_k = min(kTile, a.k_hi - t.k0);
+    // bulk path: rows 16 B aligned, sizes multiples of 16 B, no padding inside the tile
+    t.bulk = ((a.T & 3) == 0) && ((t.k0 & 3) == 0) && ((t.n_k & 3) == 0) && ((((size_t)a.traj) & 15) == 0);
+    if (t.bulk && a.lengths) {
+        const int *len = a.lengths + (long long)t.plan * a.R;
+        for (int r = 0; r < a.R; ++r) t.bulk &= len[r] >= t.k0 + t.n_k;
+    }
+    return t;
+}
+
+// Persistent CTAs walk over (plan, time tile) items; while one tile is being tested the TMA engine already
+// fetches the next one into the other shared-memory buffer.
 template <bool FUSED>
 __global__ void __launch_bounds__(kTile)
-k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ ConflictArgs a, int tiles_per_plan)
+k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ ConflictArgs a, int tiles_per_plan,
+                int n_items)
 {
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ int s_last;
 
     const int R = a.R, T = a.T;
-    const int plan = blockIdx.x / tiles_per_plan;
-    const int tile = blockIdx.x - plan * tiles_per_plan;
-    const int k0 = a.k_lo + tile * kTile;
+    const int Rp = (R + kATile - 1) / kATile * kATile;  // rows incl. sentinel robots of the last register tile
     const int tid = threadIdx.x;
-    const int k = k0 + tid;
-    const float *base = a.traj + (long long)plan * R * 3 * T;
-    const int *len = a.lengths ? a.lengths + (long long)plan * R : nullptr;
-    float *xs = smem;              // [R][kTile]
-    float *ys = smem + R * kTile;  // [R][kTile]
+    float *bufs[2] = {smem, smem + 2 * Rp * kTile};     // each: xs [Rp][kTile], ys [Rp][kTile]
 
-    unsigned long long key = kNoConflict;
-
-    // a conflict already recorded at an earlier time index makes this tile irrelevant
-    const unsigned long long seen = *(volatile const unsigned long long *)(a.keys + plan);
-    const bool skip = seen != kNoConflict && (long long)(seen >> 16) < (long long)k0;
-
-    if (!skip) {
-        const int n_k = min(kTile, a.k_hi - k0);   // time indices of this tile
-        // bulk path: rows 16 B aligned, sizes multiples of 16 B, no padding inside the tile
-        bool bulk = ((T & 3) == 0) && ((k0 & 3) == 0) && ((n_k & 3) == 0) && ((((size_t)a.traj) & 15) == 0);
-        if (bulk && len) {
-            for (int r = 0; r < R; ++r) bulk &= len[r] >= k0 + n_k;
+    // sentinel robots: far apart from everything and from each other, written once
+    for (int b = 0; b < 2; ++b)
+        for (int r = R; r < Rp; ++r) {
+            bufs[b][r * kTile + tid] = 1.0e18f * (float)(r - R + 1);
+            bufs[b][(Rp + r) * kTile + tid] = 0.0f;
         }
-        if (bulk) {
-            if (tid == 0) {
-                mbar_init(&s_bar, 1);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](const TileInfo &t, int b) {  // start the bulk copies of tile t into buffer b
+        if (tid == 0) mbar_expect_tx(&s_bar[b], (unsigned)(2 * R * t.n_k * sizeof(float)));
+        if (tid < 2 * R) {
+            const int r = tid >> 1, c = tid & 1;
+            const float *src = a.traj + (long long)t.plan * R * 3 * T + ((long long)r * 3 + c) * T + t.k0;
+            bulk_g2s(bufs[b] + (c * Rp + r) * kTile, src, (unsigned)(t.n_k * sizeof(float)), &s_bar[b]);
+        }
+    };
+
+    unsigned phase[2] = {0, 0};
+    int item = blockIdx.x;
+    TileInfo cur = tile_info(a, min(item, n_items - 1), tiles_per_plan);
+    bool cur_issued = false;
+    if (item < n_items && cur.bulk) {
+        issue(cur, 0);
+        cur_issued = true;
+    }
+
+    for (int it = 0; item < n_items; ++it, item += gridDim.x) {
+        const int b = it & 1;
+        const int plan = cur.plan, k0 = cur.k0, n_k = cur.n_k;
+        const int k = k0 + tid;
+        const float *base = a.traj + (long long)plan * R * 3 * T;
+        const int *len = a.lengths ? a.lengths + (long long)plan * R : nullptr;
+        float *xs = bufs[b], *ys = bufs[b] + Rp * kTile;
+
+        // prefetch the next tile of this CTA into the other buffer
+        const int next_item = item + gridDim.x;
+        TileInfo nxt = cur;
+        bool nxt_issued = false;
+        if (next_item < n_items) {
+            nxt = tile_info(a, next_item, tiles_per_plan);
+            if (nxt.bulk) {
+                issue(nxt, b ^ 1);
+                nxt_issued = true;
             }
-            __syncthreads();
-            // arrive + expect_tx is one atomic update, so copies may complete before or after it
-            if (tid == 0) mbar_expect_tx(&s_bar, (unsigned)(2 * R * n_k * sizeof(float)));
-            if (tid < 2 * R) {
-                const int r = tid >> 1, c = tid & 1;
-                bulk_g2s((c ? ys : xs) + r * kTile, base + ((long long)r * 3 + c) * T + k0, (unsigned)(n_k * sizeof(float)), &s_bar);
-            }
-            mbar_wait(&s_bar, 0);
-        } else {
+        }
+
+        // a conflict already recorded at an earlier time index makes this tile irrelevant
+        const unsigned long long seen = *(volatile const unsigned long long *)(a.keys + plan);
+        const bool skip = seen != kNoConflict && (long long)(seen >> 16) < (long long)k0;
+
+        if (cur_issued) {
+            mbar_wait(&s_bar[b], phase[b]);
+            phase[b] ^= 1;
+        } else if (!skip) {
 #pragma unroll 4
             for (int r = 0; r < R; ++r) {
                 const int kk = clamp_k(k, T, len, r);
@@ -167,7 +217,9 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
                 ys[r * kTile + tid] = __ldcs(base + ((long long)r * 3 + 1) * T + kk);
             }
         }
-        const bool active = tid < n_k;
+
+        unsigned long long key = kNoConflict;
+        const bool active = !skip && tid < n_k;
 
         // ---- broad phase: min over pairs of the Chebyshev centre distance -----------------------------
         float m = 3.0e38f;
@@ -176,10 +228,8 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
                 float xa[kATile], ya[kATile];
 #pragma unroll
                 for (int q = 0; q < kATile; ++q) {
-                    const bool in = a0 + q < R;
-                    // distinct far-away sentinels for the missing robots of a partial tile
-                    xa[q] = in ? xs[(a0 + q) * kTile + tid] : 1.0e18f * (float)(q + 1);
-                    ya[q] = in ? ys[(a0 + q) * kTile + tid] : 0.0f;
+                    xa[q] = xs[(a0 + q) * kTile + tid];
+                    ya[q] = ys[(a0 + q) * kTile + tid];
                 }
 #pragma unroll
                 for (int q = 0; q < kATile; ++q)
@@ -231,27 +281,30 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
             }
             if ((tid & 31) == 0) atomicMin(a.keys + plan, key);
         }
-    }
 
-    if (FUSED) {
-        // last CTA of the plan finishes it and leaves key + ticket clean for the next call
+        // all reads of this buffer are done (it is refilled two iterations from now) and all atomics issued
         __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            const int ticket = atomicAdd(a.tickets + plan, 1);
-            s_last = (ticket == tiles_per_plan - 1);
-        }
-        __syncthreads();
-        if (s_last && tid < 32) {
-            __threadfence();
-            const unsigned long long best = *(volatile const unsigned long long *)(a.keys + plan);
-            const kcbs_conflict c = finish_plan(w, best, base, len, T, tid);
+        if (FUSED) {
+            // the last tile of a plan finishes it and leaves key + ticket clean for the next call
             if (tid == 0) {
-                a.out[plan] = c;
-                a.keys[plan] = kNoConflict;
-                a.tickets[plan] = 0;
+                __threadfence();
+                const int ticket = atomicAdd(a.tickets + plan, 1);
+                s_last = (ticket == tiles_per_plan - 1);
+            }
+            __syncthreads();
+            if (s_last && tid < 32) {
+                __threadfence();
+                const unsigned long long best = *(volatile const unsigned long long *)(a.keys + plan);
+                const kcbs_conflict c = finish_plan(w, best, base, len, T, tid);
+                if (tid == 0) {
+                    a.out[plan] = c;
+                    a.keys[plan] = kNoConflict;
+                    a.tickets[plan] = 0;
+                }
             }
         }
+        cur = nxt;
+        cur_issued = nxt_issued;
     }
 }
 
@@ -288,12 +341,21 @@ cudaError_t launch_conflict_keys(const DevWorld &w, const ConflictArgs &a, cudaS
 {
     if (a.P <= 0 || a.k_hi <= a.k_lo) return cudaSuccess;
     const int tiles = (a.k_hi - a.k_lo + kTile - 1) / kTile;
-    const size_t smem = (size_t)2 * a.R * kTile * sizeof(float);
-    const unsigned grid = (unsigned)((long long)tiles * a.P);
+    const long long items = (long long)tiles * a.P;
+    if (items > 0x7fffffffll) return cudaErrorInvalidValue;
+    const int Rp = (a.R + kATile - 1) / kATile * kATile;
+    const size_t smem = (size_t)2 * 2 * Rp * kTile * sizeof(float);  // two buffers of x and y rows
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    const long long want = (long long)sms * per_sm;
+    const unsigned grid = (unsigned)(items < want ? items : want);
     if (a.out)
-        k_conflict_keys<true><<<grid, kTile, smem, stream>>>(w, a, tiles);
+        k_conflict_keys<true><<<grid, kTile, smem, stream>>>(w, a, tiles, (int)items);
     else
-        k_conflict_keys<false><<<grid, kTile, smem, stream>>>(w, a, tiles);
+        k_conflict_keys<false><<<grid, kTile, smem, stream>>>(w, a, tiles, (int)items);
     return cudaGetLastError();
 }
 
@@ -307,7 +369,7 @@ cudaError_t launch_conflict_finish(const DevWorld &w, const FinishArgs &a, cudaS
 
 cudaError_t init_conflict_kernels()
 {
-    const int bytes = 2 * KCBS_MAX_ROBOTS * kTile * (int)sizeof(float);
+    const int bytes = 2 * 2 * KCBS_MAX_ROBOTS * kTile * (int)sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(k_conflict_keys<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_conflict_keys<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

@@ -11,19 +11,24 @@
 //   * vdot = a and phidot = w are constant: the v / phi stage values are exact linear functions of
 //     time, stages 2 and 3 share v, phi, tan(phi) and k_theta, and stage 4 of a sub-step is stage 1
 //     of the next one.
-//   * phi advances by the constant (h/2) w per half sub-step, so (sin phi, cos phi) advance by one
-//     fixed rotation (4 FFMA) and tan(phi) costs one MUFU.RCP; re-anchored by sincosf every step.
+//   * phi advances by the constant delta = (h/2) w per half sub-step, so tan(phi) follows the addition
+//     formula tan(phi + delta) = (T + t) / (1 - T t) (FADD + FFMA + MUFU.RCP + FMUL); re-anchored by an
+//     accurate sincosf every propagation step.
 //   * the four stage headings of a sub-step differ by at most h*|k_theta| <= 0.035 rad, so their
 //     (cos, sin) follow from the previous stage by a 2nd-order rotation (FFMA only, truncation
 //     < 1e-6 which enters the position with weight h/6); re-anchored by MUFU sincos every step.
 //     This moves the kernel off the MUFU pipe (10 -> 2 MUFU per sub-step) onto the FMA pipe.
+//   * k_theta is carried pre-scaled by h/2 and v pre-scaled by h/6, both as exact linear sequences, so a
+//     sub-step is ~45 FMA-pipe instructions + 2 MUFU.
 //   * positions and the heading are accumulated as small offsets from the parent / the step start,
 //     so FP32 rounding at |x| ~ 32 happens once per written state, not once per sub-step.
 //
 // Work distribution: requested durations are U{1..10} (SimpleDirectedControlSampler), which would
-// idle 45 % of the lanes of a warp.  Each CTA therefore counting-sorts its 256 samples by duration
-// in shared memory so that warps hold (almost) equal durations; propagated states are staged in a
-// shared-memory tile at the sample's original slot and leave in one coalesced, streaming pass.
+// idle 45 % of the lanes of a warp.  Each CTA (128 threads) therefore counting-sorts its 256 samples by
+// duration in shared memory and every thread runs two of them: rank t (long) and rank 255 - t (short).
+// Lanes of a warp then hold (almost) equal durations in both rounds and every thread of the CTA has the
+// same total work, so neither lanes nor warps idle.  States are written straight to their original
+// slots (a warp's stores stay inside the CTA's 1 KB row windows, which L2 merges into full lines).
 #include <cstddef>
 
 #include "kcbs_device.cuh"
@@ -31,8 +36,8 @@
 
 namespace kcbs {
 
-constexpr int kPropBlock = 256;
-constexpr int kStageSteps = 10;  // segments up to this many steps are staged in shared memory
+constexpr int kPropThreads = 128;  // threads per CTA
+constexpr int kPropSamples = 256;  // samples per CTA (two per thread)
 
 __device__ __forceinline__ float rcp_approx(float x)
 {
@@ -41,119 +46,78 @@ __device__ __forceinline__ float rcp_approx(float x)
     return r;
 }
 
-struct PropSmem {
-    int nv[kPropBlock];
-    int hist[KCBS_MAX_STEPS + 1];
-    unsigned short perm[kPropBlock];
-    float tile[5 * kStageSteps * kPropBlock];  // [c][j][slot]; only allocated by the staged variant
-};
-
-template <bool HAS_OBS, bool STAGED>
-__global__ void __launch_bounds__(kPropBlock)
-k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs a)
+// propagateWhileValid for one sample; writes the segment, the final state and the valid-step count.
+template <bool HAS_OBS>
+__device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropArgs &a, long long i, int st)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    PropSmem &sm = *reinterpret_cast<PropSmem *>(smem_raw);
+    const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
+    const float x0 = a.parents[0 * a.n_parents + pi];
+    const float y0 = a.parents[1 * a.n_parents + pi];
+    const float v0 = a.parents[2 * a.n_parents + pi];
+    const float phi0 = a.parents[3 * a.n_parents + pi];
+    const float th0 = a.parents[4 * a.n_parents + pi];
+    const float ua = a.controls[i];
+    const float uw = a.controls[a.n + i];
 
-    const int tid = threadIdx.x;
-    const long long b0 = (long long)blockIdx.x * kPropBlock;
-
-    // ---- counting sort of the CTA's samples by requested duration (longest first) ----------------
-    int slot = tid;  // original slot of the sample this thread works on
-    {
-        const long long i = b0 + tid;
-        int st = 0;
-        if (i < a.n) {
-            st = a.steps ? a.steps[i] : a.max_steps;
-            st = min(max(st, 0), a.max_steps);
-        }
-        if (tid <= KCBS_MAX_STEPS) sm.hist[tid] = 0;
-        __syncthreads();
-        const int within = atomicAdd(&sm.hist[st], 1);
-        __syncthreads();
-        int before = 0;  // samples with a longer duration come first
-        for (int s = KCBS_MAX_STEPS; s > st; --s) before += sm.hist[s];
-        sm.perm[before + within] = (unsigned short)tid;
-        __syncthreads();
-        slot = sm.perm[tid];
-    }
-
-    const long long i = b0 + slot;
-    const bool live = i < a.n;
-    int st = 0;
-    float x0 = 0.f, y0 = 0.f, v0 = 0.f, phi0 = 0.f, th0 = 0.f, ua = 0.f, uw = 0.f;
-    if (live) {
-        st = a.steps ? a.steps[i] : a.max_steps;
-        st = min(max(st, 0), a.max_steps);
-        const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
-        x0 = a.parents[0 * a.n_parents + pi];
-        y0 = a.parents[1 * a.n_parents + pi];
-        v0 = a.parents[2 * a.n_parents + pi];
-        phi0 = a.parents[3 * a.n_parents + pi];
-        th0 = a.parents[4 * a.n_parents + pi];
-        ua = a.controls[i];
-        uw = a.controls[a.n + i];
-    }
-
-    const float h = w.h, hh = 0.5f * w.h, h6 = w.h * (1.0f / 6.0f), h3 = w.h * (1.0f / 3.0f);
-    const float il = w.inv_len;
+    const float h = w.h, hh = 0.5f * w.h, h6 = w.h * (1.0f / 6.0f);
     const float hl = w.rob_hl[a.robot], hw = w.rob_hw[a.robot];
+    const float kscale = hh * w.inv_len;  // K = (h/2) k_theta = kscale * v * tan(phi)
 
-    // rotation by delta = (h/2) w for the (sin phi, cos phi) recurrence: sin(delta), 1 - cos(delta)
+    // tan of the half-sub-step increment of phi
     const float dl = hh * uw, dl2 = dl * dl;
-    const float sd = dl * fmaf(dl2, fmaf(dl2, 1.0f / 120.0f, -1.0f / 6.0f), 1.0f);
-    const float ed = 0.5f * dl2 * fmaf(dl2, fmaf(dl2, 1.0f / 360.0f, -1.0f / 12.0f), 1.0f);
-    const float dvh = hh * ua, dv = h * ua;
+    const float td = dl * fmaf(dl2, fmaf(dl2, 2.0f / 15.0f, 1.0f / 3.0f), 1.0f);
+    // per-sub-step increments of U = kscale * v and W = (h/6) v
+    const float dUh = kscale * hh * ua, dU = kscale * h * ua;
+    const float dW2 = 2.0f * h6 * hh * ua, dW = h6 * h * ua;
 
     float offx = 0.0f, offy = 0.0f;                         // position offset from the parent
     float xs = x0, ys = y0, vs = v0, ps = phi0, ts = th0;   // last valid state
     int nv = 0;
+    const long long plane = (long long)a.max_steps * a.n;
 
     for (int j = 0; j < st; ++j) {
         float sp, cp, s1, c1;
         sincosf(ps, &sp, &cp);
         __sincosf(ts, &s1, &c1);
-        float k1 = vs * il * (sp * rcp_approx(cp));  // k_theta at stage 1 of sub-step 0
-        float toff = 0.0f;                            // heading offset from ts within this step
-        float v1 = vs, hv1 = h6 * vs;
+        float T = sp * rcp_approx(cp);
+        float U1 = kscale * vs, W1 = h6 * vs;
+        float K1 = U1 * T;   // (h/2) k_theta at stage 1 of sub-step 0
+        float toff = 0.0f;   // heading offset from ts within this step
 
 #pragma unroll 2
         for (int n = 0; n < w.n_sub; ++n) {
-            const float v2 = v1 + dvh, v4 = v1 + dv;
-            // phi -> phi + delta -> phi + 2 delta
-            const float s2p = fmaf(cp, sd, fmaf(-sp, ed, sp));
-            const float c2p = fmaf(-sp, sd, fmaf(-cp, ed, cp));
-            const float k2 = v2 * il * (s2p * rcp_approx(c2p));
-            sp = fmaf(c2p, sd, fmaf(-s2p, ed, s2p));
-            cp = fmaf(-s2p, sd, fmaf(-c2p, ed, c2p));
-            const float k4 = v4 * il * (sp * rcp_approx(cp));
+            const float U2 = U1 + dUh, U4 = U1 + dU;
+            const float W2 = fmaf(2.0f, W1, dW2), W4 = W1 + dW;
+            // tan(phi) at the half and the full sub-step
+            const float T2 = (T + td) * rcp_approx(fmaf(-T, td, 1.0f));
+            T = (T2 + td) * rcp_approx(fmaf(-T2, td, 1.0f));
+            const float K2 = U2 * T2, K4 = U4 * T;
 
-            // stage 2 heading = stage 1 + (h/2) k1
-            const float e2 = hh * k1, g2 = -0.5f * e2 * e2;
-            const float c2 = fmaf(c1, g2, fmaf(-s1, e2, c1));
-            const float s2 = fmaf(s1, g2, fmaf(c1, e2, s1));
-            // stage 3 heading = stage 2 + (h/2)(k2 - k1): only cos2 + cos3 and sin2 + sin3 are needed
-            const float e3 = hh * (k2 - k1);
+            // stage 2 heading = stage 1 + K1 (2nd-order rotation)
+            const float h2 = -0.5f * K1;
+            const float c2 = fmaf(fmaf(c1, h2, -s1), K1, c1);
+            const float s2 = fmaf(fmaf(s1, h2, c1), K1, s1);
+            // stage 3 heading = stage 2 + (K2 - K1): only cos2 + cos3 and sin2 + sin3 are needed
+            const float e3 = K2 - K1;
             const float c23 = fmaf(-s2, e3, c2 + c2);
             const float s23 = fmaf(c2, e3, s2 + s2);
-            // stage 4 heading = stage 1 + h k2 (k3 == k2) = stage 2 + (h k2 - (h/2) k1)
-            const float e4 = fmaf(h, k2, -e2), g4 = -0.5f * e4 * e4;
-            const float c4 = fmaf(c2, g4, fmaf(-s2, e4, c2));
-            const float s4 = fmaf(s2, g4, fmaf(c2, e4, s2));
+            // stage 4 heading = stage 1 + 2 K2 (k3 == k2) = stage 2 + (2 K2 - K1)
+            const float e4 = fmaf(2.0f, K2, -K1), h4 = -0.5f * e4;
+            const float c4 = fmaf(fmaf(c2, h4, -s2), e4, c2);
+            const float s4 = fmaf(fmaf(s2, h4, c2), e4, s2);
 
-            const float hv2 = h3 * v2, hv4 = h6 * v4;
-            offx = fmaf(hv1, c1, fmaf(hv2, c23, fmaf(hv4, c4, offx)));
-            offy = fmaf(hv1, s1, fmaf(hv2, s23, fmaf(hv4, s4, offy)));
+            offx = fmaf(W1, c1, fmaf(W2, c23, fmaf(W4, c4, offx)));
+            offy = fmaf(W1, s1, fmaf(W2, s23, fmaf(W4, s4, offy)));
 
-            // heading: theta += h/6 (k1 + 4 k2 + k4); next stage 1 = stage 4 + (that - h k2)
-            const float dth = h6 * fmaf(4.0f, k2, k1 + k4);
+            // heading: theta += h/6 (k1 + 4 k2 + k4) = (K1 + 4 K2 + K4) / 3; next stage 1 = stage 4 + (that - 2 K2)
+            const float dth = (1.0f / 3.0f) * fmaf(4.0f, K2, K1 + K4);
             toff += dth;
-            const float e1 = fmaf(-h, k2, dth);
+            const float e1 = fmaf(-2.0f, K2, dth);
             c1 = fmaf(-s4, e1, c4);
             s1 = fmaf(c4, e1, s4);
-            k1 = k4;
-            v1 = v4;
-            hv1 = hv4;
+            K1 = K4;
+            U1 = U4;
+            W1 = W4;
         }
 
         const float t1 = (float)(j + 1) * w.step;
@@ -170,79 +134,83 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         xs = xn; ys = yn; vs = vn; ps = pn; ts = tn;
         nv = j + 1;
         if (a.seg) {
-            if (STAGED) {
-                float *o = sm.tile + j * kPropBlock + slot;
-                o[0 * kStageSteps * kPropBlock] = xn;
-                o[1 * kStageSteps * kPropBlock] = yn;
-                o[2 * kStageSteps * kPropBlock] = vn;
-                o[3 * kStageSteps * kPropBlock] = pn;
-                o[4 * kStageSteps * kPropBlock] = tn;
-            } else {
-                const long long plane = (long long)a.max_steps * a.n;
-                float *o = a.seg + (long long)j * a.n + i;
-                __stcs(o, xn);
-                __stcs(o + plane, yn);
-                __stcs(o + 2 * plane, vn);
-                __stcs(o + 3 * plane, pn);
-                __stcs(o + 4 * plane, tn);
-            }
+            float *o = a.seg + (long long)j * a.n + i;
+            __stcs(o, xn);
+            __stcs(o + plane, yn);
+            __stcs(o + 2 * plane, vn);
+            __stcs(o + 3 * plane, pn);
+            __stcs(o + 4 * plane, tn);
         }
     }
 
-    if (live) {
-        if (a.valid_steps) a.valid_steps[i] = nv;
-        if (a.fin) {
-            a.fin[i] = xs;
-            a.fin[a.n + i] = ys;
-            a.fin[2 * a.n + i] = vs;
-            a.fin[3 * a.n + i] = ps;
-            a.fin[4 * a.n + i] = ts;
-        }
+    if (a.valid_steps) a.valid_steps[i] = nv;
+    if (a.fin) {
+        a.fin[i] = xs;
+        a.fin[a.n + i] = ys;
+        a.fin[2 * a.n + i] = vs;
+        a.fin[3 * a.n + i] = ps;
+        a.fin[4 * a.n + i] = ts;
     }
+}
 
-    if (STAGED && a.seg) {
-        // coalesced streaming write-out of the staged segments: thread t owns original slot t
-        sm.nv[slot] = nv;
-        __syncthreads();
-        const long long io = b0 + tid;
-        if (io < a.n) {
-            const int mine = sm.nv[tid];
-            const long long plane = (long long)a.max_steps * a.n;
-            for (int j = 0; j < mine; ++j) {
-                const float *t = sm.tile + j * kPropBlock + tid;
-                float *o = a.seg + (long long)j * a.n + io;
+template <bool HAS_OBS>
+__global__ void __launch_bounds__(kPropThreads)
+k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs a)
+{
+    __shared__ int s_hist[KCBS_MAX_STEPS + 1];
+    __shared__ unsigned char s_perm[kPropSamples];   // rank -> slot
+    __shared__ unsigned char s_steps[kPropSamples];  // slot -> clamped duration
+
+    const int tid = threadIdx.x;
+    const long long b0 = (long long)blockIdx.x * kPropSamples;
+
+    // ---- counting sort of the CTA's samples by requested duration (longest first) ----------------
+    if (tid <= KCBS_MAX_STEPS) s_hist[tid] = 0;
+    __syncthreads();
+    int st2[2], within[2];
 #pragma unroll
-                for (int c = 0; c < 5; ++c) __stcs(o + c * plane, t[c * kStageSteps * kPropBlock]);
-            }
+    for (int u = 0; u < 2; ++u) {
+        const int slot = tid + u * kPropThreads;
+        const long long i = b0 + slot;
+        int st = 0;
+        if (i < a.n) {
+            st = a.steps ? a.steps[i] : a.max_steps;
+            st = min(max(st, 0), a.max_steps);
         }
+        st2[u] = st;
+        s_steps[slot] = (unsigned char)st;
+        within[u] = atomicAdd(&s_hist[st], 1);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        int before = 0;  // samples with a longer duration come first
+        for (int s = KCBS_MAX_STEPS; s > st2[u]; --s) before += s_hist[s];
+        s_perm[before + within[u]] = (unsigned char)(tid + u * kPropThreads);
+    }
+    __syncthreads();
+
+    // ---- two samples per thread: rank tid (long) and rank 255 - tid (short) ------------------------
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+        const int rank = round == 0 ? tid : kPropSamples - 1 - tid;
+        const int slot = s_perm[rank];
+        const long long i = b0 + slot;
+        if (i < a.n) propagate_sample<HAS_OBS>(w, a, i, (int)s_steps[slot]);
     }
 }
 
-template <bool HAS_OBS, bool STAGED>
-static cudaError_t launch_variant(const DevWorld &w, const PropArgs &a, cudaStream_t stream)
-{
-    const long long grid = (a.n + kPropBlock - 1) / kPropBlock;
-    const size_t smem = STAGED ? sizeof(PropSmem) : offsetof(PropSmem, tile);
-    k_propagate<HAS_OBS, STAGED><<<(unsigned)grid, kPropBlock, smem, stream>>>(w, a);
-    return cudaGetLastError();
-}
-
-cudaError_t init_propagate_kernels()
-{
-    cudaError_t e;
-    const int bytes = (int)sizeof(PropSmem);
-    if ((e = cudaFuncSetAttribute(k_propagate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-    if ((e = cudaFuncSetAttribute(k_propagate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
-    return cudaSuccess;
-}
+cudaError_t init_propagate_kernels() { return cudaSuccess; }
 
 cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t stream)
 {
     if (a.n <= 0) return cudaSuccess;
-    const bool staged = a.seg != nullptr && a.max_steps <= kStageSteps;
+    const long long grid = (a.n + kPropSamples - 1) / kPropSamples;
     if (w.n_obs > 0)
-        return staged ? launch_variant<true, true>(w, a, stream) : launch_variant<true, false>(w, a, stream);
-    return staged ? launch_variant<false, true>(w, a, stream) : launch_variant<false, false>(w, a, stream);
+        k_propagate<true><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+    else
+        k_propagate<false><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+    return cudaGetLastError();
 }
 
 }  // namespace kcbs

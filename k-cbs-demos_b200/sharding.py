@@ -1,0 +1,66 @@
+"""Host-side partitioning of the hot path across ranks (one process per GPU, torch.distributed).
+
+Only two things on the path cross ranks:
+  * per-robot replans / plan batches are independent -> contiguous or round-robin shards, no collective;
+  * one plan scanned in time slabs -> one unsigned 64-bit min all-reduce of the packed (k, r1, r2) keys.
+The same functions run under NCCL on the GPU box and under gloo in the CPU tests."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+NO_CONFLICT_KEY = -1  # 0xFFFF_FFFF_FFFF_FFFF viewed as int64
+TILE = 128            # time indices per CTA tile of k_conflict_keys; slabs are aligned to it
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n independent units (plans, states, samples)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def round_robin(n_jobs: int, rank: int, world: int) -> List[int]:
+    """(node, robot) replan jobs dealt round-robin over the ranks (config: 20 replans over 8 GPUs)."""
+    return list(range(rank, n_jobs, world))
+
+
+def time_slab(T: int, rank: int, world: int, align: int = TILE) -> Tuple[int, int]:
+    """Time slab [k_lo, k_hi) of a T-step plan for this rank, aligned to the kernel's tile size so every
+    rank keeps the bulk-copy path; empty slabs are possible when T < world * align."""
+    tiles = (T + align - 1) // align
+    lo, hi = shard_range(tiles, rank, world)
+    return min(lo * align, T), min(hi * align, T)
+
+
+def pack_key(k: int, r1: int, r2: int) -> int:
+    return (k << 16) | (r1 << 8) | r2
+
+
+def unpack_key(key: int):
+    if key == NO_CONFLICT_KEY or key == 0xFFFFFFFFFFFFFFFF:
+        return None
+    key &= 0xFFFFFFFFFFFFFFFF
+    return key >> 16, (key >> 8) & 0xFF, key & 0xFF
+
+
+def reduce_min_keys(keys: torch.Tensor) -> torch.Tensor:
+    """In-place all-reduce of per-plan packed keys to the global first conflict.  Keys are unsigned 64-bit
+    stored in int64 tensors (no-conflict = all ones = -1); flipping the sign bit turns the unsigned order
+    into the signed order that ReduceOp.MIN implements."""
+    assert keys.dtype == torch.int64
+    bias = torch.iinfo(torch.int64).min
+    keys.bitwise_xor_(bias)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN)
+    keys.bitwise_xor_(bias)
+    return keys
+
+
+def gather_plans(results: torch.Tensor, world: int) -> torch.Tensor:
+    """All-gathers equally sized per-rank result blocks ([P/world, 4] int32 conflicts or trajectories)."""
+    if not (dist.is_initialized() and world > 1):
+        return results
+    out = [torch.empty_like(results) for _ in range(world)]
+    dist.all_gather(out, results)
+    return torch.cat(out, dim=0)

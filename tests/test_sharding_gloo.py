@@ -1,0 +1,120 @@
+"""world_size-2 CPU (gloo) tests of the host-side multi-GPU logic: time-slab partitioning of the conflict
+scan with the unsigned-min key reduction, plan sharding + all-gather, and replan round-robin.  The per-rank
+scan is played by the CPU oracle here (no GPU in this container); on the GPU box the same sharding functions
+drive kcbs_conflict_keys_dev / kcbs_conflict_finish_dev (tests/test_gpu_conflict.py, bench.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _slab_keys(oracle, sharding, traj, k_lo, k_hi):
+    """Packed first-conflict key of every plan restricted to time indices [k_lo, k_hi) (CPU stand-in for
+    kcbs_conflict_keys_dev)."""
+    P = traj.shape[0]
+    keys = torch.full((P,), sharding.NO_CONFLICT_KEY, dtype=torch.int64)
+    if k_hi <= k_lo:
+        return keys
+    res, _ = oracle.first_conflict_batch(np.ascontiguousarray(traj[..., k_lo:k_hi]))
+    for p in range(P):
+        if res[p]["r1"] >= 0:
+            key = sharding.pack_key(int(res[p]["k_start"]) + k_lo, int(res[p]["r1"]), int(res[p]["r2"]))
+            keys[p] = key if key < (1 << 63) else key - (1 << 64)
+    return keys
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as graft
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pkg = graft.load_package()
+        orc = graft.load_oracle()
+        from kcbs_b200 import sharding, workloads
+        scene = "Empty32x32_10robots"
+        oracle = orc.Oracle(pkg.scenes.world(scene))
+        P, R, T = 6, 10, 700
+        traj = workloads.cell_plans(scene, P, T, seed=21)
+        workloads.plant_conflict(traj, 0, 2, 3, 50)          # rank 0's slab
+        workloads.plant_conflict(traj, 1, 4, 9, 650, 20)     # rank 1's slab
+        workloads.plant_conflict(traj, 2, 7, 8, 600)         # both slabs: earlier one must win
+        workloads.plant_conflict(traj, 2, 0, 1, 100, 3)
+        workloads.plant_conflict(traj, 3, 5, 6, 383, 4)      # run crossing the slab border (384)
+        full, _ = oracle.first_conflict_batch(traj)
+
+        # (1) one plan set scanned in time slabs + unsigned-min all-reduce of the keys
+        k_lo, k_hi = sharding.time_slab(T, rank, world)
+        assert k_lo % sharding.TILE == 0
+        keys = _slab_keys(oracle, sharding, traj, k_lo, k_hi)
+        sharding.reduce_min_keys(keys)
+        got = [sharding.unpack_key(int(k)) for k in keys]
+        want = [None if r["r1"] < 0 else (int(r["k_start"]), int(r["r1"]), int(r["r2"])) for r in full]
+        assert got == want, (got, want)
+
+        # (2) plans sharded across ranks, results all-gathered
+        lo, hi = sharding.shard_range(P, rank, world)
+        mine, _ = oracle.first_conflict_batch(np.ascontiguousarray(traj[lo:hi]))
+        block = torch.from_numpy(np.stack([mine["r1"], mine["r2"], mine["k_start"], mine["k_end"]], axis=1).astype(np.int32))
+        allres = sharding.gather_plans(block, world)
+        ref = np.stack([full["r1"], full["r2"], full["k_start"], full["k_end"]], axis=1)
+        assert (allres.numpy() == ref).all()
+
+        # (3) replan jobs round-robin: every job exactly once
+        jobs = torch.zeros(20, dtype=torch.int64)
+        for j in sharding.round_robin(20, rank, world):
+            jobs[j] += 1
+        dist.all_reduce(jobs)
+        assert (jobs == 1).all()
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharding_gloo(orc):
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_partition_helpers(pkg):
+    from kcbs_b200 import sharding
+    for n, world in ((10, 3), (256, 8), (5, 8), (0, 2)):
+        cover = []
+        for r in range(world):
+            lo, hi = sharding.shard_range(n, r, world)
+            cover += list(range(lo, hi))
+        assert cover == list(range(n))
+    for T in (1, 127, 128, 1000, 10000):
+        for world in (1, 2, 8):
+            slabs = [sharding.time_slab(T, r, world) for r in range(world)]
+            assert slabs[0][0] == 0 and slabs[-1][1] == T
+            for (a, b), (c, d) in zip(slabs, slabs[1:]):
+                assert b == c and a <= b
+    assert sharding.unpack_key(sharding.pack_key(9999, 28, 29)) == (9999, 28, 29)
+    assert sharding.unpack_key(-1) is None
+    # unsigned order survives the int64 storage: a key with the top bit set is larger than a small key but
+    # smaller than "no conflict"
+    k = torch.tensor([-1, 5, (1 << 63) - (1 << 64) + 7], dtype=torch.int64)
+    assert sharding.reduce_min_keys(k.clone()).tolist() == k.tolist()   # single process: identity
+    bias = torch.iinfo(torch.int64).min
+    assert int((k ^ bias).min() ^ bias) == 5

@@ -33,6 +33,11 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps
 
 
+if what in ("probe", "all"):
+    ctx = pkg.Context(pkg.scenes.world("Empty32x32_10robots"))
+    print(f"FFMA probe {ctx.measure_fp32_peak():.1f} TFLOP/s; packed fma.rn.f32x2 probe {ctx.measure_fp32x2_peak():.1f} TFLOP/s")
+    ctx.close()
+
 if what in ("propagate", "all"):
     for scene, fixed in (("Empty32x32_10robots", None), ("Empty32x32_10robots", 10), ("Congested10x10_7robots", None)):
         ctx = pkg.Context(pkg.scenes.world(scene))
