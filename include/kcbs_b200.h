@@ -153,6 +153,73 @@ KCBS_API int kcbs_conflict_finish_dev(kcbs_ctx *ctx, int n_plans, int R, int T, 
                                       const int32_t *lengths, const uint64_t *keys, kcbs_conflict *out,
                                       void *stream);
 
+/* ---- (4) "next" rows: batched low-level planner and K-CBS high level -----------
+ * These replace the un-vendored planners the reference allocates: oc::RRT through allocateControlRRT
+ * (PlannerAllocatorDatabase.h:40-45) and omrc::KCBS (demo_*.cpp:155-168, Benchmark.h:151-173).  They are
+ * built from the three kernels above plus tree bookkeeping kernels; all planning state lives in HBM. */
+
+typedef struct kcbs_rrt_params {
+    int32_t n_targets;      /* tree nodes expanded per iteration                  (default 2048)   */
+    int32_t n_controls;     /* sampled controls per expanded node                 (default 32)     *
+                             * n_targets * n_controls = 65,536 controls per expansion round        */
+    int32_t max_nodes;      /* tree capacity                                      (default 1<<20)  */
+    int32_t max_iterations; /*                                                    (default 4096)   */
+    int32_t min_steps;      /* setMinMaxControlDuration(1, 10), demo_*.cpp:118                      */
+    int32_t max_steps;
+    float goal_bias;        /* oc::RRT goal bias                                  (default 0.05)   */
+    float goal_radius;      /* GoalRegion2ndOrderCar threshold, GoalRegionDatabase.h:48 (0.5)       */
+    double time_limit_s;    /* setLowLevelSolveTime(5.), Benchmark.h:153                            */
+    uint64_t seed;
+} kcbs_rrt_params;
+
+typedef struct kcbs_rrt_stats {
+    int32_t solved;      /* 1 when a node inside the goal region was found */
+    int32_t iterations;
+    int32_t nodes;
+    int32_t path_steps;  /* propagation steps of the returned path */
+    double seconds;
+} kcbs_rrt_stats;
+
+typedef struct kcbs_kcbs_params {
+    kcbs_rrt_params low_level;
+    double time_limit_s;  /* planner->solve(180.0), demo_*.cpp:168 */
+    int32_t max_nodes;    /* constraint-tree nodes to expand at most (0 = unlimited) */
+} kcbs_kcbs_params;
+
+typedef struct kcbs_kcbs_stats {
+    int32_t solved;
+    int32_t nodes_expanded;         /* KCBS::getNumberOfNodesExpanded, Benchmark.h:167            */
+    int32_t approximate_solutions;  /* KCBS::getNumberOfApproximateSolutions, Benchmark.h:168     */
+    int32_t low_level_calls;
+    double root_seconds;            /* KCBS::getRootSolveTime, Benchmark.h:166                     */
+    double seconds;
+    int64_t conflict_checks;        /* plans validated by kcbs_first_conflict                      */
+} kcbs_kcbs_stats;
+
+KCBS_API void kcbs_rrt_defaults(kcbs_rrt_params *p);
+KCBS_API void kcbs_kcbs_defaults(kcbs_kcbs_params *p);
+
+/* Kinodynamic RRT for robot `robot` from `start` (5 reals) to the disc of goal_radius around goal_xy,
+ * expanding n_targets tree nodes x n_controls controls per round through k_propagate.  Dynamic-obstacle
+ * constraints (the K-CBS low-level input): constraint c forbids overlapping robot cons_robot[c] placed at
+ * cons_states[(s*total) + cons_offset[c] + (k - cons_k0[c])] (s = x, y, theta plane; total = sum of
+ * cons_len) at absolute time index k in [cons_k0[c], cons_k0[c] + cons_len[c]).  The robot is taken to
+ * wait at its last state after its path ends.  traj_out = [5][max_T] planes (state at every propagation
+ * step, index 0 = start); *T_out = number of states.  All pointers are HOST pointers. */
+KCBS_API int kcbs_rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *goal_xy,
+                           const kcbs_rrt_params *params, int n_cons, const int32_t *cons_robot,
+                           const int32_t *cons_k0, const int32_t *cons_len, const int32_t *cons_offset,
+                           const float *cons_states, int max_T, float *traj_out, int32_t *T_out,
+                           kcbs_rrt_stats *stats);
+
+/* K-CBS over the R robots of the world: root = independent low-level plans; best-first search over the
+ * constraint tree with kcbs_first_conflict as the plan validator; every conflict spawns two children that
+ * re-plan one robot each against the other's colliding states.  starts = [5][R] planes, goals = [R][2];
+ * plan_out = [R][5][max_T], lengths_out = [R].  Merging (SystemMerger) is not performed. */
+KCBS_API int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goals,
+                             const kcbs_kcbs_params *params, int max_T, float *plan_out, int32_t *lengths_out,
+                             kcbs_kcbs_stats *stats);
+
 /* ---- measurement support ------------------------------------------------------------------- */
 
 /* Runs an FFMA-saturating kernel and reports the device's sustained FP32 rate in TFLOP/s

@@ -13,6 +13,8 @@ from .capi import (  # noqa: F401
     Conflict,
     Context,
     KcbsError,
+    KcbsParams,
+    RrtParams,
     World,
     lib_path,
     load_library,

@@ -47,6 +47,30 @@ class Conflict(C.Structure):
         return (self.r1, self.r2, self.k_start, self.k_end)
 
 
+class RrtParams(C.Structure):
+    """kcbs_rrt_params"""
+
+    _fields_ = [("n_targets", C.c_int32), ("n_controls", C.c_int32), ("max_nodes", C.c_int32),
+                ("max_iterations", C.c_int32), ("min_steps", C.c_int32), ("max_steps", C.c_int32),
+                ("goal_bias", C.c_float), ("goal_radius", C.c_float), ("time_limit_s", C.c_double),
+                ("seed", C.c_uint64)]
+
+
+class RrtStats(C.Structure):
+    _fields_ = [("solved", C.c_int32), ("iterations", C.c_int32), ("nodes", C.c_int32), ("path_steps", C.c_int32),
+                ("seconds", C.c_double)]
+
+
+class KcbsParams(C.Structure):
+    _fields_ = [("low_level", RrtParams), ("time_limit_s", C.c_double), ("max_nodes", C.c_int32)]
+
+
+class KcbsStats(C.Structure):
+    _fields_ = [("solved", C.c_int32), ("nodes_expanded", C.c_int32), ("approximate_solutions", C.c_int32),
+                ("low_level_calls", C.c_int32), ("root_seconds", C.c_double), ("seconds", C.c_double),
+                ("conflict_checks", C.c_int64)]
+
+
 CONFLICT_DTYPE = np.dtype([("r1", "<i4"), ("r2", "<i4"), ("k_start", "<i4"), ("k_end", "<i4")])
 
 EXPORTS = [
@@ -54,7 +78,8 @@ EXPORTS = [
     "kcbs_last_error", "kcbs_sync", "kcbs_host_alloc", "kcbs_host_free", "kcbs_propagate_batch",
     "kcbs_propagate_batch_dev", "kcbs_validity_batch", "kcbs_validity_batch_dev", "kcbs_first_conflict",
     "kcbs_first_conflict_dev", "kcbs_conflict_keys_dev", "kcbs_conflict_finish_dev",
-    "kcbs_measure_fp32_peak", "kcbs_measure_fp32x2_peak", "kcbs_launch_count",
+    "kcbs_measure_fp32_peak", "kcbs_measure_fp32x2_peak", "kcbs_launch_count", "kcbs_rrt_defaults",
+    "kcbs_kcbs_defaults", "kcbs_rrt_plan", "kcbs_kcbs_solve",
 ]
 
 
@@ -97,6 +122,13 @@ def load_library() -> C.CDLL:
     lib.kcbs_conflict_finish_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.kcbs_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.kcbs_measure_fp32x2_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.kcbs_rrt_defaults.restype = None
+    lib.kcbs_rrt_defaults.argtypes = [C.POINTER(RrtParams)]
+    lib.kcbs_kcbs_defaults.restype = None
+    lib.kcbs_kcbs_defaults.argtypes = [C.POINTER(KcbsParams)]
+    lib.kcbs_rrt_plan.argtypes = [vp, i32, vp, vp, C.POINTER(RrtParams), i32, vp, vp, vp, vp, vp, i32, vp,
+                                  C.POINTER(C.c_int32), C.POINTER(RrtStats)]
+    lib.kcbs_kcbs_solve.argtypes = [vp, i32, vp, vp, C.POINTER(KcbsParams), i32, vp, vp, C.POINTER(KcbsStats)]
     lib.kcbs_launch_count.restype = i64
     lib.kcbs_launch_count.argtypes = [vp]
     _LIB = lib
@@ -293,3 +325,56 @@ class Context:
     def conflict_finish_dev(self, P, R, T, traj, lengths, keys, out, stream=None):
         self._check(self._lib.kcbs_conflict_finish_dev(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(keys),
                                                        _ptr(out), _stream(stream)))
+
+    # -- (4) next rows: batched low-level planner and K-CBS -----------------------------------
+    def rrt_params(self, **kw) -> RrtParams:
+        p = RrtParams()
+        self._lib.kcbs_rrt_defaults(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def kcbs_params(self, low_level=None, **kw) -> KcbsParams:
+        p = KcbsParams()
+        self._lib.kcbs_kcbs_defaults(C.byref(p))
+        if low_level is not None:
+            p.low_level = low_level
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def rrt_plan(self, robot, start, goal_xy, params=None, constraints=(), max_T=4096):
+        """kcbs_rrt_plan.  constraints: iterable of (other_robot, k0, states [3, len]).  Returns
+        (traj [5, T] float32, RrtStats)."""
+        start = np.ascontiguousarray(start, dtype=np.float32)
+        goal = np.ascontiguousarray(goal_xy, dtype=np.float32)
+        params = params if params is not None else self.rrt_params()
+        cons = list(constraints)
+        total = sum(c[2].shape[1] for c in cons)
+        rob = np.array([c[0] for c in cons], np.int32)
+        k0 = np.array([c[1] for c in cons], np.int32)
+        ln = np.array([c[2].shape[1] for c in cons], np.int32)
+        off = np.concatenate([[0], np.cumsum(ln)[:-1]]).astype(np.int32) if cons else np.zeros(0, np.int32)
+        states = np.zeros((3, max(total, 1)), np.float32)
+        for c, o in zip(cons, off):
+            states[:, o:o + c[2].shape[1]] = c[2]
+        out = np.zeros((5, max_T), np.float32)
+        T = C.c_int32()
+        st = RrtStats()
+        self._check(self._lib.kcbs_rrt_plan(self._h, robot, _ptr(start), _ptr(goal), C.byref(params), len(cons), _ptr(rob),
+                                            _ptr(k0), _ptr(ln), _ptr(off), _ptr(states), max_T, _ptr(out), C.byref(T),
+                                            C.byref(st)))
+        return out[:, :T.value].copy(), st
+
+    def kcbs_solve(self, starts, goals, params=None, max_T=4096):
+        """kcbs_kcbs_solve.  starts [5, R], goals [R, 2].  Returns (plan [R, 5, max_T], lengths [R], KcbsStats)."""
+        starts = np.ascontiguousarray(starts, dtype=np.float32)
+        goals = np.ascontiguousarray(goals, dtype=np.float32)
+        R = starts.shape[1]
+        params = params if params is not None else self.kcbs_params()
+        plan = np.zeros((R, 5, max_T), np.float32)
+        lengths = np.zeros(R, np.int32)
+        st = KcbsStats()
+        self._check(self._lib.kcbs_kcbs_solve(self._h, R, _ptr(starts), _ptr(goals), C.byref(params), max_T, _ptr(plan),
+                                              _ptr(lengths), C.byref(st)))
+        return plan, lengths, st

@@ -11,41 +11,17 @@
 #include <string>
 #include <vector>
 
-#include "kcbs_device.cuh"
-#include "kernels.h"
+#include "ctx.h"
 
 using namespace kcbs;
 
 namespace {
-
 thread_local std::string g_create_error;
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-};
-
 }  // namespace
 
-struct kcbs_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevWorld world;
-    int n_robots = 0;
-    long long launches = 0;
-    std::string err;
-    // grow-only device workspaces for the host-buffer entry points
-    DevBuf in0, in1, in2, in3, out0, out1, out2, keys;
-    int key_plans = 0;      // plans the keys/tickets workspace was laid out for
-    void *scene = nullptr;  // cull grid + obstacle table in device memory
-    std::vector<unsigned long long> h_grid;
-    std::vector<float> h_obs4;
-};
+namespace kcbs {
 
-namespace {
-
-int fail(kcbs_ctx *ctx, int status, const char *what, cudaError_t e = cudaSuccess)
+int fail(kcbs_ctx *ctx, int status, const char *what, cudaError_t e)
 {
     std::string msg = what;
     if (e != cudaSuccess) {
@@ -58,12 +34,6 @@ int fail(kcbs_ctx *ctx, int status, const char *what, cudaError_t e = cudaSucces
         g_create_error = msg;
     return status;
 }
-
-#define KCBS_CUDA(ctx, call)                                              \
-    do {                                                                  \
-        cudaError_t e_ = (call);                                          \
-        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? KCBS_ERR_OUT_OF_MEMORY : KCBS_ERR_CUDA, #call, e_); \
-    } while (0)
 
 int reserve(kcbs_ctx *ctx, DevBuf &b, size_t bytes)
 {
@@ -79,6 +49,10 @@ int reserve(kcbs_ctx *ctx, DevBuf &b, size_t bytes)
     b.cap = want;
     return KCBS_OK;
 }
+
+}  // namespace kcbs
+
+namespace {
 
 // Largest float f with ((double)f - eps <= hi)  /  smallest float f with ((double)f + eps >= lo):
 // the float image of OMPL's RealVectorStateSpace::satisfiesBounds test.
@@ -295,6 +269,7 @@ void kcbs_destroy(kcbs_ctx *ctx)
     DevBuf *bufs[] = {&ctx->in0, &ctx->in1, &ctx->in2, &ctx->in3, &ctx->out0, &ctx->out1, &ctx->out2, &ctx->keys};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    destroy_rrt_workspace(ctx);
     if (ctx->scene) cudaFree(ctx->scene);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -346,6 +321,7 @@ int kcbs_propagate_batch_dev(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_pare
     a.n = n; a.n_parents = n_parents; a.parents = parents; a.parent_idx = parent_idx; a.controls = controls;
     a.steps = steps; a.seg = seg_out; a.fin = final_out; a.valid_steps = valid_steps; a.max_steps = max_steps;
     a.robot = robot;
+    a.parent_time = nullptr; a.cons = nullptr; a.cons_states = nullptr; a.n_cons = 0; a.cons_total = 0;
     KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
     KCBS_CUDA(ctx, launch_propagate(ctx->world, a, pick(ctx, stream)));
     ctx->launches += 1;

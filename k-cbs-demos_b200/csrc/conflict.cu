@@ -12,10 +12,12 @@
 //     thread holds load registers and the whole tile is one memory round trip.  Tiles that touch the
 //     padding of a short path, or misaligned plans (T % 4 != 0), take a per-element path.
 //   * Broad phase: robots are processed as register tiles of 8 ("A") against the remaining robots
-//     streamed from shared memory ("B").  Only min over pairs of max(|dx|, |dy|) is tracked (2 FADD +
-//     1.5 FMNMX per pair): the reference's circle test (:134-141) can only clear pairs that the exact
-//     test clears as well, and a pair whose centres differ by more than r1 + r2 along an axis is
-//     outside the circle, so the verdict is unchanged.
+//     streamed from shared memory ("B").  Only min over pairs of max(|dx|, |dy|) is tracked: the
+//     reference's circle test (:134-141) can only clear pairs that the exact test clears as well, and a
+//     pair whose centres differ by more than r1 + r2 along an axis is outside the circle, so the verdict
+//     is unchanged.  The subtractions use the packed add.rn.f32x2 (two pairs per instruction), the
+//     max/min chain FMNMX / FMNMX3: 3 issue slots per pair.  Robots missing from the last register tile
+//     are sentinel rows far away from everything.
 //   * Narrow phase (rare): threads whose minimum is inside the bounding circles run the rectangle SAT in
 //     scan order; heading planes are read only here.
 //   * Reduction: the packed key (k, r1, r2) is min-reduced by warp shuffles and one 64-bit atomicMin
@@ -70,6 +72,25 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                  : "memory");
 }
 
+// packed FP32 pairs (sm_100 add.rn.f32x2): two subtractions per issued instruction
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // Pair test at one time index, used by the k_end extension.
 __device__ __forceinline__ bool pair_collides(const DevWorld &w, const float *base, const int *len, int T, int r1,
                                               int r2, int k)
@@ -114,102 +135,61 @@ __device__ __forceinline__ kcbs_conflict finish_plan(const DevWorld &w, unsigned
     return c;
 }
 
-// Tile descriptor of the persistent loop.
-struct TileInfo {
-    int plan, k0, n_k;
-    bool bulk;
-};
-
-__device__ __forceinline__ TileInfo tile_info(const ConflictArgs &a, int item, int tiles_per_plan)
-{
-    TileInfo t;
-    t.plan = item / tiles_per_plan;
-    t.k0 = a.k_lo + (item - t.plan * tiles_per_plan) * kTile;
-    t.n_k = min(kTile, a.k_hi - t.k0);
-    // bulk path: rows 16 B aligned, sizes multiples of 16 B, no padding inside the tile
-    t.bulk = ((a.T & 3) == 0) && ((t.k0 & 3) == 0) && ((t.n_k & 3) == 0) && ((((size_t)a.traj) & 15) == 0);
-    if (t.bulk && a.lengths) {
-        const int *len = a.lengths + (long long)t.plan * a.R;
-        for (int r = 0; r < a.R; ++r) t.bulk &= len[r] >= t.k0 + t.n_k;
-    }
-    return t;
-}
-
-// Persistent CTAs walk over (plan, time tile) items; while one tile is being tested the TMA engine already
-// fetches the next one into the other shared-memory buffer.
 template <bool FUSED>
 __global__ void __launch_bounds__(kTile)
-k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ ConflictArgs a, int tiles_per_plan,
-                int n_items)
+k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ ConflictArgs a, int tiles_per_plan)
 {
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int s_last;
 
     const int R = a.R, T = a.T;
-    const int Rp = (R + kATile - 1) / kATile * kATile;  // rows incl. sentinel robots of the last register tile
+    const int plan = blockIdx.x / tiles_per_plan;
+    const int tile = blockIdx.x - plan * tiles_per_plan;
+    const int k0 = a.k_lo + tile * kTile;
     const int tid = threadIdx.x;
-    float *bufs[2] = {smem, smem + 2 * Rp * kTile};     // each: xs [Rp][kTile], ys [Rp][kTile]
+    const int k = k0 + tid;
+    const float *base = a.traj + (long long)plan * R * 3 * T;
+    const int *len = a.lengths ? a.lengths + (long long)plan * R : nullptr;
+    const int Rp = (R + kATile - 1) / kATile * kATile;  // rows incl. the sentinel robots of the last register tile
+    float *xs = smem;               // [Rp][kTile]
+    float *ys = smem + Rp * kTile;  // [Rp][kTile]
 
-    // sentinel robots: far apart from everything and from each other, written once
-    for (int b = 0; b < 2; ++b)
-        for (int r = R; r < Rp; ++r) {
-            bufs[b][r * kTile + tid] = 1.0e18f * (float)(r - R + 1);
-            bufs[b][(Rp + r) * kTile + tid] = 0.0f;
-        }
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    unsigned long long key = kNoConflict;
+
+    const int n_k = min(kTile, a.k_hi - k0);   // time indices of this tile
+    // bulk path: rows 16 B aligned, sizes multiples of 16 B, no padding inside the tile
+    bool bulk = ((T & 3) == 0) && ((k0 & 3) == 0) && ((n_k & 3) == 0) && ((((size_t)a.traj) & 15) == 0);
+    if (bulk && len) {
+        for (int r = 0; r < R; ++r) bulk &= len[r] >= k0 + n_k;
     }
-    __syncthreads();
-
-    auto issue = [&](const TileInfo &t, int b) {  // start the bulk copies of tile t into buffer b
-        if (tid == 0) mbar_expect_tx(&s_bar[b], (unsigned)(2 * R * t.n_k * sizeof(float)));
+    if (bulk) {   // start the tile's copies first; everything below overlaps with them
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        // arrive + expect_tx is one atomic update, so copies may complete before or after it
+        if (tid == 0) mbar_expect_tx(&s_bar, (unsigned)(2 * R * n_k * sizeof(float)));
         if (tid < 2 * R) {
             const int r = tid >> 1, c = tid & 1;
-            const float *src = a.traj + (long long)t.plan * R * 3 * T + ((long long)r * 3 + c) * T + t.k0;
-            bulk_g2s(bufs[b] + (c * Rp + r) * kTile, src, (unsigned)(t.n_k * sizeof(float)), &s_bar[b]);
+            bulk_g2s((c ? ys : xs) + r * kTile, base + ((long long)r * 3 + c) * T + k0, (unsigned)(n_k * sizeof(float)), &s_bar);
         }
-    };
-
-    unsigned phase[2] = {0, 0};
-    int item = blockIdx.x;
-    TileInfo cur = tile_info(a, min(item, n_items - 1), tiles_per_plan);
-    bool cur_issued = false;
-    if (item < n_items && cur.bulk) {
-        issue(cur, 0);
-        cur_issued = true;
+    }
+    // sentinel robots: far away from everything and from each other
+    for (int r = R; r < Rp; ++r) {
+        xs[r * kTile + tid] = 1.0e18f * (float)(r - R + 1);
+        ys[r * kTile + tid] = 0.0f;
     }
 
-    for (int it = 0; item < n_items; ++it, item += gridDim.x) {
-        const int b = it & 1;
-        const int plan = cur.plan, k0 = cur.k0, n_k = cur.n_k;
-        const int k = k0 + tid;
-        const float *base = a.traj + (long long)plan * R * 3 * T;
-        const int *len = a.lengths ? a.lengths + (long long)plan * R : nullptr;
-        float *xs = bufs[b], *ys = bufs[b] + Rp * kTile;
+    // a conflict already recorded at an earlier time index makes this tile irrelevant
+    const unsigned long long seen = *(volatile const unsigned long long *)(a.keys + plan);
+    const bool skip = seen != kNoConflict && (long long)(seen >> 16) < (long long)k0;
 
-        // prefetch the next tile of this CTA into the other buffer
-        const int next_item = item + gridDim.x;
-        TileInfo nxt = cur;
-        bool nxt_issued = false;
-        if (next_item < n_items) {
-            nxt = tile_info(a, next_item, tiles_per_plan);
-            if (nxt.bulk) {
-                issue(nxt, b ^ 1);
-                nxt_issued = true;
-            }
-        }
+    if (bulk) mbar_wait(&s_bar, 0);   // (also when skipping: the copies must land before the CTA exits)
 
-        // a conflict already recorded at an earlier time index makes this tile irrelevant
-        const unsigned long long seen = *(volatile const unsigned long long *)(a.keys + plan);
-        const bool skip = seen != kNoConflict && (long long)(seen >> 16) < (long long)k0;
-
-        if (cur_issued) {
-            mbar_wait(&s_bar[b], phase[b]);
-            phase[b] ^= 1;
-        } else if (!skip) {
+    if (!skip) {
+        if (!bulk) {
 #pragma unroll 4
             for (int r = 0; r < R; ++r) {
                 const int kk = clamp_k(k, T, len, r);
@@ -217,19 +197,23 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
                 ys[r * kTile + tid] = __ldcs(base + ((long long)r * 3 + 1) * T + kk);
             }
         }
-
-        unsigned long long key = kNoConflict;
-        const bool active = !skip && tid < n_k;
+        const bool active = tid < n_k;
 
         // ---- broad phase: min over pairs of the Chebyshev centre distance -----------------------------
         float m = 3.0e38f;
         if (active) {
             for (int a0 = 0; a0 < R; a0 += kATile) {
                 float xa[kATile], ya[kATile];
+                f32x2 xa2[kATile / 2], ya2[kATile / 2];
 #pragma unroll
                 for (int q = 0; q < kATile; ++q) {
                     xa[q] = xs[(a0 + q) * kTile + tid];
                     ya[q] = ys[(a0 + q) * kTile + tid];
+                }
+#pragma unroll
+                for (int q = 0; q < kATile / 2; ++q) {
+                    xa2[q] = pack2(xa[2 * q], xa[2 * q + 1]);
+                    ya2[q] = pack2(ya[2 * q], ya[2 * q + 1]);
                 }
 #pragma unroll
                 for (int q = 0; q < kATile; ++q)
@@ -239,8 +223,14 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
 #pragma unroll 2
                 for (int r2 = a0 + kATile; r2 < R; ++r2) {
                     const float xb = xs[r2 * kTile + tid], yb = ys[r2 * kTile + tid];
+                    const f32x2 xb2 = pack2(xb, xb), yb2 = pack2(yb, yb);
 #pragma unroll
-                    for (int q = 0; q < kATile; ++q) m = fminf(m, fmaxf(fabsf(xa[q] - xb), fabsf(ya[q] - yb)));
+                    for (int q = 0; q < kATile / 2; ++q) {
+                        float dx0, dx1, dy0, dy1;
+                        unpack2(sub2(xa2[q], xb2), dx0, dx1);
+                        unpack2(sub2(ya2[q], yb2), dy0, dy1);
+                        m = fminf(m, fminf(fmaxf(fabsf(dx0), fabsf(dy0)), fmaxf(fabsf(dx1), fabsf(dy1))));
+                    }
                 }
             }
         }
@@ -281,30 +271,27 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
             }
             if ((tid & 31) == 0) atomicMin(a.keys + plan, key);
         }
+    }
 
-        // all reads of this buffer are done (it is refilled two iterations from now) and all atomics issued
+    if (FUSED) {
+        // last CTA of the plan finishes it and leaves key + ticket clean for the next call
         __syncthreads();
-        if (FUSED) {
-            // the last tile of a plan finishes it and leaves key + ticket clean for the next call
+        if (tid == 0) {
+            __threadfence();
+            const int ticket = atomicAdd(a.tickets + plan, 1);
+            s_last = (ticket == tiles_per_plan - 1);
+        }
+        __syncthreads();
+        if (s_last && tid < 32) {
+            __threadfence();
+            const unsigned long long best = *(volatile const unsigned long long *)(a.keys + plan);
+            const kcbs_conflict c = finish_plan(w, best, base, len, T, tid);
             if (tid == 0) {
-                __threadfence();
-                const int ticket = atomicAdd(a.tickets + plan, 1);
-                s_last = (ticket == tiles_per_plan - 1);
-            }
-            __syncthreads();
-            if (s_last && tid < 32) {
-                __threadfence();
-                const unsigned long long best = *(volatile const unsigned long long *)(a.keys + plan);
-                const kcbs_conflict c = finish_plan(w, best, base, len, T, tid);
-                if (tid == 0) {
-                    a.out[plan] = c;
-                    a.keys[plan] = kNoConflict;
-                    a.tickets[plan] = 0;
-                }
+                a.out[plan] = c;
+                a.keys[plan] = kNoConflict;
+                a.tickets[plan] = 0;
             }
         }
-        cur = nxt;
-        cur_issued = nxt_issued;
     }
 }
 
@@ -341,21 +328,13 @@ cudaError_t launch_conflict_keys(const DevWorld &w, const ConflictArgs &a, cudaS
 {
     if (a.P <= 0 || a.k_hi <= a.k_lo) return cudaSuccess;
     const int tiles = (a.k_hi - a.k_lo + kTile - 1) / kTile;
-    const long long items = (long long)tiles * a.P;
-    if (items > 0x7fffffffll) return cudaErrorInvalidValue;
     const int Rp = (a.R + kATile - 1) / kATile * kATile;
-    const size_t smem = (size_t)2 * 2 * Rp * kTile * sizeof(float);  // two buffers of x and y rows
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-    const long long want = (long long)sms * per_sm;
-    const unsigned grid = (unsigned)(items < want ? items : want);
+    const size_t smem = (size_t)2 * Rp * kTile * sizeof(float);
+    const unsigned grid = (unsigned)((long long)tiles * a.P);
     if (a.out)
-        k_conflict_keys<true><<<grid, kTile, smem, stream>>>(w, a, tiles, (int)items);
+        k_conflict_keys<true><<<grid, kTile, smem, stream>>>(w, a, tiles);
     else
-        k_conflict_keys<false><<<grid, kTile, smem, stream>>>(w, a, tiles, (int)items);
+        k_conflict_keys<false><<<grid, kTile, smem, stream>>>(w, a, tiles);
     return cudaGetLastError();
 }
 
@@ -369,7 +348,7 @@ cudaError_t launch_conflict_finish(const DevWorld &w, const FinishArgs &a, cudaS
 
 cudaError_t init_conflict_kernels()
 {
-    const int bytes = 2 * 2 * KCBS_MAX_ROBOTS * kTile * (int)sizeof(float);
+    const int bytes = 2 * KCBS_MAX_ROBOTS * kTile * (int)sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(k_conflict_keys<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_conflict_keys<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

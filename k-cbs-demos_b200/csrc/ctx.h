@@ -1,0 +1,52 @@
+// ctx.h -- the context object behind kcbs_ctx and the error / workspace helpers shared by api.cu and
+// planner.cu (internal).
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "kcbs_device.cuh"
+#include "kernels.h"
+
+namespace kcbs {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct RrtWorkspace;  // planner.cu
+
+}  // namespace kcbs
+
+struct kcbs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    kcbs::DevWorld world;
+    int n_robots = 0;
+    long long launches = 0;
+    std::string err;
+    // grow-only device workspaces for the host-buffer entry points
+    kcbs::DevBuf in0, in1, in2, in3, out0, out1, out2, keys;
+    int key_plans = 0;      // plans the keys/tickets workspace was laid out for
+    void *scene = nullptr;  // cull grid + obstacle table in device memory
+    std::vector<unsigned long long> h_grid;
+    std::vector<float> h_obs4;
+    kcbs::RrtWorkspace *rrt = nullptr;  // planner state, created on first use
+};
+
+namespace kcbs {
+
+int fail(kcbs_ctx *ctx, int status, const char *what, cudaError_t e = cudaSuccess);
+int reserve(kcbs_ctx *ctx, DevBuf &b, size_t bytes);
+void destroy_rrt_workspace(kcbs_ctx *ctx);
+
+#define KCBS_CUDA(ctx, call)                                                                                    \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            return kcbs::fail(ctx, e_ == cudaErrorMemoryAllocation ? KCBS_ERR_OUT_OF_MEMORY : KCBS_ERR_CUDA, #call, e_); \
+    } while (0)
+
+}  // namespace kcbs

@@ -10,6 +10,12 @@ namespace kcbs {
 
 struct DevWorld;
 
+// One dynamic-obstacle constraint of the K-CBS low level: at absolute time index k in [k0, k0 + len) the robot
+// must not overlap robot `other` placed at cons_states[plane * total + offset + (k - k0)].
+struct ConsDesc {
+    int other, k0, len, offset;
+};
+
 struct PropArgs {
     long long n, n_parents;
     const float *parents;      // [5][n_parents]
@@ -21,6 +27,11 @@ struct PropArgs {
     int *valid_steps;          // [n] or null
     int max_steps;
     int robot;
+    // dynamic-obstacle constraints (planner only; n_cons == 0 otherwise)
+    const int *parent_time;    // [n_parents] absolute time index of each parent, or null (= 0)
+    const ConsDesc *cons;      // [n_cons]
+    const float *cons_states;  // [3][cons_total]
+    int n_cons, cons_total;
 };
 
 struct ValidArgs {

@@ -1,0 +1,700 @@
+// planner.cu -- "next" rows of the scope table: a batched kinodynamic RRT low level and a
+// minimal K-CBS high level, built on the three hot-path kernels.
+//
+// They stand in for the planners the reference obtains from the un-vendored OMPL fork:
+//   oc::RRT            allocated by allocateControlRRT, PlannerAllocatorDatabase.h:40-45
+//   omrc::KCBS         demo_*.cpp:155-168, Benchmark.h:151-173
+// with the reference's plugin semantics: controls uniform in [-1, 1]^2 (ControlSpaceDatabase.h:48-51),
+// durations UniformInt{1..10} x 0.1 s (demo_*.cpp:115,118), state distance of the compound space
+// (StateSpaceDatabase.h:45-46: L2 over (x, y, v, phi) + SO2 arc, weights 1), goal = disc of 0.5 around the goal
+// position (GoalRegionDatabase.h:48-55), conflicts = kcbs_first_conflict.
+//
+// Low level, per round (all state in HBM, one stream):
+//   k_rrt_targets   n_targets random states (goal biased), packed (distance, index) keys reset
+//   k_rrt_nearest   tiled all-pairs nearest tree node per target, 64-bit atomicMin on (distance bits, index)
+//   k_rrt_samples   n_targets x n_controls (parent index, control, duration) triples
+//   k_propagate     the K1 expansion kernel with dynamic-obstacle constraints and per-parent time indices
+//   k_rrt_select    per target the sample that ends closest to it becomes a tree node; goal test
+// A found path is re-expanded edge by edge with k_propagate (identical arithmetic) to emit every 0.1 s state.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <queue>
+#include <vector>
+
+#include "ctx.h"
+
+namespace kcbs {
+
+struct RrtWorkspace {
+    int max_nodes = 0, n_samples = 0, n_targets = 0, cons_cap = 0, cons_desc_cap = 0, path_cap = 0;
+    float *nodes = nullptr;        // [5][max_nodes] states
+    int *parent = nullptr;         // [max_nodes]
+    int *time = nullptr;           // [max_nodes] absolute time index (propagation steps from the root)
+    float *ctrl = nullptr;         // [2][max_nodes] control of the edge into the node
+    int *steps = nullptr;          // [max_nodes] duration of the edge into the node
+    float *targets = nullptr;      // [5][n_targets]
+    unsigned long long *nn = nullptr;  // [n_targets] packed (distance bits << 32 | node)
+    int *s_parent = nullptr;       // [n_samples]
+    float *s_ctrl = nullptr;       // [2][n_samples]
+    int *s_steps = nullptr;        // [n_samples]
+    float *s_fin = nullptr;        // [5][n_samples]
+    int *s_valid = nullptr;        // [n_samples]
+    int *counters = nullptr;       // [0] = node count, [1] = (unused)
+    unsigned long long *goal_key = nullptr;  // packed (time << 32 | node) of the best goal node
+    ConsDesc *cons = nullptr;
+    float *cons_states = nullptr;
+    // path extraction
+    int *path_nodes = nullptr;     // [path_cap]
+    float *path_ctrl = nullptr;    // [2][path_cap]
+    int *path_steps = nullptr, *path_parent = nullptr, *path_valid = nullptr;
+    float *path_seg = nullptr;     // [5][KCBS_MAX_STEPS][path_cap]
+    unsigned long long *h_goal = nullptr;  // pinned
+    int *h_counters = nullptr;             // pinned
+};
+
+namespace {
+
+__device__ __forceinline__ unsigned hash32(unsigned x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// counter-based uniform in [0, 1): (seed, round, index, stream) -> 24 random bits
+__device__ __forceinline__ float urand(unsigned long long seed, unsigned round, unsigned idx, unsigned stream)
+{
+    unsigned h = hash32((unsigned)seed ^ 0x9e3779b9u);
+    h = hash32(h ^ (unsigned)(seed >> 32));
+    h = hash32(h ^ round * 0x85ebca6bu);
+    h = hash32(h ^ idx * 0xc2b2ae35u);
+    h = hash32(h ^ stream * 0x27d4eb2fu);
+    return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+struct RrtArgs {
+    RrtWorkspace ws;
+    float goal_x, goal_y, goal_radius, goal_bias;
+    float lo[4], hi[4];
+    unsigned long long seed;
+    unsigned round;
+    int n_targets, n_controls, min_steps, max_steps, robot;
+    int n_cons, cons_total;
+};
+
+__global__ void k_rrt_init(RrtArgs a, float x, float y, float v, float phi, float th)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int M = a.ws.max_nodes;
+        a.ws.nodes[0] = x; a.ws.nodes[M] = y; a.ws.nodes[2 * M] = v; a.ws.nodes[3 * M] = phi; a.ws.nodes[4 * M] = th;
+        a.ws.parent[0] = -1; a.ws.time[0] = 0; a.ws.steps[0] = 0;
+        a.ws.ctrl[0] = 0.f; a.ws.ctrl[M] = 0.f;
+        a.ws.counters[0] = 1;
+        *a.ws.goal_key = ~0ull;
+    }
+}
+
+// Random target states: uniform over the state bounds, or the goal position with random v, phi, theta.
+__global__ void k_rrt_targets(RrtArgs a)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_targets) return;
+    const int B = a.n_targets;
+    float q[5];
+    for (int c = 0; c < 4; ++c) q[c] = a.lo[c] + (a.hi[c] - a.lo[c]) * urand(a.seed, a.round, t, c);
+    q[4] = -kPi + kTwoPi * urand(a.seed, a.round, t, 4);
+    if (urand(a.seed, a.round, t, 5) < a.goal_bias) {
+        q[0] = a.goal_x;
+        q[1] = a.goal_y;
+    }
+    for (int c = 0; c < 5; ++c) a.ws.targets[c * B + t] = q[c];
+    a.ws.nn[t] = ~0ull;
+}
+
+// ob::CompoundStateSpace::distance with unit weights: L2 over (x, y, v, phi) + SO2 arc length.
+__device__ __forceinline__ float state_distance(float x, float y, float v, float p, float th, float tx, float ty,
+                                                float tv, float tp, float tth)
+{
+    const float dx = x - tx, dy = y - ty, dv = v - tv, dp = p - tp;
+    float d = fabsf(th - tth);
+    d = d > kPi ? kTwoPi - d : d;
+    return sqrtf(fmaf(dx, dx, fmaf(dy, dy, fmaf(dv, dv, dp * dp)))) + d;
+}
+
+constexpr int kNNThreads = 256;
+constexpr int kNNChunk = 2048;  // nodes per CTA
+
+// grid = (ceil(n_targets / 256), ceil(n_nodes / kNNChunk)): every thread owns one target and scans one chunk
+// of nodes staged through shared memory.
+__global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a, int n_nodes)
+{
+    __shared__ float s[5][kNNThreads];
+    const int B = a.n_targets, M = a.ws.max_nodes;
+    const int t = blockIdx.x * kNNThreads + threadIdx.x;
+    const bool live = t < B;
+    float q[5] = {0, 0, 0, 0, 0};
+    if (live)
+        for (int c = 0; c < 5; ++c) q[c] = a.ws.targets[c * B + t];
+    const int n0 = blockIdx.y * kNNChunk, n1 = min(n0 + kNNChunk, n_nodes);
+    float best = 3.0e38f;
+    int best_i = 0;
+    for (int base = n0; base < n1; base += kNNThreads) {
+        const int i = base + threadIdx.x;
+        __syncthreads();
+        if (i < n1)
+            for (int c = 0; c < 5; ++c) s[c][threadIdx.x] = a.ws.nodes[c * M + i];
+        __syncthreads();
+        const int m = min(kNNThreads, n1 - base);
+        for (int j = 0; j < m; ++j) {
+            const float d = state_distance(s[0][j], s[1][j], s[2][j], s[3][j], s[4][j], q[0], q[1], q[2], q[3], q[4]);
+            if (d < best) {
+                best = d;
+                best_i = base + j;
+            }
+        }
+    }
+    if (live && n1 > n0)
+        atomicMin(a.ws.nn + t, ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)best_i);
+}
+
+// (parent, control, duration) for every sample: sample s belongs to target s / n_controls.
+__global__ void k_rrt_samples(RrtArgs a)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = a.n_targets * a.n_controls;
+    if (s >= n) return;
+    const int t = s / a.n_controls;
+    a.ws.s_parent[s] = (int)(a.ws.nn[t] & 0xffffffffu);
+    a.ws.s_ctrl[s] = -1.0f + 2.0f * urand(a.seed, a.round, s, 8);       // ControlSpaceDatabase.h:48-51
+    a.ws.s_ctrl[n + s] = -1.0f + 2.0f * urand(a.seed, a.round, s, 9);
+    const int span = a.max_steps - a.min_steps + 1;
+    a.ws.s_steps[s] = a.min_steps + min(span - 1, (int)(urand(a.seed, a.round, s, 10) * (float)span));
+}
+
+// A robot waiting at its final state must also respect the constraints that come later.
+__device__ bool parked_state_clear(const DevWorld &w, const RrtArgs &a, int t_node, float x, float y, float th)
+{
+    const float hl = w.rob_hl[a.robot], hw = w.rob_hw[a.robot], rad = w.rob_rad[a.robot];
+    float s, c;
+    sincosf(th, &s, &c);
+    for (int q = 0; q < a.n_cons; ++q) {
+        const ConsDesc d = a.ws.cons[q];
+        for (int k = max(t_node + 1, d.k0); k < d.k0 + d.len; ++k) {
+            const float *st = a.ws.cons_states + d.offset + (k - d.k0);
+            const float ox = st[0], oy = st[a.cons_total], dx = ox - x, dy = oy - y;
+            const float rs = rad + w.rob_rad[d.other];
+            if (fmaf(dy, dy, dx * dx) > rs * rs * 1.000001f) continue;
+            float oc, os;
+            sincosf(st[2 * a.cons_total], &os, &oc);
+            if (sat_gap_robots(x, y, c, s, hl, hw, ox, oy, oc, os, w.rob_hl[d.other], w.rob_hw[d.other]) <= 0.0f)
+                return false;
+        }
+    }
+    return true;
+}
+
+// One warp per target: the valid sample that ends closest to the target becomes a tree node.
+__global__ void __launch_bounds__(256) k_rrt_select(const __grid_constant__ DevWorld w, RrtArgs a)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.n_targets) return;
+    const int B = a.n_targets, C = a.n_controls, n = B * C, M = a.ws.max_nodes;
+    float q[5];
+    for (int c = 0; c < 5; ++c) q[c] = a.ws.targets[c * B + warp];
+    float best = 3.0e38f;
+    int best_s = -1;
+    for (int j = lane; j < C; j += 32) {
+        const int s = warp * C + j;
+        if (a.ws.s_valid[s] >= a.min_steps) {
+            const float d = state_distance(a.ws.s_fin[s], a.ws.s_fin[n + s], a.ws.s_fin[2 * n + s], a.ws.s_fin[3 * n + s],
+                                           a.ws.s_fin[4 * n + s], q[0], q[1], q[2], q[3], q[4]);
+            if (d < best) {
+                best = d;
+                best_s = s;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int os = __shfl_xor_sync(0xffffffffu, best_s, off);
+        if (ob < best || (ob == best && os >= 0 && (best_s < 0 || os < best_s))) {
+            best = ob;
+            best_s = os;
+        }
+    }
+    if (lane != 0 || best_s < 0) return;
+    const int idx = atomicAdd(a.ws.counters, 1);
+    if (idx >= M) {
+        atomicSub(a.ws.counters, 1);
+        return;
+    }
+    const int s = best_s, par = a.ws.s_parent[s], nv = a.ws.s_valid[s];
+    const float x = a.ws.s_fin[s], y = a.ws.s_fin[n + s], th = a.ws.s_fin[4 * n + s];
+    a.ws.nodes[idx] = x;
+    a.ws.nodes[M + idx] = y;
+    a.ws.nodes[2 * M + idx] = a.ws.s_fin[2 * n + s];
+    a.ws.nodes[3 * M + idx] = a.ws.s_fin[3 * n + s];
+    a.ws.nodes[4 * M + idx] = th;
+    a.ws.parent[idx] = par;
+    const int t_node = a.ws.time[par] + nv;
+    a.ws.time[idx] = t_node;
+    a.ws.ctrl[idx] = a.ws.s_ctrl[s];
+    a.ws.ctrl[M + idx] = a.ws.s_ctrl[n + s];
+    a.ws.steps[idx] = nv;
+    // GoalRegion2ndOrderCar::distanceGoal <= threshold (GoalRegionDatabase.h:48-55)
+    const float gx = x - a.goal_x, gy = y - a.goal_y;
+    if (sqrtf(fmaf(gx, gx, gy * gy)) <= a.goal_radius) {
+        if (a.n_cons == 0 || parked_state_clear(w, a, t_node, x, y, th))
+            atomicMin(a.ws.goal_key, ((unsigned long long)(unsigned)t_node << 32) | (unsigned)idx);
+    }
+}
+
+// Walks goal -> root (one thread) and emits the edges root -> goal as k_propagate inputs.
+__global__ void k_rrt_path(RrtArgs a, int goal_node, int path_cap, int *n_edges_out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int M = a.ws.max_nodes;
+    int n = 0;
+    for (int i = goal_node; a.ws.parent[i] >= 0 && n < path_cap; i = a.ws.parent[i]) a.ws.path_nodes[n++] = i;
+    for (int e = 0; e < n; ++e) {
+        const int i = a.ws.path_nodes[n - 1 - e];
+        a.ws.path_parent[e] = a.ws.parent[i];
+        a.ws.path_ctrl[e] = a.ws.ctrl[i];
+        a.ws.path_ctrl[path_cap + e] = a.ws.ctrl[M + i];
+        a.ws.path_steps[e] = a.ws.steps[i];
+    }
+    *n_edges_out = n;
+}
+
+template <class T>
+int dev_alloc(kcbs_ctx *ctx, T *&p, size_t n)
+{
+    KCBS_CUDA(ctx, cudaMalloc((void **)&p, sizeof(T) * (n ? n : 1)));
+    return KCBS_OK;
+}
+
+void free_workspace(RrtWorkspace &ws)
+{
+    void *d[] = {ws.nodes, ws.parent, ws.time, ws.ctrl, ws.steps, ws.targets, ws.nn, ws.s_parent, ws.s_ctrl, ws.s_steps,
+                 ws.s_fin, ws.s_valid, ws.counters, ws.goal_key, ws.cons, ws.cons_states, ws.path_nodes, ws.path_ctrl,
+                 ws.path_steps, ws.path_parent, ws.path_valid, ws.path_seg};
+    for (void *p : d)
+        if (p) cudaFree(p);
+    if (ws.h_goal) cudaFreeHost(ws.h_goal);
+    if (ws.h_counters) cudaFreeHost(ws.h_counters);
+    ws = RrtWorkspace();
+}
+
+int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int cons_total, int n_cons)
+{
+    if (!ctx->rrt) ctx->rrt = new RrtWorkspace();
+    RrtWorkspace &ws = *ctx->rrt;
+    const int n_samples = p.n_targets * p.n_controls;
+    if (ws.max_nodes != p.max_nodes || ws.n_samples != n_samples || ws.n_targets != p.n_targets) {
+        KCBS_CUDA(ctx, cudaDeviceSynchronize());
+        free_workspace(ws);
+        int st;
+        const size_t M = (size_t)p.max_nodes, S = (size_t)n_samples, B = (size_t)p.n_targets;
+        ws.path_cap = 8192;
+        const size_t PC = (size_t)ws.path_cap;
+        if ((st = dev_alloc(ctx, ws.nodes, 5 * M)) || (st = dev_alloc(ctx, ws.parent, M)) || (st = dev_alloc(ctx, ws.time, M)) ||
+            (st = dev_alloc(ctx, ws.ctrl, 2 * M)) || (st = dev_alloc(ctx, ws.steps, M)) || (st = dev_alloc(ctx, ws.targets, 5 * B)) ||
+            (st = dev_alloc(ctx, ws.nn, B)) || (st = dev_alloc(ctx, ws.s_parent, S)) || (st = dev_alloc(ctx, ws.s_ctrl, 2 * S)) ||
+            (st = dev_alloc(ctx, ws.s_steps, S)) || (st = dev_alloc(ctx, ws.s_fin, 5 * S)) || (st = dev_alloc(ctx, ws.s_valid, S)) ||
+            (st = dev_alloc(ctx, ws.counters, 4)) || (st = dev_alloc(ctx, ws.goal_key, 1)) || (st = dev_alloc(ctx, ws.path_nodes, PC)) ||
+            (st = dev_alloc(ctx, ws.path_ctrl, 2 * PC)) || (st = dev_alloc(ctx, ws.path_steps, PC)) ||
+            (st = dev_alloc(ctx, ws.path_parent, PC)) || (st = dev_alloc(ctx, ws.path_valid, PC)) ||
+            (st = dev_alloc(ctx, ws.path_seg, 5 * (size_t)KCBS_MAX_STEPS * PC)))
+            return st;
+        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_goal, sizeof(unsigned long long), cudaHostAllocDefault));
+        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_counters, 4 * sizeof(int), cudaHostAllocDefault));
+        ws.max_nodes = p.max_nodes;
+        ws.n_samples = n_samples;
+        ws.n_targets = p.n_targets;
+    }
+    if (cons_total > ws.cons_cap) {
+        KCBS_CUDA(ctx, cudaDeviceSynchronize());
+        if (ws.cons_states) cudaFree(ws.cons_states);
+        ws.cons_states = nullptr;
+        ws.cons_cap = cons_total + cons_total / 2 + 1024;
+        int st = dev_alloc(ctx, ws.cons_states, 3 * (size_t)ws.cons_cap);
+        if (st) return st;
+    }
+    if (n_cons > ws.cons_desc_cap) {
+        KCBS_CUDA(ctx, cudaDeviceSynchronize());
+        if (ws.cons) cudaFree(ws.cons);
+        ws.cons = nullptr;
+        ws.cons_desc_cap = n_cons + 64;
+        int st = dev_alloc(ctx, ws.cons, (size_t)ws.cons_desc_cap);
+        if (st) return st;
+    }
+    return KCBS_OK;
+}
+
+double now_s()
+{
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+int check_rrt_params(kcbs_ctx *ctx, const kcbs_rrt_params &p)
+{
+    if (p.n_targets < 1 || p.n_controls < 1 || p.max_nodes < 2 || p.max_iterations < 1 || p.min_steps < 1 ||
+        p.max_steps < p.min_steps || p.max_steps > KCBS_MAX_STEPS || !(p.goal_radius > 0) ||
+        (long long)p.n_targets * p.n_controls > (1ll << 26))
+        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "kcbs_rrt_params out of range");
+    return KCBS_OK;
+}
+
+}  // namespace
+
+void destroy_rrt_workspace(kcbs_ctx *ctx)
+{
+    if (ctx->rrt) {
+        free_workspace(*ctx->rrt);
+        delete ctx->rrt;
+        ctx->rrt = nullptr;
+    }
+}
+
+// The low-level planner proper (host orchestration; every arithmetic step is a kernel).
+static int rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *goal_xy, const kcbs_rrt_params &p,
+                    int n_cons, const int32_t *cons_robot, const int32_t *cons_k0, const int32_t *cons_len,
+                    const int32_t *cons_offset, const float *cons_states, int max_T, float *traj_out, int32_t *T_out,
+                    kcbs_rrt_stats *stats)
+{
+    const double t_begin = now_s();
+    int st = check_rrt_params(ctx, p);
+    if (st) return st;
+    if (robot < 0 || robot >= ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "robot index out of range");
+    if (!start || !goal_xy || !traj_out || !T_out || max_T < 1) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "null argument");
+    int cons_total = 0;
+    for (int c = 0; c < n_cons; ++c) {
+        if (cons_robot[c] < 0 || cons_robot[c] >= ctx->n_robots || cons_len[c] < 0 || cons_offset[c] < 0)
+            return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "bad constraint");
+        cons_total = std::max(cons_total, cons_offset[c] + cons_len[c]);
+    }
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((st = ensure_workspace(ctx, p, cons_total, n_cons))) return st;
+    RrtWorkspace &ws = *ctx->rrt;
+    cudaStream_t s = ctx->stream;
+
+    if (n_cons > 0) {
+        std::vector<ConsDesc> desc(n_cons);
+        for (int c = 0; c < n_cons; ++c) desc[c] = ConsDesc{cons_robot[c], cons_k0[c], cons_len[c], cons_offset[c]};
+        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.cons, desc.data(), sizeof(ConsDesc) * n_cons, cudaMemcpyHostToDevice, s));
+        // host planes have stride cons_total; keep the same stride on the device
+        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.cons_states, cons_states, sizeof(float) * 3 * (size_t)cons_total, cudaMemcpyHostToDevice, s));
+        KCBS_CUDA(ctx, cudaStreamSynchronize(s));  // desc is a local
+    }
+
+    RrtArgs a;
+    a.ws = ws;
+    a.goal_x = goal_xy[0]; a.goal_y = goal_xy[1]; a.goal_radius = p.goal_radius; a.goal_bias = p.goal_bias;
+    // sampling box = the state bounds the validity test uses (thresholds are within one ulp of them)
+    for (int c = 0; c < 4; ++c) { a.lo[c] = ctx->world.lo_t[c]; a.hi[c] = ctx->world.hi_t[c]; }
+    a.seed = p.seed; a.round = 0;
+    a.n_targets = p.n_targets; a.n_controls = p.n_controls; a.min_steps = p.min_steps; a.max_steps = p.max_steps;
+    a.robot = robot; a.n_cons = n_cons; a.cons_total = cons_total;
+    const int n = p.n_targets * p.n_controls;
+
+    PropArgs pa;
+    pa.n = n; pa.n_parents = ws.max_nodes; pa.parents = ws.nodes; pa.parent_idx = ws.s_parent; pa.controls = ws.s_ctrl;
+    pa.steps = ws.s_steps; pa.seg = nullptr; pa.fin = ws.s_fin; pa.valid_steps = ws.s_valid; pa.max_steps = p.max_steps;
+    pa.robot = robot; pa.parent_time = ws.time; pa.cons = ws.cons; pa.cons_states = ws.cons_states; pa.n_cons = n_cons;
+    pa.cons_total = cons_total;
+
+    k_rrt_init<<<1, 32, 0, s>>>(a, start[0], start[1], start[2], start[3], start[4]);
+    ctx->launches += 1;
+    int n_nodes = 1, iters = 0;
+    unsigned long long goal = ~0ull;
+    // the start itself may already satisfy the goal
+    {
+        const float gx = start[0] - goal_xy[0], gy = start[1] - goal_xy[1];
+        if (std::sqrt(gx * gx + gy * gy) <= p.goal_radius && n_cons == 0) goal = 0;
+    }
+    while (goal == ~0ull && iters < p.max_iterations && n_nodes < p.max_nodes) {
+        if (p.time_limit_s > 0 && now_s() - t_begin > p.time_limit_s) break;
+        a.round = (unsigned)iters;
+        k_rrt_targets<<<(p.n_targets + 255) / 256, 256, 0, s>>>(a);
+        dim3 g((p.n_targets + kNNThreads - 1) / kNNThreads, (n_nodes + kNNChunk - 1) / kNNChunk);
+        k_rrt_nearest<<<g, kNNThreads, 0, s>>>(a, n_nodes);
+        k_rrt_samples<<<(n + 255) / 256, 256, 0, s>>>(a);
+        KCBS_CUDA(ctx, launch_propagate(ctx->world, pa, s));
+        k_rrt_select<<<(p.n_targets * 32 + 255) / 256, 256, 0, s>>>(ctx->world, a);
+        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters, ws.counters, sizeof(int), cudaMemcpyDeviceToHost, s));
+        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_goal, ws.goal_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->launches += 5;
+        n_nodes = std::min(ws.h_counters[0], p.max_nodes);
+        goal = *ws.h_goal;
+        ++iters;
+    }
+
+    int T = 0;
+    if (goal != ~0ull) {
+        // states of the path: start, then every edge re-expanded by k_propagate (same arithmetic as the search)
+        const int goal_node = (int)(goal & 0xffffffffu);
+        for (int c = 0; c < 5; ++c) traj_out[(size_t)c * max_T] = start[c];
+        T = 1;
+        if (goal_node != 0) {
+            int *d_n = ws.counters + 2;
+            k_rrt_path<<<1, 32, 0, s>>>(a, goal_node, ws.path_cap, d_n);
+            KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters + 2, d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
+            KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+            const int E = ws.h_counters[2];
+            PropArgs pe = pa;
+            pe.n = E; pe.parent_idx = ws.path_parent; pe.controls = ws.path_ctrl; pe.steps = ws.path_steps;
+            pe.seg = ws.path_seg; pe.fin = nullptr; pe.valid_steps = ws.path_valid; pe.max_steps = p.max_steps;
+            // controls planes of the path have stride path_cap: compact them to stride E for the kernel
+            KCBS_CUDA(ctx, cudaMemcpyAsync(ws.path_ctrl + E, ws.path_ctrl + ws.path_cap, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
+            KCBS_CUDA(ctx, launch_propagate(ctx->world, pe, s));
+            ctx->launches += 2;
+            std::vector<float> seg((size_t)5 * p.max_steps * E);
+            std::vector<int> valid(E);
+            KCBS_CUDA(ctx, cudaMemcpyAsync(seg.data(), ws.path_seg, sizeof(float) * seg.size(), cudaMemcpyDeviceToHost, s));
+            KCBS_CUDA(ctx, cudaMemcpyAsync(valid.data(), ws.path_valid, sizeof(int) * E, cudaMemcpyDeviceToHost, s));
+            KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+            for (int e = 0; e < E; ++e)
+                for (int j = 0; j < valid[e] && T < max_T; ++j, ++T)
+                    for (int c = 0; c < 5; ++c) traj_out[(size_t)c * max_T + T] = seg[((size_t)c * p.max_steps + j) * E + e];
+        }
+    }
+    *T_out = T;
+    if (stats) {
+        stats->solved = goal != ~0ull;
+        stats->iterations = iters;
+        stats->nodes = n_nodes;
+        stats->path_steps = T > 0 ? T - 1 : 0;
+        stats->seconds = now_s() - t_begin;
+    }
+    return KCBS_OK;
+}
+
+}  // namespace kcbs
+
+using namespace kcbs;
+
+extern "C" {
+
+void kcbs_rrt_defaults(kcbs_rrt_params *p)
+{
+    if (!p) return;
+    p->n_targets = 2048;
+    p->n_controls = 32;
+    p->max_nodes = 1 << 20;
+    p->max_iterations = 4096;
+    p->min_steps = 1;    // demo_*.cpp:118
+    p->max_steps = 10;
+    p->goal_bias = 0.05f;
+    p->goal_radius = 0.5f;  // GoalRegionDatabase.h:48
+    p->time_limit_s = 5.0;  // Benchmark.h:153
+    p->seed = 1;
+}
+
+void kcbs_kcbs_defaults(kcbs_kcbs_params *p)
+{
+    if (!p) return;
+    kcbs_rrt_defaults(&p->low_level);
+    p->time_limit_s = 180.0;  // demo_*.cpp:168
+    p->max_nodes = 0;
+}
+
+int kcbs_rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *goal_xy, const kcbs_rrt_params *params,
+                  int n_cons, const int32_t *cons_robot, const int32_t *cons_k0, const int32_t *cons_len,
+                  const int32_t *cons_offset, const float *cons_states, int max_T, float *traj_out, int32_t *T_out,
+                  kcbs_rrt_stats *stats)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    kcbs_rrt_params p;
+    if (params)
+        p = *params;
+    else
+        kcbs_rrt_defaults(&p);
+    if (n_cons < 0 || (n_cons > 0 && (!cons_robot || !cons_k0 || !cons_len || !cons_offset || !cons_states)))
+        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "constraint arrays are null");
+    return rrt_plan(ctx, robot, start, goal_xy, p, n_cons, cons_robot, cons_k0, cons_len, cons_offset, cons_states, max_T,
+                    traj_out, T_out, stats);
+}
+
+// ---- K-CBS high level ------------------------------------------------------------------------------------
+
+namespace {
+
+struct Constraint {
+    int other, k0;
+    std::vector<float> x, y, th;  // states of `other` at k0 .. k0 + len - 1
+};
+
+struct CbsNode {
+    std::vector<std::vector<float>> traj;        // per robot [5][T_r] planes, stride T_r
+    std::vector<int> len;                        // T_r
+    std::vector<std::vector<std::shared_ptr<Constraint>>> cons;  // per robot
+    long long cost = 0;                          // sum of path lengths (propagation steps)
+    long long id = 0;
+};
+
+struct NodeOrder {
+    bool operator()(const std::shared_ptr<CbsNode> &a, const std::shared_ptr<CbsNode> &b) const
+    {
+        return a->cost != b->cost ? a->cost > b->cost : a->id > b->id;
+    }
+};
+
+int plan_robot(kcbs_ctx *ctx, int r, const float *starts, const float *goals, int R, const kcbs_rrt_params &p,
+               const std::vector<std::shared_ptr<Constraint>> &cons, int max_T, std::vector<float> &traj, int &len,
+               kcbs_rrt_stats &rs)
+{
+    float start[5];
+    for (int c = 0; c < 5; ++c) start[c] = starts[(size_t)c * R + r];
+    std::vector<int32_t> robot, k0, ln, off;
+    int total = 0;
+    for (const auto &c : cons) {
+        robot.push_back(c->other); k0.push_back(c->k0); ln.push_back((int)c->x.size()); off.push_back(total);
+        total += (int)c->x.size();
+    }
+    std::vector<float> states((size_t)3 * std::max(total, 1));
+    for (size_t q = 0; q < cons.size(); ++q)
+        for (size_t j = 0; j < cons[q]->x.size(); ++j) {
+            states[off[q] + j] = cons[q]->x[j];
+            states[(size_t)total + off[q] + j] = cons[q]->y[j];
+            states[(size_t)2 * total + off[q] + j] = cons[q]->th[j];
+        }
+    std::vector<float> out((size_t)5 * max_T);
+    int32_t T = 0;
+    const int st = kcbs_rrt_plan(ctx, r, start, goals + 2 * r, &p, (int)cons.size(), robot.data(), k0.data(), ln.data(),
+                                 off.data(), states.data(), max_T, out.data(), &T, &rs);
+    if (st != KCBS_OK) return st;
+    len = T;
+    traj.assign((size_t)5 * std::max(T, 1), 0.0f);
+    for (int c = 0; c < 5; ++c)
+        for (int k = 0; k < T; ++k) traj[(size_t)c * T + k] = out[(size_t)c * max_T + k];
+    return KCBS_OK;
+}
+
+}  // namespace
+
+int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goals, const kcbs_kcbs_params *params,
+                    int max_T, float *plan_out, int32_t *lengths_out, kcbs_kcbs_stats *stats)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    if (R < 1 || R > ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "R exceeds the robots of this world");
+    if (!starts || !goals || !plan_out || !lengths_out || max_T < 2) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "null argument");
+    kcbs_kcbs_params P;
+    if (params)
+        P = *params;
+    else
+        kcbs_kcbs_defaults(&P);
+    const double t_begin = now_s();
+    kcbs_kcbs_stats S;
+    std::memset(&S, 0, sizeof S);
+    long long next_id = 0;
+
+    // root: every robot planned on its own (KCBS::solve root node)
+    auto root = std::make_shared<CbsNode>();
+    root->traj.resize(R); root->len.assign(R, 0); root->cons.resize(R);
+    bool root_ok = true;
+    for (int r = 0; r < R && root_ok; ++r) {
+        kcbs_rrt_params lp = P.low_level;
+        lp.seed = P.low_level.seed * 1000003ull + (unsigned long long)r;
+        kcbs_rrt_stats rs;
+        int st = plan_robot(ctx, r, starts, goals, R, lp, root->cons[r], max_T, root->traj[r], root->len[r], rs);
+        if (st != KCBS_OK) return st;
+        ++S.low_level_calls;
+        if (!rs.solved) root_ok = false;
+        root->cost += root->len[r];
+    }
+    S.root_seconds = now_s() - t_begin;
+    std::priority_queue<std::shared_ptr<CbsNode>, std::vector<std::shared_ptr<CbsNode>>, NodeOrder> open;
+    if (root_ok) {
+        root->id = next_id++;
+        open.push(root);
+    }
+
+    std::shared_ptr<CbsNode> solution;
+    std::vector<float> traj3;
+    std::vector<int32_t> lens(R);
+    while (!open.empty()) {
+        if (P.time_limit_s > 0 && now_s() - t_begin > P.time_limit_s) break;
+        if (P.max_nodes > 0 && S.nodes_expanded >= P.max_nodes) break;
+        auto node = open.top();
+        open.pop();
+        ++S.nodes_expanded;
+        // validate the plan: [R][3][T] with short paths padded (the kernel applies the padding rule)
+        int T = 1;
+        for (int r = 0; r < R; ++r) T = std::max(T, node->len[r]);
+        const int Tp = (T + 3) & ~3;  // keeps rows 16-byte aligned for the bulk-copy path
+        traj3.assign((size_t)R * 3 * Tp, 0.0f);
+        for (int r = 0; r < R; ++r) {
+            const int L = node->len[r];
+            lens[r] = L;
+            for (int k = 0; k < L; ++k) {
+                traj3[((size_t)r * 3 + 0) * Tp + k] = node->traj[r][(size_t)0 * L + k];
+                traj3[((size_t)r * 3 + 1) * Tp + k] = node->traj[r][(size_t)1 * L + k];
+                traj3[((size_t)r * 3 + 2) * Tp + k] = node->traj[r][(size_t)4 * L + k];
+            }
+        }
+        kcbs_conflict cf;
+        // time indices beyond T are never scanned: every path is padded to T, and k_hi = Tp only repeats the
+        // padded states of [T, Tp), which cannot introduce an earlier conflict than the ones in [0, T)
+        int st = kcbs_first_conflict(ctx, 1, R, Tp, traj3.data(), lens.data(), &cf);
+        if (st != KCBS_OK) return st;
+        ++S.conflict_checks;
+        if (cf.r1 < 0) {
+            solution = node;
+            break;
+        }
+        cf.k_end = std::min(cf.k_end, T - 1);
+        // two children: each re-plans one robot against the other's states during the conflict
+        const int pair[2][2] = {{cf.r1, cf.r2}, {cf.r2, cf.r1}};
+        for (int ch = 0; ch < 2; ++ch) {
+            const int me = pair[ch][0], other = pair[ch][1];
+            auto c = std::make_shared<Constraint>();
+            c->other = other;
+            c->k0 = cf.k_start;
+            const int Lo = node->len[other];
+            for (int k = cf.k_start; k <= cf.k_end; ++k) {
+                const int kk = std::min(k, Lo - 1);
+                c->x.push_back(node->traj[other][(size_t)0 * Lo + kk]);
+                c->y.push_back(node->traj[other][(size_t)1 * Lo + kk]);
+                c->th.push_back(node->traj[other][(size_t)4 * Lo + kk]);
+            }
+            auto child = std::make_shared<CbsNode>(*node);
+            child->cons[me].push_back(c);
+            kcbs_rrt_params lp = P.low_level;
+            lp.seed = P.low_level.seed * 1000003ull + (unsigned long long)(next_id * 131 + me);
+            kcbs_rrt_stats rs;
+            st = plan_robot(ctx, me, starts, goals, R, lp, child->cons[me], max_T, child->traj[me], child->len[me], rs);
+            if (st != KCBS_OK) return st;
+            ++S.low_level_calls;
+            if (!rs.solved) {
+                ++S.approximate_solutions;  // the fork counts low-level time-outs as approximate solutions
+                continue;
+            }
+            child->cost = 0;
+            for (int r = 0; r < R; ++r) child->cost += child->len[r];
+            child->id = next_id++;
+            open.push(child);
+        }
+    }
+
+    if (solution) {
+        for (int r = 0; r < R; ++r) {
+            const int L = solution->len[r];
+            lengths_out[r] = L;
+            for (int c = 0; c < 5; ++c)
+                for (int k = 0; k < max_T; ++k)
+                    plan_out[((size_t)r * 5 + c) * max_T + k] = k < L ? solution->traj[r][(size_t)c * L + k] : 0.0f;
+        }
+        S.solved = 1;
+    } else {
+        for (int r = 0; r < R; ++r) lengths_out[r] = 0;
+    }
+    S.seconds = now_s() - t_begin;
+    if (stats) *stats = S;
+    return KCBS_OK;
+}
+
+}  // extern "C"

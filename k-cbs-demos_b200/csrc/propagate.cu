@@ -24,7 +24,9 @@
 //     so FP32 rounding at |x| ~ 32 happens once per written state, not once per sub-step.
 //
 // Work distribution: requested durations are U{1..10} (SimpleDirectedControlSampler), which would
-// idle 45 % of the lanes of a warp.  Each CTA (128 threads) therefore counting-sorts its 256 samples by
+// idle 45 % of the lanes of a warp; and because v, phi are linear in time, the step at which a sample
+// leaves the v / phi bounds is known up front, so its effective duration is too (the doomed step is never
+// integrated).  Each CTA (128 threads) therefore counting-sorts its 256 samples by
 // duration in shared memory and every thread runs two of them: rank t (long) and rank 255 - t (short).
 // Lanes of a warp then hold (almost) equal durations in both rounds and every thread of the CTA has the
 // same total work, so neither lanes nor warps idle.  States are written straight to their original
@@ -46,11 +48,38 @@ __device__ __forceinline__ float rcp_approx(float x)
     return r;
 }
 
+// Dynamic-obstacle constraints of the K-CBS low level (the fork tests `next` against the constraining robot's
+// state at that time through areStatesValid, StateValidityCheckerDatabase.h:78-125).
+__device__ __forceinline__ bool constraints_clear(const DevWorld &w, const PropArgs &a, int k, float x, float y,
+                                                  float th, float hl, float hw, float rad)
+{
+    bool ok = true, have = false;
+    float c = 1.0f, s = 0.0f;
+    for (int q = 0; q < a.n_cons; ++q) {
+        const ConsDesc d = a.cons[q];
+        const int rel = k - d.k0;
+        if (rel < 0 || rel >= d.len) continue;
+        const float *st = a.cons_states + d.offset + rel;
+        const float ox = st[0], oy = st[a.cons_total], dx = ox - x, dy = oy - y;
+        const float rs = rad + w.rob_rad[d.other];
+        if (fmaf(dy, dy, dx * dx) > rs * rs * 1.000001f) continue;
+        if (!have) {
+            sincosf(th, &s, &c);
+            have = true;
+        }
+        float oc, os;
+        sincosf(st[2 * a.cons_total], &os, &oc);
+        ok &= sat_gap_robots(x, y, c, s, hl, hw, ox, oy, oc, os, w.rob_hl[d.other], w.rob_hw[d.other]) > 0.0f;
+    }
+    return ok;
+}
+
 // propagateWhileValid for one sample; writes the segment, the final state and the valid-step count.
-template <bool HAS_OBS>
+template <bool HAS_OBS, bool HAS_CONS>
 __device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropArgs &a, long long i, int st)
 {
     const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
+    const int t0 = (HAS_CONS && a.parent_time) ? a.parent_time[pi] : 0;
     const float x0 = a.parents[0 * a.n_parents + pi];
     const float y0 = a.parents[1 * a.n_parents + pi];
     const float v0 = a.parents[2 * a.n_parents + pi];
@@ -129,6 +158,9 @@ __device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropAr
         if (HAS_OBS) {
             if (ok) ok = obstacles_clear_grid(w, w.grid, w.obs4, xn, yn, tn, hl, hw);
         }
+        if (HAS_CONS) {
+            if (ok) ok = constraints_clear(w, a, t0 + j + 1, xn, yn, tn, hl, hw, w.rob_rad[a.robot]);
+        }
         if (!ok) break;
 
         xs = xn; ys = yn; vs = vn; ps = pn; ts = tn;
@@ -153,7 +185,7 @@ __device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropAr
     }
 }
 
-template <bool HAS_OBS>
+template <bool HAS_OBS, bool HAS_CONS>
 __global__ void __launch_bounds__(kPropThreads)
 k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs a)
 {
@@ -176,6 +208,21 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         if (i < a.n) {
             st = a.steps ? a.steps[i] : a.max_steps;
             st = min(max(st, 0), a.max_steps);
+            // v and phi are linear in time, so the first step at which they leave their bounds is known
+            // before integrating anything: that step would fail isValid, so the segment ends just before
+            // it (same result as propagating it and testing).  Sorting by this effective duration keeps
+            // warps uniform even when many samples leave the v / phi bounds early.
+            const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
+            const float v0 = a.parents[2 * a.n_parents + pi], phi0 = a.parents[3 * a.n_parents + pi];
+            const float ua = a.controls[i], uw = a.controls[a.n + i];
+            int ok_steps = 0;
+            for (int j = 0; j < st; ++j) {
+                const float t1 = (float)(j + 1) * w.step;
+                const float vn = fmaf(ua, t1, v0), pn = fmaf(uw, t1, phi0);
+                if (!((vn >= w.lo_t[2]) & (vn <= w.hi_t[2]) & (pn >= w.lo_t[3]) & (pn <= w.hi_t[3]))) break;
+                ok_steps = j + 1;
+            }
+            st = ok_steps;
         }
         st2[u] = st;
         s_steps[slot] = (unsigned char)st;
@@ -196,7 +243,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         const int rank = round == 0 ? tid : kPropSamples - 1 - tid;
         const int slot = s_perm[rank];
         const long long i = b0 + slot;
-        if (i < a.n) propagate_sample<HAS_OBS>(w, a, i, (int)s_steps[slot]);
+        if (i < a.n) propagate_sample<HAS_OBS, HAS_CONS>(w, a, i, (int)s_steps[slot]);
     }
 }
 
@@ -206,10 +253,16 @@ cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t 
 {
     if (a.n <= 0) return cudaSuccess;
     const long long grid = (a.n + kPropSamples - 1) / kPropSamples;
-    if (w.n_obs > 0)
-        k_propagate<true><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
-    else
-        k_propagate<false><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+    if (a.n_cons > 0) {
+        if (w.n_obs > 0)
+            k_propagate<true, true><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+        else
+            k_propagate<false, true><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+    } else if (w.n_obs > 0) {
+        k_propagate<true, false><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+    } else {
+        k_propagate<false, false><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+    }
     return cudaGetLastError();
 }
 

@@ -1,0 +1,84 @@
+"""GPU tests of the "next" rows: the batched low-level planner (kcbs_rrt_plan) and the K-CBS
+high level (kcbs_kcbs_solve).  Plans are checked with the CPU oracle: every state valid, consecutive states
+connected by one reference propagation step under an admissible control, goals reached, and the multi-robot plan
+conflict free under the reference's scan."""
+import numpy as np
+import pytest
+
+from helpers import state_close
+
+pytestmark = pytest.mark.gpu
+
+
+def check_path(oracle, traj, start, goal, robot=0, radius=0.5):
+    """traj [5, T]: dynamically feasible under the reference propagator, valid, start -> goal region."""
+    T = traj.shape[1]
+    assert T >= 1
+    assert (traj[:, 0] == np.asarray(start, np.float32)).all()
+    assert np.hypot(traj[0, -1] - goal[0], traj[1, -1] - goal[1]) <= radius + 1e-4
+    for k in range(T - 1):
+        q, qn = traj[:, k].astype(np.float64), traj[:, k + 1].astype(np.float64)
+        u = np.array([(qn[2] - q[2]) / 0.1, (qn[3] - q[3]) / 0.1])
+        assert np.abs(u).max() <= 1.0 + 1e-3, f"step {k}: control {u} outside [-1, 1]^2"
+        ref = oracle.propagate(q, np.clip(u, -1, 1))
+        ok, d = state_close(qn.astype(np.float32)[:, None], ref[:, None])
+        assert ok.all(), f"step {k}: {d.ravel()}"
+        valid, margin = oracle.is_valid(qn, robot)
+        assert valid or abs(margin) < 2e-5, f"state {k + 1} invalid (margin {margin})"
+
+
+@pytest.mark.parametrize("scene,robot", [("Empty32x32_10robots", 0), ("Empty32x32_10robots", 7), ("Corridor10x10_4robots", 1)])
+def test_rrt_reaches_goal(pkg, orc, gpu_ctx_factory, scene, robot):
+    ctx = gpu_ctx_factory(scene)
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    start = pkg.scenes.start_states(scene)[:, robot]
+    goal = pkg.scenes.goals(scene)[robot]
+    traj, st = ctx.rrt_plan(robot, start, goal, ctx.rrt_params(seed=3))
+    assert st.solved == 1 and st.iterations >= 1 and st.nodes > 1
+    assert traj.shape[1] == st.path_steps + 1
+    check_path(oracle, traj, start, goal, robot)
+
+
+def test_rrt_respects_constraints(pkg, orc, gpu_ctx_factory):
+    # a robot parked across the straight line to the goal for the whole horizon must be avoided
+    scene = "Empty32x32_10robots"
+    ctx = gpu_ctx_factory(scene)
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    start = np.array([5.0, 16.0, 0, 0, 0], np.float32)
+    goal = np.array([12.0, 16.0], np.float32)
+    K = 600
+    block = np.zeros((3, K), np.float32)
+    block[0], block[1], block[2] = 8.5, 16.0, np.pi / 2
+    traj, st = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=5), constraints=[(1, 0, block)])
+    assert st.solved == 1
+    check_path(oracle, traj, start, goal)
+    for k in range(traj.shape[1]):
+        ok, _ = oracle.pair_valid(0, traj[[0, 1, 4], k], 1, block[:, min(k, K - 1)])
+        assert ok, f"constraint violated at step {k}"
+    # without the constraint the planner is free to drive through that spot
+    free, st2 = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=5))
+    assert st2.solved == 1 and free.shape[1] <= traj.shape[1] + 200
+
+
+def test_rrt_unreachable_goal_times_out(pkg, gpu_ctx_factory):
+    ctx = gpu_ctx_factory("Corridor10x10_4robots")
+    # goal inside the long obstacle (0.5, 1.8, 9.0, 1.0): never reachable
+    traj, st = ctx.rrt_plan(0, [1.0, 0.5, 0, 0, 0], [5.0, 2.3], ctx.rrt_params(max_iterations=20, goal_radius=0.2))
+    assert st.solved == 0 and traj.shape[1] == 0 and st.iterations == 20
+
+
+@pytest.mark.parametrize("scene", ["Empty32x32_10robots", "Corridor10x10_4robots"])
+def test_kcbs_solves_demo_scene(pkg, orc, gpu_ctx_factory, scene):
+    ctx = gpu_ctx_factory(scene)
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    starts, goals = pkg.scenes.start_states(scene), pkg.scenes.goals(scene)
+    R = starts.shape[1]
+    plan, lengths, st = ctx.kcbs_solve(starts, goals, ctx.kcbs_params(time_limit_s=120.0))
+    assert st.solved == 1, f"K-CBS failed: {st.nodes_expanded} nodes, {st.low_level_calls} low-level calls"
+    assert st.nodes_expanded >= 1 and st.root_seconds > 0 and st.seconds >= st.root_seconds
+    T = int(lengths.max())
+    for r in range(R):
+        check_path(oracle, plan[r, :, :lengths[r]], starts[:, r], goals[r], r)
+    traj = np.ascontiguousarray(plan[:, [0, 1, 4], :T])
+    res, _, _ = oracle.first_conflict(traj, lengths)
+    assert res == (-1, -1, -1, -1), f"plan has a conflict {res}"
