@@ -4,7 +4,7 @@
  * This is the drop-in boundary: plain pointers and sizes, no C++/torch types, integer status
  * returns, never throws.  Each entry point names the reference interface it replaces
  * (file:line relative to the K-CBS-Demos tree).  The host-side mirror of the reference's OMPL
- * plugin classes (k-cbs-demos_b200/includes/*.h) is written on top of these calls.
+ * plugin classes (k-cbs-demos_b200/includes/) is written on top of these calls.
  *
  * Conventions
  *   state  s = (x, y, v, phi, theta)   OMPL "reals" order, StatePropagatorDatabase.h:46

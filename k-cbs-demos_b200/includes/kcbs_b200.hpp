@@ -46,6 +46,9 @@ public:
         n_robots_ = w.n_robots;
     }
 
+    // adopts a context created directly through the C ABI
+    Context(kcbs_ctx *h, int n_robots) : h_(h, kcbs_destroy), n_robots_(n_robots) {}
+
     kcbs_ctx *get() const { return h_.get(); }
     int robots() const { return n_robots_; }
 
