@@ -12,6 +12,7 @@
 #include "SystemMergerDatabase.h"
 #include "Benchmark.h"
 
+#include <array>
 #include <cstdio>
 
 static int failures = 0;
@@ -31,14 +32,14 @@ struct Problem {
     omrb::ProblemDefinitionPtr ma_pdef;
 };
 
-// Corridor10x10 with 4 robots, as in src/demo_Corridor10x10_4robots_dyn2ndOrderCars.cpp:61-146
-static Problem corridor()
+// Builds the multi-robot problem exactly like the reference mains do (src/demo_Corridor10x10_4robots_dyn2ndOrderCars.cpp:61-146)
+static Problem make_problem(std::map<std::string, std::pair<double, double>> starts, std::map<std::string, std::pair<double, double>> goals,
+                            std::vector<std::array<double, 4>> obstacles)
 {
     Problem p;
-    p.start_map = {{"Robot 1", {1.0, 0.5}}, {"Robot 2", {1.0, 3.5}}, {"Robot 3", {9.0, 0.5}}, {"Robot 4", {9.0, 3.5}}};
-    p.goal_map = {{"Robot 1", {9.0, 0.5}}, {"Robot 2", {9.0, 9.0}}, {"Robot 3", {1.0, 0.5}}, {"Robot 4", {1.0, 9.0}}};
-    p.obs_set.insert(new RectangularObstacle(0.5, 1.8, 9.0, 1.0));
-    p.obs_set.insert(new RectangularObstacle(4.0, 5.0, 2.0, 2.0));
+    p.start_map = std::move(starts);
+    p.goal_map = std::move(goals);
+    for (const auto &o : obstacles) p.obs_set.insert(new RectangularObstacle(o[0], o[1], o[2], o[3]));
     for (auto &kv : p.start_map) p.robot_map[kv.first] = new RectangularRobot(kv.first, 1.0, 1.0);
     p.ma_si = std::make_shared<omrc::SpaceInformation>();
     p.ma_pdef = std::make_shared<omrb::ProblemDefinition>(p.ma_si);
@@ -67,6 +68,21 @@ static Problem corridor()
     return p;
 }
 
+// Corridor10x10 with 4 robots (src/demo_Corridor10x10_4robots_dyn2ndOrderCars.cpp:61-78)
+static Problem corridor()
+{
+    return make_problem({{"Robot 1", {1.0, 0.5}}, {"Robot 2", {1.0, 3.5}}, {"Robot 3", {9.0, 0.5}}, {"Robot 4", {9.0, 3.5}}},
+                        {{"Robot 1", {9.0, 0.5}}, {"Robot 2", {9.0, 9.0}}, {"Robot 3", {1.0, 0.5}}, {"Robot 4", {1.0, 9.0}}},
+                        {{0.5, 1.8, 9.0, 1.0}, {4.0, 5.0, 2.0, 2.0}});
+}
+
+// three robots crossing an open 10 x 10 workspace: easy enough for prioritized planning
+static Problem crossing()
+{
+    return make_problem({{"Robot 1", {1.0, 1.0}}, {"Robot 2", {9.0, 1.0}}, {"Robot 3", {5.0, 9.0}}},
+                        {{"Robot 1", {9.0, 9.0}}, {"Robot 2", {1.0, 9.0}}, {"Robot 3", {5.0, 1.0}}}, {});
+}
+
 static void set_state(ob::ScopedState<> &s, double x, double y, double v, double phi, double th)
 {
     s[0] = x; s[1] = y; s[2] = v; s[3] = phi; s[4] = th;
@@ -74,7 +90,8 @@ static void set_state(ob::ScopedState<> &s, double x, double y, double v, double
 
 int main()
 {
-    Problem p = corridor();
+    Problem corridor_problem = corridor();
+    Problem &p = corridor_problem;
     auto si = p.ma_si->getIndividual(0);
     auto space = si->getStateSpace();
     CHECK(space->getDimension() == 5 && space->getName() == "Robot 1");
@@ -195,7 +212,11 @@ int main()
     }
 
     // ---- K-CBS and PP ----------------------------------------------------------------------------------------------
+    Problem open_space = crossing();
     for (const char *name : {"K-CBS", "PP"}) {
+        // K-CBS on the corridor scene; prioritized planning (incomplete by nature) on the open crossing scene
+        Problem &p = std::string(name) == "K-CBS" ? corridor_problem : open_space;
+        const unsigned int R = p.ma_si->getIndividualCount();
         omrb::PlannerPtr planner;
         if (std::string(name) == "K-CBS") {
             omrc::SystemMergerPtr merger = std::make_shared<homogeneous2ndOrderCarSystemMerger>(p.ma_si, p.ma_pdef, p.robot_map, p.obs_set, 10,
@@ -213,14 +234,14 @@ int main()
         CHECK(solved);
         if (solved) {
             auto plan = p.ma_pdef->getSolutionPlan()->as<omrc::PlanControl>();
-            CHECK(plan->getPathCount() == 4);
+            CHECK(plan->getPathCount() == R);
             // pairwise validity of the plan through the scalar virtual, with the padding rule
             size_t T = 0;
-            for (unsigned int r = 0; r < 4; ++r) T = std::max(T, plan->getPath(r)->getStateCount());
+            for (unsigned int r = 0; r < R; ++r) T = std::max(T, plan->getPath(r)->getStateCount());
             int conflicts = 0;
             for (size_t k = 0; k < T; ++k)
-                for (unsigned int r1 = 0; r1 < 4; ++r1)
-                    for (unsigned int r2 = r1 + 1; r2 < 4; ++r2) {
+                for (unsigned int r1 = 0; r1 < R; ++r1)
+                    for (unsigned int r2 = r1 + 1; r2 < R; ++r2) {
                         auto &p1 = plan->getPath(r1)->getStates();
                         auto &p2 = plan->getPath(r2)->getStates();
                         const ob::State *s1 = p1[std::min(k, p1.size() - 1)], *s2 = p2[std::min(k, p2.size() - 1)];
@@ -229,7 +250,7 @@ int main()
             CHECK(conflicts == 0);
             std::ofstream out(std::string("plan_") + name + ".txt");
             plan->printAsMatrix(out, "Robot");
-            std::printf("%s solved Corridor10x10_4robots: %zu steps\n", name, T);
+            std::printf("%s solved its %u-robot problem: %zu steps\n", name, R, T);
         }
         if (std::string(name) == "K-CBS") {
             auto *k = planner->as<omrc::KCBS>();
