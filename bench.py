@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step's launches from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -278,8 +279,11 @@ def main():
     valid = torch.zeros((n_robots, n_exp, N_CONTROLS), dtype=torch.int32, device="cuda")
 
     def gpu_step():
+        """One step: every robot planner issues its expansions on its own stream (fork from / join into the
+        current stream, so the whole step can be captured into one CUDA graph)."""
+        cur = torch.cuda.current_stream()
         ev = torch.cuda.Event()
-        ev.record(main_stream)
+        ev.record(cur)
         for r in range(n_robots):
             streams[r].wait_event(ev)
             sp = streams[r].cuda_stream
@@ -289,7 +293,7 @@ def main():
         for r in range(n_robots):
             done = torch.cuda.Event()
             done.record(streams[r])
-            main_stream.wait_event(done)
+            cur.wait_event(done)
 
     fp32_peak_before = ctxs[0].measure_fp32_peak()
 
@@ -301,19 +305,34 @@ def main():
     units_step = float(torch.minimum(steps_all, valid + 1).sum().item())
     samples_step = n_robots * n_exp * N_CONTROLS
     written_step = float(valid.sum().item())
+    launches_per_step = n_robots * n_exp
+
+    # The step is launch-bound from Python (250 C-ABI calls of ~20 us of GPU work each), so it is captured once
+    # into a CUDA graph (the same kernels, streams and dependencies) and replayed.
+    run_step = gpu_step
+    graphed = False
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            gpu_step()
+        run_step = graph.replay
+        graphed = True
+        for _ in range(max(args.warmup, 1)):
+            run_step()
+        barrier()
+        assert float(torch.minimum(steps_all, valid + 1).sum().item()) == units_step
 
     sampler = ClockSampler(local_rank)
-    launches0 = sum(c.launch_count() for c in ctxs)
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main_stream)
     for _ in range(args.steps):
-        gpu_step()
+        run_step()
     e1.record(main_stream)
     barrier()
     clocks = sampler.stop()
-    launches = sum(c.launch_count() for c in ctxs) - launches0
+    launches = launches_per_step * args.steps
     elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
     total_units = sum_over_ranks(units_step) * args.steps
     value = total_units / (elapsed_ms * 1e-3)
@@ -372,6 +391,25 @@ def main():
            "calls_per_step": calls, "steps": e2e_steps,
            "note": "kcbs_propagate_batch with pinned host buffers; whole segments + final states + counts copied back"}
 
+    # the same calls asking only for what propagateWhileValid(state, control, steps, result) returns (the final
+    # state and the step count, 24 B per sample instead of 224 B): what a planner that does not keep intermediate
+    # states would transfer
+    def e2e_final_step():
+        for r in range(n_robots):
+            for e in range(e2e_exp):
+                pp, pc, ps = pin[r][e]
+                ctxs[r].propagate_batch(r, pp, pc, ps, max_steps=MAX_STEPS, out=(None, out_fin, out_valid))
+
+    e2e_final_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_final_step()
+    barrier()
+    e2e_final_s = max_over_ranks(time.perf_counter() - t0)
+    e2e["final_state_only"] = {"value": sum_over_ranks(e2e_units) * e2e_steps / e2e_final_s, "unit": "states/s",
+                               "d2h_bytes_per_step": calls * N_CONTROLS * 24}
+
     # ---- secondary metrics: validity (K2) and conflict scan (K3), device resident ------------------
     secondary = {}
     if not args.no_secondary:
@@ -393,6 +431,7 @@ def main():
                        "expansions_per_robot_per_step": n_exp, "max_steps": MAX_STEPS,
                        "durations": "U{1..10}" if args.fixed_steps is None else f"fixed {args.fixed_steps}",
                        "parents": "one shared tree node per expansion", "streams": n_robots,
+                       "launch": "one CUDA graph per step (captured C-ABI launches)" if graphed else "eager C-ABI calls from Python",
                        "states_per_step_per_gpu": units_step,
                        "l2": f"each step writes {samples_step * 200 / 1e6:.0f} MB of distinct segment buffers per GPU (> 126 MB L2); no flush needed",
                        "parallelism": f"{world_size} x independent per-robot replans, no data-path collective"},
