@@ -521,6 +521,21 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
                            "roofline": {"kernel": "k_conflict_keys", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                                         "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                                         "note": "per GPU; algorithmic 12 B per trajectory state (x, y, theta), the scan itself reads 8 B"}}
+    # ---- K-CBS solve time (Empty32x32): the whole planner (kcbs_kcbs_solve), rank-local -------------------------
+    solve = {}
+    for scene in ("Empty32x32_10robots", "Benchmark_Empty32x32_30robots"):
+        with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
+            starts, goals = pkg.scenes.start_states(scene), pkg.scenes.goals(scene)
+            times, ok = [], 0
+            for seed in (1, 2, 3):
+                t0 = time.perf_counter()
+                _, _, st = ctx.kcbs_solve(starts, goals, ctx.kcbs_params(low_level=ctx.rrt_params(seed=seed), time_limit_s=60.0))
+                times.append(time.perf_counter() - t0)
+                ok += int(st.solved)
+            solve[scene] = {"robots": int(starts.shape[1]), "median_s": float(np.median(times)), "runs_s": [round(t, 4) for t in times],
+                            "solved": ok, "of": 3}
+    out["kcbs_solve"] = {"metric": "K-CBS solve time (Empty32x32)", "unit": "s", "higher_is_better": False, "scenes": solve,
+                         "note": "batched GPU RRT low level + K-CBS high level; reference budget is 180 s per solve (demo_*.cpp:168)"}
     return out
 
 

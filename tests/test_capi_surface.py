@@ -99,3 +99,12 @@ def test_scene_fixtures(pkg):
     assert (s["Empty32x32_10robots"]["robot_length"], s["Empty32x32_10robots"]["robot_width"]) == (0.7, 0.5)
     st = pkg.scenes.start_states("Corridor10x10_4robots")
     assert st[:2].T.tolist() == [[1.0, 0.5], [1.0, 3.5], [9.0, 0.5], [9.0, 3.5]]
+
+
+def test_missing_library_fails_loudly(pkg, monkeypatch):
+    """No silent fallback: without libkcbs_b200.so the binding raises instead of computing anything."""
+    from kcbs_b200 import capi
+    monkeypatch.setattr(capi, "_LIB", None)
+    monkeypatch.setattr(capi, "lib_path", lambda: "/nonexistent/libkcbs_b200.so")
+    with pytest.raises(ImportError):
+        capi.load_library()

@@ -136,3 +136,29 @@ def test_errors(pkg, gpu_ctx_factory):
         ctx.first_conflict(np.zeros((1, 9, 3, 10), np.float32))
     assert e.value.status == 5
     assert ctx.first_conflict(np.zeros((0, 4, 3, 10), np.float32)).shape == (0,)
+
+
+@pytest.mark.parametrize("R", [2, 9, 33, 64])
+def test_robot_counts_and_mixed_footprints(pkg, orc, gpu_ctx_factory, R):
+    # register tiles of 8 robots: partial last tile (sentinel rows), exactly full tiles, the 64-robot maximum;
+    # robots of different sizes use their own rectangles and radii
+    rng = np.random.default_rng(R)
+    dims = [[0.7, 0.5] if r % 3 else [1.2, 0.4] for r in range(R)]
+    w = pkg.World(x_max=32, y_max=32, robot_dims=dims)
+    ctx = gpu_ctx_factory(w)
+    oracle = orc.Oracle(w)
+    P, T = 4, 300
+    traj = np.zeros((P, R, 3, T), np.float32)
+    for p in range(P):
+        pos = rng.uniform(1, 31, (R, 2))
+        vel = rng.uniform(-0.05, 0.05, (R, 2))
+        for k in range(T):
+            vel += rng.normal(0, 0.005, (R, 2))
+            pos = np.clip(pos + vel, 0.5, 31.5)
+            traj[p, :, 0, k], traj[p, :, 1, k] = pos[:, 0], pos[:, 1]
+            traj[p, :, 2, k] = np.arctan2(vel[:, 1], vel[:, 0])
+    got = _t(ctx.first_conflict(traj))
+    for p in range(P):
+        ref, min_margin, _ = oracle.first_conflict(traj[p])
+        if min_margin > BAND:
+            assert got[p] == ref, f"R={R} plan {p}: gpu {got[p]} oracle {ref}"

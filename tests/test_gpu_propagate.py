@@ -137,3 +137,23 @@ def test_errors(pkg, gpu_ctx_factory):
     with pytest.raises(pkg.KcbsError) as e:   # unknown robot index mirrors unordered_map::at
         ctx.propagate_batch(99, p, np.zeros((2, 3), np.float32))
     assert e.value.status == 5
+
+
+def test_long_horizon_20_steps(pkg, orc, workloads, gpu_ctx_factory):
+    # setMinMaxControlDuration beyond the demos' (1, 10): up to KCBS_MAX_STEPS = 32 steps per segment
+    scene = "Empty32x32_10robots"
+    ctx = gpu_ctx_factory(scene)
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    n = 6000
+    parents, controls, _ = workloads.expansion_batch(scene, n, seed=12, interior=3.0)
+    controls *= np.float32(0.5)
+    steps = np.random.default_rng(5).integers(1, 21, n).astype(np.int32)
+    seg, fin, valid = ctx.propagate_batch(0, parents, controls, steps, max_steps=20)
+    oseg, ofin, ovalid, _ = oracle.propagate_batch(0, parents, controls, steps, max_steps=20, n_threads=8)
+    assert (valid == ovalid).mean() >= 0.998
+    for j in range(20):
+        idx = np.nonzero(np.minimum(valid, ovalid) > j)[0]
+        if len(idx):
+            ok, d = state_close(seg[:, j, idx], oseg[:, j, idx])
+            assert ok.all(), f"step {j}: {d.max():.3e}"
+    assert (valid > 10).any()
