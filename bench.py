@@ -473,27 +473,26 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
                                         "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src}}
         del sets, mask
     # ---- conflict scan: Empty32x32 30 robots, 435 pairs x 10K steps, 256 plans (config 5) --------------
-    # N > 1: the fixed 256-plan batch is sharded by plan (strong scaling); the only exchange is the
-    # all-gather of the 16-byte results.
+    # N > 1: every rank scans its own 256-plan batch (weak); one batch sharded by plan is reported as well (strong).
     from kcbs_b200 import sharding
     scene = "Benchmark_Empty32x32_30robots"
     P, R, T = 256, 30, 10000
     world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
-    lo, hi = sharding.shard_range(P, rank, world)
-    Pl = hi - lo
     with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
-        traj = workloads.cell_plans(scene, P, T, seed=1, xp=torch)[lo:hi].contiguous()   # 922 MB total >> L2, conflict free
-        res = torch.empty((Pl, 4), dtype=torch.int32, device="cuda")
+        # every rank validates its own batch of 256 candidate plans (e.g. plans of different constraint-tree nodes);
+        # the only exchange is the all-gather of the 16-byte verdicts
+        traj = workloads.cell_plans(scene, P, T, seed=1 + rank, xp=torch)   # 922 MB per GPU >> L2, conflict free
+        res = torch.empty((P, 4), dtype=torch.int32, device="cuda")
         st = torch.cuda.current_stream()
 
-        def scan():
-            ctx.first_conflict_dev(Pl, R, T, traj, None, res, st)
-            return sharding.gather_plans(res, world)
+        def scan(n_plans=P):
+            ctx.first_conflict_dev(n_plans, R, T, traj, None, res[:n_plans], st)
+            return sharding.gather_plans(res[:n_plans], world)
 
         for _ in range(3):
             allres = scan()
         barrier()
-        assert allres.shape[0] == P and int((allres[:, 0] >= 0).sum().item()) == 0, "throughput plans must be conflict free"
+        assert allres.shape[0] == P * world and int((allres[:, 0] >= 0).sum().item()) == 0, "throughput plans must be conflict free"
         reps = 10
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -503,8 +502,19 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
         pairs = P * (R * (R - 1) // 2) * T
-        rate = float(pairs) * reps / (ms * 1e-3)
-        gbs = CONFLICT_BYTES_PER_TRAJ_STATE * Pl * R * T * reps / (e0.elapsed_time(e1) * 1e-3) * 1e-9
+        rate = float(pairs) * world * reps / (ms * 1e-3)
+        gbs = CONFLICT_BYTES_PER_TRAJ_STATE * P * R * T * reps / (e0.elapsed_time(e1) * 1e-3) * 1e-9
+        # strong scaling of ONE 256-plan batch: plans sharded over the ranks, verdicts all-gathered
+        lo, hi = sharding.shard_range(P, rank, world)
+        for _ in range(3):
+            scan(hi - lo)
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            scan(hi - lo)
+        e1.record()
+        barrier()
+        strong_rate = float(pairs) * reps / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
         # single-plan latency (435 pairs x 10K steps, L2 resident), rank-local
         one = traj[:1].contiguous()
         for _ in range(3):
@@ -516,11 +526,34 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
         e1.record()
         torch.cuda.synchronize()
         out["conflict"] = {"metric": "conflict-checked state-pairs/s", "value": rate, "scene": scene, "plans": P,
-                           "pairs": R * (R - 1) // 2, "timesteps": T, "scaling": "strong (plans sharded over ranks, results all-gathered)",
+                           "pairs": R * (R - 1) // 2, "timesteps": T, "scaling": "weak (256 plans per rank, verdicts all-gathered)",
+                           "strong_scaling_value": strong_rate,
                            "single_plan_latency_us": 1e3 * e0.elapsed_time(e1) / 50,
                            "roofline": {"kernel": "k_conflict_keys", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                                         "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                                         "note": "per GPU; algorithmic 12 B per trajectory state (x, y, theta), the scan itself reads 8 B"}}
+    # ---- per-robot replans sharded over the ranks (config 4: Empty32x32 20 robots) ------------------------------
+    scene = "Empty32x32_20robots"
+    with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
+        starts, goals = pkg.scenes.start_states(scene), pkg.scenes.goals(scene)
+        R20, max_T = starts.shape[1], 1024
+        res = torch.empty((1, 4), dtype=torch.int32, device="cuda")
+        times = []
+        for rep in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            plan, lengths, ok = sharding.plan_replans_sharded(ctx, starts, goals, rank, world, max_T, seed=11 + rep)
+            T = int(lengths.max().item())
+            Tp = (T + 3) // 4 * 4
+            traj3 = plan[:, [0, 1, 4], :Tp].contiguous().unsqueeze(0)
+            ctx.first_conflict_dev(1, R20, Tp, traj3, lengths.unsqueeze(0).contiguous(), res, torch.cuda.current_stream())
+            barrier()
+            times.append(max_over_ranks(time.perf_counter() - t0))
+            assert ok
+        out["replans"] = {"metric": "20 per-robot replans + all-gather + plan validation", "scene": scene, "unit": "s",
+                          "higher_is_better": False, "median_s": float(np.median(times[1:])), "runs_s": [round(t, 4) for t in times],
+                          "scaling": "strong (replans dealt round-robin over ranks, trajectories merged with one all-reduce)"}
+
     # ---- K-CBS solve time (Empty32x32): the whole planner (kcbs_kcbs_solve), rank-local -------------------------
     solve = {}
     for scene in ("Empty32x32_10robots", "Benchmark_Empty32x32_30robots"):

@@ -106,7 +106,7 @@ KCBS_API int kcbs_host_free(kcbs_ctx *ctx, void *p);
  *   controls    2 planes of n floats (a, phidot).
  *   steps       n requested step counts in [0, max_steps], or NULL for max_steps everywhere.
  *   seg_out     [5][max_steps][n] floats: seg_out[(c*max_steps + j)*n + i] is component c of
- *               sample i after j+1 steps, written for j < valid_steps[i] only.  May be NULL.
+ *               sample i after j+1 steps for j < valid_steps[i]; rows j >= valid_steps[i] are zero.  May be NULL.
  *   final_out   [5][n] floats, last valid state (the parent when 0 steps are valid). May be NULL.
  *   valid_steps n ints: the propagateWhileValid return value.
  */

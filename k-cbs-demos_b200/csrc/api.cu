@@ -352,8 +352,6 @@ int kcbs_propagate_batch(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents,
     KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in1.p, controls, b_ctl, cudaMemcpyHostToDevice, s));
     if (parent_idx) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in2.p, parent_idx, b_idx, cudaMemcpyHostToDevice, s));
     if (steps) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in3.p, steps, b_idx, cudaMemcpyHostToDevice, s));
-    // unwritten tail states of a segment read back as zero rather than stale workspace contents
-    if (seg_out) KCBS_CUDA(ctx, cudaMemsetAsync(ctx->out0.p, 0, b_seg, s));
     st = kcbs_propagate_batch_dev(ctx, robot, n, n_parents, (const float *)ctx->in0.p,
                                   parent_idx ? (const int32_t *)ctx->in2.p : nullptr, (const float *)ctx->in1.p,
                                   steps ? (const int32_t *)ctx->in3.p : nullptr, max_steps,

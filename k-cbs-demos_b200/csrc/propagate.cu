@@ -175,6 +175,15 @@ __device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropAr
         }
     }
 
+    if (a.seg) {
+        // rows past the last valid state are zero-filled: every 32 B sector of the segment buffer is then written
+        // completely, so L2 never has to read-modify-write partially written sectors from HBM
+        for (int j = nv; j < a.max_steps; ++j) {
+            float *o = a.seg + (long long)j * a.n + i;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) __stcs(o + c * plane, 0.0f);
+        }
+    }
     if (a.valid_steps) a.valid_steps[i] = nv;
     if (a.fin) {
         a.fin[i] = xs;

@@ -64,3 +64,40 @@ def gather_plans(results: torch.Tensor, world: int) -> torch.Tensor:
     out = [torch.empty_like(results) for _ in range(world)]
     dist.all_gather(out, results)
     return torch.cat(out, dim=0)
+
+
+def merge_owned_rows(buf: torch.Tensor, owned: List[int]) -> torch.Tensor:
+    """Every rank filled the rows it owns (all other rows zero); after the call every rank holds every row.
+    A SUM all-reduce over disjoint owners is an all-gather that tolerates uneven row counts."""
+    mask = torch.zeros(buf.shape[0], dtype=torch.bool, device=buf.device)
+    if len(owned):
+        mask[torch.as_tensor(owned, device=buf.device)] = True
+    buf[~mask] = 0
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return buf
+
+
+def plan_replans_sharded(ctx, starts, goals, rank: int, world: int, max_T: int, seed: int = 1, device="cuda"):
+    """Config 'per-robot replans sharded across GPUs': the R independent low-level replans of a K-CBS node are dealt
+    round-robin over the ranks (kcbs_rrt_plan on each rank's own GPU and stream), the planned trajectories are
+    merged on every rank (NCCL over NVLink), and the merged plan is validated there with kcbs_first_conflict.
+    Returns (plan [R, 5, max_T] tensor, lengths [R] tensor, all_solved flag)."""
+    R = starts.shape[1]
+    mine = round_robin(R, rank, world)
+    plan = torch.zeros((R, 5, max_T), dtype=torch.float32, device=device)
+    lengths = torch.zeros(R, dtype=torch.int32, device=device)
+    solved = torch.ones(1, dtype=torch.int32, device=device)
+    for r in mine:
+        traj, st = ctx.rrt_plan(r, starts[:, r], goals[r], ctx.rrt_params(seed=seed * 1000003 + r), max_T=max_T)
+        if not st.solved:
+            solved[0] = 0
+            continue
+        T = traj.shape[1]
+        plan[r, :, :T] = torch.from_numpy(traj).to(device)
+        lengths[r] = T
+    merge_owned_rows(plan, mine)
+    merge_owned_rows(lengths, mine)
+    if dist.is_initialized() and world > 1:
+        dist.all_reduce(solved, op=dist.ReduceOp.MIN)
+    return plan, lengths, bool(solved.item())

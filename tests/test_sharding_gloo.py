@@ -76,6 +76,14 @@ def _worker(rank, world, port, ret):
         ref = np.stack([full["r1"], full["r2"], full["k_start"], full["k_end"]], axis=1)
         assert (allres.numpy() == ref).all()
 
+        # (2b) rows owned round-robin (replanned trajectories) merged on every rank
+        owned = sharding.round_robin(R, rank, world)
+        buf = torch.full((R, 3, T), 123.0)                      # stale values in rows this rank does not own
+        for r in owned:
+            buf[r] = torch.from_numpy(traj[0, r])
+        sharding.merge_owned_rows(buf, owned)
+        assert (buf.numpy() == traj[0]).all()
+
         # (3) replan jobs round-robin: every job exactly once
         jobs = torch.zeros(20, dtype=torch.int64)
         for j in sharding.round_robin(20, rank, world):
