@@ -153,6 +153,37 @@ KCBS_API int kcbs_conflict_finish_dev(kcbs_ctx *ctx, int n_plans, int R, int T, 
                                       const int32_t *lengths, const uint64_t *keys, kcbs_conflict *out,
                                       void *stream);
 
+/* ---- (3b) merged pair (two cars planned as one 10-d system after SystemMerger::merge) -------------------
+ * State q = (x1, y1, v1, phi1, theta1, x2, y2, v2, phi2, theta2), control = (a1, phidot1, a2, phidot2):
+ * 10 / 4 SoA planes.  robot1 / robot2 index the world's robot_dims rows of the two cars.
+ *
+ * kcbs_propagate_pair_batch replaces propagateWhileValid over TwoSecondOrderCarStatePropagator::propagate
+ * (StatePropagatorDatabase.h:130-153: both cars integrated by TwoSecondOrderCarsODE :77-102 with the theta wrap of
+ * :106-117, then a car that was within hold_radius (1.5, :170) of its goal before the step keeps its state) and
+ * homogeneousTwo2ndOrderCarSystemSVC::isValid (StateValidityCheckerDatabase.h:225-261).  goals = (gx1, gy1, gx2, gy2).
+ * kcbs_validity_pair_batch replaces that isValid alone.  Layouts as in (1) / (2) with 10 planes. */
+KCBS_API int kcbs_propagate_pair_batch(kcbs_ctx *ctx, int robot1, int robot2, int64_t n, int64_t n_parents,
+                                       const float *parents, const int32_t *parent_idx, const float *controls,
+                                       const int32_t *steps, int max_steps, const float *goals, float hold_radius,
+                                       float *seg_out, float *final_out, int32_t *valid_steps);
+KCBS_API int kcbs_propagate_pair_batch_dev(kcbs_ctx *ctx, int robot1, int robot2, int64_t n, int64_t n_parents,
+                                           const float *parents, const int32_t *parent_idx, const float *controls,
+                                           const int32_t *steps, int max_steps, const float *goals, float hold_radius,
+                                           float *seg_out, float *final_out, int32_t *valid_steps, void *stream);
+KCBS_API int kcbs_validity_pair_batch(kcbs_ctx *ctx, int robot1, int robot2, int64_t n, const float *states,
+                                      uint32_t *bitmask);
+KCBS_API int kcbs_validity_pair_batch_dev(kcbs_ctx *ctx, int robot1, int robot2, int64_t n, const float *states,
+                                          uint32_t *bitmask, void *stream);
+/* Plan validation when some individuals are merged pairs: traj rows are BODIES (a merged individual contributes
+ * two consecutive rows), group[R] names the individual of every body; bodies of one individual are never tested
+ * against each other (areStatesValid of StateValidityCheckerDatabase.h:87-107 / :264-287 tests a merged
+ * individual's two cars against the other robot only).  Results name bodies.  group is a HOST pointer in both. */
+KCBS_API int kcbs_first_conflict_groups(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj,
+                                        const int32_t *lengths, const int32_t *group, kcbs_conflict *out);
+KCBS_API int kcbs_first_conflict_groups_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj,
+                                            const int32_t *lengths, const int32_t *group, kcbs_conflict *out,
+                                            void *stream);
+
 /* ---- (4) "next" rows: batched low-level planner and K-CBS high level -----------
  * These replace the un-vendored planners the reference allocates: oc::RRT through allocateControlRRT
  * (PlannerAllocatorDatabase.h:40-45) and omrc::KCBS (demo_*.cpp:155-168, Benchmark.h:151-173).  They are

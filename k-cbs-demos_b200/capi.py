@@ -79,7 +79,8 @@ EXPORTS = [
     "kcbs_propagate_batch_dev", "kcbs_validity_batch", "kcbs_validity_batch_dev", "kcbs_first_conflict",
     "kcbs_first_conflict_dev", "kcbs_conflict_keys_dev", "kcbs_conflict_finish_dev",
     "kcbs_measure_fp32_peak", "kcbs_measure_fp32x2_peak", "kcbs_launch_count", "kcbs_rrt_defaults",
-    "kcbs_kcbs_defaults", "kcbs_rrt_plan", "kcbs_kcbs_solve",
+    "kcbs_kcbs_defaults", "kcbs_rrt_plan", "kcbs_kcbs_solve", "kcbs_propagate_pair_batch", "kcbs_propagate_pair_batch_dev",
+    "kcbs_validity_pair_batch", "kcbs_validity_pair_batch_dev", "kcbs_first_conflict_groups", "kcbs_first_conflict_groups_dev",
 ]
 
 
@@ -129,6 +130,13 @@ def load_library() -> C.CDLL:
     lib.kcbs_rrt_plan.argtypes = [vp, i32, vp, vp, C.POINTER(RrtParams), i32, vp, vp, vp, vp, vp, i32, vp,
                                   C.POINTER(C.c_int32), C.POINTER(RrtStats)]
     lib.kcbs_kcbs_solve.argtypes = [vp, i32, vp, vp, C.POINTER(KcbsParams), i32, vp, vp, C.POINTER(KcbsStats)]
+    pair = [vp, i32, i32, i64, i64, vp, vp, vp, vp, i32, vp, C.c_float, vp, vp, vp]
+    lib.kcbs_propagate_pair_batch.argtypes = pair
+    lib.kcbs_propagate_pair_batch_dev.argtypes = pair + [vp]
+    lib.kcbs_validity_pair_batch.argtypes = [vp, i32, i32, i64, vp, vp]
+    lib.kcbs_validity_pair_batch_dev.argtypes = [vp, i32, i32, i64, vp, vp, vp]
+    lib.kcbs_first_conflict_groups.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.kcbs_first_conflict_groups_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.kcbs_launch_count.restype = i64
     lib.kcbs_launch_count.argtypes = [vp]
     _LIB = lib
@@ -325,6 +333,45 @@ class Context:
     def conflict_finish_dev(self, P, R, T, traj, lengths, keys, out, stream=None):
         self._check(self._lib.kcbs_conflict_finish_dev(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(keys),
                                                        _ptr(out), _stream(stream)))
+
+    # -- (3b) merged pair ------------------------------------------------------------------------
+    def propagate_pair_batch(self, robot1, robot2, parents, controls, goals, steps=None, parent_idx=None, max_steps=10,
+                             hold_radius=1.5):
+        """kcbs_propagate_pair_batch.  parents [10, n_parents], controls [4, n], goals (gx1, gy1, gx2, gy2).
+        Returns (seg [10, max_steps, n], final [10, n], valid_steps [n])."""
+        parents = np.ascontiguousarray(parents, dtype=np.float32)
+        controls = np.ascontiguousarray(controls, dtype=np.float32)
+        goals = np.ascontiguousarray(goals, dtype=np.float32)
+        n, n_parents = controls.shape[1], parents.shape[1]
+        steps = None if steps is None else np.ascontiguousarray(steps, dtype=np.int32)
+        parent_idx = None if parent_idx is None else np.ascontiguousarray(parent_idx, dtype=np.int32)
+        seg = np.zeros((10, max_steps, n), np.float32)
+        fin = np.zeros((10, n), np.float32)
+        valid = np.zeros(n, np.int32)
+        self._check(self._lib.kcbs_propagate_pair_batch(self._h, robot1, robot2, n, n_parents, _ptr(parents), _ptr(parent_idx),
+                                                        _ptr(controls), _ptr(steps), max_steps, _ptr(goals), hold_radius,
+                                                        _ptr(seg), _ptr(fin), _ptr(valid)))
+        return seg, fin, valid
+
+    def validity_pair_batch(self, robot1, robot2, states):
+        """kcbs_validity_pair_batch.  states [10, n] -> packed uint32 bitmask."""
+        states = np.ascontiguousarray(states, dtype=np.float32)
+        n = states.shape[1]
+        mask = np.zeros((n + 31) // 32, np.uint32)
+        self._check(self._lib.kcbs_validity_pair_batch(self._h, robot1, robot2, n, _ptr(states), _ptr(mask)))
+        return mask
+
+    def first_conflict_groups(self, traj, group, lengths=None):
+        """kcbs_first_conflict_groups.  traj [P, R, 3, T] rows are bodies; group [R] = individual of each body."""
+        traj = np.ascontiguousarray(traj, dtype=np.float32)
+        if traj.ndim == 3:
+            traj = traj[None]
+        P, R, _, T = traj.shape
+        group = np.ascontiguousarray(group, dtype=np.int32)
+        lengths = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int32).reshape(P, R)
+        res = np.zeros(P, CONFLICT_DTYPE)
+        self._check(self._lib.kcbs_first_conflict_groups(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(group), _ptr(res)))
+        return res
 
     # -- (4) next rows: batched low-level planner and K-CBS -----------------------------------
     def rrt_params(self, **kw) -> RrtParams:

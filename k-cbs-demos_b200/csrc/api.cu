@@ -428,7 +428,7 @@ int kcbs_conflict_keys_dev(kcbs_ctx *ctx, int n_plans, int R, int T, int k_lo, i
     ctx->launches += 1;
     if (k_hi > k_lo) {
         ConflictArgs a;
-        a.traj = traj; a.lengths = lengths; a.keys = (unsigned long long *)keys; a.tickets = nullptr; a.out = nullptr;
+        a.traj = traj; a.lengths = lengths; a.keys = (unsigned long long *)keys; a.group = nullptr; a.tickets = nullptr; a.out = nullptr;
         a.P = n_plans; a.R = R; a.T = T; a.k_lo = k_lo; a.k_hi = k_hi;
         KCBS_CUDA(ctx, launch_conflict_keys(ctx->world, a, s));
         ctx->launches += 1;
@@ -453,8 +453,8 @@ int kcbs_conflict_finish_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const flo
     return KCBS_OK;
 }
 
-int kcbs_first_conflict_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
-                            kcbs_conflict *out, void *stream)
+static int first_conflict_dev_impl(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
+                                   const int *d_group, kcbs_conflict *out, void *stream)
 {
     if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
     int st = check_plan_args(ctx, n_plans, R, T);
@@ -483,15 +483,46 @@ int kcbs_first_conflict_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const floa
     }
     ConflictArgs a;
     a.traj = traj; a.lengths = lengths; a.keys = (unsigned long long *)ctx->keys.p;
-    a.tickets = (int *)((uint64_t *)ctx->keys.p + ctx->key_plans); a.out = out;
+    a.tickets = (int *)((uint64_t *)ctx->keys.p + ctx->key_plans); a.out = out; a.group = d_group;
     a.P = n_plans; a.R = R; a.T = T; a.k_lo = 0; a.k_hi = T;
     KCBS_CUDA(ctx, launch_conflict_keys(ctx->world, a, s));
     ctx->launches += 1;
     return KCBS_OK;
 }
 
+int kcbs_first_conflict_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
+                            kcbs_conflict *out, void *stream)
+{
+    return first_conflict_dev_impl(ctx, n_plans, R, T, traj, lengths, nullptr, out, stream);
+}
+
+// uploads the body -> individual table (tiny) into the context and runs the grouped scan
+int kcbs_first_conflict_groups_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
+                                   const int32_t *group, kcbs_conflict *out, void *stream)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    if (!group) return first_conflict_dev_impl(ctx, n_plans, R, T, traj, lengths, nullptr, out, stream);
+    if (R < 1 || R > ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "R exceeds the robots of this world");
+    int st = reserve(ctx, ctx->in3, sizeof(int32_t) * KCBS_MAX_ROBOTS);
+    if (st != KCBS_OK) return st;
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in3.p, group, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+    KCBS_CUDA(ctx, cudaStreamSynchronize(s));  // `group` is the caller's host buffer
+    return first_conflict_dev_impl(ctx, n_plans, R, T, traj, lengths, (const int *)ctx->in3.p, out, stream);
+}
+
+int kcbs_first_conflict_groups(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
+                               const int32_t *group, kcbs_conflict *out);
+
 int kcbs_first_conflict(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
                         kcbs_conflict *out)
+{
+    return kcbs_first_conflict_groups(ctx, n_plans, R, T, traj, lengths, nullptr, out);
+}
+
+int kcbs_first_conflict_groups(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
+                               const int32_t *group, kcbs_conflict *out)
 {
     if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
     int st = check_plan_args(ctx, n_plans, R, T);
@@ -507,10 +538,110 @@ int kcbs_first_conflict(kcbs_ctx *ctx, int n_plans, int R, int T, const float *t
         return st;
     if (b_traj) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in0.p, traj, b_traj, cudaMemcpyHostToDevice, s));
     if (lengths) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in2.p, lengths, b_len, cudaMemcpyHostToDevice, s));
-    st = kcbs_first_conflict_dev(ctx, n_plans, R, T, (const float *)ctx->in0.p,
-                                 lengths ? (const int32_t *)ctx->in2.p : nullptr, (kcbs_conflict *)ctx->out0.p, s);
+    st = kcbs_first_conflict_groups_dev(ctx, n_plans, R, T, (const float *)ctx->in0.p,
+                                        lengths ? (const int32_t *)ctx->in2.p : nullptr, group, (kcbs_conflict *)ctx->out0.p, s);
     if (st != KCBS_OK) return st;
     KCBS_CUDA(ctx, cudaMemcpyAsync(out, ctx->out0.p, b_out, cudaMemcpyDeviceToHost, s));
+    KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+    return KCBS_OK;
+}
+
+/* ---- (3b) merged pair ----------------------------------------------------------------------- */
+
+int kcbs_propagate_pair_batch_dev(kcbs_ctx *ctx, int robot1, int robot2, int64_t n, int64_t n_parents, const float *parents,
+                                  const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,
+                                  const float *goals, float hold_radius, float *seg_out, float *final_out,
+                                  int32_t *valid_steps, void *stream)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    int st;
+    if ((st = check_robot(ctx, robot1)) || (st = check_robot(ctx, robot2))) return st;
+    if (n < 0 || n_parents < 1 || max_steps < 0 || max_steps > KCBS_MAX_STEPS)
+        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n, n_parents or max_steps out of range");
+    if (n == 0) return KCBS_OK;
+    if (!parents || !controls || !goals) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "parents / controls / goals is null");
+    if (!parent_idx && n_parents != 1 && n_parents != n)
+        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "without parent_idx, n_parents must be 1 or n");
+    PairArgs a;
+    a.n = n; a.n_parents = n_parents; a.parents = parents; a.parent_idx = parent_idx; a.controls = controls; a.steps = steps;
+    a.seg = seg_out; a.fin = final_out; a.valid_steps = valid_steps; a.max_steps = max_steps; a.robot1 = robot1; a.robot2 = robot2;
+    for (int i = 0; i < 4; ++i) a.goals[i] = goals[i];
+    a.hold_radius = hold_radius;
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCBS_CUDA(ctx, launch_propagate_pair(ctx->world, a, pick(ctx, stream)));
+    ctx->launches += 1;
+    return KCBS_OK;
+}
+
+int kcbs_propagate_pair_batch(kcbs_ctx *ctx, int robot1, int robot2, int64_t n, int64_t n_parents, const float *parents,
+                              const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,
+                              const float *goals, float hold_radius, float *seg_out, float *final_out, int32_t *valid_steps)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    if (n < 0 || n_parents < 1 || max_steps < 0 || max_steps > KCBS_MAX_STEPS)
+        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n, n_parents or max_steps out of range");
+    if (n == 0) return KCBS_OK;
+    if (!parents || !controls || !goals) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "parents / controls / goals is null");
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t b_par = sizeof(float) * 10 * (size_t)n_parents, b_ctl = sizeof(float) * 4 * (size_t)n;
+    const size_t b_idx = sizeof(int32_t) * (size_t)n;
+    const size_t b_seg = sizeof(float) * 10 * (size_t)max_steps * (size_t)n, b_fin = sizeof(float) * 10 * (size_t)n;
+    int st;
+    if ((st = reserve(ctx, ctx->in0, b_par)) || (st = reserve(ctx, ctx->in1, b_ctl)) ||
+        (st = reserve(ctx, ctx->in2, parent_idx ? b_idx : 0)) || (st = reserve(ctx, ctx->in3, steps ? b_idx : 0)) ||
+        (st = reserve(ctx, ctx->out0, seg_out ? b_seg : 0)) || (st = reserve(ctx, ctx->out1, final_out ? b_fin : 0)) ||
+        (st = reserve(ctx, ctx->out2, b_idx)))
+        return st;
+    KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in0.p, parents, b_par, cudaMemcpyHostToDevice, s));
+    KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in1.p, controls, b_ctl, cudaMemcpyHostToDevice, s));
+    if (parent_idx) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in2.p, parent_idx, b_idx, cudaMemcpyHostToDevice, s));
+    if (steps) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in3.p, steps, b_idx, cudaMemcpyHostToDevice, s));
+    st = kcbs_propagate_pair_batch_dev(ctx, robot1, robot2, n, n_parents, (const float *)ctx->in0.p,
+                                       parent_idx ? (const int32_t *)ctx->in2.p : nullptr, (const float *)ctx->in1.p,
+                                       steps ? (const int32_t *)ctx->in3.p : nullptr, max_steps, goals, hold_radius,
+                                       seg_out ? (float *)ctx->out0.p : nullptr, final_out ? (float *)ctx->out1.p : nullptr,
+                                       (int32_t *)ctx->out2.p, s);
+    if (st != KCBS_OK) return st;
+    if (seg_out) KCBS_CUDA(ctx, cudaMemcpyAsync(seg_out, ctx->out0.p, b_seg, cudaMemcpyDeviceToHost, s));
+    if (final_out) KCBS_CUDA(ctx, cudaMemcpyAsync(final_out, ctx->out1.p, b_fin, cudaMemcpyDeviceToHost, s));
+    if (valid_steps) KCBS_CUDA(ctx, cudaMemcpyAsync(valid_steps, ctx->out2.p, b_idx, cudaMemcpyDeviceToHost, s));
+    KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+    return KCBS_OK;
+}
+
+int kcbs_validity_pair_batch_dev(kcbs_ctx *ctx, int robot1, int robot2, int64_t n, const float *states, uint32_t *bitmask,
+                                 void *stream)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    int st;
+    if ((st = check_robot(ctx, robot1)) || (st = check_robot(ctx, robot2))) return st;
+    if (n < 0) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n is negative");
+    if (n == 0) return KCBS_OK;
+    if (!states || !bitmask) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "states / bitmask is null");
+    PairValidArgs a;
+    a.n = n; a.states = states; a.bitmask = bitmask; a.robot1 = robot1; a.robot2 = robot2;
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCBS_CUDA(ctx, launch_validity_pair(ctx->world, a, pick(ctx, stream)));
+    ctx->launches += 1;
+    return KCBS_OK;
+}
+
+int kcbs_validity_pair_batch(kcbs_ctx *ctx, int robot1, int robot2, int64_t n, const float *states, uint32_t *bitmask)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    if (n < 0) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n is negative");
+    if (n == 0) return KCBS_OK;
+    if (!states || !bitmask) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "states / bitmask is null");
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t b_in = sizeof(float) * 10 * (size_t)n, b_out = sizeof(uint32_t) * (size_t)((n + 31) / 32);
+    int st;
+    if ((st = reserve(ctx, ctx->in0, b_in)) || (st = reserve(ctx, ctx->out0, b_out))) return st;
+    KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in0.p, states, b_in, cudaMemcpyHostToDevice, s));
+    st = kcbs_validity_pair_batch_dev(ctx, robot1, robot2, n, (const float *)ctx->in0.p, (uint32_t *)ctx->out0.p, s);
+    if (st != KCBS_OK) return st;
+    KCBS_CUDA(ctx, cudaMemcpyAsync(bitmask, ctx->out0.p, b_out, cudaMemcpyDeviceToHost, s));
     KCBS_CUDA(ctx, cudaStreamSynchronize(s));
     return KCBS_OK;
 }

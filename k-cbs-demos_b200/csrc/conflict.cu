@@ -242,6 +242,7 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
                 bool have1 = false;
                 float c1 = 1.0f, s1 = 0.0f;
                 for (int r2 = r1 + 1; r2 < R; ++r2) {
+                    if (a.group && a.group[r1] == a.group[r2]) continue;  // two bodies of one merged individual
                     const float x2 = xs[r2 * kTile + tid], y2 = ys[r2 * kTile + tid];
                     const float dx = x2 - x1, dy = y2 - y1;
                     const float rs = w.rob_rad[r1] + w.rob_rad[r2];

@@ -41,10 +41,32 @@ struct ValidArgs {
     int robot;
 };
 
+struct PairArgs {              // merged pair: 10-d states, 4-d controls
+    long long n, n_parents;
+    const float *parents;      // [10][n_parents]
+    const int *parent_idx;
+    const float *controls;     // [4][n]
+    const int *steps;
+    float *seg;                // [10][max_steps][n] or null
+    float *fin;                // [10][n] or null
+    int *valid_steps;
+    int max_steps, robot1, robot2;
+    float goals[4];            // gx1, gy1, gx2, gy2
+    float hold_radius;         // 1.5, StatePropagatorDatabase.h:170
+};
+
+struct PairValidArgs {
+    long long n;
+    const float *states;       // [10][n]
+    uint32_t *bitmask;
+    int robot1, robot2;
+};
+
 struct ConflictArgs {
     const float *traj;         // [P][R][3][T]
     const int *lengths;        // [P][R] or null
     unsigned long long *keys;  // [P], pre-set to kNoConflict
+    const int *group;          // [R] individual of each body (same group = never tested against each other) or null
     int *tickets;              // [P] zeroed CTA tickets (fused finish) or null
     kcbs_conflict *out;        // [P] results written by the last CTA of each plan (fused finish) or null
     int P, R, T;
@@ -61,6 +83,8 @@ struct FinishArgs {
 
 cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t stream);
 cudaError_t launch_validity(const DevWorld &w, const ValidArgs &a, cudaStream_t stream);
+cudaError_t launch_propagate_pair(const DevWorld &w, const PairArgs &a, cudaStream_t stream);
+cudaError_t launch_validity_pair(const DevWorld &w, const PairValidArgs &a, cudaStream_t stream);
 cudaError_t launch_conflict_keys(const DevWorld &w, const ConflictArgs &a, cudaStream_t stream);
 cudaError_t launch_conflict_finish(const DevWorld &w, const FinishArgs &a, cudaStream_t stream);
 cudaError_t launch_fill_keys(unsigned long long *keys, int *tickets, int n, cudaStream_t stream);

@@ -33,20 +33,13 @@
 // slots (a warp's stores stay inside the CTA's 1 KB row windows, which L2 merges into full lines).
 #include <cstddef>
 
-#include "kcbs_device.cuh"
+#include "car_dynamics.cuh"
 #include "kernels.h"
 
 namespace kcbs {
 
 constexpr int kPropThreads = 128;  // threads per CTA
 constexpr int kPropSamples = 256;  // samples per CTA (two per thread)
-
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 
 // Dynamic-obstacle constraints of the K-CBS low level (the fork tests `next` against the constraining robot's
 // state at that time through areStatesValid, StateValidityCheckerDatabase.h:78-125).
@@ -88,16 +81,8 @@ __device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropAr
     const float ua = a.controls[i];
     const float uw = a.controls[a.n + i];
 
-    const float h = w.h, hh = 0.5f * w.h, h6 = w.h * (1.0f / 6.0f);
     const float hl = w.rob_hl[a.robot], hw = w.rob_hw[a.robot];
-    const float kscale = hh * w.inv_len;  // K = (h/2) k_theta = kscale * v * tan(phi)
-
-    // tan of the half-sub-step increment of phi
-    const float dl = hh * uw, dl2 = dl * dl;
-    const float td = dl * fmaf(dl2, fmaf(dl2, 2.0f / 15.0f, 1.0f / 3.0f), 1.0f);
-    // per-sub-step increments of U = kscale * v and W = (h/6) v
-    const float dUh = kscale * hh * ua, dU = kscale * h * ua;
-    const float dW2 = 2.0f * h6 * hh * ua, dW = h6 * h * ua;
+    const CarConsts k = car_consts(w, ua, uw);
 
     float offx = 0.0f, offy = 0.0f;                         // position offset from the parent
     float xs = x0, ys = y0, vs = v0, ps = phi0, ts = th0;   // last valid state
@@ -105,49 +90,7 @@ __device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropAr
     const long long plane = (long long)a.max_steps * a.n;
 
     for (int j = 0; j < st; ++j) {
-        float sp, cp, s1, c1;
-        sincosf(ps, &sp, &cp);
-        __sincosf(ts, &s1, &c1);
-        float T = sp * rcp_approx(cp);
-        float U1 = kscale * vs, W1 = h6 * vs;
-        float K1 = U1 * T;   // (h/2) k_theta at stage 1 of sub-step 0
-        float toff = 0.0f;   // heading offset from ts within this step
-
-#pragma unroll 2
-        for (int n = 0; n < w.n_sub; ++n) {
-            const float U2 = U1 + dUh, U4 = U1 + dU;
-            const float W2 = fmaf(2.0f, W1, dW2), W4 = W1 + dW;
-            // tan(phi) at the half and the full sub-step
-            const float T2 = (T + td) * rcp_approx(fmaf(-T, td, 1.0f));
-            T = (T2 + td) * rcp_approx(fmaf(-T2, td, 1.0f));
-            const float K2 = U2 * T2, K4 = U4 * T;
-
-            // stage 2 heading = stage 1 + K1 (2nd-order rotation)
-            const float h2 = -0.5f * K1;
-            const float c2 = fmaf(fmaf(c1, h2, -s1), K1, c1);
-            const float s2 = fmaf(fmaf(s1, h2, c1), K1, s1);
-            // stage 3 heading = stage 2 + (K2 - K1): only cos2 + cos3 and sin2 + sin3 are needed
-            const float e3 = K2 - K1;
-            const float c23 = fmaf(-s2, e3, c2 + c2);
-            const float s23 = fmaf(c2, e3, s2 + s2);
-            // stage 4 heading = stage 1 + 2 K2 (k3 == k2) = stage 2 + (2 K2 - K1)
-            const float e4 = fmaf(2.0f, K2, -K1), h4 = -0.5f * e4;
-            const float c4 = fmaf(fmaf(c2, h4, -s2), e4, c2);
-            const float s4 = fmaf(fmaf(s2, h4, c2), e4, s2);
-
-            offx = fmaf(W1, c1, fmaf(W2, c23, fmaf(W4, c4, offx)));
-            offy = fmaf(W1, s1, fmaf(W2, s23, fmaf(W4, s4, offy)));
-
-            // heading: theta += h/6 (k1 + 4 k2 + k4) = (K1 + 4 K2 + K4) / 3; next stage 1 = stage 4 + (that - 2 K2)
-            const float dth = (1.0f / 3.0f) * fmaf(4.0f, K2, K1 + K4);
-            toff += dth;
-            const float e1 = fmaf(-2.0f, K2, dth);
-            c1 = fmaf(-s4, e1, c4);
-            s1 = fmaf(c4, e1, s4);
-            K1 = K4;
-            U1 = U4;
-            W1 = W4;
-        }
+        const float toff = car_step(k, w.n_sub, vs, ps, ts, offx, offy);
 
         const float t1 = (float)(j + 1) * w.step;
         const float xn = x0 + offx, yn = y0 + offy;

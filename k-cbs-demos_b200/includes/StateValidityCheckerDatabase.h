@@ -99,12 +99,12 @@ public:
     // both cars inside the bounds and clear of every obstacle, and not overlapping each other (reference :225-261)
     bool isValid(const ob::State *state) const override
     {
-        float a[5], b[5];
-        kcbs::car_reals(state, 0, a);
-        kcbs::car_reals(state, 1, b);
-        auto ctx = context();  // robots: 0 = robot1, 1 = robot2
-        if (!kcbs::gpu_is_valid(*ctx, 0, a) || !kcbs::gpu_is_valid(*ctx, 1, b)) return false;
-        return kcbs::gpu_pair_valid(*ctx, a, b);
+        float q[10];
+        kcbs::car_reals(state, 0, q);
+        kcbs::car_reals(state, 1, q + 5);
+        uint32_t mask = 0;
+        context()->isValidPair(0, 1, 1, q, &mask);  // robots of the context: 0 = robot1, 1 = robot2 (k_validity_pair)
+        return (mask & 1u) != 0;
     }
 
     // do both cars avoid the (single) robot of state2.first at state2.second?  (reference :264-287)

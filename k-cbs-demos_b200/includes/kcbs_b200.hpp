@@ -75,6 +75,12 @@ public:
         check(kcbs_validity_batch(h_.get(), robot, n, states, bitmask));
     }
 
+    // homogeneousTwo2ndOrderCarSystemSVC::isValid for n 10-d states (merged pair robot1 + robot2)
+    void isValidPair(int robot1, int robot2, int64_t n, const float *states, uint32_t *bitmask) const
+    {
+        check(kcbs_validity_pair_batch(h_.get(), robot1, robot2, n, states, bitmask));
+    }
+
     // KCBS::findConflicts for n_plans plans
     void firstConflict(int n_plans, int R, int T, const float *traj, const int32_t *lengths, kcbs_conflict *out) const
     {

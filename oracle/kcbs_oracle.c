@@ -477,7 +477,7 @@ static void traj_state(const float *traj, int T, int r, int k, const int32_t *le
 }
 
 static int64_t first_conflict_impl(const orc_world *w, int R, int T, const float *traj, const int32_t *lengths,
-                                   orc_conflict *out, double *min_margin, int full_scan)
+                                   orc_conflict *out, double *min_margin, int full_scan, const int32_t *group)
 {
     int k, r1, r2, found = 0;
     int64_t evals = 0;
@@ -490,6 +490,7 @@ static int64_t first_conflict_impl(const orc_world *w, int R, int T, const float
             for (r2 = r1 + 1; r2 < R; ++r2) {
                 double s2[3], m;
                 int ok;
+                if (group && group[r1] == group[r2]) continue;
                 traj_state(traj, T, r2, k, lengths, s2);
                 ok = orc_pair_valid(w, r1, s1, r2, s2, min_margin ? &m : NULL);
                 ++evals;
@@ -523,7 +524,13 @@ static int64_t first_conflict_impl(const orc_world *w, int R, int T, const float
 int64_t orc_first_conflict(const orc_world *w, int R, int T, const float *traj, const int32_t *lengths,
                            orc_conflict *out, double *min_margin)
 {
-    return first_conflict_impl(w, R, T, traj, lengths, out, min_margin, 0);
+    return first_conflict_impl(w, R, T, traj, lengths, out, min_margin, 0, NULL);
+}
+
+int64_t orc_first_conflict_groups(const orc_world *w, int R, int T, const float *traj, const int32_t *lengths,
+                                  const int32_t *group, orc_conflict *out, double *min_margin)
+{
+    return first_conflict_impl(w, R, T, traj, lengths, out, min_margin, 0, group);
 }
 
 typedef struct {
@@ -542,7 +549,7 @@ static void fc_range(void *p, int64_t lo, int64_t hi)
     int64_t i, ev = 0;
     for (i = lo; i < hi; ++i)
         ev += first_conflict_impl(j->w, j->R, j->T, j->traj + i * (int64_t)j->R * 3 * j->T,
-                                  j->lengths ? j->lengths + i * j->R : NULL, &j->out[i], NULL, j->full_scan);
+                                  j->lengths ? j->lengths + i * j->R : NULL, &j->out[i], NULL, j->full_scan, NULL);
     pthread_mutex_lock(&j->mu);
     j->evals += ev;
     pthread_mutex_unlock(&j->mu);
@@ -558,4 +565,157 @@ int64_t orc_first_conflict_batch(const orc_world *w, int P, int R, int T, const 
     parallel_for(P, n_threads, fc_range, &j);
     pthread_mutex_destroy(&j.mu);
     return j.evals;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Merged pair: StatePropagatorDatabase.h:77-171, StateValidityCheckerDatabase.h:214-261
+ * ---------------------------------------------------------------------------------------- */
+int orc_pair_is_valid(const orc_world *w, int r1, int r2, const double q[10], double *margin)
+{
+    double m1, m2, mp;
+    int ok = 1;
+    const double sa[3] = {q[0], q[1], q[4]}, sb[3] = {q[5], q[6], q[9]};
+    /* si_->satisfiesBounds on the 10-d compound space (:228) followed by the pair test (:237-241) and both cars
+     * against the obstacles (:244-258); orc_is_valid covers bounds + obstacles of one car */
+    if (!orc_is_valid(w, r1, q, &m1)) ok = 0;
+    if (!orc_is_valid(w, r2, q + 5, &m2)) ok = 0;
+    if (!orc_pair_valid(w, r1, sa, r2, sb, &mp)) ok = 0;
+    if (margin) {
+        double m = m1 < m2 ? m1 : m2;
+        *margin = m < mp ? m : mp;
+    }
+    return ok;
+}
+
+void orc_pair_propagate(const orc_world *w, const double q_in[10], const double u[4], double duration, const double goals[4],
+                        double hold_radius, double q_out[10])
+{
+    int c, i;
+    for (c = 0; c < 2; ++c) {
+        /* TwoSecondOrderCarsODE integrates the cars independently (:87-101): same RK4 per car */
+        orc_propagate(w, q_in + 5 * c, u + 2 * c, duration, q_out + 5 * c);
+        /* override when the car was in its goal region before the step (:137-152) */
+        if (sqrt(pow(q_in[5 * c] - goals[2 * c], 2) + pow(q_in[5 * c + 1] - goals[2 * c + 1], 2)) < hold_radius)
+            for (i = 0; i < 5; ++i) q_out[5 * c + i] = q_in[5 * c + i];
+    }
+}
+
+int orc_pair_propagate_while_valid(const orc_world *w, int r1, int r2, const double q0[10], const double u[4], int steps,
+                                   const double goals[4], double hold_radius, double *seg, double q_final[10])
+{
+    double cur[10], next[10];
+    int i;
+    memcpy(cur, q0, sizeof cur);
+    for (i = 0; i < steps; ++i) {
+        orc_pair_propagate(w, cur, u, w->step_size, goals, hold_radius, next);
+        if (!orc_pair_is_valid(w, r1, r2, next, NULL)) break;
+        memcpy(cur, next, sizeof cur);
+        if (seg) memcpy(seg + 10 * i, cur, sizeof cur);
+    }
+    if (q_final) memcpy(q_final, cur, sizeof cur);
+    return i;
+}
+
+typedef struct {
+    const orc_world *w;
+    int r1, r2;
+    int64_t n, n_parents;
+    const float *parents;
+    const int32_t *parent_idx;
+    const float *controls;
+    const int32_t *steps;
+    int max_steps;
+    const double *goals;
+    double hold_radius;
+    double *seg_out, *final_out, *hold_margin;
+    int32_t *valid_steps;
+    int64_t calls;
+    pthread_mutex_t mu;
+} pair_job;
+
+static void pair_range(void *p, int64_t lo, int64_t hi)
+{
+    pair_job *j = (pair_job *)p;
+    int64_t i, calls = 0;
+    double seg[10 * 64];
+    for (i = lo; i < hi; ++i) {
+        const int64_t pi = j->parent_idx ? j->parent_idx[i] : (j->n_parents == 1 ? 0 : i);
+        double q0[10], qf[10], u[4];
+        int c, s, nv, st = j->steps ? j->steps[i] : j->max_steps;
+        if (st > j->max_steps) st = j->max_steps;
+        if (st > 64) st = 64;
+        for (c = 0; c < 10; ++c) q0[c] = (double)j->parents[c * j->n_parents + pi];
+        for (c = 0; c < 4; ++c) u[c] = (double)j->controls[c * j->n + i];
+        nv = orc_pair_propagate_while_valid(j->w, j->r1, j->r2, q0, u, st, j->goals, j->hold_radius, seg, qf);
+        calls += (nv < st) ? nv + 1 : nv;
+        if (j->valid_steps) j->valid_steps[i] = nv;
+        if (j->seg_out)
+            for (s = 0; s < nv; ++s)
+                for (c = 0; c < 10; ++c) j->seg_out[((int64_t)c * j->max_steps + s) * j->n + i] = seg[10 * s + c];
+        if (j->final_out)
+            for (c = 0; c < 10; ++c) j->final_out[c * j->n + i] = qf[c];
+        if (j->hold_margin) {
+            /* how close any freeze decision of this sample came to the hold radius */
+            double mm = INFINITY;
+            const double *cur = q0;
+            for (s = 0; s <= nv && s < st; ++s) {
+                for (c = 0; c < 2; ++c) {
+                    const double d = sqrt(pow(cur[5 * c] - j->goals[2 * c], 2) + pow(cur[5 * c + 1] - j->goals[2 * c + 1], 2));
+                    if (fabs(d - j->hold_radius) < mm) mm = fabs(d - j->hold_radius);
+                }
+                if (s < nv) cur = seg + 10 * s;
+            }
+            j->hold_margin[i] = mm;
+        }
+    }
+    pthread_mutex_lock(&j->mu);
+    j->calls += calls;
+    pthread_mutex_unlock(&j->mu);
+}
+
+int64_t orc_pair_propagate_batch(const orc_world *w, int r1, int r2, int64_t n, int64_t n_parents, const float *parents,
+                                 const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,
+                                 const double goals[4], double hold_radius, double *seg_out, double *final_out,
+                                 int32_t *valid_steps, double *hold_margin, int n_threads)
+{
+    pair_job j;
+    j.w = w; j.r1 = r1; j.r2 = r2; j.n = n; j.n_parents = n_parents; j.parents = parents; j.parent_idx = parent_idx;
+    j.controls = controls; j.steps = steps; j.max_steps = max_steps; j.goals = goals; j.hold_radius = hold_radius;
+    j.seg_out = seg_out; j.final_out = final_out; j.hold_margin = hold_margin; j.valid_steps = valid_steps; j.calls = 0;
+    pthread_mutex_init(&j.mu, NULL);
+    parallel_for(n, n_threads, pair_range, &j);
+    pthread_mutex_destroy(&j.mu);
+    return j.calls;
+}
+
+typedef struct {
+    const orc_world *w;
+    int r1, r2;
+    int64_t n;
+    const float *states;
+    uint8_t *valid;
+    double *margin;
+} pval_job;
+
+static void pval_range(void *p, int64_t lo, int64_t hi)
+{
+    pval_job *j = (pval_job *)p;
+    int64_t i;
+    for (i = lo; i < hi; ++i) {
+        double q[10], m;
+        int c, ok;
+        for (c = 0; c < 10; ++c) q[c] = (double)j->states[c * j->n + i];
+        ok = orc_pair_is_valid(j->w, j->r1, j->r2, q, &m);
+        if (j->valid) j->valid[i] = (uint8_t)ok;
+        if (j->margin) j->margin[i] = m;
+    }
+}
+
+int64_t orc_pair_validity_batch(const orc_world *w, int r1, int r2, int64_t n, const float *states, uint8_t *valid,
+                                double *margin, int n_threads)
+{
+    pval_job j;
+    j.w = w; j.r1 = r1; j.r2 = r2; j.n = n; j.states = states; j.valid = valid; j.margin = margin;
+    parallel_for(n, n_threads, pval_range, &j);
+    return n;
 }

@@ -128,6 +128,39 @@ int64_t orc_first_conflict(const orc_world *w, int R, int T, const float *traj, 
 int64_t orc_first_conflict_batch(const orc_world *w, int P, int R, int T, const float *traj, const int32_t *lengths,
                                  orc_conflict *out, int full_scan, int n_threads);
 
+/* ---- merged pair (two cars planned as one 10-d system after a K-CBS merge) ------------------------------ */
+
+/* homogeneousTwo2ndOrderCarSystemSVC::isValid, StateValidityCheckerDatabase.h:225-261: both cars inside the bounds,
+ * the two cars not overlapping, both cars clear of every obstacle.  q = (x1, y1, v1, phi1, theta1, x2, ...).
+ * Each car is tested with its own rectangle (the reference uses robot1_'s shape and radius for both in the obstacle
+ * loop, :245-256, which is the same thing in its homogeneous scenes). */
+int orc_pair_is_valid(const orc_world *w, int r1, int r2, const double q[10], double *margin);
+
+/* TwoSecondOrderCarStatePropagator::propagate, StatePropagatorDatabase.h:130-153: both cars are integrated
+ * (TwoSecondOrderCarsODE :77-102 + post-integration wrap :106-117), then a car whose position BEFORE the step was
+ * within hold_radius (1.5, :170) of its goal keeps its previous state.  goals = (gx1, gy1, gx2, gy2). */
+void orc_pair_propagate(const orc_world *w, const double q_in[10], const double u[4], double duration, const double goals[4],
+                        double hold_radius, double q_out[10]);
+
+/* propagateWhileValid of the merged system. seg (optional) = steps x 10 doubles. */
+int orc_pair_propagate_while_valid(const orc_world *w, int r1, int r2, const double q0[10], const double u[4], int steps,
+                                   const double goals[4], double hold_radius, double *seg, double q_final[10]);
+
+/* Batched drivers, float32 I/O: parents [10][n_parents], controls [4][n], seg_out [10][max_steps][n] doubles,
+ * final_out [10][n], hold_margin (optional) [n] = min over (step, car) of |distance to goal - hold_radius|. */
+int64_t orc_pair_propagate_batch(const orc_world *w, int r1, int r2, int64_t n, int64_t n_parents, const float *parents,
+                                 const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,
+                                 const double goals[4], double hold_radius, double *seg_out, double *final_out,
+                                 int32_t *valid_steps, double *hold_margin, int n_threads);
+int64_t orc_pair_validity_batch(const orc_world *w, int r1, int r2, int64_t n, const float *states, uint8_t *valid,
+                                double *margin, int n_threads);
+
+/* findConflicts over individuals some of which are merged: bodies with the same group id belong to one individual
+ * and are never tested against each other (their mutual collision is part of that individual's isValid).
+ * Results name bodies (rows of traj). */
+int64_t orc_first_conflict_groups(const orc_world *w, int R, int T, const float *traj, const int32_t *lengths,
+                                  const int32_t *group, orc_conflict *out, double *min_margin);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,15 @@ def lib():
         L.orc_first_conflict.argtypes = [W, i32, i32, vp, vp, C.POINTER(OrcConflict), dp]
         L.orc_first_conflict_batch.restype = i64
         L.orc_first_conflict_batch.argtypes = [W, i32, i32, i32, vp, vp, vp, i32, i32]
+        L.orc_pair_is_valid.argtypes = [W, i32, i32, dp, dp]
+        L.orc_pair_propagate.argtypes = [W, dp, dp, dbl, dp, dbl, dp]
+        L.orc_pair_propagate_while_valid.argtypes = [W, i32, i32, dp, dp, i32, dp, dbl, dp, dp]
+        L.orc_pair_propagate_batch.restype = i64
+        L.orc_pair_propagate_batch.argtypes = [W, i32, i32, i64, i64, vp, vp, vp, vp, i32, dp, dbl, vp, vp, vp, vp, i32]
+        L.orc_pair_validity_batch.restype = i64
+        L.orc_pair_validity_batch.argtypes = [W, i32, i32, i64, vp, vp, vp, i32]
+        L.orc_first_conflict_groups.restype = i64
+        L.orc_first_conflict_groups.argtypes = [W, i32, i32, vp, vp, vp, C.POINTER(OrcConflict), dp]
         _LIB = L
     return _LIB
 
@@ -235,3 +244,54 @@ class Oracle:
         evals = self.L.orc_first_conflict_batch(C.byref(self.w), P, R, T, _p(traj), _p(lengths), _p(out),
                                                 int(full_scan), n_threads)
         return out, int(evals)
+
+    # ---- merged pair -------------------------------------------------------------------------------
+    def pair_is_valid(self, q, r1=0, r2=1):
+        qa, qp = _d(q)
+        m = C.c_double()
+        ok = self.L.orc_pair_is_valid(C.byref(self.w), r1, r2, qp, C.byref(m))
+        return bool(ok), m.value
+
+    def pair_propagate(self, q, u, goals, duration=None, hold_radius=1.5):
+        qa, qp = _d(q)
+        ua, up = _d(u)
+        ga, gp = _d(goals)
+        out = np.zeros(10)
+        self.L.orc_pair_propagate(C.byref(self.w), qp, up, self.w.step_size if duration is None else duration, gp, hold_radius,
+                                  out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def pair_propagate_batch(self, r1, r2, parents, controls, goals, steps=None, parent_idx=None, max_steps=10, hold_radius=1.5,
+                             n_threads=1):
+        parents = np.ascontiguousarray(parents, dtype=np.float32)
+        controls = np.ascontiguousarray(controls, dtype=np.float32)
+        ga, gp = _d(goals)
+        n, n_parents = controls.shape[1], parents.shape[1]
+        steps = None if steps is None else np.ascontiguousarray(steps, dtype=np.int32)
+        parent_idx = None if parent_idx is None else np.ascontiguousarray(parent_idx, dtype=np.int32)
+        seg = np.zeros((10, max_steps, n))
+        fin = np.zeros((10, n))
+        valid = np.zeros(n, np.int32)
+        hold = np.zeros(n)
+        calls = self.L.orc_pair_propagate_batch(C.byref(self.w), r1, r2, n, n_parents, _p(parents), _p(parent_idx), _p(controls),
+                                                _p(steps), max_steps, gp, hold_radius, _p(seg), _p(fin), _p(valid), _p(hold),
+                                                n_threads)
+        return seg, fin, valid, hold, int(calls)
+
+    def pair_validity_batch(self, r1, r2, states, n_threads=1):
+        states = np.ascontiguousarray(states, dtype=np.float32)
+        n = states.shape[1]
+        valid = np.zeros(n, np.uint8)
+        margin = np.zeros(n)
+        self.L.orc_pair_validity_batch(C.byref(self.w), r1, r2, n, _p(states), _p(valid), _p(margin), n_threads)
+        return valid.astype(bool), margin
+
+    def first_conflict_groups(self, traj, group, lengths=None):
+        traj = np.ascontiguousarray(traj, dtype=np.float32)
+        R, _, T = traj.shape
+        group = np.ascontiguousarray(group, dtype=np.int32)
+        lengths = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int32)
+        out = OrcConflict()
+        mm = C.c_double()
+        self.L.orc_first_conflict_groups(C.byref(self.w), R, T, _p(traj), _p(lengths), _p(group), C.byref(out), C.byref(mm))
+        return (out.r1, out.r2, out.k_start, out.k_end), mm.value

@@ -244,3 +244,39 @@ def test_first_conflict_padding(pkg, orc):
     res = o.first_conflict(traj, lengths)[0]
     assert res[0] == 0 and res[1] == 1 and res[2] > 10
     assert o.first_conflict(traj, None)[0] == (-1, -1, -1, -1)
+
+
+def test_merged_pair_oracle(pkg, orc):
+    # StatePropagatorDatabase.h:130-153 and StateValidityCheckerDatabase.h:225-261 (merged pair)
+    o = orc.Oracle(pkg.scenes.world("Corridor10x10_4robots"))
+    goals = [9.0, 0.5, 9.0, 9.0]
+    # both cars far from their goals: each moves like a single car
+    q = [1.0, 0.5, 0.5, 0.0, 0.0, 1.0, 3.5, 0.3, 0.1, 0.2]
+    u = [1.0, 0.0, -0.5, 0.4]
+    out = o.pair_propagate(q, u, goals)
+    assert np.allclose(out[:5], o.propagate(q[:5], u[:2]), atol=0) and np.allclose(out[5:], o.propagate(q[5:], u[2:]), atol=0)
+    # car 1 within 1.5 of its goal before the step keeps its state, car 2 still moves
+    q2 = [8.0, 0.5, 0.5, 0.0, 0.0, 1.0, 3.5, 0.3, 0.1, 0.2]
+    out = o.pair_propagate(q2, u, goals)
+    assert list(out[:5]) == q2[:5] and out[5] != q2[5]
+    # exactly at the hold radius is NOT inside (strict <)
+    q3 = [7.5, 0.5, 0.5, 0.0, 0.0, 1.0, 3.5, 0.3, 0.1, 0.2]
+    assert o.pair_propagate(q3, u, goals)[0] != 7.5
+    # validity: both in bounds and obstacle free, not overlapping each other
+    assert o.pair_is_valid([1.0, 0.5, 0, 0, 0, 1.0, 3.5, 0, 0, 0])[0]
+    assert not o.pair_is_valid([1.0, 0.5, 0, 0, 0, 1.5, 0.5, 0, 0, 0])[0]       # the cars overlap
+    assert not o.pair_is_valid([1.0, 0.5, 0, 0, 0, 2.0, 0.5, 0, 0, 0])[0]       # touching
+    assert not o.pair_is_valid([1.0, 0.5, 0, 0, 0, 5.0, 2.3, 0, 0, 0])[0]       # second car inside the obstacle
+    assert not o.pair_is_valid([1.0, 0.5, 1.2, 0, 0, 1.0, 3.5, 0, 0, 0])[0]     # first car's speed out of bounds
+
+
+def test_first_conflict_groups(pkg, orc):
+    # bodies of one merged individual are never tested against each other
+    o = orc.Oracle(pkg.scenes.world("Empty32x32_10robots"))
+    R, T = 5, 30
+    traj = _line_plan(R, T)
+    traj[4, 0, :] = traj[3, 0, :] + 0.2          # bodies 3 and 4 overlap all the time
+    traj[2, 0, 12:15] = traj[0, 0, 12:15] + 0.1  # bodies 0 and 2 collide at 12..14
+    assert o.first_conflict(traj)[0] == (3, 4, 0, T - 1)
+    assert o.first_conflict_groups(traj, [0, 1, 2, 3, 3])[0] == (0, 2, 12, 14)
+    assert o.first_conflict_groups(traj, [0, 1, 0, 3, 3])[0] == (-1, -1, -1, -1)
