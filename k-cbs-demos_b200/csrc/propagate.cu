@@ -29,17 +29,16 @@
 // integrated).  Each CTA (128 threads) therefore counting-sorts its 256 samples by
 // duration in shared memory and every thread runs two of them: rank t (long) and rank 255 - t (short).
 // Lanes of a warp then hold (almost) equal durations in both rounds and every thread of the CTA has the
-// same total work, so neither lanes nor warps idle.  States are written straight to their original
-// slots (a warp's stores stay inside the CTA's 1 KB row windows, which L2 merges into full lines).
+// same total work, so neither lanes nor warps idle.  Segments are staged in shared memory at their original
+// slots (x, y, theta per step; v and phi are recomputed from their exact linear form) and leave in one
+// coalesced pass that also zero-fills the rows past the last valid state: every 32 B sector is written
+// completely (no partial-sector traffic at L2, no read-modify-write at HBM).
 #include <cstddef>
 
 #include "car_dynamics.cuh"
 #include "kernels.h"
 
 namespace kcbs {
-
-constexpr int kPropThreads = 128;  // threads per CTA
-constexpr int kPropSamples = 256;  // samples per CTA (two per thread)
 
 // Dynamic-obstacle constraints of the K-CBS low level (the fork tests `next` against the constraining robot's
 // state at that time through areStatesValid, StateValidityCheckerDatabase.h:78-125).
@@ -67,9 +66,33 @@ __device__ __forceinline__ bool constraints_clear(const DevWorld &w, const PropA
     return ok;
 }
 
+constexpr int kPropThreads = 128;  // threads per CTA
+constexpr int kPropSamples = 256;  // samples per CTA (two per thread)
+constexpr int kStageSteps = 10;    // segments up to this many steps are staged in shared memory
+
+// Shared-memory staging of one CTA's segments: x, y, theta of every (step, slot), plus the four numbers from which
+// v and phi of any step follow exactly (they are linear in time).  35 KB -> 6 CTAs (24 warps) per SM.
+struct PropStage {
+    float xyt[3][kStageSteps][kPropSamples];
+    float v0[kPropSamples], ua[kPropSamples], p0[kPropSamples], uw[kPropSamples];
+    unsigned char nv[kPropSamples];
+};
+
+template <bool STAGED>
+struct StageStorage {
+    using type = PropStage;
+    __device__ static PropStage *get(type &t) { return &t; }
+};
+template <>
+struct StageStorage<false> {  // direct-store variants carry no stage
+    using type = int;
+    __device__ static PropStage *get(type &) { return nullptr; }
+};
+
 // propagateWhileValid for one sample; writes the segment, the final state and the valid-step count.
-template <bool HAS_OBS, bool HAS_CONS>
-__device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropArgs &a, long long i, int st)
+template <bool HAS_OBS, bool HAS_CONS, bool STAGED>
+__device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropArgs &a, long long i, int st, PropStage *stage,
+                                                 int slot)
 {
     const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
     const int t0 = (HAS_CONS && a.parent_time) ? a.parent_time[pi] : 0;
@@ -108,7 +131,11 @@ __device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropAr
 
         xs = xn; ys = yn; vs = vn; ps = pn; ts = tn;
         nv = j + 1;
-        if (a.seg) {
+        if (STAGED) {
+            stage->xyt[0][j][slot] = xn;
+            stage->xyt[1][j][slot] = yn;
+            stage->xyt[2][j][slot] = tn;
+        } else if (a.seg) {
             float *o = a.seg + (long long)j * a.n + i;
             __stcs(o, xn);
             __stcs(o + plane, yn);
@@ -118,9 +145,14 @@ __device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropAr
         }
     }
 
-    if (a.seg) {
-        // rows past the last valid state are zero-filled: every 32 B sector of the segment buffer is then written
-        // completely, so L2 never has to read-modify-write partially written sectors from HBM
+    if (STAGED) {
+        stage->v0[slot] = v0;
+        stage->ua[slot] = ua;
+        stage->p0[slot] = phi0;
+        stage->uw[slot] = uw;
+        stage->nv[slot] = (unsigned char)nv;
+    } else if (a.seg) {
+        // rows past the last valid state are zero-filled (as the staged path does)
         for (int j = nv; j < a.max_steps; ++j) {
             float *o = a.seg + (long long)j * a.n + i;
 #pragma unroll
@@ -137,18 +169,20 @@ __device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropAr
     }
 }
 
-template <bool HAS_OBS, bool HAS_CONS>
+template <bool HAS_OBS, bool HAS_CONS, bool STAGED>
 __global__ void __launch_bounds__(kPropThreads)
 k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs a)
 {
     __shared__ int s_hist[KCBS_MAX_STEPS + 1];
     __shared__ unsigned char s_perm[kPropSamples];   // rank -> slot
-    __shared__ unsigned char s_steps[kPropSamples];  // slot -> clamped duration
+    __shared__ unsigned char s_steps[kPropSamples];  // slot -> effective duration
+    __shared__ typename StageStorage<STAGED>::type s_stage_mem;
+    PropStage *stage = StageStorage<STAGED>::get(s_stage_mem);
 
     const int tid = threadIdx.x;
     const long long b0 = (long long)blockIdx.x * kPropSamples;
 
-    // ---- counting sort of the CTA's samples by requested duration (longest first) ----------------
+    // ---- counting sort of the CTA's samples by effective duration (longest first) ----------------
     if (tid <= KCBS_MAX_STEPS) s_hist[tid] = 0;
     __syncthreads();
     int st2[2], within[2];
@@ -178,6 +212,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         }
         st2[u] = st;
         s_steps[slot] = (unsigned char)st;
+        if (STAGED) stage->nv[slot] = 0;
         within[u] = atomicAdd(&s_hist[st], 1);
     }
     __syncthreads();
@@ -195,27 +230,61 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         const int rank = round == 0 ? tid : kPropSamples - 1 - tid;
         const int slot = s_perm[rank];
         const long long i = b0 + slot;
-        if (i < a.n) propagate_sample<HAS_OBS, HAS_CONS>(w, a, i, (int)s_steps[slot]);
+        if (i < a.n) propagate_sample<HAS_OBS, HAS_CONS, STAGED>(w, a, i, (int)s_steps[slot], stage, slot);
+    }
+
+    if (STAGED) {
+        // ---- coalesced write-out: every row of every plane leaves as full 128 B lines; rows past the last valid
+        // state are zero, so no sector of the segment buffer is ever partially written --------------------------
+        __syncthreads();
+        const long long plane = (long long)a.max_steps * a.n;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int slot = tid + u * kPropThreads;
+            const long long i = b0 + slot;
+            if (i >= a.n) continue;
+            const int nv = stage->nv[slot];
+            const float v0 = stage->v0[slot], ua = stage->ua[slot], p0 = stage->p0[slot], uw = stage->uw[slot];
+            for (int j = 0; j < a.max_steps; ++j) {
+                float *o = a.seg + (long long)j * a.n + i;
+                const bool live = j < nv;
+                const float t1 = (float)(j + 1) * w.step;
+                __stcs(o, live ? stage->xyt[0][j][slot] : 0.0f);
+                __stcs(o + plane, live ? stage->xyt[1][j][slot] : 0.0f);
+                __stcs(o + 2 * plane, live ? fmaf(ua, t1, v0) : 0.0f);   // same expression as the integrator's
+                __stcs(o + 3 * plane, live ? fmaf(uw, t1, p0) : 0.0f);
+                __stcs(o + 4 * plane, live ? stage->xyt[2][j][slot] : 0.0f);
+            }
+        }
     }
 }
 
 cudaError_t init_propagate_kernels() { return cudaSuccess; }
 
-cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t stream)
+template <bool STAGED>
+static cudaError_t launch_staged(const DevWorld &w, const PropArgs &a, cudaStream_t stream)
 {
-    if (a.n <= 0) return cudaSuccess;
     const long long grid = (a.n + kPropSamples - 1) / kPropSamples;
     if (a.n_cons > 0) {
         if (w.n_obs > 0)
-            k_propagate<true, true><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+            k_propagate<true, true, STAGED><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
         else
-            k_propagate<false, true><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+            k_propagate<false, true, STAGED><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
     } else if (w.n_obs > 0) {
-        k_propagate<true, false><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+        k_propagate<true, false, STAGED><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
     } else {
-        k_propagate<false, false><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+        k_propagate<false, false, STAGED><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t stream)
+{
+    if (a.n <= 0) return cudaSuccess;
+    // whole segments of up to kStageSteps steps leave through the shared-memory stage (coalesced);
+    // longer horizons and final-state-only calls write directly
+    if (a.seg != nullptr && a.max_steps <= kStageSteps) return launch_staged<true>(w, a, stream);
+    return launch_staged<false>(w, a, stream);
 }
 
 }  // namespace kcbs
