@@ -147,10 +147,18 @@ __global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a, int n_nod
         __syncthreads();
         const int m = min(kNNThreads, n1 - base);
         for (int j = 0; j < m; ++j) {
-            const float d = state_distance(s[0][j], s[1][j], s[2][j], s[3][j], s[4][j], q[0], q[1], q[2], q[3], q[4]);
-            if (d < best) {
-                best = d;
-                best_i = base + j;
+            // the real-vector part alone already bounds the distance from below: most nodes are rejected on the
+            // squared L2 without the square root and the SO2 term
+            const float dx = s[0][j] - q[0], dy = s[1][j] - q[1], dv = s[2][j] - q[2], dp = s[3][j] - q[3];
+            const float l2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dv, dv, dp * dp)));
+            if (l2 < best * best) {
+                float dth = fabsf(s[4][j] - q[4]);
+                dth = dth > kPi ? kTwoPi - dth : dth;
+                const float d = sqrtf(l2) + dth;
+                if (d < best) {
+                    best = d;
+                    best_i = base + j;
+                }
             }
         }
     }
@@ -484,8 +492,8 @@ void kcbs_rrt_defaults(kcbs_rrt_params *p)
     if (!p) return;
     p->n_targets = 2048;
     p->n_controls = 32;
-    p->max_nodes = 1 << 20;
-    p->max_iterations = 4096;
+    p->max_nodes = 1 << 18;
+    p->max_iterations = 512;
     p->min_steps = 1;    // demo_*.cpp:118
     p->max_steps = 10;
     p->goal_bias = 0.05f;
