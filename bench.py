@@ -42,6 +42,15 @@ VALIDITY_BYTES_PER_STATE = 20.125      # 5 f32 read + 1 bit written
 FP32_NOMINAL_TFLOPS = 74.4   # 148 SM x 128 lanes x 2 x 1.965 GHz
 
 
+def read_traffic():
+    """DRAM traffic per launch from the committed ncu captures (profiles/traffic_r1.json); None when absent."""
+    path = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        return json.load(f)
+
+
 def read_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -343,9 +352,16 @@ def main():
     kern_ms = e0.elapsed_time(e1) / max(launches, 1)      # average launch duration (streams overlap: busy time / launches)
     ach_tflops = FLOPS_PER_STATE * units_step * args.steps / (e0.elapsed_time(e1) * 1e-3) * 1e-12
     ach_gbs = (BYTES_PER_STATE * written_step + BYTES_PER_SAMPLE * samples_step) * args.steps / (e0.elapsed_time(e1) * 1e-3) * 1e-9
+    traffic = read_traffic()
+    tp = traffic.get("k_propagate")
+    # ncu capture is one launch of 655,360 samples; a bench launch is one expansion of 65,536 samples of the same mix
+    k1_traffic = None if not tp else (tp["dram_read_bytes"] + tp["segment_buffer_bytes"]) * N_CONTROLS / tp["samples"]
     roofline = {
         "kernel": "k_propagate", "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": ach_tflops / fp32_peak if fp32_peak else None, "traffic": None,
+        "frac": ach_tflops / fp32_peak if fp32_peak else None, "traffic": k1_traffic,
+        "traffic_unit": "bytes per launch (ncu dram read + the whole zero-filled segment buffer written, scaled from the "
+                        "655,360-sample capture in profiles/r1_k_propagate.md)",
+        "algorithmic_bytes_per_launch": (BYTES_PER_STATE * written_step + BYTES_PER_SAMPLE * samples_step) / launches_per_step,
         "peak_source": "FFMA saturation probe run in this process (kcbs_measure_fp32_peak); nominal 74.4",
         "frac_of_nominal": ach_tflops / FP32_NOMINAL_TFLOPS,
         "algorithmic_flops_per_state": FLOPS_PER_STATE, "avg_launch_ms": kern_ms,
@@ -419,7 +435,7 @@ def main():
     # ---- secondary metrics: validity (K2) and conflict scan (K3), device resident ------------------
     secondary = {}
     if not args.no_secondary:
-        secondary = run_secondary(pkg, workloads, local_rank, hbm_peak, peak_src, max_over_ranks, sum_over_ranks, barrier, rank)
+        secondary = run_secondary(pkg, workloads, local_rank, hbm_peak, peak_src, max_over_ranks, sum_over_ranks, barrier, rank, traffic)
 
     cpu = None
     if rank == 0 and world_size == 1 and not args.no_cpu:
@@ -452,7 +468,7 @@ def main():
         dist.destroy_process_group()
 
 
-def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_over_ranks, barrier, rank):
+def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_over_ranks, barrier, rank, traffic):
     import torch
     out = {}
     # ---- validity: Congested10x10, 2^24 states ------------------------------
@@ -477,7 +493,10 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
         gbs = VALIDITY_BYTES_PER_STATE * n * reps / (e0.elapsed_time(e1) * 1e-3) * 1e-9
         out["validity"] = {"metric": "validity-checked states/s", "value": rate, "scene": scene, "states": n,
                            "roofline": {"kernel": "k_validity", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
-                                        "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src}}
+                                        "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src,
+                                        "traffic": None if "k_validity" not in traffic else
+                                        traffic["k_validity"]["dram_read_bytes"] + traffic["k_validity"]["dram_write_bytes"],
+                                        "algorithmic_bytes_per_launch": VALIDITY_BYTES_PER_STATE * n}}
         del sets, mask
     # ---- conflict scan: Empty32x32 30 robots, 435 pairs x 10K steps, 256 plans (config 5) --------------
     # N > 1: every rank scans its own 256-plan batch (weak); one batch sharded by plan is reported as well (strong).
@@ -537,7 +556,10 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
                            "strong_scaling_value": strong_rate,
                            "single_plan_latency_us": 1e3 * e0.elapsed_time(e1) / 50,
                            "roofline": {"kernel": "k_conflict_keys", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
-                                        "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                                        "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src,
+                                        "traffic": None if "k_conflict_keys" not in traffic else
+                                        traffic["k_conflict_keys"]["dram_read_bytes"] + traffic["k_conflict_keys"]["dram_write_bytes"],
+                                        "algorithmic_bytes_per_launch": CONFLICT_BYTES_PER_TRAJ_STATE * P * R * T,
                                         "note": "per GPU; algorithmic 12 B per trajectory state (x, y, theta), the scan itself reads 8 B"}}
     # ---- per-robot replans sharded over the ranks (config 4: Empty32x32 20 robots) ------------------------------
     scene = "Empty32x32_20robots"

@@ -85,7 +85,8 @@ EXPORTS = [
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libkcbs_b200.so")
+    # KCBS_B200_LIB selects an alternative build of the same library (A/B experiments); never a different backend
+    return os.environ.get("KCBS_B200_LIB") or os.path.join(_HERE, "libkcbs_b200.so")
 
 
 def load_library() -> C.CDLL:

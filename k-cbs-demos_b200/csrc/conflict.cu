@@ -28,7 +28,10 @@
 
 namespace kcbs {
 
-constexpr int kTile = 128;   // time indices (threads) per CTA
+#ifndef KCBS_CONFLICT_TILE
+#define KCBS_CONFLICT_TILE 128
+#endif
+constexpr int kTile = KCBS_CONFLICT_TILE;   // time indices (threads) per CTA
 constexpr int kATile = 8;    // robots held in registers
 
 __device__ __forceinline__ int clamp_k(int k, int T, const int *len, int r)
@@ -171,8 +174,8 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
         __syncthreads();
         // arrive + expect_tx is one atomic update, so copies may complete before or after it
         if (tid == 0) mbar_expect_tx(&s_bar, (unsigned)(2 * R * n_k * sizeof(float)));
-        if (tid < 2 * R) {
-            const int r = tid >> 1, c = tid & 1;
+        for (int row = tid; row < 2 * R; row += kTile) {
+            const int r = row >> 1, c = row & 1;
             bulk_g2s((c ? ys : xs) + r * kTile, base + ((long long)r * 3 + c) * T + k0, (unsigned)(n_k * sizeof(float)), &s_bar);
         }
     }

@@ -19,9 +19,10 @@ def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for s in ("kcbs_create", "kcbs_destroy", "kcbs_propagate_batch", "kcbs_propagate_batch_dev", "kcbs_validity_batch",
               "kcbs_validity_batch_dev", "kcbs_first_conflict", "kcbs_first_conflict_dev", "kcbs_conflict_keys_dev",
-              "kcbs_conflict_finish_dev", "kcbs_last_error", "kcbs_sync"):
+              "kcbs_conflict_finish_dev", "kcbs_last_error", "kcbs_sync", "kcbs_propagate_pair_batch", "kcbs_validity_pair_batch",
+              "kcbs_first_conflict_groups", "kcbs_rrt_plan", "kcbs_kcbs_solve"):
         assert s in syms
-    assert len(syms) >= 19
+    assert len(syms) >= 30
 
 
 def test_library_exports_every_declared_symbol(pkg):
