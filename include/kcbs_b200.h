@@ -82,6 +82,14 @@ KCBS_API const char *kcbs_status_string(int status);
  * (StateSpaceDatabase.h:42-62) for x_max, y_max; step 0.1, integration step 0.01, car length 0.5. */
 KCBS_API void kcbs_world_defaults(kcbs_world *w, double x_max, double y_max);
 
+/* Host-only introspection (needs no device): the three-valued obstacle grid kcbs_create derives from `world` and the
+ * validity / propagation kernels consult before the exact footprint test of
+ * StateValidityCheckerDatabase.h:62-73,180-205.  codes[iy * dim + ix] over a dim x dim grid spanning [lo, hi] of (x, y):
+ * 0 = no obstacle can touch a robot centred in the cell, 0xffff = every heading collides, 0xfffe = more than two
+ * obstacles need the exact test, else (o1 + 1) | (o2 + 1) << 8 = the one or two obstacles that need it.
+ * Pass codes = NULL to query *dim only. */
+KCBS_API int kcbs_scene_grid(const kcbs_world *world, int32_t *dim, uint16_t *codes);
+
 /* Creates a context on CUDA device `device`.  Fails with KCBS_ERR_NO_DEVICE when the device is
  * absent or not compute capability 10.x. */
 KCBS_API int kcbs_create(const kcbs_world *world, int device, kcbs_ctx **out);

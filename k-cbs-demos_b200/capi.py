@@ -81,6 +81,7 @@ EXPORTS = [
     "kcbs_measure_fp32_peak", "kcbs_measure_fp32x2_peak", "kcbs_launch_count", "kcbs_rrt_defaults",
     "kcbs_kcbs_defaults", "kcbs_rrt_plan", "kcbs_kcbs_solve", "kcbs_propagate_pair_batch", "kcbs_propagate_pair_batch_dev",
     "kcbs_validity_pair_batch", "kcbs_validity_pair_batch_dev", "kcbs_first_conflict_groups", "kcbs_first_conflict_groups_dev",
+    "kcbs_scene_grid",
 ]
 
 
@@ -138,6 +139,7 @@ def load_library() -> C.CDLL:
     lib.kcbs_validity_pair_batch_dev.argtypes = [vp, i32, i32, i64, vp, vp, vp]
     lib.kcbs_first_conflict_groups.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     lib.kcbs_first_conflict_groups_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.kcbs_scene_grid.argtypes = [C.POINTER(_CWorld), C.POINTER(C.c_int32), vp]
     lib.kcbs_launch_count.restype = i64
     lib.kcbs_launch_count.argtypes = [vp]
     _LIB = lib
@@ -191,6 +193,36 @@ def _ptr(a) -> Optional[int]:
     raise TypeError(type(a))
 
 
+def _c_world(world: World):
+    """kcbs_world for `world`, plus the arrays it points into (keep them alive while it is used)."""
+    lo, hi = world.bounds()
+    obs = np.ascontiguousarray(np.asarray(world.obstacles, dtype=np.float64).reshape(-1, 4))
+    dims = np.ascontiguousarray(np.asarray(world.robot_dims, dtype=np.float64).reshape(-1, 2))
+    cw = _CWorld()
+    cw.lo[:] = lo
+    cw.hi[:] = hi
+    cw.step_size, cw.integration_step, cw.car_length = world.step_size, world.integration_step, world.car_length
+    cw.n_obstacles, cw.n_robots = len(obs), len(dims)
+    cw.obstacles = obs.ctypes.data_as(C.POINTER(C.c_double)) if len(obs) else None
+    cw.robot_dims = dims.ctypes.data_as(C.POINTER(C.c_double))
+    return cw, obs, dims
+
+
+def scene_grid(world: World) -> np.ndarray:
+    """kcbs_scene_grid: the [dim, dim] uint16 obstacle cell codes derived from `world` (host only, no device needed)."""
+    lib = load_library()
+    cw, _obs, _dims = _c_world(world)
+    dim = C.c_int32()
+    st = lib.kcbs_scene_grid(C.byref(cw), C.byref(dim), None)
+    if st != 0:
+        raise KcbsError(st, lib.kcbs_last_error(None).decode())
+    codes = np.zeros((dim.value, dim.value), np.uint16)
+    st = lib.kcbs_scene_grid(C.byref(cw), C.byref(dim), codes.ctypes.data)
+    if st != 0:
+        raise KcbsError(st, lib.kcbs_last_error(None).decode())
+    return codes
+
+
 class Context:
     """kcbs_ctx.  Host-array methods mirror the reference-facing host entry points; *_dev methods
     take torch CUDA tensors (or raw device pointers) and are asynchronous on `stream`."""
@@ -198,16 +230,7 @@ class Context:
     def __init__(self, world: World, device: int = 0):
         self._lib = load_library()
         self.world = world
-        lo, hi = world.bounds()
-        self._obs = np.ascontiguousarray(np.asarray(world.obstacles, dtype=np.float64).reshape(-1, 4))
-        self._dims = np.ascontiguousarray(np.asarray(world.robot_dims, dtype=np.float64).reshape(-1, 2))
-        cw = _CWorld()
-        cw.lo[:] = lo
-        cw.hi[:] = hi
-        cw.step_size, cw.integration_step, cw.car_length = world.step_size, world.integration_step, world.car_length
-        cw.n_obstacles, cw.n_robots = len(self._obs), len(self._dims)
-        cw.obstacles = self._obs.ctypes.data_as(C.POINTER(C.c_double)) if len(self._obs) else None
-        cw.robot_dims = self._dims.ctypes.data_as(C.POINTER(C.c_double))
+        cw, self._obs, self._dims = _c_world(world)
         h = C.c_void_p()
         st = self._lib.kcbs_create(C.byref(cw), device, C.byref(h))
         if st != 0:

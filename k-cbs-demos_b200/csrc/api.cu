@@ -58,14 +58,14 @@ namespace {
 // the float image of OMPL's RealVectorStateSpace::satisfiesBounds test.
 float hi_threshold(double hi, double eps)
 {
-    float f = (float)hi;
+    float f = (float)(hi + eps);  // within an ulp or two of the answer, so the exact searches below are short
     while ((double)f - eps > hi) f = nextafterf(f, -INFINITY);
     while ((double)nextafterf(f, INFINITY) - eps <= hi) f = nextafterf(f, INFINITY);
     return f;
 }
 float lo_threshold(double lo, double eps)
 {
-    float f = (float)lo;
+    float f = (float)(lo - eps);
     while ((double)f + eps < lo) f = nextafterf(f, INFINITY);
     while ((double)nextafterf(f, -INFINITY) + eps >= lo) f = nextafterf(f, -INFINITY);
     return f;
@@ -172,6 +172,69 @@ void build_grid(const kcbs_world *src, DevWorld &w, std::vector<unsigned long lo
     }
 }
 
+// Euclidean distance from the point (px, py) to the axis-aligned rectangle [x0, x1] x [y0, y1].
+double point_rect_distance(double px, double py, double x0, double y0, double x1, double y1)
+{
+    const double dx = std::max(0.0, std::max(x0 - px, px - x1)), dy = std::max(0.0, std::max(y0 - py, py - y1));
+    return std::sqrt(dx * dx + dy * dy);
+}
+
+// Fine three-valued grid (kcbs_device.cuh, cell_code): classification of every cell against every obstacle, valid for
+// any heading of any robot of the scene.  The margins (1e-5 relative + 1e-5 absolute on the radii, 1e-3 of a cell for
+// the float cell lookup on the device) keep "free" and "hit" away from the decision boundary of the exact test.
+void build_fine_grid(const kcbs_world *src, DevWorld &w, std::vector<unsigned short> &fine)
+{
+    const int G = kFineDim;
+    const double x0 = src->lo[0], y0 = src->lo[1];
+    const double sx = std::max(src->hi[0] - src->lo[0], 1e-9), sy = std::max(src->hi[1] - src->lo[1], 1e-9);
+    const double cw = sx / G, ch = sy / G;
+    w.fdim = G;
+    w.finvx = (float)(G / sx);
+    w.finvy = (float)(G / sy);
+    fine.assign((size_t)G * G, 0);
+    if (src->n_obstacles == 0) return;
+    double max_rad = 0.0, min_in = INFINITY;
+    for (int r = 0; r < src->n_robots; ++r) {
+        const double *d = src->robot_dims + 2 * r;
+        max_rad = std::max(max_rad, std::sqrt(d[0] * d[0] / 4 + d[1] * d[1] / 4));
+        min_in = std::min(min_in, std::min(d[0], d[1]) / 2);
+    }
+    const double r_free = max_rad * (1.0 + 1e-5) + 1e-5, r_hit = min_in * (1.0 - 1e-5) - 1e-5;
+    for (int iy = 0; iy < G; ++iy)
+        for (int ix = 0; ix < G; ++ix) {
+            // the cell as the device may see it: in-bounds states just outside the workspace clamp into the border cells
+            const double sl = 1e-3;
+            const double ax = x0 + (ix - sl) * cw - (ix == 0 ? 1e-3 : 0), bx = x0 + (ix + 1 + sl) * cw + (ix == G - 1 ? 1e-3 : 0);
+            const double ay = y0 + (iy - sl) * ch - (iy == 0 ? 1e-3 : 0), by = y0 + (iy + 1 + sl) * ch + (iy == G - 1 ? 1e-3 : 0);
+            bool hit = false;
+            int n_maybe = 0, cand[2] = {0, 0};
+            for (int o = 0; o < src->n_obstacles && !hit; ++o) {
+                const double *ob = src->obstacles + 4 * o;
+                const double ox0 = ob[0], oy0 = ob[1], ox1 = ob[0] + ob[2], oy1 = ob[1] + ob[3];
+                const double gx = std::max(0.0, std::max(ox0 - bx, ax - ox1)), gy = std::max(0.0, std::max(oy0 - by, ay - oy1));
+                if (std::sqrt(gx * gx + gy * gy) > r_free) continue;  // free
+                const double far = std::max(std::max(point_rect_distance(ax, ay, ox0, oy0, ox1, oy1),
+                                                     point_rect_distance(bx, ay, ox0, oy0, ox1, oy1)),
+                                            std::max(point_rect_distance(ax, by, ox0, oy0, ox1, oy1),
+                                                     point_rect_distance(bx, by, ox0, oy0, ox1, oy1)));
+                if (far < r_hit) {
+                    hit = true;
+                } else {
+                    if (n_maybe < 2) cand[n_maybe] = o + 1;
+                    ++n_maybe;
+                }
+            }
+            unsigned code = 0;
+            if (hit)
+                code = kCellHit;
+            else if (n_maybe > 2)
+                code = kCellMany;
+            else
+                code = (unsigned)cand[0] | ((unsigned)cand[1] << 8);
+            fine[(size_t)iy * G + ix] = (unsigned short)code;
+        }
+}
+
 cudaStream_t pick(kcbs_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
 
 int check_robot(kcbs_ctx *ctx, int robot)
@@ -213,6 +276,20 @@ void kcbs_world_defaults(kcbs_world *w, double x_max, double y_max)
     w->car_length = 0.5;         // StatePropagatorDatabase.h:53
 }
 
+int kcbs_scene_grid(const kcbs_world *world, int32_t *dim, uint16_t *codes)
+{
+    DevWorld w;
+    int st = build_world(world, w);
+    if (st != KCBS_OK) return st;
+    if (!dim) return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "dim is null");
+    *dim = kFineDim;
+    if (!codes) return KCBS_OK;
+    std::vector<unsigned short> fine;
+    build_fine_grid(world, w, fine);
+    std::memcpy(codes, fine.data(), sizeof(unsigned short) * fine.size());
+    return KCBS_OK;
+}
+
 int kcbs_create(const kcbs_world *world, int device, kcbs_ctx **out)
 {
     if (!out) return fail(nullptr, KCBS_ERR_INVALID_ARGUMENT, "out is null");
@@ -236,26 +313,30 @@ int kcbs_create(const kcbs_world *world, int device, kcbs_ctx **out)
     if (!ctx) return fail(nullptr, KCBS_ERR_OUT_OF_MEMORY, "host allocation failed");
     ctx->device = device;
     build_grid(world, w, ctx->h_grid, ctx->h_obs4);
+    build_fine_grid(world, w, ctx->h_fine);
     ctx->world = w;
     ctx->n_robots = world->n_robots;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
-        (e = init_conflict_kernels()) != cudaSuccess || (e = init_propagate_kernels()) != cudaSuccess) {
+        (e = init_conflict_kernels()) != cudaSuccess || (e = init_validity_kernels()) != cudaSuccess || (e = init_propagate_kernels()) != cudaSuccess) {
         fail(nullptr, KCBS_ERR_CUDA, "context setup", e);
         kcbs_destroy(ctx);
         return KCBS_ERR_CUDA;
     }
     {
         const size_t b_grid = sizeof(unsigned long long) * ctx->h_grid.size(), b_obs = sizeof(float) * ctx->h_obs4.size();
-        if ((e = cudaMalloc(&ctx->scene, b_grid + b_obs)) != cudaSuccess ||
+        const size_t b_fine = sizeof(unsigned short) * ctx->h_fine.size();
+        if ((e = cudaMalloc(&ctx->scene, b_grid + b_obs + b_fine)) != cudaSuccess ||
             (e = cudaMemcpy(ctx->scene, ctx->h_grid.data(), b_grid, cudaMemcpyHostToDevice)) != cudaSuccess ||
-            (e = cudaMemcpy((char *)ctx->scene + b_grid, ctx->h_obs4.data(), b_obs, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            (e = cudaMemcpy((char *)ctx->scene + b_grid, ctx->h_obs4.data(), b_obs, cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy((char *)ctx->scene + b_grid + b_obs, ctx->h_fine.data(), b_fine, cudaMemcpyHostToDevice)) != cudaSuccess) {
             fail(nullptr, KCBS_ERR_CUDA, "scene upload", e);
             kcbs_destroy(ctx);
             return KCBS_ERR_CUDA;
         }
         ctx->world.grid = (const unsigned long long *)ctx->scene;
         ctx->world.obs4 = (const float4 *)((char *)ctx->scene + b_grid);
+        ctx->world.fine = (const unsigned short *)((char *)ctx->scene + b_grid + b_obs);
     }
     *out = ctx;
     return KCBS_OK;

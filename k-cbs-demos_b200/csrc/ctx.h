@@ -33,6 +33,7 @@ struct kcbs_ctx {
     void *scene = nullptr;  // cull grid + obstacle table in device memory
     std::vector<unsigned long long> h_grid;
     std::vector<float> h_obs4;
+    std::vector<unsigned short> h_fine;  // fine three-valued obstacle grid
     kcbs::RrtWorkspace *rrt = nullptr;  // planner state, created on first use
 };
 

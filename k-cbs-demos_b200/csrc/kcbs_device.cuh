@@ -36,6 +36,10 @@ struct DevWorld {
     float gx0, gy0;          // grid origin = lower workspace bound
     float ginvx, ginvy;      // cells per metre
     const unsigned long long *grid;  // [gdim * gdim]
+    // Fine three-valued obstacle grid (built on the host at kcbs_create): one 16-bit code per cell, see cell_code().
+    int fdim;                        // cells per side (kFineDim)
+    float finvx, finvy;              // fine cells per metre
+    const unsigned short *fine;      // [fdim * fdim]
     const float4 *obs4;              // [n_obs] (cx, cy, hx, hy), same values as the arrays below
     float obs_cx[KCBS_MAX_OBSTACLES];  // Obstacle.h:85-86 centre
     float obs_cy[KCBS_MAX_OBSTACLES];
@@ -156,6 +160,60 @@ __device__ __forceinline__ bool obstacles_clear_grid(const DevWorld &w, const un
         ok &= sep;
     }
     return ok;
+}
+
+// ---- fine obstacle grid ------------------------------------------------------------------------------------------
+// Every cell of a kFineDim x kFineDim grid over the workspace is classified on the host, in double, against every
+// obstacle for ANY heading of ANY robot of the scene:
+//   free   the cell is farther from the obstacle than the largest bounding radius: isValid cannot fail on it
+//   hit    every point of the cell is closer to the obstacle than the smallest inscribed radius min(L, W) / 2: the
+//          footprint contains that disc, so the exact test (StateValidityCheckerDatabase.h:180-205) reports a collision
+//          whatever the heading
+//   maybe  the exact rectangle test decides
+// Cell code: 0 = all obstacles free; kCellHit = some obstacle hits; kCellMany = more than two maybes (decided through
+// the coarse 64-bit mask grid); otherwise the one or two maybe obstacles as (index + 1) in the low / high byte.
+constexpr int kFineDim = 128;
+constexpr unsigned kCellHit = 0xffffu, kCellMany = 0xfffeu;
+
+__device__ __forceinline__ int fine_cell(const DevWorld &w, float x, float y)
+{
+    const int ix = min(kFineDim - 1, max(0, (int)((x - w.gx0) * w.finvx)));
+    const int iy = min(kFineDim - 1, max(0, (int)((y - w.gy0) * w.finvy)));
+    return iy * kFineDim + ix;
+}
+
+// true when a separating axis exists between the robot rectangle (centre (x, y), heading cos / sin c, s, half extents
+// hl, hw; ex, ey = its extents along world x / y) and the obstacle rectangle ob = (cx, cy, hx, hy).
+__device__ __forceinline__ bool separated_from(const float4 ob, float x, float y, float c, float s, float ac, float as,
+                                               float ex, float ey, float hl, float hw)
+{
+    const float dx = ob.x - x, dy = ob.y - y;
+    return (fabsf(dx) > ob.z + ex) | (fabsf(dy) > ob.w + ey) |
+           (fabsf(fmaf(dx, c, -dy * s)) > hl + fmaf(ob.z, ac, ob.w * as)) |
+           (fabsf(fmaf(dx, s, dy * c)) > hw + fmaf(ob.z, as, ob.w * ac));
+}
+
+// Exact part of the obstacle test for a state whose cell code is neither 0 nor kCellHit.
+__device__ __forceinline__ bool obstacles_clear_code(const DevWorld &w, unsigned code, const float4 *obs, float x, float y,
+                                                     float th, float hl, float hw)
+{
+    if (code == kCellMany) return obstacles_clear_grid(w, w.grid, w.obs4, x, y, th, hl, hw);
+    float s, c;
+    sincosf(th, &s, &c);
+    const float ac = fabsf(c), as = fabsf(s);
+    const float ex = fmaf(hl, ac, hw * as), ey = fmaf(hl, as, hw * ac);
+    bool ok = separated_from(obs[(code & 0xffu) - 1], x, y, c, s, ac, as, ex, ey, hl, hw);
+    if (code >> 8) ok &= separated_from(obs[(code >> 8) - 1], x, y, c, s, ac, as, ex, ey, hl, hw);
+    return ok;
+}
+
+// Obstacle part of isValid through the fine grid read from global memory (k_propagate, pair kernels).
+__device__ __forceinline__ bool obstacles_clear_fine(const DevWorld &w, float x, float y, float th, float hl, float hw)
+{
+    const unsigned code = __ldg(w.fine + fine_cell(w, x, y));
+    if (code == 0u) return true;
+    if (code == kCellHit) return false;
+    return obstacles_clear_code(w, code, w.obs4, x, y, th, hl, hw);
 }
 
 // Packed first-conflict key: lexicographic (k, r1, r2) order == integer order.

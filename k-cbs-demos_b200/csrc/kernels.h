@@ -92,6 +92,7 @@ cudaError_t launch_fill_keys(unsigned long long *keys, int *tickets, int n, cuda
 cudaError_t launch_fp32_probe(float *sink, int iters, cudaStream_t stream, double *flops);
 cudaError_t launch_fp32x2_probe(float *sink, int iters, cudaStream_t stream, double *flops);
 cudaError_t init_propagate_kernels();
+cudaError_t init_validity_kernels();
 cudaError_t init_conflict_kernels();  // per-device function attributes; call once per context
 
 }  // namespace kcbs

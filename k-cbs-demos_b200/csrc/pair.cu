@@ -29,8 +29,8 @@ __device__ __forceinline__ bool pair_state_valid(const DevWorld &w, int r1, int 
             return false;
     }
     if (w.n_obs > 0) {
-        if (!obstacles_clear_grid(w, w.grid, w.obs4, a[0], a[1], a[4], w.rob_hl[r1], w.rob_hw[r1])) return false;
-        if (!obstacles_clear_grid(w, w.grid, w.obs4, b[0], b[1], b[4], w.rob_hl[r2], w.rob_hw[r2])) return false;
+        if (!obstacles_clear_fine(w, a[0], a[1], a[4], w.rob_hl[r1], w.rob_hw[r1])) return false;
+        if (!obstacles_clear_fine(w, b[0], b[1], b[4], w.rob_hl[r2], w.rob_hw[r2])) return false;
     }
     return true;
 }

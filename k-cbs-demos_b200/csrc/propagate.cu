@@ -122,7 +122,7 @@ __device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropAr
 
         bool ok = in_bounds(w, xn, yn, vn, pn, tn);
         if (HAS_OBS) {
-            if (ok) ok = obstacles_clear_grid(w, w.grid, w.obs4, xn, yn, tn, hl, hw);
+            if (ok) ok = obstacles_clear_fine(w, xn, yn, tn, hl, hw);
         }
         if (HAS_CONS) {
             if (ok) ok = constraints_clear(w, a, t0 + j + 1, xn, yn, tn, hl, hw, w.rob_rad[a.robot]);
