@@ -110,6 +110,7 @@ int build_world(const kcbs_world *src, DevWorld &w)
         while (!((double)f > lo)) f = nextafterf(f, INFINITY);
         w.th_lo_t = f;
     }
+    w.sym_bounds = (w.lo_t[2] == -w.hi_t[2]) && (w.lo_t[3] == -w.hi_t[3]) && (w.th_lo_t == -w.th_hi_t);
     w.h = (float)src->integration_step;
     w.step = (float)src->step_size;
     w.inv_len = (float)(1.0 / src->car_length);
@@ -191,6 +192,8 @@ void build_fine_grid(const kcbs_world *src, DevWorld &w, std::vector<unsigned sh
     w.fdim = G;
     w.finvx = (float)(G / sx);
     w.finvy = (float)(G / sy);
+    w.foffx = (float)(-x0 * (G / sx));
+    w.foffy = (float)(-y0 * (G / sy));
     fine.assign((size_t)G * G, 0);
     if (src->n_obstacles == 0) return;
     double max_rad = 0.0, min_in = INFINITY;
@@ -313,7 +316,16 @@ int kcbs_create(const kcbs_world *world, int device, kcbs_ctx **out)
     if (!ctx) return fail(nullptr, KCBS_ERR_OUT_OF_MEMORY, "host allocation failed");
     ctx->device = device;
     build_grid(world, w, ctx->h_grid, ctx->h_obs4);
-    build_fine_grid(world, w, ctx->h_fine);
+    {
+        // device layout of the fine grid: padded pitch, last row / column repeated (kcbs_device.cuh)
+        std::vector<unsigned short> logical;
+        build_fine_grid(world, w, logical);
+        ctx->h_fine.assign((size_t)kFineRows * kFinePitch, 0);
+        for (int iy = 0; iy < kFineRows; ++iy)
+            for (int ix = 0; ix <= kFineDim; ++ix)
+                ctx->h_fine[(size_t)iy * kFinePitch + ix] =
+                    logical[(size_t)std::min(iy, kFineDim - 1) * kFineDim + std::min(ix, kFineDim - 1)];
+    }
     ctx->world = w;
     ctx->n_robots = world->n_robots;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||

@@ -39,7 +39,9 @@ struct DevWorld {
     // Fine three-valued obstacle grid (built on the host at kcbs_create): one 16-bit code per cell, see cell_code().
     int fdim;                        // cells per side (kFineDim)
     float finvx, finvy;              // fine cells per metre
-    const unsigned short *fine;      // [fdim * fdim]
+    float foffx, foffy;              // -origin * cells per metre: cell = (int)fma(x, finvx, foffx)
+    const unsigned short *fine;      // [kFineRows][kFinePitch], see fine_cell()
+    int sym_bounds;                  // v, phi and theta thresholds are symmetric about 0 (one compare each)
     const float4 *obs4;              // [n_obs] (cx, cy, hx, hy), same values as the arrays below
     float obs_cx[KCBS_MAX_OBSTACLES];  // Obstacle.h:85-86 centre
     float obs_cy[KCBS_MAX_OBSTACLES];
@@ -77,6 +79,15 @@ __device__ __forceinline__ bool in_bounds(const DevWorld &w, float x, float y, f
     ok &= (v >= w.lo_t[2]) & (v <= w.hi_t[2]);
     ok &= (phi >= w.lo_t[3]) & (phi <= w.hi_t[3]);
     ok &= (th >= w.th_lo_t) & (th <= w.th_hi_t);
+    return ok;
+}
+
+// Same test when the v, phi and theta thresholds are symmetric about zero (DevWorld::sym_bounds; true for every demo).
+__device__ __forceinline__ bool in_bounds_sym(const DevWorld &w, float x, float y, float v, float phi, float th)
+{
+    bool ok = (x >= w.lo_t[0]) & (x <= w.hi_t[0]);
+    ok &= (y >= w.lo_t[1]) & (y <= w.hi_t[1]);
+    ok &= (fabsf(v) <= w.hi_t[2]) & (fabsf(phi) <= w.hi_t[3]) & (fabsf(th) <= w.th_hi_t);
     return ok;
 }
 
@@ -173,13 +184,16 @@ __device__ __forceinline__ bool obstacles_clear_grid(const DevWorld &w, const un
 // Cell code: 0 = all obstacles free; kCellHit = some obstacle hits; kCellMany = more than two maybes (decided through
 // the coarse 64-bit mask grid); otherwise the one or two maybe obstacles as (index + 1) in the low / high byte.
 constexpr int kFineDim = 128;
+// Device layout: one extra row and column (copies of the last ones) so that a state sitting exactly on the upper bound
+// indexes without a clamp; pitch padded to a multiple of 16 bytes.
+constexpr int kFineRows = kFineDim + 1, kFinePitch = 136;
 constexpr unsigned kCellHit = 0xffffu, kCellMany = 0xfffeu;
 
 __device__ __forceinline__ int fine_cell(const DevWorld &w, float x, float y)
 {
-    const int ix = min(kFineDim - 1, max(0, (int)((x - w.gx0) * w.finvx)));
-    const int iy = min(kFineDim - 1, max(0, (int)((y - w.gy0) * w.finvy)));
-    return iy * kFineDim + ix;
+    const int ix = min(kFineDim - 1, max(0, (int)fmaf(x, w.finvx, w.foffx)));
+    const int iy = min(kFineDim - 1, max(0, (int)fmaf(y, w.finvy, w.foffy)));
+    return iy * kFinePitch + ix;
 }
 
 // true when a separating axis exists between the robot rectangle (centre (x, y), heading cos / sin c, s, half extents

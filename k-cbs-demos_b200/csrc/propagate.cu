@@ -23,13 +23,17 @@
 //   * positions and the heading are accumulated as small offsets from the parent / the step start,
 //     so FP32 rounding at |x| ~ 32 happens once per written state, not once per sub-step.
 //
+//   * every thread integrates TWO samples at once in packed FP32 pairs (fma / mul / add .f32x2, SASS FFMA2 ...): the
+//     kernel is bound by issue slots, and a packed instruction does two samples' worth of FMA-pipe work in one
+//     slot (car_step2 in car_dynamics.cuh: 43 packed instructions + 4 MUFU.RCP per sub-step of two samples).
+//
 // Work distribution: requested durations are U{1..10} (SimpleDirectedControlSampler), which would
 // idle 45 % of the lanes of a warp; and because v, phi are linear in time, the step at which a sample
 // leaves the v / phi bounds is known up front, so its effective duration is too (the doomed step is never
-// integrated).  Each CTA (128 threads) therefore counting-sorts its 256 samples by
-// duration in shared memory and every thread runs two of them: rank t (long) and rank 255 - t (short).
-// Lanes of a warp then hold (almost) equal durations in both rounds and every thread of the CTA has the
-// same total work, so neither lanes nor warps idle.  Segments are staged in shared memory at their original
+// integrated).  Each CTA (64 threads) therefore counting-sorts its 256 samples by duration in shared memory and every
+// thread runs two packed pairs of neighbouring ranks: ranks (2t, 2t+1) (long) and then (254-2t, 255-2t) (short).
+// Both halves of a pair and the lanes of a warp then hold (almost) equal durations in both rounds and every thread
+// of the CTA has the same total work, so neither lanes nor warps idle.  Segments are staged in shared memory at their original
 // slots (x, y, theta per step; v and phi are recomputed from their exact linear form) and leave in one
 // coalesced pass that also zero-fills the rows past the last valid state: every 32 B sector is written
 // completely (no partial-sector traffic at L2, no read-modify-write at HBM).
@@ -66,16 +70,20 @@ __device__ __forceinline__ bool constraints_clear(const DevWorld &w, const PropA
     return ok;
 }
 
-constexpr int kPropThreads = 128;  // threads per CTA
-constexpr int kPropSamples = 256;  // samples per CTA (two per thread)
+#ifndef KCBS_PROP_MINB
+#define KCBS_PROP_MINB 8
+#endif
+constexpr int kPropThreads = 64;   // threads per CTA
+constexpr int kPropSamples = 256;  // samples per CTA (two packed pairs per thread)
+constexpr int kPropPer = kPropSamples / kPropThreads;
 constexpr int kStageSteps = 10;    // segments up to this many steps are staged in shared memory
 
 // Shared-memory staging of one CTA's segments: x, y, theta of every (step, slot), plus the four numbers from which
-// v and phi of any step follow exactly (they are linear in time).  35 KB -> 6 CTAs (24 warps) per SM.
-struct PropStage {
+// v and phi of any step follow exactly (they are linear in time).  35 KB -> 6 CTAs per SM.
+struct __align__(16) PropStage {
     float xyt[3][kStageSteps][kPropSamples];
     float v0[kPropSamples], ua[kPropSamples], p0[kPropSamples], uw[kPropSamples];
-    unsigned char nv[kPropSamples];
+    __align__(16) unsigned char nv[kPropSamples];
 };
 
 template <bool STAGED>
@@ -89,93 +97,123 @@ struct StageStorage<false> {  // direct-store variants carry no stage
     __device__ static PropStage *get(type &) { return nullptr; }
 };
 
-// propagateWhileValid for one sample; writes the segment, the final state and the valid-step count.
+// propagateWhileValid for the two samples i[0], i[1] (effective durations st[0], st[1]; st = 0 for a slot past the end
+// of the batch): writes their segments, final states and valid-step counts.
 template <bool HAS_OBS, bool HAS_CONS, bool STAGED>
-__device__ __forceinline__ void propagate_sample(const DevWorld &w, const PropArgs &a, long long i, int st, PropStage *stage,
-                                                 int slot)
+__device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs &a, const long long i[2], const int st[2],
+                                              PropStage *stage, unsigned char *s_nv, const int slot[2])
 {
-    const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
-    const int t0 = (HAS_CONS && a.parent_time) ? a.parent_time[pi] : 0;
-    const float x0 = a.parents[0 * a.n_parents + pi];
-    const float y0 = a.parents[1 * a.n_parents + pi];
-    const float v0 = a.parents[2 * a.n_parents + pi];
-    const float phi0 = a.parents[3 * a.n_parents + pi];
-    const float th0 = a.parents[4 * a.n_parents + pi];
-    const float ua = a.controls[i];
-    const float uw = a.controls[a.n + i];
-
-    const float hl = w.rob_hl[a.robot], hw = w.rob_hw[a.robot];
-    const CarConsts k = car_consts(w, ua, uw);
-
-    float offx = 0.0f, offy = 0.0f;                         // position offset from the parent
-    float xs = x0, ys = y0, vs = v0, ps = phi0, ts = th0;   // last valid state
-    int nv = 0;
-    const long long plane = (long long)a.max_steps * a.n;
-
-    for (int j = 0; j < st; ++j) {
-        const float toff = car_step(k, w.n_sub, vs, ps, ts, offx, offy);
-
-        const float t1 = (float)(j + 1) * w.step;
-        const float xn = x0 + offx, yn = y0 + offy;
-        const float vn = fmaf(ua, t1, v0), pn = fmaf(uw, t1, phi0);
-        const float tn = wrap_angle(ts + toff);
-
-        bool ok = in_bounds(w, xn, yn, vn, pn, tn);
-        if (HAS_OBS) {
-            if (ok) ok = obstacles_clear_fine(w, xn, yn, tn, hl, hw);
-        }
-        if (HAS_CONS) {
-            if (ok) ok = constraints_clear(w, a, t0 + j + 1, xn, yn, tn, hl, hw, w.rob_rad[a.robot]);
-        }
-        if (!ok) break;
-
-        xs = xn; ys = yn; vs = vn; ps = pn; ts = tn;
-        nv = j + 1;
-        if (STAGED) {
-            stage->xyt[0][j][slot] = xn;
-            stage->xyt[1][j][slot] = yn;
-            stage->xyt[2][j][slot] = tn;
-        } else if (a.seg) {
-            float *o = a.seg + (long long)j * a.n + i;
-            __stcs(o, xn);
-            __stcs(o + plane, yn);
-            __stcs(o + 2 * plane, vn);
-            __stcs(o + 3 * plane, pn);
-            __stcs(o + 4 * plane, tn);
-        }
-    }
-
-    if (STAGED) {
-        stage->v0[slot] = v0;
-        stage->ua[slot] = ua;
-        stage->p0[slot] = phi0;
-        stage->uw[slot] = uw;
-        stage->nv[slot] = (unsigned char)nv;
-    } else if (a.seg) {
-        // rows past the last valid state are zero-filled (as the staged path does)
-        for (int j = nv; j < a.max_steps; ++j) {
-            float *o = a.seg + (long long)j * a.n + i;
+    float x0[2], y0[2], v0[2], phi0[2], th0[2], ua[2], uw[2];
+    int t0[2];
 #pragma unroll
-            for (int c = 0; c < 5; ++c) __stcs(o + c * plane, 0.0f);
+    for (int e = 0; e < 2; ++e) {
+        const long long pi = a.parent_idx ? (long long)a.parent_idx[i[e]] : (a.n_parents == 1 ? 0 : i[e]);
+        t0[e] = (HAS_CONS && a.parent_time) ? a.parent_time[pi] : 0;
+        x0[e] = a.parents[0 * a.n_parents + pi];
+        y0[e] = a.parents[1 * a.n_parents + pi];
+        v0[e] = a.parents[2 * a.n_parents + pi];
+        phi0[e] = a.parents[3 * a.n_parents + pi];
+        th0[e] = a.parents[4 * a.n_parents + pi];
+        ua[e] = a.controls[i[e]];
+        uw[e] = a.controls[a.n + i[e]];
+    }
+    const float hl = w.rob_hl[a.robot], hw = w.rob_hw[a.robot];
+    const CarConsts2 k = car_consts2(w, ua, uw);
+
+    f32x2 offx = pk1(0.0f), offy = pk1(0.0f);  // position offsets from the parents
+    float xs[2] = {x0[0], x0[1]}, ys[2] = {y0[0], y0[1]}, vs[2] = {v0[0], v0[1]};   // last valid states
+    float ps[2] = {phi0[0], phi0[1]}, ts[2] = {th0[0], th0[1]};
+    // tan(phi) at the start of the current step: accurate once per sample, then advanced step by step with the
+    // addition formula and tan(step * w) (one rounding-level error per step instead of one sincosf per step)
+    float Ts[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        float sp, cp;
+        sincosf(phi0[e], &sp, &cp);
+        Ts[e] = __fdividef(sp, cp);
+    }
+    int nv[2] = {0, 0};
+    bool alive[2] = {st[0] > 0, st[1] > 0};
+    const long long plane = (long long)a.max_steps * a.n;
+    const int jmax = max(st[0], st[1]);
+
+    for (int j = 0; j < jmax && (alive[0] | alive[1]); ++j) {
+        const f32x2 toff2 = w.n_sub == 10 ? car_step2<10>(k, 10, vs, Ts, ts, offx, offy)
+                                          : car_step2<0>(k, w.n_sub, vs, Ts, ts, offx, offy);
+        float ox[2], oy[2], toff[2];
+        upk(offx, ox[0], ox[1]);
+        upk(offy, oy[0], oy[1]);
+        upk(toff2, toff[0], toff[1]);
+        const float t1 = (float)(j + 1) * w.step;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (!alive[e]) continue;  // a finished half keeps integrating from its last state; nothing of it is used
+            const float xn = x0[e] + ox[e], yn = y0[e] + oy[e];
+            const float vn = fmaf(ua[e], t1, v0[e]), pn = fmaf(uw[e], t1, phi0[e]);
+            const float tn = wrap_angle(ts[e] + toff[e]);
+            // v and phi of every step below st were tested when st was derived (same expressions): x, y, theta remain
+            bool ok = (xn >= w.lo_t[0]) & (xn <= w.hi_t[0]) & (yn >= w.lo_t[1]) & (yn <= w.hi_t[1]) & (tn >= w.th_lo_t) &
+                      (tn <= w.th_hi_t);
+            if (HAS_OBS) {
+                if (ok) ok = obstacles_clear_fine(w, xn, yn, tn, hl, hw);
+            }
+            if (HAS_CONS) {
+                if (ok) ok = constraints_clear(w, a, t0[e] + j + 1, xn, yn, tn, hl, hw, w.rob_rad[a.robot]);
+            }
+            if (!ok) {
+                alive[e] = false;
+                continue;
+            }
+            xs[e] = xn; ys[e] = yn; vs[e] = vn; ps[e] = pn; ts[e] = tn;
+            Ts[e] = __fdividef(Ts[e] + k.tstep[e], fmaf(-Ts[e], k.tstep[e], 1.0f));
+            nv[e] = j + 1;
+            alive[e] = j + 1 < st[e];
+            if (STAGED) {
+                stage->xyt[0][j][slot[e]] = xn;
+                stage->xyt[1][j][slot[e]] = yn;
+                stage->xyt[2][j][slot[e]] = tn;
+            } else if (a.seg) {
+                // straight to the sample's own slot: the CTA's stores of a row stay inside one 1 KB window, L2 merges
+                // them (and the epilogue's) into full lines; v and phi are written by the epilogue
+                float *o = a.seg + (long long)j * a.n + i[e];
+                __stcs(o, xn);
+                __stcs(o + plane, yn);
+                __stcs(o + 4 * plane, tn);
+            }
         }
     }
-    if (a.valid_steps) a.valid_steps[i] = nv;
-    if (a.fin) {
-        a.fin[i] = xs;
-        a.fin[a.n + i] = ys;
-        a.fin[2 * a.n + i] = vs;
-        a.fin[3 * a.n + i] = ps;
-        a.fin[4 * a.n + i] = ts;
+
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        if (slot[e] < 0) continue;  // past the end of the batch
+        if (STAGED) {
+            stage->v0[slot[e]] = v0[e];
+            stage->ua[slot[e]] = ua[e];
+            stage->p0[slot[e]] = phi0[e];
+            stage->uw[slot[e]] = uw[e];
+            stage->nv[slot[e]] = (unsigned char)nv[e];
+        } else {
+            s_nv[slot[e]] = (unsigned char)nv[e];
+        }
+        if (a.valid_steps) a.valid_steps[i[e]] = nv[e];
+        if (a.fin) {
+            a.fin[i[e]] = xs[e];
+            a.fin[a.n + i[e]] = ys[e];
+            a.fin[2 * a.n + i[e]] = vs[e];
+            a.fin[3 * a.n + i[e]] = ps[e];
+            a.fin[4 * a.n + i[e]] = ts[e];
+        }
     }
 }
 
 template <bool HAS_OBS, bool HAS_CONS, bool STAGED>
-__global__ void __launch_bounds__(kPropThreads)
+__global__ void __launch_bounds__(kPropThreads, STAGED ? 6 : KCBS_PROP_MINB)
 k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs a)
 {
-    __shared__ int s_hist[KCBS_MAX_STEPS + 1];
+    __shared__ int s_hist[KCBS_MAX_STEPS + 1], s_first[KCBS_MAX_STEPS + 1];
     __shared__ unsigned char s_perm[kPropSamples];   // rank -> slot
     __shared__ unsigned char s_steps[kPropSamples];  // slot -> effective duration
+    __shared__ unsigned char s_nv[kPropSamples];     // slot -> valid steps (direct path)
     __shared__ typename StageStorage<STAGED>::type s_stage_mem;
     PropStage *stage = StageStorage<STAGED>::get(s_stage_mem);
 
@@ -185,9 +223,9 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
     // ---- counting sort of the CTA's samples by effective duration (longest first) ----------------
     if (tid <= KCBS_MAX_STEPS) s_hist[tid] = 0;
     __syncthreads();
-    int st2[2], within[2];
+    int st4[kPropPer], within[kPropPer];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kPropPer; ++u) {
         const int slot = tid + u * kPropThreads;
         const long long i = b0 + slot;
         int st = 0;
@@ -201,36 +239,88 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
             const float v0 = a.parents[2 * a.n_parents + pi], phi0 = a.parents[3 * a.n_parents + pi];
             const float ua = a.controls[i], uw = a.controls[a.n + i];
-            int ok_steps = 0;
-            for (int j = 0; j < st; ++j) {
+            // fmaf(u, t, v0) is monotonic in t, so the valid steps form a prefix; when the first and the last requested
+            // step are inside, all of them are (the common case: two evaluations instead of a loop)
+            auto inside = [&](int j) {
                 const float t1 = (float)(j + 1) * w.step;
                 const float vn = fmaf(ua, t1, v0), pn = fmaf(uw, t1, phi0);
-                if (!((vn >= w.lo_t[2]) & (vn <= w.hi_t[2]) & (pn >= w.lo_t[3]) & (pn <= w.hi_t[3]))) break;
-                ok_steps = j + 1;
+                return (vn >= w.lo_t[2]) & (vn <= w.hi_t[2]) & (pn >= w.lo_t[3]) & (pn <= w.hi_t[3]);
+            };
+            int ok_steps = 0;
+            if (st > 0 && inside(0)) {
+                if (inside(st - 1)) {
+                    ok_steps = st;
+                } else {
+                    ok_steps = 1;
+                    while (ok_steps < st && inside(ok_steps)) ++ok_steps;
+                }
             }
             st = ok_steps;
         }
-        st2[u] = st;
+        st4[u] = st;
         s_steps[slot] = (unsigned char)st;
         if (STAGED) stage->nv[slot] = 0;
+        else s_nv[slot] = 0;
         within[u] = atomicAdd(&s_hist[st], 1);
     }
     __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        int before = 0;  // samples with a longer duration come first
-        for (int s = KCBS_MAX_STEPS; s > st2[u]; --s) before += s_hist[s];
-        s_perm[before + within[u]] = (unsigned char)(tid + u * kPropThreads);
+    if (tid <= KCBS_MAX_STEPS) {  // s_first[d] = rank of the first sample of duration d (longer durations come first)
+        int before = 0;
+        for (int d = KCBS_MAX_STEPS; d > tid; --d) before += s_hist[d];
+        s_first[tid] = before;
     }
     __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPropPer; ++u) s_perm[s_first[st4[u]] + within[u]] = (unsigned char)(tid + u * kPropThreads);
+    __syncthreads();
 
-    // ---- two samples per thread: rank tid (long) and rank 255 - tid (short) ------------------------
+    // ---- two packed pairs per thread: ranks (2t, 2t+1) (long) and (254-2t, 255-2t) (short) -------------
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
-        const int rank = round == 0 ? tid : kPropSamples - 1 - tid;
-        const int slot = s_perm[rank];
-        const long long i = b0 + slot;
-        if (i < a.n) propagate_sample<HAS_OBS, HAS_CONS, STAGED>(w, a, i, (int)s_steps[slot], stage, slot);
+        const int r0 = round == 0 ? 2 * tid : kPropSamples - 2 - 2 * tid;
+        int slot[2], st[2];
+        long long i[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            slot[e] = s_perm[r0 + e];
+            i[e] = b0 + slot[e];
+            st[e] = (int)s_steps[slot[e]];
+            if (i[e] >= a.n) {  // past the end of the batch: integrate nothing, write nothing
+                i[e] = a.n - 1;
+                st[e] = 0;
+                slot[e] = -1;
+            }
+        }
+        if (slot[0] >= 0 || slot[1] >= 0) propagate_two<HAS_OBS, HAS_CONS, STAGED>(w, a, i, st, stage, s_nv, slot);
+    }
+
+    if (!STAGED && a.seg) {
+        // ---- coalesced epilogue of the direct path: every thread owns the slots it sorted; it writes v and phi of the
+        // valid rows (exact linear functions of time, the very expressions the integrator tested) and zero-fills all
+        // five planes of the rows past the last valid state.  Disjoint from the x / y / theta stores above.
+        __syncthreads();
+        const long long plane = (long long)a.max_steps * a.n;
+#pragma unroll
+        for (int u = 0; u < kPropPer; ++u) {
+            const int slot = tid + u * kPropThreads;
+            const long long i = b0 + slot;
+            if (i >= a.n) continue;
+            const int nv = s_nv[slot];
+            const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
+            const float v0 = a.parents[2 * a.n_parents + pi], p0 = a.parents[3 * a.n_parents + pi];
+            const float ua = a.controls[i], uw = a.controls[a.n + i];
+            for (int j = 0; j < a.max_steps; ++j) {
+                float *o = a.seg + (long long)j * a.n + i;
+                const float t1 = (float)(j + 1) * w.step;
+                if (j < nv) {
+                    __stcs(o + 2 * plane, fmaf(ua, t1, v0));
+                    __stcs(o + 3 * plane, fmaf(uw, t1, p0));
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) __stcs(o + c * plane, 0.0f);
+                }
+            }
+        }
     }
 
     if (STAGED) {
@@ -238,22 +328,57 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         // state are zero, so no sector of the segment buffer is ever partially written --------------------------
         __syncthreads();
         const long long plane = (long long)a.max_steps * a.n;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int slot = tid + u * kPropThreads;
+        if ((a.n & 3) == 0 && (reinterpret_cast<uintptr_t>(a.seg) & 15) == 0) {
+            // 16 B stores: the thread owns four consecutive slots
+            const int slot = 4 * tid;
             const long long i = b0 + slot;
-            if (i >= a.n) continue;
-            const int nv = stage->nv[slot];
-            const float v0 = stage->v0[slot], ua = stage->ua[slot], p0 = stage->p0[slot], uw = stage->uw[slot];
-            for (int j = 0; j < a.max_steps; ++j) {
-                float *o = a.seg + (long long)j * a.n + i;
-                const bool live = j < nv;
-                const float t1 = (float)(j + 1) * w.step;
-                __stcs(o, live ? stage->xyt[0][j][slot] : 0.0f);
-                __stcs(o + plane, live ? stage->xyt[1][j][slot] : 0.0f);
-                __stcs(o + 2 * plane, live ? fmaf(ua, t1, v0) : 0.0f);   // same expression as the integrator's
-                __stcs(o + 3 * plane, live ? fmaf(uw, t1, p0) : 0.0f);
-                __stcs(o + 4 * plane, live ? stage->xyt[2][j][slot] : 0.0f);
+            if (i < a.n) {
+                const uchar4 nv4 = *reinterpret_cast<const uchar4 *>(&stage->nv[slot]);
+                const int nv[4] = {nv4.x, nv4.y, nv4.z, nv4.w};
+                const float4 v0 = *reinterpret_cast<const float4 *>(&stage->v0[slot]);
+                const float4 ua = *reinterpret_cast<const float4 *>(&stage->ua[slot]);
+                const float4 p0 = *reinterpret_cast<const float4 *>(&stage->p0[slot]);
+                const float4 uw = *reinterpret_cast<const float4 *>(&stage->uw[slot]);
+                float *o = a.seg + i;
+                for (int j = 0; j < a.max_steps; ++j, o += a.n) {
+                    const float t1 = (float)(j + 1) * w.step;
+                    const bool l0 = j < nv[0], l1 = j < nv[1], l2 = j < nv[2], l3 = j < nv[3];
+                    const float4 X = *reinterpret_cast<const float4 *>(&stage->xyt[0][j][slot]);
+                    const float4 Y = *reinterpret_cast<const float4 *>(&stage->xyt[1][j][slot]);
+                    const float4 T = *reinterpret_cast<const float4 *>(&stage->xyt[2][j][slot]);
+                    __stcs(reinterpret_cast<float4 *>(o),
+                           make_float4(l0 ? X.x : 0.0f, l1 ? X.y : 0.0f, l2 ? X.z : 0.0f, l3 ? X.w : 0.0f));
+                    __stcs(reinterpret_cast<float4 *>(o + plane),
+                           make_float4(l0 ? Y.x : 0.0f, l1 ? Y.y : 0.0f, l2 ? Y.z : 0.0f, l3 ? Y.w : 0.0f));
+                    // same expressions as the integrator's
+                    __stcs(reinterpret_cast<float4 *>(o + 2 * plane),
+                           make_float4(l0 ? fmaf(ua.x, t1, v0.x) : 0.0f, l1 ? fmaf(ua.y, t1, v0.y) : 0.0f,
+                                       l2 ? fmaf(ua.z, t1, v0.z) : 0.0f, l3 ? fmaf(ua.w, t1, v0.w) : 0.0f));
+                    __stcs(reinterpret_cast<float4 *>(o + 3 * plane),
+                           make_float4(l0 ? fmaf(uw.x, t1, p0.x) : 0.0f, l1 ? fmaf(uw.y, t1, p0.y) : 0.0f,
+                                       l2 ? fmaf(uw.z, t1, p0.z) : 0.0f, l3 ? fmaf(uw.w, t1, p0.w) : 0.0f));
+                    __stcs(reinterpret_cast<float4 *>(o + 4 * plane),
+                           make_float4(l0 ? T.x : 0.0f, l1 ? T.y : 0.0f, l2 ? T.z : 0.0f, l3 ? T.w : 0.0f));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kPropPer; ++u) {
+                const int slot = tid + u * kPropThreads;
+                const long long i = b0 + slot;
+                if (i >= a.n) continue;
+                const int nv = stage->nv[slot];
+                const float v0 = stage->v0[slot], ua = stage->ua[slot], p0 = stage->p0[slot], uw = stage->uw[slot];
+                float *o = a.seg + i;
+                for (int j = 0; j < a.max_steps; ++j, o += a.n) {
+                    const bool live = j < nv;
+                    const float t1 = (float)(j + 1) * w.step;
+                    __stcs(o, live ? stage->xyt[0][j][slot] : 0.0f);
+                    __stcs(o + plane, live ? stage->xyt[1][j][slot] : 0.0f);
+                    __stcs(o + 2 * plane, live ? fmaf(ua, t1, v0) : 0.0f);
+                    __stcs(o + 3 * plane, live ? fmaf(uw, t1, p0) : 0.0f);
+                    __stcs(o + 4 * plane, live ? stage->xyt[2][j][slot] : 0.0f);
+                }
             }
         }
     }
@@ -283,7 +408,9 @@ cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t 
     if (a.n <= 0) return cudaSuccess;
     // whole segments of up to kStageSteps steps leave through the shared-memory stage (coalesced);
     // longer horizons and final-state-only calls write directly
+#ifndef KCBS_PROP_DIRECT  // experiment builds only: bypass the shared-memory stage
     if (a.seg != nullptr && a.max_steps <= kStageSteps) return launch_staged<true>(w, a, stream);
+#endif
     return launch_staged<false>(w, a, stream);
 }
 

@@ -10,8 +10,8 @@ SCENES = ["Congested10x10_7robots", "Corridor10x10_4robots", "Benchmark_Corridor
 def _cells(world, dim, x, y):
     lo, hi = world.bounds()
     # the device lookup (kcbs_device.cuh, fine_cell) in float
-    fx = (x.astype(np.float32) - np.float32(lo[0])) * np.float32(dim / (hi[0] - lo[0]))
-    fy = (y.astype(np.float32) - np.float32(lo[1])) * np.float32(dim / (hi[1] - lo[1]))
+    fx = x.astype(np.float32) * np.float32(dim / (hi[0] - lo[0])) + np.float32(-lo[0] * dim / (hi[0] - lo[0]))
+    fy = y.astype(np.float32) * np.float32(dim / (hi[1] - lo[1])) + np.float32(-lo[1] * dim / (hi[1] - lo[1]))
     ix = np.clip(fx.astype(np.int64), 0, dim - 1)
     iy = np.clip(fy.astype(np.int64), 0, dim - 1)
     return iy, ix
