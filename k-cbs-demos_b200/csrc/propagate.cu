@@ -109,6 +109,17 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
     for (int e = 0; e < 2; ++e) {
         const long long pi = a.parent_idx ? (long long)a.parent_idx[i[e]] : (a.n_parents == 1 ? 0 : i[e]);
         t0[e] = (HAS_CONS && a.parent_time) ? a.parent_time[pi] : 0;
+        if (STAGED) {  // the sort pass left the sample's inputs in shared memory (slot -1: any slot, nothing is used)
+            const int sl = max(slot[e], 0);
+            x0[e] = stage->xyt[0][kStageSteps - 1][sl];
+            y0[e] = stage->xyt[1][kStageSteps - 1][sl];
+            th0[e] = stage->xyt[2][kStageSteps - 1][sl];
+            v0[e] = stage->v0[sl];
+            phi0[e] = stage->p0[sl];
+            ua[e] = stage->ua[sl];
+            uw[e] = stage->uw[sl];
+            continue;
+        }
         x0[e] = a.parents[0 * a.n_parents + pi];
         y0[e] = a.parents[1 * a.n_parents + pi];
         v0[e] = a.parents[2 * a.n_parents + pi];
@@ -147,27 +158,30 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
         const float t1 = (float)(j + 1) * w.step;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            if (!alive[e]) continue;  // a finished half keeps integrating from its last state; nothing of it is used
+            // straight-line code with predicated commits, so that the two halves interleave; a finished half keeps
+            // integrating from its last state and nothing of it is used
             const float xn = x0[e] + ox[e], yn = y0[e] + oy[e];
             const float vn = fmaf(ua[e], t1, v0[e]), pn = fmaf(uw[e], t1, phi0[e]);
             const float tn = wrap_angle(ts[e] + toff[e]);
+            const float Tn = __fdividef(Ts[e] + k.tstep[e], fmaf(-Ts[e], k.tstep[e], 1.0f));
             // v and phi of every step below st were tested when st was derived (same expressions): x, y, theta remain
-            bool ok = (xn >= w.lo_t[0]) & (xn <= w.hi_t[0]) & (yn >= w.lo_t[1]) & (yn <= w.hi_t[1]) & (tn >= w.th_lo_t) &
-                      (tn <= w.th_hi_t);
+            bool ok = alive[e] & (xn >= w.lo_t[0]) & (xn <= w.hi_t[0]) & (yn >= w.lo_t[1]) & (yn <= w.hi_t[1]) &
+                      (tn >= w.th_lo_t) & (tn <= w.th_hi_t);
             if (HAS_OBS) {
                 if (ok) ok = obstacles_clear_fine(w, xn, yn, tn, hl, hw);
             }
             if (HAS_CONS) {
                 if (ok) ok = constraints_clear(w, a, t0[e] + j + 1, xn, yn, tn, hl, hw, w.rob_rad[a.robot]);
             }
-            if (!ok) {
-                alive[e] = false;
-                continue;
-            }
-            xs[e] = xn; ys[e] = yn; vs[e] = vn; ps[e] = pn; ts[e] = tn;
-            Ts[e] = __fdividef(Ts[e] + k.tstep[e], fmaf(-Ts[e], k.tstep[e], 1.0f));
-            nv[e] = j + 1;
-            alive[e] = j + 1 < st[e];
+            xs[e] = ok ? xn : xs[e];
+            ys[e] = ok ? yn : ys[e];
+            vs[e] = ok ? vn : vs[e];
+            ps[e] = ok ? pn : ps[e];
+            ts[e] = ok ? tn : ts[e];
+            Ts[e] = ok ? Tn : Ts[e];
+            nv[e] = ok ? j + 1 : nv[e];
+            alive[e] = ok & (j + 1 < st[e]);
+            if (!ok) continue;
             if (STAGED) {
                 stage->xyt[0][j][slot[e]] = xn;
                 stage->xyt[1][j][slot[e]] = yn;
@@ -187,10 +201,6 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
     for (int e = 0; e < 2; ++e) {
         if (slot[e] < 0) continue;  // past the end of the batch
         if (STAGED) {
-            stage->v0[slot[e]] = v0[e];
-            stage->ua[slot[e]] = ua[e];
-            stage->p0[slot[e]] = phi0[e];
-            stage->uw[slot[e]] = uw[e];
             stage->nv[slot[e]] = (unsigned char)nv[e];
         } else {
             s_nv[slot[e]] = (unsigned char)nv[e];
@@ -256,6 +266,17 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 }
             }
             st = ok_steps;
+            if (STAGED) {
+                // inputs of the sample for propagate_two and the write-out; x0, y0, theta0 borrow the sample's own last
+                // stage row, which the sample overwrites only when it completes its final step
+                stage->v0[slot] = v0;
+                stage->p0[slot] = phi0;
+                stage->ua[slot] = ua;
+                stage->uw[slot] = uw;
+                stage->xyt[0][kStageSteps - 1][slot] = a.parents[0 * a.n_parents + pi];
+                stage->xyt[1][kStageSteps - 1][slot] = a.parents[1 * a.n_parents + pi];
+                stage->xyt[2][kStageSteps - 1][slot] = a.parents[4 * a.n_parents + pi];
+            }
         }
         st4[u] = st;
         s_steps[slot] = (unsigned char)st;
