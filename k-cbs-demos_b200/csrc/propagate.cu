@@ -71,11 +71,15 @@ __device__ __forceinline__ bool constraints_clear(const DevWorld &w, const PropA
 }
 
 #ifndef KCBS_PROP_MINB
-#define KCBS_PROP_MINB 8
+#define KCBS_PROP_MINB 4
 #endif
-constexpr int kPropThreads = 64;   // threads per CTA
-constexpr int kPropSamples = 256;  // samples per CTA (two packed pairs per thread)
+#ifndef KCBS_PROP_THREADS
+#define KCBS_PROP_THREADS 128
+#endif
+constexpr int kPropThreads = KCBS_PROP_THREADS;  // threads per CTA
+constexpr int kPropSamples = 4 * kPropThreads;   // samples per CTA (two packed pairs per thread)
 constexpr int kPropPer = kPropSamples / kPropThreads;
+constexpr int kStagedCtasPerSm = 384 / kPropThreads;  // 12 warps per SM: what the 35 KB per 256 samples stage allows
 constexpr int kStageSteps = 10;    // segments up to this many steps are staged in shared memory
 
 // Shared-memory staging of one CTA's segments: x, y, theta of every (step, slot), plus the four numbers from which
@@ -84,17 +88,6 @@ struct __align__(16) PropStage {
     float xyt[3][kStageSteps][kPropSamples];
     float v0[kPropSamples], ua[kPropSamples], p0[kPropSamples], uw[kPropSamples];
     __align__(16) unsigned char nv[kPropSamples];
-};
-
-template <bool STAGED>
-struct StageStorage {
-    using type = PropStage;
-    __device__ static PropStage *get(type &t) { return &t; }
-};
-template <>
-struct StageStorage<false> {  // direct-store variants carry no stage
-    using type = int;
-    __device__ static PropStage *get(type &) { return nullptr; }
 };
 
 // propagateWhileValid for the two samples i[0], i[1] (effective durations st[0], st[1]; st = 0 for a slot past the end
@@ -217,15 +210,15 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
 }
 
 template <bool HAS_OBS, bool HAS_CONS, bool STAGED>
-__global__ void __launch_bounds__(kPropThreads, STAGED ? 6 : KCBS_PROP_MINB)
+__global__ void __launch_bounds__(kPropThreads, STAGED ? kStagedCtasPerSm : KCBS_PROP_MINB)
 k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs a)
 {
     __shared__ int s_hist[KCBS_MAX_STEPS + 1], s_first[KCBS_MAX_STEPS + 1];
-    __shared__ unsigned char s_perm[kPropSamples];   // rank -> slot
+    __shared__ unsigned short s_perm[kPropSamples];  // rank -> slot
     __shared__ unsigned char s_steps[kPropSamples];  // slot -> effective duration
     __shared__ unsigned char s_nv[kPropSamples];     // slot -> valid steps (direct path)
-    __shared__ typename StageStorage<STAGED>::type s_stage_mem;
-    PropStage *stage = StageStorage<STAGED>::get(s_stage_mem);
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // the stage (staged variants only)
+    PropStage *stage = STAGED ? reinterpret_cast<PropStage *>(s_dyn) : nullptr;
 
     const int tid = threadIdx.x;
     const long long b0 = (long long)blockIdx.x * kPropSamples;
@@ -292,7 +285,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
     }
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < kPropPer; ++u) s_perm[s_first[st4[u]] + within[u]] = (unsigned char)(tid + u * kPropThreads);
+    for (int u = 0; u < kPropPer; ++u) s_perm[s_first[st4[u]] + within[u]] = (unsigned short)(tid + u * kPropThreads);
     __syncthreads();
 
     // ---- two packed pairs per thread: ranks (2t, 2t+1) (long) and (254-2t, 255-2t) (short) -------------
@@ -405,21 +398,30 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
     }
 }
 
-cudaError_t init_propagate_kernels() { return cudaSuccess; }
+cudaError_t init_propagate_kernels()
+{
+    const int bytes = (int)sizeof(PropStage);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_propagate<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_propagate<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_propagate<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_propagate<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
 
 template <bool STAGED>
 static cudaError_t launch_staged(const DevWorld &w, const PropArgs &a, cudaStream_t stream)
 {
     const long long grid = (a.n + kPropSamples - 1) / kPropSamples;
+    const size_t smem = STAGED ? sizeof(PropStage) : 0;
     if (a.n_cons > 0) {
         if (w.n_obs > 0)
-            k_propagate<true, true, STAGED><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+            k_propagate<true, true, STAGED><<<(unsigned)grid, kPropThreads, smem, stream>>>(w, a);
         else
-            k_propagate<false, true, STAGED><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+            k_propagate<false, true, STAGED><<<(unsigned)grid, kPropThreads, smem, stream>>>(w, a);
     } else if (w.n_obs > 0) {
-        k_propagate<true, false, STAGED><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+        k_propagate<true, false, STAGED><<<(unsigned)grid, kPropThreads, smem, stream>>>(w, a);
     } else {
-        k_propagate<false, false, STAGED><<<(unsigned)grid, kPropThreads, 0, stream>>>(w, a);
+        k_propagate<false, false, STAGED><<<(unsigned)grid, kPropThreads, smem, stream>>>(w, a);
     }
     return cudaGetLastError();
 }
