@@ -254,8 +254,13 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 if (inside(st - 1)) {
                     ok_steps = st;
                 } else {
-                    ok_steps = 1;
-                    while (ok_steps < st && inside(ok_steps)) ++ok_steps;
+                    // estimate the crossing from the linear form, then settle it with the exact test (0-1 moves each way)
+                    const float cv = __fdividef((ua > 0.0f ? w.hi_t[2] : w.lo_t[2]) - v0, ua * w.step);
+                    const float cp = __fdividef((uw > 0.0f ? w.hi_t[3] : w.lo_t[3]) - phi0, uw * w.step);
+                    const float c = fminf(ua != 0.0f ? cv : 1.0e9f, uw != 0.0f ? cp : 1.0e9f);
+                    ok_steps = min(max((int)c, 1), st - 1);
+                    while (ok_steps < st - 1 && inside(ok_steps)) ++ok_steps;
+                    while (ok_steps > 1 && !inside(ok_steps - 1)) --ok_steps;
                 }
             }
             st = ok_steps;
@@ -278,10 +283,16 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         within[u] = atomicAdd(&s_hist[st], 1);
     }
     __syncthreads();
-    if (tid <= KCBS_MAX_STEPS) {  // s_first[d] = rank of the first sample of duration d (longer durations come first)
-        int before = 0;
-        for (int d = KCBS_MAX_STEPS; d > tid; --d) before += s_hist[d];
-        s_first[tid] = before;
+    if (tid < 32) {  // s_first[d] = rank of the first sample of duration d (longer durations come first): suffix sums
+        static_assert(KCBS_MAX_STEPS == 32, "one warp scans bins 1..32");
+        int sum = s_hist[tid + 1];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int up = __shfl_down_sync(0xffffffffu, sum, off);
+            if (tid + off < 32) sum += up;
+        }
+        s_first[tid] = sum;  // hist[tid + 1] + ... + hist[32]
+        if (tid == 0) s_first[KCBS_MAX_STEPS] = 0;
     }
     __syncthreads();
 #pragma unroll
