@@ -413,8 +413,9 @@ def main():
            "h2d_bytes_per_step": calls * (5 * 4 + N_CONTROLS * 12),
            "d2h_bytes_per_step": calls * (N_CONTROLS * (5 * MAX_STEPS * 4 + 5 * 4 + 4)),
            "calls_per_step": calls, "steps": e2e_steps,
+           "pcie_d2h_gbs": calls * (N_CONTROLS * (5 * MAX_STEPS * 4 + 5 * 4 + 4)) * e2e_steps / e2e_s * 1e-9,
            "note": "kcbs_propagate_batch with pinned host buffers, one host thread per robot planner; whole segments + "
-                   "final states + counts copied back"}
+                   "final states + counts copied back (224 B per sample: bound by the PCIe device-to-host rate, pcie_d2h_gbs)"}
 
     # the same calls asking only for what propagateWhileValid(state, control, steps, result) returns (the final
     # state and the step count, 24 B per sample instead of 224 B): what a planner that does not keep intermediate
