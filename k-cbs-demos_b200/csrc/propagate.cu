@@ -227,60 +227,80 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
     if (tid <= KCBS_MAX_STEPS) s_hist[tid] = 0;
     __syncthreads();
     int st4[kPropPer], within[kPropPer];
+    {
+        // all global loads of the thread's four samples are issued before anything depends on them (indices clamped
+        // instead of branched on): one or two memory round trips per CTA instead of a dozen serialised ones
+        long long ii[kPropPer], pi[kPropPer];
+        int st_req[kPropPer];
+        float v0[kPropPer], phi0[kPropPer], ua[kPropPer], uw[kPropPer], x0[kPropPer], y0[kPropPer], th0[kPropPer];
 #pragma unroll
-    for (int u = 0; u < kPropPer; ++u) {
-        const int slot = tid + u * kPropThreads;
-        const long long i = b0 + slot;
-        int st = 0;
-        if (i < a.n) {
-            st = a.steps ? a.steps[i] : a.max_steps;
-            st = min(max(st, 0), a.max_steps);
-            // v and phi are linear in time, so the first step at which they leave their bounds is known
-            // before integrating anything: that step would fail isValid, so the segment ends just before
-            // it (same result as propagating it and testing).  Sorting by this effective duration keeps
-            // warps uniform even when many samples leave the v / phi bounds early.
-            const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
-            const float v0 = a.parents[2 * a.n_parents + pi], phi0 = a.parents[3 * a.n_parents + pi];
-            const float ua = a.controls[i], uw = a.controls[a.n + i];
-            // fmaf(u, t, v0) is monotonic in t, so the valid steps form a prefix; when the first and the last requested
-            // step are inside, all of them are (the common case: two evaluations instead of a loop)
-            auto inside = [&](int j) {
-                const float t1 = (float)(j + 1) * w.step;
-                const float vn = fmaf(ua, t1, v0), pn = fmaf(uw, t1, phi0);
-                return (vn >= w.lo_t[2]) & (vn <= w.hi_t[2]) & (pn >= w.lo_t[3]) & (pn <= w.hi_t[3]);
-            };
-            int ok_steps = 0;
-            if (st > 0 && inside(0)) {
-                if (inside(st - 1)) {
-                    ok_steps = st;
-                } else {
-                    // estimate the crossing from the linear form, then settle it with the exact test (0-1 moves each way)
-                    const float cv = __fdividef((ua > 0.0f ? w.hi_t[2] : w.lo_t[2]) - v0, ua * w.step);
-                    const float cp = __fdividef((uw > 0.0f ? w.hi_t[3] : w.lo_t[3]) - phi0, uw * w.step);
-                    const float c = fminf(ua != 0.0f ? cv : 1.0e9f, uw != 0.0f ? cp : 1.0e9f);
-                    ok_steps = min(max((int)c, 1), st - 1);
-                    while (ok_steps < st - 1 && inside(ok_steps)) ++ok_steps;
-                    while (ok_steps > 1 && !inside(ok_steps - 1)) --ok_steps;
-                }
-            }
-            st = ok_steps;
+        for (int u = 0; u < kPropPer; ++u) {
+            ii[u] = min(b0 + tid + u * kPropThreads, a.n - 1);
+            pi[u] = a.parent_idx ? (long long)a.parent_idx[ii[u]] : (a.n_parents == 1 ? 0 : ii[u]);
+            st_req[u] = a.steps ? a.steps[ii[u]] : a.max_steps;
+            ua[u] = a.controls[ii[u]];
+            uw[u] = a.controls[a.n + ii[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < kPropPer; ++u) {
+            v0[u] = a.parents[2 * a.n_parents + pi[u]];
+            phi0[u] = a.parents[3 * a.n_parents + pi[u]];
             if (STAGED) {
-                // inputs of the sample for propagate_two and the write-out; x0, y0, theta0 borrow the sample's own last
-                // stage row, which the sample overwrites only when it completes its final step
-                stage->v0[slot] = v0;
-                stage->p0[slot] = phi0;
-                stage->ua[slot] = ua;
-                stage->uw[slot] = uw;
-                stage->xyt[0][kStageSteps - 1][slot] = a.parents[0 * a.n_parents + pi];
-                stage->xyt[1][kStageSteps - 1][slot] = a.parents[1 * a.n_parents + pi];
-                stage->xyt[2][kStageSteps - 1][slot] = a.parents[4 * a.n_parents + pi];
+                x0[u] = a.parents[0 * a.n_parents + pi[u]];
+                y0[u] = a.parents[1 * a.n_parents + pi[u]];
+                th0[u] = a.parents[4 * a.n_parents + pi[u]];
             }
         }
-        st4[u] = st;
-        s_steps[slot] = (unsigned char)st;
-        if (STAGED) stage->nv[slot] = 0;
-        else s_nv[slot] = 0;
-        within[u] = atomicAdd(&s_hist[st], 1);
+#pragma unroll
+        for (int u = 0; u < kPropPer; ++u) {
+            const int slot = tid + u * kPropThreads;
+            int st = 0;
+            if (b0 + slot < a.n) {
+                st = min(max(st_req[u], 0), a.max_steps);
+                // v and phi are linear in time, so the first step at which they leave their bounds is known
+                // before integrating anything: that step would fail isValid, so the segment ends just before
+                // it (same result as propagating it and testing).  Sorting by this effective duration keeps
+                // warps uniform even when many samples leave the v / phi bounds early.
+                // fmaf(u, t, v0) is monotonic in t, so the valid steps form a prefix; when the first and the last
+                // requested step are inside, all of them are (the common case: two evaluations instead of a loop)
+                auto inside = [&](int j) {
+                    const float t1 = (float)(j + 1) * w.step;
+                    const float vn = fmaf(ua[u], t1, v0[u]), pn = fmaf(uw[u], t1, phi0[u]);
+                    return (vn >= w.lo_t[2]) & (vn <= w.hi_t[2]) & (pn >= w.lo_t[3]) & (pn <= w.hi_t[3]);
+                };
+                int ok_steps = 0;
+                if (st > 0 && inside(0)) {
+                    if (inside(st - 1)) {
+                        ok_steps = st;
+                    } else {
+                        // estimate the crossing from the linear form, then settle it with the exact test (0-1 moves)
+                        const float cv = __fdividef((ua[u] > 0.0f ? w.hi_t[2] : w.lo_t[2]) - v0[u], ua[u] * w.step);
+                        const float cp = __fdividef((uw[u] > 0.0f ? w.hi_t[3] : w.lo_t[3]) - phi0[u], uw[u] * w.step);
+                        const float c = fminf(ua[u] != 0.0f ? cv : 1.0e9f, uw[u] != 0.0f ? cp : 1.0e9f);
+                        ok_steps = min(max((int)c, 1), st - 1);
+                        while (ok_steps < st - 1 && inside(ok_steps)) ++ok_steps;
+                        while (ok_steps > 1 && !inside(ok_steps - 1)) --ok_steps;
+                    }
+                }
+                st = ok_steps;
+                if (STAGED) {
+                    // inputs of the sample for propagate_two and the write-out; x0, y0, theta0 borrow the sample's own
+                    // last stage row, which the sample overwrites only when it completes its final step
+                    stage->v0[slot] = v0[u];
+                    stage->p0[slot] = phi0[u];
+                    stage->ua[slot] = ua[u];
+                    stage->uw[slot] = uw[u];
+                    stage->xyt[0][kStageSteps - 1][slot] = x0[u];
+                    stage->xyt[1][kStageSteps - 1][slot] = y0[u];
+                    stage->xyt[2][kStageSteps - 1][slot] = th0[u];
+                }
+            }
+            st4[u] = st;
+            s_steps[slot] = (unsigned char)st;
+            if (STAGED) stage->nv[slot] = 0;
+            else s_nv[slot] = 0;
+            within[u] = atomicAdd(&s_hist[st], 1);
+        }
     }
     __syncthreads();
     if (tid < 32) {  // s_first[d] = rank of the first sample of duration d (longer durations come first): suffix sums
