@@ -70,6 +70,21 @@ def test_expansion_prefix_and_broadcast_parent(expansion):
     assert (segi == seg).all() and (fini == fin).all()
 
 
+def test_expansion_variants_agree(expansion):
+    # the final-state-only call (direct kernel variant, what propagateWhileValid(state, control, steps, result) returns),
+    # a batch whose size is not a multiple of 4 (scalar write-out) and a 12-step buffer (direct variant with segments)
+    # all reproduce the staged 16 B path bit for bit
+    _, ctx, parents, controls, steps, seg, fin, valid = expansion
+    _, fin_only, valid_only = ctx.propagate_batch(3, parents, controls, steps, want_seg=False)
+    assert (fin_only == fin).all() and (valid_only == valid).all()
+    m = N_EXP - 3
+    seg_m, fin_m, valid_m = ctx.propagate_batch(3, parents, np.ascontiguousarray(controls[:, :m]), steps[:m])
+    assert (seg_m == seg[:, :, :m]).all() and (fin_m == fin[:, :m]).all() and (valid_m == valid[:m]).all()
+    seg12, fin12, valid12 = ctx.propagate_batch(3, parents, controls, steps, max_steps=12)
+    assert (valid12 == valid).all() and (fin12 == fin).all()
+    assert (seg12[:, :10] == seg).all() and (seg12[:, 10:] == 0).all()
+
+
 def test_expansion_composes(expansion):
     # 10 steps == 5 steps, then 5 more from the state reached (same control): the flow property of the integrator
     scene, ctx, parents, controls, steps, _, _, _ = expansion
