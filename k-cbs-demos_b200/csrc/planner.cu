@@ -123,7 +123,7 @@ __device__ __forceinline__ float state_distance(float x, float y, float v, float
 }
 
 constexpr int kNNThreads = 256;
-constexpr int kNNChunk = 2048;  // nodes per CTA
+constexpr int kNNChunk = 256;   // nodes per CTA (small: the grid must fill 148 SMs while the tree is still small)
 
 // grid = (ceil(n_targets / 256), ceil(n_nodes / kNNChunk)): every thread owns one target and scans one chunk
 // of nodes staged through shared memory.
