@@ -5,13 +5,17 @@
  * call this.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it, and there only as the checker / the reported CPU baseline.
  *
- * PARITY UNPINNED: the reference (/root/reference) ships no tests or golden vectors, and its
- * integrator, bounds test, angle wrap and conflict scan loop live in un-vendored dependencies
- * (an unpinned OMPL fork with K-CBS, Boost.odeint, Boost.Geometry) that are absent from this
- * image, so the reference cannot be compiled or run here.  Every function below cites the
- * reference file:line it follows; semantics that live upstream are marked [UPSTREAM] and are
- * restated from the published algorithms of those libraries, anchored on the reference's own
- * call sites.  Each [UPSTREAM] rule is a named switch so it can be re-pinned in one place.
+ * PARITY PARTLY PINNED, OTHERWISE UNPINNED: the reference (/root/reference) ships no tests or golden
+ * vectors, and its integrator, bounds test, angle wrap and conflict scan loop live in un-vendored
+ * dependencies (an unpinned OMPL fork with K-CBS, Boost.odeint, Boost.Geometry) that are absent from
+ * this image, so the reference's path cannot be compiled or run here as a whole.  What does compile --
+ * the ODE right-hand sides, the state and control bounds and the goal test, which the reference's
+ * headers compute themselves -- is built from /root/reference/includes by ref_partial.cpp and pins
+ * orc_car_ode and the scene constants bit for bit (tests/test_ref_partial.py, tests/golden/ref_partial.npz).
+ * Everything else is unpinned: every function below cites the reference file:line it follows;
+ * semantics that live upstream are marked [UPSTREAM] and are restated from the published algorithms of
+ * those libraries, anchored on the reference's own call sites.  Each [UPSTREAM] rule is a named switch
+ * so it can be re-pinned in one place.
  */
 #ifndef KCBS_ORACLE_H
 #define KCBS_ORACLE_H

@@ -295,3 +295,28 @@ class Oracle:
         mm = C.c_double()
         self.L.orc_first_conflict_groups(C.byref(self.w), R, T, _p(traj), _p(lengths), _p(group), C.byref(out), C.byref(mm))
         return (out.r1, out.r2, out.k_start, out.k_end), mm.value
+
+
+# ---- the part of the reference that compiles here (oracle/ref_partial.cpp -> oracle/_ref/) ---------------------------
+_REF = None
+
+
+def ref_partial():
+    """ctypes handle of oracle/_ref/libkcbs_ref_partial.so (the reference's own ODE right-hand sides, bounds and goal
+    test, compiled from /root/reference/includes against the OMPL API shim), or None when it has not been built
+    (the GPU box has no /root/reference; the committed tests/golden/ref_partial.npz carries its outputs there)."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libkcbs_ref_partial.so")
+        if not os.path.exists(path):
+            return None
+        L = C.CDLL(path)
+        dp = C.POINTER(C.c_double)
+        L.ref_second_order_car_ode.argtypes = [dp, dp, dp]
+        L.ref_two_second_order_cars_ode.argtypes = [dp, dp, dp]
+        L.ref_state_bounds.argtypes = [C.c_uint, C.c_uint, dp, dp]
+        L.ref_control_bounds.argtypes = [dp, dp]
+        L.ref_goal_distance.restype = C.c_double
+        L.ref_goal_distance.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, dp]
+        _REF = L
+    return _REF
