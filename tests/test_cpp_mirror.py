@@ -66,3 +66,38 @@ def test_demo_driver_on_gpu(tmp_path, scene, planner):
     assert plan.startswith("Robot 0")
     if planner == "K-CBS":
         assert "nodes expanded" in open(tmp_path / "tree.txt").read()
+
+
+REF_BINS = os.path.join(DEMOS, "_ref")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("demo", ["demo_Corridor10x10_4robots_dyn2ndOrderCars", "demo_Congested10x10_7robots_dyn2ndOrderCars",
+                                  "demo_Empty32x32_10robots_dyn2ndOrderCars"])
+def test_reference_demo_main_runs_on_gpu(tmp_path, demo):
+    """The reference's OWN demo main (compiled where it lies under /root/reference/src by demos/Makefile, linked against
+    the mirror headers + libkcbs_b200.so) plans on the GPU and writes the files the reference writes."""
+    exe = os.path.join(REF_BINS, demo)
+    if not os.path.exists(exe):
+        pytest.skip("demos/_ref/ not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "Found Solution" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert open(tmp_path / "plan.txt").read().startswith("Robot 0")       # demo_*.cpp:176-180
+    assert os.path.exists(tmp_path / "tree.txt")                          # demo_*.cpp:182-186
+
+
+@pytest.mark.gpu
+def test_reference_benchmark_main_runs_on_gpu(tmp_path):
+    """demo_Benchmark_Empty32x32_30robots: Benchmark::runKCBS (Benchmark.h:151-173), one solve of the 30-robot scene,
+    a header and one row appended to the CSV (Benchmark.h:200-219)."""
+    exe = os.path.join(REF_BINS, "demo_Benchmark_Empty32x32_30robots_dyn2ndOrderCars")
+    if not os.path.exists(exe):
+        pytest.skip("demos/_ref/ not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    csvs = [f for f in os.listdir(tmp_path) if f.endswith(".csv")]
+    assert csvs, os.listdir(tmp_path)
+    rows = open(tmp_path / csvs[0]).read().strip().splitlines()
+    assert len(rows) >= 2 and "Success" in rows[0] and "Computation Time" in rows[0]
+    cols = dict(zip(rows[0].split(","), rows[1].split(",")))
+    assert [v for k, v in cols.items() if "Success" in k] == ["1"], cols
