@@ -35,6 +35,9 @@ struct kcbs_ctx {
     std::vector<float> h_obs4;
     std::vector<unsigned short> h_fine;  // fine three-valued obstacle grid
     kcbs::RrtWorkspace *rrt = nullptr;  // planner state, created on first use
+    // planner workers: shallow clones (same device, world and scene buffers; own stream and planner workspace) on which
+    // kcbs_kcbs_solve runs independent low-level plans concurrently; owned by this context
+    std::vector<kcbs_ctx *> workers;
 };
 
 namespace kcbs {

@@ -17,11 +17,13 @@
 //   k_rrt_select    per target the sample that ends closest to it becomes a tree node; goal test
 // A found path is re-expanded edge by edge with k_propagate (identical arithmetic) to emit every 0.1 s state.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
 #include <queue>
+#include <thread>
 #include <vector>
 
 #include "ctx.h"
@@ -360,6 +362,13 @@ int check_rrt_params(kcbs_ctx *ctx, const kcbs_rrt_params &p)
 
 void destroy_rrt_workspace(kcbs_ctx *ctx)
 {
+    for (kcbs_ctx *w : ctx->workers) {  // planner workers share the scene buffers and own only what they created
+        if (w->stream) cudaStreamSynchronize(w->stream);
+        destroy_rrt_workspace(w);
+        if (w->stream) cudaStreamDestroy(w->stream);
+        delete w;
+    }
+    ctx->workers.clear();
     if (ctx->rrt) {
         free_workspace(*ctx->rrt);
         delete ctx->rrt;
@@ -551,6 +560,64 @@ struct NodeOrder {
     }
 };
 
+extern "C++" {
+// Context the i-th concurrent planner job runs on: the caller's own context for i == 0, else a worker clone.
+kcbs_ctx *planner_lane(kcbs_ctx *ctx, int i)
+{
+    if (i == 0) return ctx;
+    while ((int)ctx->workers.size() < i) {
+        kcbs_ctx *w = new kcbs_ctx();
+        w->device = ctx->device;
+        w->world = ctx->world;  // device pointers of the scene are shared, read only
+        w->n_robots = ctx->n_robots;
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete w;
+            return nullptr;
+        }
+        ctx->workers.push_back(w);
+    }
+    return ctx->workers[i - 1];
+}
+
+// Runs job(lane context, j) for j in [0, n_jobs) on up to max_lanes host threads, each driving its own stream and
+// planner workspace, so that independent low-level plans overlap on the GPU (every plan is a chain of small launches
+// with a host read-back per RRT iteration).  Returns the first non-OK status.
+template <class Job>
+int run_planner_jobs(kcbs_ctx *ctx, int n_jobs, int max_lanes, Job job)
+{
+    const int lanes = std::max(1, std::min(n_jobs, max_lanes));
+    std::vector<kcbs_ctx *> lane_ctx(lanes);
+    for (int i = 0; i < lanes; ++i)
+        if (!(lane_ctx[i] = planner_lane(ctx, i))) return fail(ctx, KCBS_ERR_CUDA, "planner worker creation failed");
+    std::atomic<int> next(0);
+    std::vector<int> status(lanes, KCBS_OK);
+    auto body = [&](int lane) {
+        cudaSetDevice(ctx->device);
+        for (int j = next.fetch_add(1); j < n_jobs; j = next.fetch_add(1)) {
+            const int st = job(lane_ctx[lane], j);
+            if (st != KCBS_OK && status[lane] == KCBS_OK) status[lane] = st;
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int i = 1; i < lanes; ++i) threads.emplace_back(body, i);
+    body(0);
+    for (auto &t : threads) t.join();
+    for (int i = 0; i < lanes; ++i) {
+        if (i > 0) {
+            ctx->launches += lane_ctx[i]->launches;
+            lane_ctx[i]->launches = 0;
+        }
+        if (status[i] != KCBS_OK) {
+            if (i > 0) ctx->err = lane_ctx[i]->err;
+            return status[i];
+        }
+    }
+    return KCBS_OK;
+}
+
+constexpr int kPlannerLanes = 8;
+}  // extern "C++"
+
 int plan_robot(kcbs_ctx *ctx, int r, const float *starts, const float *goals, int R, const kcbs_rrt_params &p,
                const std::vector<std::shared_ptr<Constraint>> &cons, int max_T, std::vector<float> &traj, int &len,
                kcbs_rrt_stats &rs)
@@ -604,15 +671,19 @@ int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goal
     auto root = std::make_shared<CbsNode>();
     root->traj.resize(R); root->len.assign(R, 0); root->cons.resize(R);
     bool root_ok = true;
-    for (int r = 0; r < R && root_ok; ++r) {
-        kcbs_rrt_params lp = P.low_level;
-        lp.seed = P.low_level.seed * 1000003ull + (unsigned long long)r;
-        kcbs_rrt_stats rs;
-        int st = plan_robot(ctx, r, starts, goals, R, lp, root->cons[r], max_T, root->traj[r], root->len[r], rs);
+    {
+        std::vector<kcbs_rrt_stats> rs(R);
+        const int st = run_planner_jobs(ctx, R, kPlannerLanes, [&](kcbs_ctx *lane, int r) {
+            kcbs_rrt_params lp = P.low_level;
+            lp.seed = P.low_level.seed * 1000003ull + (unsigned long long)r;
+            return plan_robot(lane, r, starts, goals, R, lp, root->cons[r], max_T, root->traj[r], root->len[r], rs[r]);
+        });
         if (st != KCBS_OK) return st;
-        ++S.low_level_calls;
-        if (!rs.solved) root_ok = false;
-        root->cost += root->len[r];
+        for (int r = 0; r < R; ++r) {
+            ++S.low_level_calls;
+            if (!rs[r].solved) root_ok = false;
+            root->cost += root->len[r];
+        }
     }
     S.root_seconds = now_s() - t_begin;
     std::priority_queue<std::shared_ptr<CbsNode>, std::vector<std::shared_ptr<CbsNode>>, NodeOrder> open;
@@ -657,7 +728,9 @@ int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goal
         cf.k_end = std::min(cf.k_end, T - 1);
         // two children: each re-plans one robot against the other's states during the conflict
         const int pair[2][2] = {{cf.r1, cf.r2}, {cf.r2, cf.r1}};
-        for (int ch = 0; ch < 2; ++ch) {
+        std::shared_ptr<CbsNode> child[2];
+        kcbs_rrt_stats crs[2];
+        st = run_planner_jobs(ctx, 2, 2, [&](kcbs_ctx *lane, int ch) {
             const int me = pair[ch][0], other = pair[ch][1];
             auto c = std::make_shared<Constraint>();
             c->other = other;
@@ -669,22 +742,24 @@ int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goal
                 c->y.push_back(node->traj[other][(size_t)1 * Lo + kk]);
                 c->th.push_back(node->traj[other][(size_t)4 * Lo + kk]);
             }
-            auto child = std::make_shared<CbsNode>(*node);
-            child->cons[me].push_back(c);
+            child[ch] = std::make_shared<CbsNode>(*node);
+            child[ch]->cons[me].push_back(c);
             kcbs_rrt_params lp = P.low_level;
-            lp.seed = P.low_level.seed * 1000003ull + (unsigned long long)(next_id * 131 + me);
-            kcbs_rrt_stats rs;
-            st = plan_robot(ctx, me, starts, goals, R, lp, child->cons[me], max_T, child->traj[me], child->len[me], rs);
-            if (st != KCBS_OK) return st;
+            // the seed depends on the expansion, the branch and the robot only, so both branches can run at once
+            lp.seed = P.low_level.seed * 1000003ull + (unsigned long long)((S.nodes_expanded * 2 + ch) * 131 + me);
+            return plan_robot(lane, me, starts, goals, R, lp, child[ch]->cons[me], max_T, child[ch]->traj[me], child[ch]->len[me], crs[ch]);
+        });
+        if (st != KCBS_OK) return st;
+        for (int ch = 0; ch < 2; ++ch) {
             ++S.low_level_calls;
-            if (!rs.solved) {
+            if (!crs[ch].solved) {
                 ++S.approximate_solutions;  // the fork counts low-level time-outs as approximate solutions
                 continue;
             }
-            child->cost = 0;
-            for (int r = 0; r < R; ++r) child->cost += child->len[r];
-            child->id = next_id++;
-            open.push(child);
+            child[ch]->cost = 0;
+            for (int r = 0; r < R; ++r) child[ch]->cost += child[ch]->len[r];
+            child[ch]->id = next_id++;
+            open.push(child[ch]);
         }
     }
 
