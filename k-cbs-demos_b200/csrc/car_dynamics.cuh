@@ -179,8 +179,8 @@ __device__ __forceinline__ CarConsts2 car_consts2(const DevWorld &w, const float
 //   sum_i w_i cos(theta_i) = c1 A - s1 B,  sum_i w_i sin(theta_i) = s1 A + c1 B,
 //   A = W1 + W2 (cos K1 + cos K2) + W4 cos 2K2,  B = W2 (sin K1 + sin K2) + W4 sin 2K2   (|K| <= 0.035:
 //   cos d = 1 - d^2/2, sin d = d to the accuracy of car_step's second-order rotations),
-// and stage 1 of the next sub-step is (c1, s1) rotated by dtheta = (K1 + 4 K2 + K4) / 3 with a 4th / 3rd-order
-// cos / sin.  43 packed instructions + 4 MUFU.RCP per sub-step of two samples.
+// and stage 1 of the next sub-step takes (c1, s1) of theta + the accumulated dtheta = (K1 + 4 K2 + K4) / 3 from MUFU.
+// 34 packed instructions + 8 MUFU (4 RCP, 2 SIN, 2 COS) per sub-step of two samples.
 template <int N_SUB>
 __device__ __forceinline__ f32x2 car_step2(const CarConsts2 &k, int n_sub, const float vs[2], const float T0[2],
                                            const float ts[2], f32x2 &offx, f32x2 &offy)
@@ -193,7 +193,6 @@ __device__ __forceinline__ f32x2 car_step2(const CarConsts2 &k, int n_sub, const
         W0[e] = k.h6 * vs[e];
     }
     const f32x2 ONE = pk1(1.0f), NHALF = pk1(-0.5f), FOUR = pk1(4.0f), THIRD = pk1(1.0f / 3.0f);
-    const f32x2 C24 = pk1(1.0f / 24.0f), N6TH = pk1(-1.0f / 6.0f);
     f32x2 T = pk(T0[0], T0[1]);
     f32x2 U1 = pk(U0[0], U0[1]), U2 = pk(U0[0] + k.hh_ua_k[0], U0[1] + k.hh_ua_k[1]);
     f32x2 W1 = pk(W0[0], W0[1]), W2 = pk(fmaf(2.0f, W0[0], k.hh_ua_w[0]), fmaf(2.0f, W0[1], k.hh_ua_w[1]));
@@ -201,6 +200,7 @@ __device__ __forceinline__ f32x2 car_step2(const CarConsts2 &k, int n_sub, const
     f32x2 K1 = mul2(U1, T);
     f32x2 Ws = add2(add2(W1, add2(W1, k.dW)), add2(W2, W2));
     f32x2 toff = pk1(0.0f);
+    const f32x2 TS = pk(ts[0], ts[1]);
 
 #pragma unroll kPropUnroll
     for (int n = 0; n < (N_SUB > 0 ? N_SUB : n_sub); ++n) {
@@ -220,12 +220,17 @@ __device__ __forceinline__ f32x2 car_step2(const CarConsts2 &k, int n_sub, const
         // heading
         const f32x2 dth = mul2(fma2(FOUR, K2, add2(K1, K4)), THIRD);
         toff = add2(toff, dth);
-        const f32x2 p = mul2(dth, dth);
-        const f32x2 cd = fma2(p, fma2(p, C24, NHALF), ONE);
-        const f32x2 sd = mul2(dth, fma2(p, N6TH, ONE));
-        const f32x2 Cn = sub2(mul2(C, cd), mul2(S, sd));
-        S = fma2(C, sd, mul2(S, cd));
-        C = Cn;
+        {
+            // stage-1 heading of the next sub-step straight from the angle: the MUFU pipe has room (4 RCP per sub-step
+            // of two samples), the FMA pipe is the one that binds, and a rotation of (C, S) costs it ten instructions;
+            // the MUFU error (5e-7) enters the position with weight W = (h/6) v and does not accumulate
+            float a0, a1, c0, c1, s0, s1;
+            upk(add2(TS, toff), a0, a1);
+            __sincosf(a0, &s0, &c0);
+            __sincosf(a1, &s1, &c1);
+            C = pk(c0, c1);
+            S = pk(s0, s1);
+        }
         K1 = K4;
         U1 = U4;
         U2 = add2(U2, k.dU);

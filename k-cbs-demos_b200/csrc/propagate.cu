@@ -25,7 +25,7 @@
 //
 //   * every thread integrates TWO samples at once in packed FP32 pairs (fma / mul / add .f32x2, SASS FFMA2 ...): the
 //     kernel is bound by issue slots, and a packed instruction does two samples' worth of FMA-pipe work in one
-//     slot (car_step2 in car_dynamics.cuh: 43 packed instructions + 4 MUFU.RCP per sub-step of two samples).
+//     slot (car_step2 in car_dynamics.cuh: 34 packed instructions + 8 MUFU per sub-step of two samples).
 //
 // Work distribution: requested durations are U{1..10} (SimpleDirectedControlSampler), which would
 // idle 45 % of the lanes of a warp; and because v, phi are linear in time, the step at which a sample
