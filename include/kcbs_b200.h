@@ -251,6 +251,15 @@ KCBS_API int kcbs_rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const f
                            const float *cons_states, int max_T, float *traj_out, int32_t *T_out,
                            kcbs_rrt_stats *stats);
 
+/* n_jobs independent, unconstrained low-level plans at once (the re-plans of different robots / constraint-tree nodes
+ * that one GPU owns when they are sharded over GPUs; also what the root of kcbs_kcbs_solve does): job j plans robot
+ * robots[j] from starts[(c * n_jobs) + j] (c = 0..4) to goals[2 j .. 2 j + 1] with seeds[j].  The jobs run concurrently
+ * on up to 8 planner lanes of the context (host thread + stream + workspace each); results do not depend on the
+ * interleaving.  traj_out = [n_jobs][5][max_T], T_out / stats = [n_jobs] (stats may be NULL). */
+KCBS_API int kcbs_rrt_plan_many(kcbs_ctx *ctx, int n_jobs, const int32_t *robots, const float *starts, const float *goals,
+                                const kcbs_rrt_params *params, const uint64_t *seeds, int max_T, float *traj_out,
+                                int32_t *T_out, kcbs_rrt_stats *stats);
+
 /* K-CBS over the R robots of the world: root = independent low-level plans; best-first search over the
  * constraint tree with kcbs_first_conflict as the plan validator; every conflict spawns two children that
  * re-plan one robot each against the other's colliding states.  starts = [5][R] planes, goals = [R][2];

@@ -81,7 +81,7 @@ EXPORTS = [
     "kcbs_measure_fp32_peak", "kcbs_measure_fp32x2_peak", "kcbs_launch_count", "kcbs_rrt_defaults",
     "kcbs_kcbs_defaults", "kcbs_rrt_plan", "kcbs_kcbs_solve", "kcbs_propagate_pair_batch", "kcbs_propagate_pair_batch_dev",
     "kcbs_validity_pair_batch", "kcbs_validity_pair_batch_dev", "kcbs_first_conflict_groups", "kcbs_first_conflict_groups_dev",
-    "kcbs_scene_grid",
+    "kcbs_scene_grid", "kcbs_rrt_plan_many",
 ]
 
 
@@ -131,6 +131,7 @@ def load_library() -> C.CDLL:
     lib.kcbs_kcbs_defaults.argtypes = [C.POINTER(KcbsParams)]
     lib.kcbs_rrt_plan.argtypes = [vp, i32, vp, vp, C.POINTER(RrtParams), i32, vp, vp, vp, vp, vp, i32, vp,
                                   C.POINTER(C.c_int32), C.POINTER(RrtStats)]
+    lib.kcbs_rrt_plan_many.argtypes = [vp, i32, vp, vp, vp, C.POINTER(RrtParams), vp, i32, vp, vp, vp]
     lib.kcbs_kcbs_solve.argtypes = [vp, i32, vp, vp, C.POINTER(KcbsParams), i32, vp, vp, C.POINTER(KcbsStats)]
     pair = [vp, i32, i32, i64, i64, vp, vp, vp, vp, i32, vp, C.c_float, vp, vp, vp]
     lib.kcbs_propagate_pair_batch.argtypes = pair
@@ -436,6 +437,22 @@ class Context:
                                             _ptr(k0), _ptr(ln), _ptr(off), _ptr(states), max_T, _ptr(out), C.byref(T),
                                             C.byref(st)))
         return out[:, :T.value].copy(), st
+
+    def rrt_plan_many(self, robots, starts, goals, params=None, seeds=None, max_T=4096):
+        """kcbs_rrt_plan_many.  robots [n], starts [5, n], goals [n, 2], seeds [n] or None.  Returns (traj [n, 5, max_T],
+        lengths [n] int32, list of RrtStats): the n independent plans run concurrently on the context's planner lanes."""
+        robots = np.ascontiguousarray(robots, dtype=np.int32)
+        n = len(robots)
+        starts = np.ascontiguousarray(starts, dtype=np.float32).reshape(5, n)
+        goals = np.ascontiguousarray(goals, dtype=np.float32).reshape(n, 2)
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        params = params if params is not None else self.rrt_params()
+        traj = np.zeros((n, 5, max_T), np.float32)
+        T = np.zeros(n, np.int32)
+        stats = (RrtStats * max(n, 1))()
+        self._check(self._lib.kcbs_rrt_plan_many(self._h, n, _ptr(robots), _ptr(starts), _ptr(goals), C.byref(params), _ptr(seeds),
+                                                 max_T, _ptr(traj), _ptr(T), C.cast(stats, C.c_void_p)))
+        return traj, T, list(stats)[:n]
 
     def kcbs_solve(self, starts, goals, params=None, max_T=4096):
         """kcbs_kcbs_solve.  starts [5, R], goals [R, 2].  Returns (plan [R, 5, max_T], lengths [R], KcbsStats)."""

@@ -44,6 +44,7 @@ struct RrtWorkspace {
     int *s_steps = nullptr;        // [n_samples]
     float *s_fin = nullptr;        // [5][n_samples]
     int *s_valid = nullptr;        // [n_samples]
+    int *sel = nullptr;            // [n_targets] sample chosen for each target this round, or -1
     int *counters = nullptr;       // [0] = node count, [1] = (unused)
     unsigned long long *goal_key = nullptr;  // packed (time << 32 | node) of the best goal node
     ConsDesc *cons = nullptr;
@@ -234,31 +235,58 @@ __global__ void __launch_bounds__(256) k_rrt_select(const __grid_constant__ DevW
             best_s = os;
         }
     }
-    if (lane != 0 || best_s < 0) return;
-    const int idx = atomicAdd(a.ws.counters, 1);
-    if (idx >= M) {
-        atomicSub(a.ws.counters, 1);
-        return;
+    if (lane == 0) a.ws.sel[warp] = best_s;
+}
+
+// Appends the chosen samples to the tree in TARGET ORDER (one CTA, block-wide prefix sum of the "found one" flags), so
+// that node indices -- and with them nearest-neighbour ties, the goal node and the whole plan -- depend only on the
+// seed, never on the order in which warps of k_rrt_select happen to finish.
+__global__ void __launch_bounds__(1024) k_rrt_append(const __grid_constant__ DevWorld w, RrtArgs a)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int B = a.n_targets, C = a.n_controls, n = B * C, M = a.ws.max_nodes;
+    if (tid == 0) s_base = a.ws.counters[0];
+    __syncthreads();
+    for (int t0 = 0; t0 < B; t0 += 1024) {
+        const int t = t0 + tid;
+        const int s = t < B ? a.ws.sel[t] : -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, s >= 0);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int q = 0; q < 32; ++q) {
+            before += q < wid ? s_warp[q] : 0;
+            total += s_warp[q];
+        }
+        const int idx = s_base + before + __popc(bal & ((1u << lane) - 1u));
+        if (s >= 0 && idx < M) {
+            const int par = a.ws.s_parent[s], nv = a.ws.s_valid[s];
+            const float x = a.ws.s_fin[s], y = a.ws.s_fin[n + s], th = a.ws.s_fin[4 * n + s];
+            a.ws.nodes[idx] = x;
+            a.ws.nodes[M + idx] = y;
+            a.ws.nodes[2 * M + idx] = a.ws.s_fin[2 * n + s];
+            a.ws.nodes[3 * M + idx] = a.ws.s_fin[3 * n + s];
+            a.ws.nodes[4 * M + idx] = th;
+            a.ws.parent[idx] = par;
+            const int t_node = a.ws.time[par] + nv;
+            a.ws.time[idx] = t_node;
+            a.ws.ctrl[idx] = a.ws.s_ctrl[s];
+            a.ws.ctrl[M + idx] = a.ws.s_ctrl[n + s];
+            a.ws.steps[idx] = nv;
+            // GoalRegion2ndOrderCar::distanceGoal <= threshold (GoalRegionDatabase.h:48-55)
+            const float gx = x - a.goal_x, gy = y - a.goal_y;
+            if (sqrtf(fmaf(gx, gx, gy * gy)) <= a.goal_radius) {
+                if (a.n_cons == 0 || parked_state_clear(w, a, t_node, x, y, th))
+                    atomicMin(a.ws.goal_key, ((unsigned long long)(unsigned)t_node << 32) | (unsigned)idx);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_base = min(s_base + total, M);
+        __syncthreads();
     }
-    const int s = best_s, par = a.ws.s_parent[s], nv = a.ws.s_valid[s];
-    const float x = a.ws.s_fin[s], y = a.ws.s_fin[n + s], th = a.ws.s_fin[4 * n + s];
-    a.ws.nodes[idx] = x;
-    a.ws.nodes[M + idx] = y;
-    a.ws.nodes[2 * M + idx] = a.ws.s_fin[2 * n + s];
-    a.ws.nodes[3 * M + idx] = a.ws.s_fin[3 * n + s];
-    a.ws.nodes[4 * M + idx] = th;
-    a.ws.parent[idx] = par;
-    const int t_node = a.ws.time[par] + nv;
-    a.ws.time[idx] = t_node;
-    a.ws.ctrl[idx] = a.ws.s_ctrl[s];
-    a.ws.ctrl[M + idx] = a.ws.s_ctrl[n + s];
-    a.ws.steps[idx] = nv;
-    // GoalRegion2ndOrderCar::distanceGoal <= threshold (GoalRegionDatabase.h:48-55)
-    const float gx = x - a.goal_x, gy = y - a.goal_y;
-    if (sqrtf(fmaf(gx, gx, gy * gy)) <= a.goal_radius) {
-        if (a.n_cons == 0 || parked_state_clear(w, a, t_node, x, y, th))
-            atomicMin(a.ws.goal_key, ((unsigned long long)(unsigned)t_node << 32) | (unsigned)idx);
-    }
+    if (tid == 0) a.ws.counters[0] = s_base;
 }
 
 // Walks goal -> root (one thread) and emits the edges root -> goal as k_propagate inputs.
@@ -288,7 +316,7 @@ int dev_alloc(kcbs_ctx *ctx, T *&p, size_t n)
 void free_workspace(RrtWorkspace &ws)
 {
     void *d[] = {ws.nodes, ws.parent, ws.time, ws.ctrl, ws.steps, ws.targets, ws.nn, ws.s_parent, ws.s_ctrl, ws.s_steps,
-                 ws.s_fin, ws.s_valid, ws.counters, ws.goal_key, ws.cons, ws.cons_states, ws.path_nodes, ws.path_ctrl,
+                 ws.s_fin, ws.s_valid, ws.sel, ws.counters, ws.goal_key, ws.cons, ws.cons_states, ws.path_nodes, ws.path_ctrl,
                  ws.path_steps, ws.path_parent, ws.path_valid, ws.path_seg};
     for (void *p : d)
         if (p) cudaFree(p);
@@ -312,7 +340,7 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int cons_total, in
         if ((st = dev_alloc(ctx, ws.nodes, 5 * M)) || (st = dev_alloc(ctx, ws.parent, M)) || (st = dev_alloc(ctx, ws.time, M)) ||
             (st = dev_alloc(ctx, ws.ctrl, 2 * M)) || (st = dev_alloc(ctx, ws.steps, M)) || (st = dev_alloc(ctx, ws.targets, 5 * B)) ||
             (st = dev_alloc(ctx, ws.nn, B)) || (st = dev_alloc(ctx, ws.s_parent, S)) || (st = dev_alloc(ctx, ws.s_ctrl, 2 * S)) ||
-            (st = dev_alloc(ctx, ws.s_steps, S)) || (st = dev_alloc(ctx, ws.s_fin, 5 * S)) || (st = dev_alloc(ctx, ws.s_valid, S)) ||
+            (st = dev_alloc(ctx, ws.s_steps, S)) || (st = dev_alloc(ctx, ws.s_fin, 5 * S)) || (st = dev_alloc(ctx, ws.s_valid, S)) || (st = dev_alloc(ctx, ws.sel, B)) ||
             (st = dev_alloc(ctx, ws.counters, 4)) || (st = dev_alloc(ctx, ws.goal_key, 1)) || (st = dev_alloc(ctx, ws.path_nodes, PC)) ||
             (st = dev_alloc(ctx, ws.path_ctrl, 2 * PC)) || (st = dev_alloc(ctx, ws.path_steps, PC)) ||
             (st = dev_alloc(ctx, ws.path_parent, PC)) || (st = dev_alloc(ctx, ws.path_valid, PC)) ||
@@ -441,10 +469,11 @@ static int rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *g
         k_rrt_samples<<<(n + 255) / 256, 256, 0, s>>>(a);
         KCBS_CUDA(ctx, launch_propagate(ctx->world, pa, s));
         k_rrt_select<<<(p.n_targets * 32 + 255) / 256, 256, 0, s>>>(ctx->world, a);
+        k_rrt_append<<<1, 1024, 0, s>>>(ctx->world, a);
         KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters, ws.counters, sizeof(int), cudaMemcpyDeviceToHost, s));
         KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_goal, ws.goal_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         KCBS_CUDA(ctx, cudaStreamSynchronize(s));
-        ctx->launches += 5;
+        ctx->launches += 6;
         n_nodes = std::min(ws.h_counters[0], p.max_nodes);
         goal = *ws.h_goal;
         ++iters;
@@ -650,6 +679,32 @@ int plan_robot(kcbs_ctx *ctx, int r, const float *starts, const float *goals, in
 }
 
 }  // namespace
+
+int kcbs_rrt_plan_many(kcbs_ctx *ctx, int n_jobs, const int32_t *robots, const float *starts, const float *goals,
+                       const kcbs_rrt_params *params, const uint64_t *seeds, int max_T, float *traj_out, int32_t *T_out,
+                       kcbs_rrt_stats *stats)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    if (n_jobs < 0 || max_T < 1) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n_jobs or max_T out of range");
+    if (n_jobs == 0) return KCBS_OK;
+    if (!robots || !starts || !goals || !traj_out || !T_out) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "null argument");
+    kcbs_rrt_params base;
+    if (params)
+        base = *params;
+    else
+        kcbs_rrt_defaults(&base);
+    return run_planner_jobs(ctx, n_jobs, kPlannerLanes, [&](kcbs_ctx *lane, int j) {
+        kcbs_rrt_params lp = base;
+        if (seeds) lp.seed = seeds[j];
+        float start[5];
+        for (int c = 0; c < 5; ++c) start[c] = starts[(size_t)c * n_jobs + j];
+        kcbs_rrt_stats rs;
+        const int st = rrt_plan(lane, robots[j], start, goals + 2 * (size_t)j, lp, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                max_T, traj_out + (size_t)j * 5 * max_T, T_out + j, &rs);
+        if (stats) stats[j] = rs;
+        return st;
+    });
+}
 
 int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goals, const kcbs_kcbs_params *params,
                     int max_T, float *plan_out, int32_t *lengths_out, kcbs_kcbs_stats *stats)

@@ -80,7 +80,7 @@ def merge_owned_rows(buf: torch.Tensor, owned: List[int]) -> torch.Tensor:
 
 def plan_replans_sharded(ctx, starts, goals, rank: int, world: int, max_T: int, seed: int = 1, device="cuda"):
     """Config 'per-robot replans sharded across GPUs': the R independent low-level replans of a K-CBS node are dealt
-    round-robin over the ranks (kcbs_rrt_plan on each rank's own GPU and stream), the planned trajectories are
+    round-robin over the ranks (kcbs_rrt_plan_many on each rank's own GPU: its jobs run concurrently), the planned trajectories are
     merged on every rank (NCCL over NVLink), and the merged plan is validated there with kcbs_first_conflict.
     Returns (plan [R, 5, max_T] tensor, lengths [R] tensor, all_solved flag)."""
     R = starts.shape[1]
@@ -88,14 +88,17 @@ def plan_replans_sharded(ctx, starts, goals, rank: int, world: int, max_T: int, 
     plan = torch.zeros((R, 5, max_T), dtype=torch.float32, device=device)
     lengths = torch.zeros(R, dtype=torch.int32, device=device)
     solved = torch.ones(1, dtype=torch.int32, device=device)
-    for r in mine:
-        traj, st = ctx.rrt_plan(r, starts[:, r], goals[r], ctx.rrt_params(seed=seed * 1000003 + r), max_T=max_T)
-        if not st.solved:
-            solved[0] = 0
-            continue
-        T = traj.shape[1]
-        plan[r, :, :T] = torch.from_numpy(traj).to(device)
-        lengths[r] = T
+    if len(mine):
+        # this rank's replans run concurrently on the context's planner lanes (kcbs_rrt_plan_many)
+        import numpy as np
+        seeds = np.array([seed * 1000003 + r for r in mine], dtype=np.uint64)
+        traj, T, stats = ctx.rrt_plan_many(mine, starts[:, mine], goals[mine], seeds=seeds, max_T=max_T)
+        for j, r in enumerate(mine):
+            if not stats[j].solved:
+                solved[0] = 0
+                continue
+            plan[r, :, :T[j]] = torch.from_numpy(traj[j, :, :T[j]]).to(device)
+            lengths[r] = int(T[j])
     merge_owned_rows(plan, mine)
     merge_owned_rows(lengths, mine)
     if dist.is_initialized() and world > 1:

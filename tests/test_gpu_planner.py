@@ -82,3 +82,38 @@ def test_kcbs_solves_demo_scene(pkg, orc, gpu_ctx_factory, scene):
     traj = np.ascontiguousarray(plan[:, [0, 1, 4], :T])
     res, _, _ = oracle.first_conflict(traj, lengths)
     assert res == (-1, -1, -1, -1), f"plan has a conflict {res}"
+
+
+def test_rrt_plan_many_equals_single_plans(pkg, orc, gpu_ctx_factory):
+    # the concurrent batch entry point returns, job by job, exactly what kcbs_rrt_plan returns alone (same seeds):
+    # the interleaving of the planner lanes does not leak into the results
+    scene = "Empty32x32_20robots"
+    ctx = gpu_ctx_factory(scene)
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    starts, goals = pkg.scenes.start_states(scene), pkg.scenes.goals(scene)
+    robots = [0, 3, 5, 8, 11, 12, 13, 17, 19, 2, 4]
+    seeds = np.array([1000 + r for r in robots], np.uint64)
+    traj, T, stats = ctx.rrt_plan_many(robots, starts[:, robots], goals[robots], seeds=seeds, max_T=1024)
+    assert all(s.solved for s in stats)
+    for j, r in enumerate(robots):
+        single, st = ctx.rrt_plan(r, starts[:, r], goals[r], ctx.rrt_params(seed=int(seeds[j])), max_T=1024)
+        assert single.shape[1] == T[j] and (single == traj[j, :, :T[j]]).all()
+        assert (traj[j, :, T[j]:] == 0).all()
+    check_path(oracle, traj[0, :, :T[0]], starts[:, robots[0]], goals[robots[0]], robots[0])
+    check_path(oracle, traj[7, :, :T[7]], starts[:, robots[7]], goals[robots[7]], robots[7])
+
+
+def test_sharded_replans_single_rank(pkg, orc, gpu_ctx_factory):
+    # config 'per-robot replans sharded across GPUs' on one rank: all 20 replans + merge + validation
+    import torch
+    from kcbs_b200 import sharding
+    scene = "Empty32x32_20robots"
+    ctx = gpu_ctx_factory(scene)
+    starts, goals = pkg.scenes.start_states(scene), pkg.scenes.goals(scene)
+    plan, lengths, ok = sharding.plan_replans_sharded(ctx, starts, goals, 0, 1, 1024, seed=11)
+    assert ok and plan.shape == (20, 5, 1024) and int(lengths.min()) > 1
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    p = plan.cpu().numpy()
+    for r in (0, 9, 19):
+        check_path(oracle, p[r, :, :int(lengths[r])], starts[:, r], goals[r], r)
+    assert torch.cuda.is_available()
