@@ -446,6 +446,9 @@ def main():
         orc = graft.load_oracle()
         orc.build()
         cpu = cpu_baseline_leg(args, pkg, orc, workloads, args.cpu_budget, os.cpu_count() or 1)
+        # the reference itself is single-threaded end to end: the same port on one thread, shorter sample
+        one = cpu_baseline_leg(args, pkg, orc, workloads, max(2.0, args.cpu_budget / 4), 1)
+        cpu["single_thread"] = {"value": one["value"], "unit": one["unit"], "sample": one["sample"]}
 
     if rank == 0:
         line = {
@@ -475,33 +478,34 @@ def main():
 def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_over_ranks, barrier, rank, traffic):
     import torch
     out = {}
-    # ---- validity: Congested10x10, 2^24 states ------------------------------
-    scene = "Congested10x10_7robots"
+    # ---- validity: Congested10x10, 2^24 states; Empty32x32 (no obstacles) beside it ----------
     n = 1 << 24
-    with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
-        sets = [torch.from_numpy(workloads.validity_states(scene, n, seed=1 + s + 100 * rank)).cuda() for s in range(2)]
-        mask = torch.empty((n + 31) // 32, dtype=torch.int32, device="cuda")
-        st = torch.cuda.current_stream()
-        for i in range(3):
-            ctx.validity_batch_dev(0, n, sets[i % 2], mask, st)
-        barrier()
-        reps = 10
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(reps):
-            ctx.validity_batch_dev(0, n, sets[i % 2], mask, st)   # 2 x 336 MB inputs alternate: > L2
-        e1.record()
-        barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        rate = sum_over_ranks(float(n)) * reps / (ms * 1e-3)
-        gbs = VALIDITY_BYTES_PER_STATE * n * reps / (e0.elapsed_time(e1) * 1e-3) * 1e-9
-        out["validity"] = {"metric": "validity-checked states/s", "value": rate, "scene": scene, "states": n,
-                           "roofline": {"kernel": "k_validity", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
-                                        "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src,
-                                        "traffic": None if "k_validity" not in traffic else
-                                        traffic["k_validity"]["dram_read_bytes"] + traffic["k_validity"]["dram_write_bytes"],
-                                        "algorithmic_bytes_per_launch": VALIDITY_BYTES_PER_STATE * n}}
-        del sets, mask
+    for key, scene in (("validity", "Congested10x10_7robots"), ("validity_no_obstacles", "Empty32x32_10robots")):
+        with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
+            sets = [torch.from_numpy(workloads.validity_states(scene, n, seed=1 + s + 100 * rank)).cuda() for s in range(2)]
+            mask = torch.empty((n + 31) // 32, dtype=torch.int32, device="cuda")
+            st = torch.cuda.current_stream()
+            for i in range(3):
+                ctx.validity_batch_dev(0, n, sets[i % 2], mask, st)
+            barrier()
+            reps = 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(reps):
+                ctx.validity_batch_dev(0, n, sets[i % 2], mask, st)   # 2 x 336 MB inputs alternate: > L2
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            rate = sum_over_ranks(float(n)) * reps / (ms * 1e-3)
+            gbs = VALIDITY_BYTES_PER_STATE * n * reps / (e0.elapsed_time(e1) * 1e-3) * 1e-9
+            has_traffic = key == "validity" and "k_validity" in traffic
+            out[key] = {"metric": "validity-checked states/s", "value": rate, "scene": scene, "states": n,
+                        "roofline": {"kernel": "k_validity", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src,
+                                     "traffic": traffic["k_validity"]["dram_read_bytes"] + traffic["k_validity"]["dram_write_bytes"]
+                                     if has_traffic else None,
+                                     "algorithmic_bytes_per_launch": VALIDITY_BYTES_PER_STATE * n}}
+            del sets, mask
     # ---- conflict scan: Empty32x32 30 robots, 435 pairs x 10K steps, 256 plans (config 5) --------------
     # N > 1: every rank scans its own 256-plan batch (weak); one batch sharded by plan is reported as well (strong).
     from kcbs_b200 import sharding
