@@ -90,6 +90,33 @@ def _worker(rank, world, port, ret):
             jobs[j] += 1
         dist.all_reduce(jobs)
         assert (jobs == 1).all()
+
+        # (4) the sharded-replans helper end to end with a stand-in for the GPU context: every rank plans its own
+        # robots through rrt_plan_many, the merged plan and lengths are complete and identical on both ranks
+        class StubCtx:
+            calls = []
+
+            def rrt_plan_many(self, robots, starts, goals, params=None, seeds=None, max_T=64):
+                self.calls.append(list(robots))
+                n = len(robots)
+                tr = np.zeros((n, 5, max_T), np.float32)
+                T = np.zeros(n, np.int32)
+                stats = []
+                for j, r in enumerate(robots):
+                    T[j] = 5 + r
+                    tr[j, :, :T[j]] = starts[:, j:j + 1] + np.arange(T[j], dtype=np.float32)[None, :] * (r + 1) + float(seeds[j] % 7)
+                    stats.append(type("S", (), {"solved": 1})())
+                return tr, T, stats
+
+        stub = StubCtx()
+        starts = np.arange(5 * R, dtype=np.float32).reshape(5, R)
+        goals = np.zeros((R, 2), np.float32)
+        plan, lengths, ok = sharding.plan_replans_sharded(stub, starts, goals, rank, world, 64, seed=3, device="cpu")
+        assert ok and stub.calls == [sharding.round_robin(R, rank, world)]
+        assert lengths.tolist() == [5 + r for r in range(R)]
+        for r in range(R):
+            want = starts[:, r:r + 1] + np.arange(5 + r, dtype=np.float32)[None, :] * (r + 1) + float((3 * 1000003 + r) % 7)
+            assert (plan[r, :, :5 + r].numpy() == want).all() and (plan[r, :, 5 + r:] == 0).all()
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
