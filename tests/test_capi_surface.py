@@ -109,3 +109,22 @@ def test_missing_library_fails_loudly(pkg, monkeypatch):
     monkeypatch.setattr(capi, "lib_path", lambda: "/nonexistent/libkcbs_b200.so")
     with pytest.raises(ImportError):
         capi.load_library()
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: the header must compile as C99 (no C++-isms), and as C++ too."""
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text('#include <kcbs_b200.h>\nint main(void) { kcbs_world w; kcbs_world_defaults(&w, 10.0, 10.0); return kcbs_abi_version() == KCBS_ABI_VERSION ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # and it links and runs against the built library without a GPU (life-cycle entry points only)
+    exe = tmp_path / "use"
+    lib_dir = os.path.join(ROOT, "k-cbs-demos_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-L", lib_dir, "-lkcbs_b200", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
