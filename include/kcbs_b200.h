@@ -223,6 +223,8 @@ typedef struct kcbs_kcbs_params {
     kcbs_rrt_params low_level;
     double time_limit_s;  /* planner->solve(180.0), demo_*.cpp:168 */
     int32_t max_nodes;    /* constraint-tree nodes to expand at most (0 = unlimited) */
+    int32_t merge_bound;  /* KCBS::setMergeBound (demo_*.cpp: 10 / 20): a pair of robots with more conflicts than this is
+                           * merged into one individual; default INT32_MAX (never), as in the fork */
 } kcbs_kcbs_params;
 
 typedef struct kcbs_kcbs_stats {
@@ -233,6 +235,8 @@ typedef struct kcbs_kcbs_stats {
     double root_seconds;            /* KCBS::getRootSolveTime, Benchmark.h:166                     */
     double seconds;
     int64_t conflict_checks;        /* plans validated by kcbs_first_conflict                      */
+    int32_t merges;                 /* pairs merged into one individual (SystemMerger::merge)      */
+    int32_t reserved_;
 } kcbs_kcbs_stats;
 
 KCBS_API void kcbs_rrt_defaults(kcbs_rrt_params *p);
@@ -263,7 +267,10 @@ KCBS_API int kcbs_rrt_plan_many(kcbs_ctx *ctx, int n_jobs, const int32_t *robots
 /* K-CBS over the R robots of the world: root = independent low-level plans; best-first search over the
  * constraint tree with kcbs_first_conflict as the plan validator; every conflict spawns two children that
  * re-plan one robot each against the other's colliding states.  starts = [5][R] planes, goals = [R][2];
- * plan_out = [R][5][max_T], lengths_out = [R].  Merging (SystemMerger) is not performed. */
+ * plan_out = [R][5][max_T], lengths_out = [R].  A pair with more than merge_bound conflicts is merged (the role of
+ * SystemMerger::merge, SystemMergerDatabase.h:55-168) and the search restarts with it as one individual whose bodies are
+ * never tested against each other; its low level is a prioritised pair planner on the single-car kernels (first car,
+ * then the second against the first car's whole path), not a 10-d RRT. */
 KCBS_API int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goals,
                              const kcbs_kcbs_params *params, int max_T, float *plan_out, int32_t *lengths_out,
                              kcbs_kcbs_stats *stats);

@@ -62,13 +62,13 @@ class RrtStats(C.Structure):
 
 
 class KcbsParams(C.Structure):
-    _fields_ = [("low_level", RrtParams), ("time_limit_s", C.c_double), ("max_nodes", C.c_int32)]
+    _fields_ = [("low_level", RrtParams), ("time_limit_s", C.c_double), ("max_nodes", C.c_int32), ("merge_bound", C.c_int32)]
 
 
 class KcbsStats(C.Structure):
     _fields_ = [("solved", C.c_int32), ("nodes_expanded", C.c_int32), ("approximate_solutions", C.c_int32),
                 ("low_level_calls", C.c_int32), ("root_seconds", C.c_double), ("seconds", C.c_double),
-                ("conflict_checks", C.c_int64)]
+                ("conflict_checks", C.c_int64), ("merges", C.c_int32), ("reserved_", C.c_int32)]
 
 
 CONFLICT_DTYPE = np.dtype([("r1", "<i4"), ("r2", "<i4"), ("k_start", "<i4"), ("k_end", "<i4")])

@@ -546,6 +546,7 @@ void kcbs_kcbs_defaults(kcbs_kcbs_params *p)
     kcbs_rrt_defaults(&p->low_level);
     p->time_limit_s = 180.0;  // demo_*.cpp:168
     p->max_nodes = 0;
+    p->merge_bound = 2147483647;  // KCBS default: never merge (the demos set 10 / 20)
 }
 
 int kcbs_rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *goal_xy, const kcbs_rrt_params *params,
@@ -706,53 +707,113 @@ int kcbs_rrt_plan_many(kcbs_ctx *ctx, int n_jobs, const int32_t *robots, const f
     });
 }
 
-int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goals, const kcbs_kcbs_params *params,
-                    int max_T, float *plan_out, int32_t *lengths_out, kcbs_kcbs_stats *stats)
-{
-    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
-    if (R < 1 || R > ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "R exceeds the robots of this world");
-    if (!starts || !goals || !plan_out || !lengths_out || max_T < 2) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "null argument");
-    kcbs_kcbs_params P;
-    if (params)
-        P = *params;
-    else
-        kcbs_kcbs_defaults(&P);
-    const double t_begin = now_s();
-    kcbs_kcbs_stats S;
-    std::memset(&S, 0, sizeof S);
-    long long next_id = 0;
+// ---- K-CBS search over a fixed set of individuals (1 robot, or 2 after a merge) -------------------------------------
 
-    // root: every robot planned on its own (KCBS::solve root node)
-    auto root = std::make_shared<CbsNode>();
-    root->traj.resize(R); root->len.assign(R, 0); root->cons.resize(R);
-    bool root_ok = true;
-    {
-        std::vector<kcbs_rrt_stats> rs(R);
-        const int st = run_planner_jobs(ctx, R, kPlannerLanes, [&](kcbs_ctx *lane, int r) {
-            kcbs_rrt_params lp = P.low_level;
-            lp.seed = P.low_level.seed * 1000003ull + (unsigned long long)r;
-            return plan_robot(lane, r, starts, goals, R, lp, root->cons[r], max_T, root->traj[r], root->len[r], rs[r]);
-        });
+extern "C++" {
+namespace {
+
+struct Search {
+    kcbs_ctx *ctx;
+    int R;
+    const float *starts, *goals;
+    kcbs_kcbs_params P;
+    int max_T;
+    double t_begin;
+    kcbs_kcbs_stats *S;
+    std::vector<std::vector<int>> ind;  // robots of every individual
+    std::vector<int> ind_of;            // robot -> individual
+};
+
+// Low-level plan of one individual into `node`: its robots one after the other, each against the individual's
+// constraints plus the whole paths (padded with the parked final state up to the horizon) of the members planned before
+// it.  Returns KCBS_OK and sets `solved`.
+int plan_individual_ordered(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsigned long long seed, bool reversed,
+                            bool &solved)
+{
+    solved = true;
+    std::vector<std::shared_ptr<Constraint>> cons = node.cons[I];
+    const size_t n = q.ind[I].size();
+    for (size_t m = 0; m < n; ++m) {
+        const int r = q.ind[I][reversed ? n - 1 - m : m];
+        kcbs_rrt_params lp = q.P.low_level;
+        lp.seed = seed * 1000003ull + (unsigned long long)r;
+        kcbs_rrt_stats rs;
+        const int st = plan_robot(lane, r, q.starts, q.goals, q.R, lp, cons, q.max_T, node.traj[r], node.len[r], rs);
         if (st != KCBS_OK) return st;
-        for (int r = 0; r < R; ++r) {
-            ++S.low_level_calls;
-            if (!rs[r].solved) root_ok = false;
-            root->cost += root->len[r];
+        if (!rs.solved) {
+            solved = false;
+            return KCBS_OK;
+        }
+        if (m + 1 < n) {  // the next member must avoid this one everywhere, also where it is parked
+            auto c = std::make_shared<Constraint>();
+            c->other = r;
+            c->k0 = 0;
+            const int L = node.len[r];
+            for (int k = 0; k < q.max_T; ++k) {
+                const int kk = std::min(k, L - 1);
+                c->x.push_back(node.traj[r][(size_t)0 * L + kk]);
+                c->y.push_back(node.traj[r][(size_t)1 * L + kk]);
+                c->th.push_back(node.traj[r][(size_t)4 * L + kk]);
+            }
+            cons.push_back(c);
         }
     }
-    S.root_seconds = now_s() - t_begin;
+    return KCBS_OK;
+}
+
+int plan_individual(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsigned long long seed, bool &solved)
+{
+    int st = plan_individual_ordered(lane, q, node, I, seed, false, solved);
+    // a merged pair whose second car finds no way around the first is tried once more in the other order
+    if (st == KCBS_OK && !solved && q.ind[I].size() > 1) st = plan_individual_ordered(lane, q, node, I, seed + 1, true, solved);
+    return st;
+}
+
+// Best-first search of the constraint tree.  Returns KCBS_OK with `solution` set, or with merge_a >= 0 when a pair of
+// single-robot individuals exceeded the merge bound (the caller merges and restarts), or with neither (time / node
+// budget exhausted, or the root has no plan).
+int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int &merge_b)
+{
+    kcbs_ctx *ctx = q.ctx;
+    kcbs_kcbs_stats &S = *q.S;
+    const int R = q.R, NI = (int)q.ind.size();
+    solution.reset();
+    merge_a = merge_b = -1;
+    long long next_id = 0;
+    std::vector<int> pair_conflicts((size_t)NI * NI, 0);
+
+    // root: every individual planned on its own (KCBS::solve root node), all at once on the planner lanes
+    auto root = std::make_shared<CbsNode>();
+    root->traj.resize(R); root->len.assign(R, 0); root->cons.resize(NI);
+    bool root_ok = true;
+    {
+        std::vector<char> ok(NI, 0);
+        const int st = run_planner_jobs(ctx, NI, kPlannerLanes, [&](kcbs_ctx *lane, int I) {
+            bool solved = false;
+            const int rc = plan_individual(lane, q, *root, I, q.P.low_level.seed + 7919ull * (unsigned long long)S.merges, solved);
+            ok[I] = solved;
+            return rc;
+        });
+        if (st != KCBS_OK) return st;
+        for (int I = 0; I < NI; ++I) {
+            S.low_level_calls += (int)q.ind[I].size();
+            if (!ok[I]) root_ok = false;
+        }
+        for (int r = 0; r < R; ++r) root->cost += root->len[r];
+    }
+    if (S.merges == 0) S.root_seconds = now_s() - q.t_begin;
     std::priority_queue<std::shared_ptr<CbsNode>, std::vector<std::shared_ptr<CbsNode>>, NodeOrder> open;
     if (root_ok) {
         root->id = next_id++;
         open.push(root);
     }
 
-    std::shared_ptr<CbsNode> solution;
     std::vector<float> traj3;
-    std::vector<int32_t> lens(R);
+    std::vector<int32_t> lens(R), group(R);
+    for (int r = 0; r < R; ++r) group[r] = q.ind_of[r];
     while (!open.empty()) {
-        if (P.time_limit_s > 0 && now_s() - t_begin > P.time_limit_s) break;
-        if (P.max_nodes > 0 && S.nodes_expanded >= P.max_nodes) break;
+        if (q.P.time_limit_s > 0 && now_s() - q.t_begin > q.P.time_limit_s) break;
+        if (q.P.max_nodes > 0 && S.nodes_expanded >= q.P.max_nodes) break;
         auto node = open.top();
         open.pop();
         ++S.nodes_expanded;
@@ -772,21 +833,30 @@ int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goal
         }
         kcbs_conflict cf;
         // time indices beyond T are never scanned: every path is padded to T, and k_hi = Tp only repeats the
-        // padded states of [T, Tp), which cannot introduce an earlier conflict than the ones in [0, T)
-        int st = kcbs_first_conflict(ctx, 1, R, Tp, traj3.data(), lens.data(), &cf);
+        // padded states of [T, Tp), which cannot introduce an earlier conflict than the ones in [0, T).  Bodies of
+        // one (merged) individual are never tested against each other: its low level keeps them apart.
+        int st = kcbs_first_conflict_groups(ctx, 1, R, Tp, traj3.data(), lens.data(), NI < R ? group.data() : nullptr, &cf);
         if (st != KCBS_OK) return st;
         ++S.conflict_checks;
         if (cf.r1 < 0) {
             solution = node;
-            break;
+            return KCBS_OK;
         }
         cf.k_end = std::min(cf.k_end, T - 1);
-        // two children: each re-plans one robot against the other's states during the conflict
+        // merge bound (KCBS::setMergeBound): a pair of single robots that keeps colliding becomes one individual
+        const int I1 = q.ind_of[cf.r1], I2 = q.ind_of[cf.r2];
+        const int n_conf = ++pair_conflicts[(size_t)std::min(I1, I2) * NI + std::max(I1, I2)];
+        if (n_conf > q.P.merge_bound && q.ind[I1].size() == 1 && q.ind[I2].size() == 1) {
+            merge_a = std::min(I1, I2);
+            merge_b = std::max(I1, I2);
+            return KCBS_OK;
+        }
+        // two children: each re-plans one individual against the other robot's states during the conflict
         const int pair[2][2] = {{cf.r1, cf.r2}, {cf.r2, cf.r1}};
         std::shared_ptr<CbsNode> child[2];
-        kcbs_rrt_stats crs[2];
+        bool solved[2] = {false, false};
         st = run_planner_jobs(ctx, 2, 2, [&](kcbs_ctx *lane, int ch) {
-            const int me = pair[ch][0], other = pair[ch][1];
+            const int me = q.ind_of[pair[ch][0]], other = pair[ch][1];
             auto c = std::make_shared<Constraint>();
             c->other = other;
             c->k0 = cf.k_start;
@@ -799,15 +869,14 @@ int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goal
             }
             child[ch] = std::make_shared<CbsNode>(*node);
             child[ch]->cons[me].push_back(c);
-            kcbs_rrt_params lp = P.low_level;
-            // the seed depends on the expansion, the branch and the robot only, so both branches can run at once
-            lp.seed = P.low_level.seed * 1000003ull + (unsigned long long)((S.nodes_expanded * 2 + ch) * 131 + me);
-            return plan_robot(lane, me, starts, goals, R, lp, child[ch]->cons[me], max_T, child[ch]->traj[me], child[ch]->len[me], crs[ch]);
+            // the seed depends on the expansion and the branch only, so both branches can run at once
+            return plan_individual(lane, q, *child[ch], me,
+                                   q.P.low_level.seed + 104729ull * (unsigned long long)(S.nodes_expanded * 2 + ch), solved[ch]);
         });
         if (st != KCBS_OK) return st;
         for (int ch = 0; ch < 2; ++ch) {
-            ++S.low_level_calls;
-            if (!crs[ch].solved) {
+            S.low_level_calls += (int)q.ind[q.ind_of[pair[ch][0]]].size();
+            if (!solved[ch]) {
                 ++S.approximate_solutions;  // the fork counts low-level time-outs as approximate solutions
                 continue;
             }
@@ -816,6 +885,48 @@ int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goal
             child[ch]->id = next_id++;
             open.push(child[ch]);
         }
+    }
+    return KCBS_OK;
+}
+
+}  // namespace
+}  // extern "C++"
+
+int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goals, const kcbs_kcbs_params *params,
+                    int max_T, float *plan_out, int32_t *lengths_out, kcbs_kcbs_stats *stats)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    if (R < 1 || R > ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "R exceeds the robots of this world");
+    if (!starts || !goals || !plan_out || !lengths_out || max_T < 2) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "null argument");
+    kcbs_kcbs_stats S;
+    std::memset(&S, 0, sizeof S);
+    Search q;
+    q.ctx = ctx; q.R = R; q.starts = starts; q.goals = goals; q.max_T = max_T; q.S = &S;
+    if (params)
+        q.P = *params;
+    else
+        kcbs_kcbs_defaults(&q.P);
+    q.t_begin = now_s();
+    q.ind.resize(R);
+    q.ind_of.resize(R);
+    for (int r = 0; r < R; ++r) {
+        q.ind[r] = {r};
+        q.ind_of[r] = r;
+    }
+
+    std::shared_ptr<CbsNode> solution;
+    for (;;) {
+        int ma = -1, mb = -1;
+        const int st = search_tree(q, solution, ma, mb);
+        if (st != KCBS_OK) return st;
+        if (solution || ma < 0) break;
+        // SystemMerger::merge(ma, mb): the pair becomes one individual and the search starts over (as the fork does)
+        q.ind[ma].insert(q.ind[ma].end(), q.ind[mb].begin(), q.ind[mb].end());
+        q.ind.erase(q.ind.begin() + mb);
+        for (size_t I = 0; I < q.ind.size(); ++I)
+            for (int r : q.ind[I]) q.ind_of[r] = (int)I;
+        ++S.merges;
+        if (q.P.time_limit_s > 0 && now_s() - q.t_begin > q.P.time_limit_s) break;
     }
 
     if (solution) {
@@ -830,7 +941,7 @@ int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goal
     } else {
         for (int r = 0; r < R; ++r) lengths_out[r] = 0;
     }
-    S.seconds = now_s() - t_begin;
+    S.seconds = now_s() - q.t_begin;
     if (stats) *stats = S;
     return KCBS_OK;
 }

@@ -315,6 +315,7 @@ inline ompl::base::PlannerStatus KCBS::solve(double solveTime)
     kcbs_kcbs_params p;
     kcbs_kcbs_defaults(&p);
     p.time_limit_s = solveTime;
+    p.merge_bound = mergeBound_;
     p.low_level.time_limit_s = llSolveTime_;
     p.low_level.min_steps = (int)sis[0]->getMinControlDuration();
     p.low_level.max_steps = (int)sis[0]->getMaxControlDuration();

@@ -117,3 +117,28 @@ def test_sharded_replans_single_rank(pkg, orc, gpu_ctx_factory):
     for r in (0, 9, 19):
         check_path(oracle, p[r, :, :int(lengths[r])], starts[:, r], goals[r], r)
     assert torch.cuda.is_available()
+
+
+@pytest.mark.parametrize("scene,bound", [("Corridor10x10_4robots", 0), ("Congested10x10_7robots", 1), ("Empty32x32_10robots", 0)])
+def test_kcbs_merges_when_the_bound_is_exceeded(pkg, orc, gpu_ctx_factory, scene, bound):
+    # KCBS::setMergeBound: a pair with more conflicts than the bound becomes one individual (planned together, its
+    # bodies never tested against each other by the high level); the plan that comes out must still be conflict free
+    # under the reference's FULL scan (no groups), every path feasible and valid
+    ctx = gpu_ctx_factory(scene)
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    starts, goals = pkg.scenes.start_states(scene), pkg.scenes.goals(scene)
+    params = ctx.kcbs_params(low_level=ctx.rrt_params(seed=2, time_limit_s=5.0), time_limit_s=120.0, merge_bound=bound)
+    plan, lengths, st = ctx.kcbs_solve(starts, goals, params, max_T=1024)
+    assert st.solved == 1
+    R = starts.shape[1]
+    T = int(lengths.max())
+    traj = np.zeros((R, 3, T), np.float32)
+    for r in range(R):
+        L = int(lengths[r])
+        traj[r, :, :L] = plan[r][[0, 1, 4], :L]
+    res, _, _ = oracle.first_conflict(traj, lengths=lengths)
+    assert res[0] == -1, f"conflict {res} in a merged plan"
+    for r in (0, R - 1):
+        check_path(oracle, plan[r][:, :int(lengths[r])], starts[:, r], goals[r], r)
+    if scene != "Empty32x32_10robots":
+        assert st.merges >= 1     # these scenes do conflict at the root
