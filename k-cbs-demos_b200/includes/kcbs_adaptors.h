@@ -336,7 +336,8 @@ inline ompl::base::PlannerStatus KCBS::solve(double solveTime)
     approximateSolutions_ = (unsigned int)st.approximate_solutions;
     std::ostringstream log;
     log << "K-CBS constraint tree: " << st.nodes_expanded << " nodes expanded, " << st.low_level_calls << " low-level plans, "
-        << st.conflict_checks << " plans validated, " << st.approximate_solutions << " approximate solutions, root "
+        << st.conflict_checks << " plans validated, " << st.approximate_solutions << " approximate solutions, " << st.merges
+        << " merges, root "
         << st.root_seconds << " s, total " << st.seconds << " s" << std::endl;
     treeLog_ = log.str();
     if (!st.solved) return ompl::base::PlannerStatus::TIMEOUT;
