@@ -235,7 +235,8 @@ typedef struct kcbs_kcbs_stats {
     double root_seconds;            /* KCBS::getRootSolveTime, Benchmark.h:166                     */
     double seconds;
     int64_t conflict_checks;        /* plans validated by kcbs_first_conflict                      */
-    int32_t merges;                 /* pairs merged into one individual (SystemMerger::merge)      */
+    int32_t merges;                 /* pairs merged into one individual (SystemMerger::merge);     *
+                                     * a merged pair without a root plan is split again            */
     int32_t reserved_;
 } kcbs_kcbs_stats;
 

@@ -722,6 +722,7 @@ struct Search {
     kcbs_kcbs_stats *S;
     std::vector<std::vector<int>> ind;  // robots of every individual
     std::vector<int> ind_of;            // robot -> individual
+    std::vector<char> no_merge;         // [R * R] pairs whose merged low level found no root plan: never merged again
 };
 
 // Low-level plan of one individual into `node`: its robots one after the other, each against the individual's
@@ -736,7 +737,7 @@ int plan_individual_ordered(kcbs_ctx *lane, const Search &q, CbsNode &node, int 
     for (size_t m = 0; m < n; ++m) {
         const int r = q.ind[I][reversed ? n - 1 - m : m];
         kcbs_rrt_params lp = q.P.low_level;
-        lp.seed = seed * 1000003ull + (unsigned long long)r;
+        lp.seed = q.P.low_level.seed * 1000003ull + seed * 131ull + (unsigned long long)r;  // seed = salt of this plan
         kcbs_rrt_stats rs;
         const int st = plan_robot(lane, r, q.starts, q.goals, q.R, lp, cons, q.max_T, node.traj[r], node.len[r], rs);
         if (st != KCBS_OK) return st;
@@ -771,9 +772,10 @@ int plan_individual(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsig
 
 // Best-first search of the constraint tree.  Returns KCBS_OK with `solution` set, or with merge_a >= 0 when a pair of
 // single-robot individuals exceeded the merge bound (the caller merges and restarts), or with neither (time / node
-// budget exhausted, or the root has no plan).
-int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int &merge_b)
+// budget exhausted, or the root has no plan: failed_root names a merged individual without a root plan, if any).
+int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int &merge_b, int &failed_root)
 {
+    failed_root = -1;
     kcbs_ctx *ctx = q.ctx;
     kcbs_kcbs_stats &S = *q.S;
     const int R = q.R, NI = (int)q.ind.size();
@@ -790,14 +792,17 @@ int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int
         std::vector<char> ok(NI, 0);
         const int st = run_planner_jobs(ctx, NI, kPlannerLanes, [&](kcbs_ctx *lane, int I) {
             bool solved = false;
-            const int rc = plan_individual(lane, q, *root, I, q.P.low_level.seed + 7919ull * (unsigned long long)S.merges, solved);
+            const int rc = plan_individual(lane, q, *root, I, 7919ull * (unsigned long long)S.merges, solved);
             ok[I] = solved;
             return rc;
         });
         if (st != KCBS_OK) return st;
         for (int I = 0; I < NI; ++I) {
             S.low_level_calls += (int)q.ind[I].size();
-            if (!ok[I]) root_ok = false;
+            if (!ok[I]) {
+                root_ok = false;
+                if (q.ind[I].size() > 1) failed_root = I;
+            }
         }
         for (int r = 0; r < R; ++r) root->cost += root->len[r];
     }
@@ -846,7 +851,8 @@ int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int
         // merge bound (KCBS::setMergeBound): a pair of single robots that keeps colliding becomes one individual
         const int I1 = q.ind_of[cf.r1], I2 = q.ind_of[cf.r2];
         const int n_conf = ++pair_conflicts[(size_t)std::min(I1, I2) * NI + std::max(I1, I2)];
-        if (n_conf > q.P.merge_bound && q.ind[I1].size() == 1 && q.ind[I2].size() == 1) {
+        if (n_conf > q.P.merge_bound && q.ind[I1].size() == 1 && q.ind[I2].size() == 1 &&
+            !q.no_merge[(size_t)std::min(cf.r1, cf.r2) * R + std::max(cf.r1, cf.r2)]) {
             merge_a = std::min(I1, I2);
             merge_b = std::max(I1, I2);
             return KCBS_OK;
@@ -871,7 +877,7 @@ int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int
             child[ch]->cons[me].push_back(c);
             // the seed depends on the expansion and the branch only, so both branches can run at once
             return plan_individual(lane, q, *child[ch], me,
-                                   q.P.low_level.seed + 104729ull * (unsigned long long)(S.nodes_expanded * 2 + ch), solved[ch]);
+                                   (unsigned long long)(S.nodes_expanded * 2 + ch) + 7919ull * (unsigned long long)S.merges, solved[ch]);
         });
         if (st != KCBS_OK) return st;
         for (int ch = 0; ch < 2; ++ch) {
@@ -914,18 +920,30 @@ int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goal
         q.ind_of[r] = r;
     }
 
+    q.no_merge.assign((size_t)R * R, 0);
     std::shared_ptr<CbsNode> solution;
     for (;;) {
-        int ma = -1, mb = -1;
-        const int st = search_tree(q, solution, ma, mb);
+        int ma = -1, mb = -1, failed = -1;
+        const int st = search_tree(q, solution, ma, mb, failed);
         if (st != KCBS_OK) return st;
-        if (solution || ma < 0) break;
-        // SystemMerger::merge(ma, mb): the pair becomes one individual and the search starts over (as the fork does)
-        q.ind[ma].insert(q.ind[ma].end(), q.ind[mb].begin(), q.ind[mb].end());
-        q.ind.erase(q.ind.begin() + mb);
+        if (solution) break;
+        if (ma >= 0) {
+            // SystemMerger::merge(ma, mb): the pair becomes one individual and the search starts over (as the fork does)
+            q.ind[ma].insert(q.ind[ma].end(), q.ind[mb].begin(), q.ind[mb].end());
+            q.ind.erase(q.ind.begin() + mb);
+            ++S.merges;
+        } else if (failed >= 0) {
+            // the prioritised pair planner found no root plan for this merged pair (e.g. two cars that must swap places
+            // in a corridor): split it again, never merge these two again, and let the constraint tree handle them
+            const int a = q.ind[failed][0], b = q.ind[failed][1];
+            q.no_merge[(size_t)std::min(a, b) * R + std::max(a, b)] = 1;
+            q.ind[failed] = {a};
+            q.ind.push_back({b});
+        } else {
+            break;
+        }
         for (size_t I = 0; I < q.ind.size(); ++I)
             for (int r : q.ind[I]) q.ind_of[r] = (int)I;
-        ++S.merges;
         if (q.P.time_limit_s > 0 && now_s() - q.t_begin > q.P.time_limit_s) break;
     }
 
