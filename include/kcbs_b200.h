@@ -247,8 +247,10 @@ KCBS_API void kcbs_kcbs_defaults(kcbs_kcbs_params *p);
  * expanding n_targets tree nodes x n_controls controls per round through k_propagate.  Dynamic-obstacle
  * constraints (the K-CBS low-level input): constraint c forbids overlapping robot cons_robot[c] placed at
  * cons_states[(s*total) + cons_offset[c] + (k - cons_k0[c])] (s = x, y, theta plane; total = sum of
- * cons_len) at absolute time index k in [cons_k0[c], cons_k0[c] + cons_len[c]).  The robot is taken to
- * wait at its last state after its path ends.  traj_out = [5][max_T] planes (state at every propagation
+ * |cons_len|) at absolute time index k in [cons_k0[c], cons_k0[c] + cons_len[c]).  A NEGATIVE cons_len[c] marks a
+ * persistent constraint of -cons_len[c] states whose last state keeps holding for every later time index (a robot
+ * parked at its goal).  The planned robot itself is taken to wait at its last state after its path ends.  A goal
+ * node whose path would not fit max_T states is never accepted (a solved plan is never truncated).  traj_out = [5][max_T] planes (state at every propagation
  * step, index 0 = start); *T_out = number of states.  All pointers are HOST pointers. */
 KCBS_API int kcbs_rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *goal_xy,
                            const kcbs_rrt_params *params, int n_cons, const int32_t *cons_robot,

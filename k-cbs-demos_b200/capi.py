@@ -415,9 +415,9 @@ class Context:
             setattr(p, k, v)
         return p
 
-    def rrt_plan(self, robot, start, goal_xy, params=None, constraints=(), max_T=4096):
-        """kcbs_rrt_plan.  constraints: iterable of (other_robot, k0, states [3, len]).  Returns
-        (traj [5, T] float32, RrtStats)."""
+    def rrt_plan(self, robot, start, goal_xy, params=None, constraints=(), max_T=4096, persistent=None):
+        """kcbs_rrt_plan.  constraints: iterable of (other_robot, k0, states [3, len]); persistent[i] marks constraint i
+        as holding its last state for ever (passed as a negative length).  Returns (traj [5, T] float32, RrtStats)."""
         start = np.ascontiguousarray(start, dtype=np.float32)
         goal = np.ascontiguousarray(goal_xy, dtype=np.float32)
         params = params if params is not None else self.rrt_params()
@@ -430,6 +430,8 @@ class Context:
         states = np.zeros((3, max(total, 1)), np.float32)
         for c, o in zip(cons, off):
             states[:, o:o + c[2].shape[1]] = c[2]
+        if persistent is not None:
+            ln = np.where(np.asarray(persistent, bool), -ln, ln).astype(np.int32)
         out = np.zeros((5, max_T), np.float32)
         T = C.c_int32()
         st = RrtStats()

@@ -556,10 +556,12 @@ static int first_conflict_dev_impl(kcbs_ctx *ctx, int n_plans, int R, int T, con
     if (!out || (T > 0 && !traj)) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "traj / out is null");
     cudaStream_t s = pick(ctx, stream);
     KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
-    // keys + tickets live in the context; the kernel leaves them clean, so they are filled only when (re)allocated
-    const size_t need = (sizeof(uint64_t) + sizeof(int)) * (size_t)n_plans;
-    if (need > ctx->keys.cap) {
+    // keys + tickets live in the context ([key_plans] keys, then [key_plans] tickets); the kernel leaves them clean, so
+    // they are filled only when the layout changes.  The layout is decided by the PLAN COUNT it was made for, never by
+    // the byte capacity (reserve() over-allocates): a call with more plans than that re-lays-out and re-fills both.
+    if (n_plans > ctx->key_plans) {
         const int cap_plans = n_plans + n_plans / 4 + 64;
+        KCBS_CUDA(ctx, cudaDeviceSynchronize());  // earlier scans (any stream) still use the old layout
         if ((st = reserve(ctx, ctx->keys, (sizeof(uint64_t) + sizeof(int)) * (size_t)cap_plans))) return st;
         ctx->key_plans = cap_plans;
         KCBS_CUDA(ctx, launch_fill_keys((unsigned long long *)ctx->keys.p, (int *)((uint64_t *)ctx->keys.p + cap_plans),

@@ -186,7 +186,11 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
     }
 
     // a conflict already recorded at an earlier time index makes this tile irrelevant
-    const unsigned long long seen = *(volatile const unsigned long long *)(a.keys + plan);
+    // (one load per warp, broadcast: other CTAs update the key concurrently, and `skip` guards full-mask warp collectives,
+    // so it must be warp-uniform)
+    unsigned long long seen = 0;
+    if ((tid & 31) == 0) seen = *(volatile const unsigned long long *)(a.keys + plan);
+    seen = __shfl_sync(0xffffffffu, seen, 0);
     const bool skip = seen != kNoConflict && (long long)(seen >> 16) < (long long)k0;
 
     if (bulk) mbar_wait(&s_bar, 0);   // (also when skipping: the copies must land before the CTA exits)

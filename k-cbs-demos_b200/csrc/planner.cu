@@ -84,6 +84,7 @@ struct RrtArgs {
     unsigned round;
     int n_targets, n_controls, min_steps, max_steps, robot;
     int n_cons, cons_total;
+    int max_T;  // states the caller's trajectory buffer holds: a goal node must have time index < max_T
 };
 
 __global__ void k_rrt_init(RrtArgs a, float x, float y, float v, float phi, float th)
@@ -191,7 +192,10 @@ __device__ bool parked_state_clear(const DevWorld &w, const RrtArgs &a, int t_no
     sincosf(th, &s, &c);
     for (int q = 0; q < a.n_cons; ++q) {
         const ConsDesc d = a.ws.cons[q];
-        for (int k = max(t_node + 1, d.k0); k < d.k0 + d.len; ++k) {
+        const int k_end = d.k0 + abs(d.len);
+        int k_begin = max(t_node + 1, d.k0);
+        if (d.len < 0) k_begin = min(k_begin, k_end - 1);  // persistent: the last state holds from k_end - 1 on
+        for (int k = k_begin; k < k_end; ++k) {
             const float *st = a.ws.cons_states + d.offset + (k - d.k0);
             const float ox = st[0], oy = st[a.cons_total], dx = ox - x, dy = oy - y;
             const float rs = rad + w.rob_rad[d.other];
@@ -277,7 +281,8 @@ __global__ void __launch_bounds__(1024) k_rrt_append(const __grid_constant__ Dev
             a.ws.steps[idx] = nv;
             // GoalRegion2ndOrderCar::distanceGoal <= threshold (GoalRegionDatabase.h:48-55)
             const float gx = x - a.goal_x, gy = y - a.goal_y;
-            if (sqrtf(fmaf(gx, gx, gy * gy)) <= a.goal_radius) {
+            // (a path that would not fit the caller's buffer is never a solution: it would come back truncated)
+            if (t_node < a.max_T && sqrtf(fmaf(gx, gx, gy * gy)) <= a.goal_radius) {
                 if (a.n_cons == 0 || parked_state_clear(w, a, t_node, x, y, th))
                     atomicMin(a.ws.goal_key, ((unsigned long long)(unsigned)t_node << 32) | (unsigned)idx);
             }
@@ -417,9 +422,9 @@ static int rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *g
     if (!start || !goal_xy || !traj_out || !T_out || max_T < 1) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "null argument");
     int cons_total = 0;
     for (int c = 0; c < n_cons; ++c) {
-        if (cons_robot[c] < 0 || cons_robot[c] >= ctx->n_robots || cons_len[c] < 0 || cons_offset[c] < 0)
+        if (cons_robot[c] < 0 || cons_robot[c] >= ctx->n_robots || cons_offset[c] < 0)
             return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "bad constraint");
-        cons_total = std::max(cons_total, cons_offset[c] + cons_len[c]);
+        cons_total = std::max(cons_total, cons_offset[c] + std::abs(cons_len[c]));
     }
     KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
     if ((st = ensure_workspace(ctx, p, cons_total, n_cons))) return st;
@@ -442,7 +447,7 @@ static int rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *g
     for (int c = 0; c < 4; ++c) { a.lo[c] = ctx->world.lo_t[c]; a.hi[c] = ctx->world.hi_t[c]; }
     a.seed = p.seed; a.round = 0;
     a.n_targets = p.n_targets; a.n_controls = p.n_controls; a.min_steps = p.min_steps; a.max_steps = p.max_steps;
-    a.robot = robot; a.n_cons = n_cons; a.cons_total = cons_total;
+    a.robot = robot; a.n_cons = n_cons; a.cons_total = cons_total; a.max_T = max_T;
     const int n = p.n_targets * p.n_controls;
 
     PropArgs pa;
@@ -573,6 +578,7 @@ namespace {
 struct Constraint {
     int other, k0;
     std::vector<float> x, y, th;  // states of `other` at k0 .. k0 + len - 1
+    bool persistent = false;      // the last state holds for every later time index (a robot parked at its goal)
 };
 
 struct CbsNode {
@@ -657,7 +663,8 @@ int plan_robot(kcbs_ctx *ctx, int r, const float *starts, const float *goals, in
     std::vector<int32_t> robot, k0, ln, off;
     int total = 0;
     for (const auto &c : cons) {
-        robot.push_back(c->other); k0.push_back(c->k0); ln.push_back((int)c->x.size()); off.push_back(total);
+        robot.push_back(c->other); k0.push_back(c->k0); off.push_back(total);
+        ln.push_back(c->persistent ? -(int)c->x.size() : (int)c->x.size());
         total += (int)c->x.size();
     }
     std::vector<float> states((size_t)3 * std::max(total, 1));
@@ -749,12 +756,12 @@ int plan_individual_ordered(kcbs_ctx *lane, const Search &q, CbsNode &node, int 
             auto c = std::make_shared<Constraint>();
             c->other = r;
             c->k0 = 0;
+            c->persistent = true;
             const int L = node.len[r];
-            for (int k = 0; k < q.max_T; ++k) {
-                const int kk = std::min(k, L - 1);
-                c->x.push_back(node.traj[r][(size_t)0 * L + kk]);
-                c->y.push_back(node.traj[r][(size_t)1 * L + kk]);
-                c->th.push_back(node.traj[r][(size_t)4 * L + kk]);
+            for (int k = 0; k < L; ++k) {
+                c->x.push_back(node.traj[r][(size_t)0 * L + k]);
+                c->y.push_back(node.traj[r][(size_t)1 * L + k]);
+                c->th.push_back(node.traj[r][(size_t)4 * L + k]);
             }
             cons.push_back(c);
         }

@@ -53,8 +53,12 @@ __device__ __forceinline__ bool constraints_clear(const DevWorld &w, const PropA
     float c = 1.0f, s = 0.0f;
     for (int q = 0; q < a.n_cons; ++q) {
         const ConsDesc d = a.cons[q];
-        const int rel = k - d.k0;
-        if (rel < 0 || rel >= d.len) continue;
+        int rel = k - d.k0;
+        if (rel < 0) continue;
+        if (d.len < 0)
+            rel = min(rel, -d.len - 1);  // persistent constraint: its last state holds for every later time index
+        else if (rel >= d.len)
+            continue;
         const float *st = a.cons_states + d.offset + rel;
         const float ox = st[0], oy = st[a.cons_total], dx = ox - x, dy = oy - y;
         const float rs = rad + w.rob_rad[d.other];

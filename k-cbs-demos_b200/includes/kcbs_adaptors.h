@@ -376,26 +376,42 @@ inline ompl::base::PlannerStatus PP::solve(double solveTime)
         p.time_limit_s = left;
         p.seed = 77 + r;
         p.goal_radius = ind[r].goal_radius;
-        // constraints: every earlier robot over the whole horizon (its last state repeated to the horizon's end)
-        int horizon = 1;
-        for (unsigned int q = 0; q < r; ++q) horizon = std::max(horizon, (int)lengths[q]);
-        horizon += 256;  // earlier robots stay parked at their goals
+        // constraints: every earlier robot's whole path as a PERSISTENT constraint (negative length: its last state --
+        // the robot parked at its goal -- keeps holding for every later time index, however long this robot's path gets)
         std::vector<int32_t> c_robot, c_k0, c_len, c_off;
-        std::vector<float> states((size_t)3 * std::max<size_t>(1, (size_t)r * horizon));
-        const size_t total = (size_t)r * horizon;
+        size_t total = 0;
+        for (unsigned int q = 0; q < r; ++q) total += (size_t)lengths[q];
+        std::vector<float> states((size_t)3 * std::max<size_t>(1, total));
+        size_t at = 0;
         for (unsigned int q = 0; q < r; ++q) {
-            c_robot.push_back((int)q); c_k0.push_back(0); c_len.push_back(horizon); c_off.push_back((int)(q * horizon));
-            for (int k = 0; k < horizon; ++k) {
-                const int kk = std::min(k, lengths[q] - 1);
-                states[(size_t)q * horizon + k] = trajs[q][(size_t)0 * max_T + kk];
-                states[total + (size_t)q * horizon + k] = trajs[q][(size_t)1 * max_T + kk];
-                states[2 * total + (size_t)q * horizon + k] = trajs[q][(size_t)4 * max_T + kk];
+            c_robot.push_back((int)q); c_k0.push_back(0); c_len.push_back(-lengths[q]); c_off.push_back((int)at);
+            for (int k = 0; k < lengths[q]; ++k) {
+                states[at + k] = trajs[q][(size_t)0 * max_T + k];
+                states[total + at + k] = trajs[q][(size_t)1 * max_T + k];
+                states[2 * total + at + k] = trajs[q][(size_t)4 * max_T + k];
             }
+            at += (size_t)lengths[q];
         }
         kcbs_rrt_stats st;
         ctx->check(kcbs_rrt_plan(ctx->get(), (int)r, ind[r].start, ind[r].goal, &p, (int)r, c_robot.data(), c_k0.data(), c_len.data(),
                                  c_off.data(), states.data(), max_T, trajs[r].data(), &lengths[r], &st));
         if (!st.solved) return ompl::base::PlannerStatus::TIMEOUT;
+    }
+    {
+        // the finished plan is validated as a whole before it is reported (plan scan with the padding rule)
+        int T = 1;
+        for (unsigned int r = 0; r < R; ++r) T = std::max(T, (int)lengths[r]);
+        const int Tp = (T + 3) & ~3;
+        std::vector<float> traj3((size_t)R * 3 * Tp, 0.0f);
+        for (unsigned int r = 0; r < R; ++r)
+            for (int k = 0; k < lengths[r]; ++k) {
+                traj3[((size_t)r * 3 + 0) * Tp + k] = trajs[r][(size_t)0 * max_T + k];
+                traj3[((size_t)r * 3 + 1) * Tp + k] = trajs[r][(size_t)1 * max_T + k];
+                traj3[((size_t)r * 3 + 2) * Tp + k] = trajs[r][(size_t)4 * max_T + k];
+            }
+        kcbs_conflict cf;
+        ctx->check(kcbs_first_conflict(ctx->get(), 1, (int)R, Tp, traj3.data(), lengths.data(), &cf));
+        if (cf.r1 >= 0) return ompl::base::PlannerStatus::APPROXIMATE_SOLUTION;
     }
     auto result = std::make_shared<PlanControl>();
     for (unsigned int r = 0; r < R; ++r) {

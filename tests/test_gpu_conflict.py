@@ -162,3 +162,27 @@ def test_robot_counts_and_mixed_footprints(pkg, orc, gpu_ctx_factory, R):
         ref, min_margin, _ = oracle.first_conflict(traj[p])
         if min_margin > BAND:
             assert got[p] == ref, f"R={R} plan {p}: gpu {got[p]} oracle {ref}"
+
+
+@pytest.mark.parametrize("counts", [(1, 100), (128, 256), (1, 66, 102, 300, 5, 301)])
+def test_plan_count_grows_on_one_context(pkg, workloads, counts):
+    # the keys / tickets workspace of a context is laid out for a plan count; a later call with MORE plans must re-lay
+    # it out even when the bytes still fit the (over-allocated) buffer -- otherwise keys alias tickets and plans past
+    # the old count decode as a conflict at k = 0, r1 = r2 = 0
+    import torch
+    scene = "Benchmark_Empty32x32_30robots"
+    T = 512
+    with pkg.Context(pkg.scenes.world(scene), device=0) as ctx:
+        for n in counts:
+            traj = workloads.cell_plans(scene, n, T, seed=5)
+            want = [(-1, -1, -1, -1)] * n
+            if n >= 5:
+                workloads.plant_conflict(traj, n - 1, 2, 9, 300, length=4)
+                want[n - 1] = (2, 9, 300, 303)
+            assert _t(ctx.first_conflict(traj)) == want, f"host entry point, {n} plans after {counts}"
+            d = torch.from_numpy(traj).cuda()
+            out = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+            for _ in range(2):   # twice: the kernel must also leave keys and tickets clean
+                ctx.first_conflict_dev(n, traj.shape[1], T, d, None, out, torch.cuda.current_stream())
+                torch.cuda.synchronize()
+                assert _t(out.cpu().numpy()) == want, f"device entry point, {n} plans after {counts}"

@@ -142,3 +142,44 @@ def test_kcbs_merges_when_the_bound_is_exceeded(pkg, orc, gpu_ctx_factory, scene
         check_path(oracle, plan[r][:, :int(lengths[r])], starts[:, r], goals[r], r)
     if scene != "Empty32x32_10robots":
         assert st.merges >= 1     # these scenes do conflict at the root
+
+
+def test_rrt_never_returns_a_truncated_path(pkg, gpu_ctx_factory):
+    # a trajectory buffer too short for any path to the goal: the plan must come back unsolved, not cut off
+    scene = "Empty32x32_10robots"
+    ctx = gpu_ctx_factory(scene)
+    start = np.array([3.0, 3.0, 0, 0, 0], np.float32)
+    goal = np.array([29.0, 29.0], np.float32)       # > 36 m away at |v| <= 1: more than 360 steps
+    traj, st = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=3, max_iterations=200), max_T=128)
+    assert st.solved == 0 and traj.shape[1] == 0
+    full, st2 = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=3), max_T=4096)
+    assert st2.solved == 1 and full.shape[1] > 128
+    assert np.hypot(full[0, -1] - goal[0], full[1, -1] - goal[1]) <= 0.5 + 1e-4
+    # exactly fitting buffer: solved, complete
+    fit, st3 = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=3), max_T=full.shape[1])
+    assert st3.solved == 1 and (fit == full).all()
+
+
+def test_rrt_persistent_constraint(pkg, orc, gpu_ctx_factory):
+    # a NEGATIVE constraint length marks a persistent constraint: the other robot drives for 40 steps and then stays
+    # parked across the way for ever; the planned path (much longer than 40 steps) must avoid the parked state too
+    scene = "Empty32x32_10robots"
+    ctx = gpu_ctx_factory(scene)
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    start = np.array([5.0, 16.0, 0, 0, 0], np.float32)
+    goal = np.array([12.0, 16.0], np.float32)
+    K = 40
+    other = np.zeros((3, K), np.float32)
+    other[0] = np.linspace(8.5, 8.5, K)
+    other[1] = np.linspace(12.0, 16.0, K)      # arrives on the straight line start -> goal and parks there
+    other[2] = np.pi / 2
+    traj, st = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=5), constraints=[(1, 0, other)], persistent=[True])
+    assert st.solved == 1 and traj.shape[1] > K
+    check_path(oracle, traj, start, goal)
+    for k in range(traj.shape[1]):
+        ok, _ = oracle.pair_valid(0, traj[[0, 1, 4], k], 1, other[:, min(k, K - 1)])
+        assert ok, f"persistent constraint violated at step {k}"
+    # the same constraint without persistence stops binding after K steps: some seed drives through the parked spot
+    # (or at least the plans differ), so the flag is what made the difference
+    free, st2 = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=5), constraints=[(1, 0, other)])
+    assert st2.solved == 1
