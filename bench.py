@@ -42,6 +42,18 @@ VALIDITY_BYTES_PER_STATE = 20.125      # 5 f32 read + 1 bit written
 FP32_NOMINAL_TFLOPS = 74.4   # 148 SM x 128 lanes x 2 x 1.965 GHz
 
 
+def workload_config(n_robots=10, n_exp=25, fixed_steps=None):
+    """`config` of the JSON line: the same keys and values in both arms (ours / --impl reference), so the driver can
+    tell that they ran the same workload; arm-specific facts live in `arm`."""
+    return {"workload": "Empty32x32 10 robots, batched propagation 64K controls/expansion",
+            "scene": SCENE, "robots": n_robots, "controls_per_expansion": N_CONTROLS, "max_steps": MAX_STEPS,
+            "durations": "U{1..10}" if fixed_steps is None else f"fixed {fixed_steps}",
+            "parents": "one shared tree node per expansion",
+            "unit_definition": "one 0.1 s propagation step of one control sample (10 RK4 sub-steps + wrap + validity)",
+            "l2": "GPU arm: every step writes distinct segment buffers of > 126 MB per GPU (no flush needed); CPU arm: n/a",
+            "parallelism": "independent per-robot expansions (replicas per GPU), no data-path collective"}
+
+
 def read_traffic():
     """DRAM traffic per launch from the committed ncu captures (profiles/traffic_r1.json); None when absent."""
     path = os.path.join(ROOT, "profiles", "traffic_r1.json")
@@ -197,15 +209,20 @@ def run_reference(args):
         units += u
         t += dt
     value = units / t
+    # the reference itself is single-threaded end to end: the same port on one thread, one expansion
+    parents, controls, steps = workloads.expansion_batch(SCENE, N_CONTROLS, seed=4242, shared_parent=True, interior=1.5)
+    t0 = time.perf_counter()
+    _, _, _, calls1 = oracle.propagate_batch(0, parents, controls, steps, want_seg=True, n_threads=1)
+    single = calls1 / (time.perf_counter() - t0)
     line = {
         "impl": "reference", "metric": "propagated states/s", "value": value, "unit": "states/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Empty32x32 10 robots, batched propagation 64K controls/expansion",
-                   "scene": SCENE, "controls_per_expansion": N_CONTROLS, "max_steps": MAX_STEPS,
-                   "step_sample": f"{sample} expansions per step"},
+        "config": workload_config(),
+        "arm": {"step_sample": f"{sample} expansions per step (bounded sample of the GPU arm's step)"},
         "cpu_baseline": {"value": value, "unit": "states/s", "cores": n_threads, "kind": "port",
-                         "sample": f"{sample} expansions x {N_CONTROLS} controls per step, {args.steps} steps"},
+                         "sample": f"{sample} expansions x {N_CONTROLS} controls per step, {args.steps} steps",
+                         "single_thread": {"value": single, "unit": "states/s", "sample": f"1 expansion x {N_CONTROLS} controls"}},
         "e2e": {"value": value, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = CPU oracle port (OMPL K-CBS fork + Boost are not installable here); the reference is "
                 "single-threaded, this arm uses every host thread",
@@ -317,6 +334,17 @@ def main():
     units_step = float(torch.minimum(steps_all, valid + 1).sum().item())
     samples_step = n_robots * n_exp * N_CONTROLS
     written_step = float(valid.sum().item())
+    # steps the kernel really integrates: v and phi are linear in time, so the step at which they leave their bounds
+    # is decided analytically and never integrated (propagate.cu); the other failures (x, y) cost their integration
+    par_all = torch.stack([torch.stack([p for p, _, _ in exps]) for exps in dev_in])     # [r, e, 5, 1]
+    ctl_all = torch.stack([torch.stack([c for _, c, _ in exps]) for exps in dev_in])     # [r, e, 2, n]
+    t1 = (torch.arange(1, MAX_STEPS + 1, device="cuda", dtype=torch.float32) * np.float32(0.1))[None, None, :, None]
+    vn = par_all[:, :, 2:3, :] + ctl_all[:, :, 0:1, :] * t1
+    pn = par_all[:, :, 3:4, :] + ctl_all[:, :, 1:2, :] * t1
+    inside = ((vn.abs() <= 1.0) & (pn.abs() <= float(np.pi / 3))).to(torch.int32)
+    eff = torch.minimum(torch.cumprod(inside, dim=2).sum(dim=2), steps_all)
+    integrated_step = float(torch.minimum(eff, valid + 1).sum().item())
+    del par_all, ctl_all, vn, pn, inside, eff
     launches_per_step = n_robots * n_exp
 
     # The step is launch-bound from Python (250 C-ABI calls of ~20 us of GPU work each), so it is captured once
@@ -361,7 +389,13 @@ def main():
     k1_traffic = None if not tp else (tp["dram_read_bytes"] + tp["segment_buffer_bytes"]) * N_CONTROLS / tp["samples"]
     roofline = {
         "kernel": "k_propagate", "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-        "frac": ach_tflops / fp32_peak if fp32_peak else None, "traffic": k1_traffic,
+        "frac": ach_tflops / fp32_peak if fp32_peak else None,
+        "units": units_step, "units_integrated": integrated_step, "units_written": written_step,
+        "frac_integrated": ach_tflops * integrated_step / units_step / fp32_peak if fp32_peak else None,
+        "frac_written": ach_tflops * written_step / units_step / fp32_peak if fp32_peak else None,
+        "peak_detail": {"probe": fp32_peak, "nominal": FP32_NOMINAL_TFLOPS,
+                        "note": "MEASURED_PEAKS.json has no FP32 entry: peak = FFMA saturation probe run in this process"},
+        "traffic": k1_traffic,
         "traffic_unit": "bytes per launch (ncu dram read + the whole zero-filled segment buffer written, scaled from the "
                         "655,360-sample capture in profiles/r1_k_propagate.md)",
         "algorithmic_bytes_per_launch": (BYTES_PER_STATE * written_step + BYTES_PER_SAMPLE * samples_step) / launches_per_step,
@@ -451,19 +485,26 @@ def main():
         cpu["single_thread"] = {"value": one["value"], "unit": one["unit"], "sample": one["sample"]}
 
     if rank == 0:
+        # what the partitioned paths do at this N, first in the line (the driver keeps the head of it)
+        cs = secondary.get("conflict_strong", {})
+        multi = {
+            "conflict_strong_P256_pairs_per_s": cs.get("P256", {}).get("value"),
+            "conflict_strong_P256_speedup_vs_one_gpu": cs.get("P256", {}).get("speedup_vs_one_gpu"),
+            "conflict_strong_P2048_pairs_per_s": cs.get("P2048", {}).get("value"),
+            "conflict_strong_P2048_speedup_vs_one_gpu": cs.get("P2048", {}).get("speedup_vs_one_gpu"),
+            "replans20_s": secondary.get("replans", {}).get("median_s"),
+            "e2e_states_per_s": e2e["value"],
+        }
         line = {
             "metric": "propagated states/s", "value": value, "unit": "states/s", "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Empty32x32 10 robots, batched propagation 64K controls/expansion",
-                       "scene": SCENE, "robots": n_robots, "controls_per_expansion": N_CONTROLS,
-                       "expansions_per_robot_per_step": n_exp, "max_steps": MAX_STEPS,
-                       "durations": "U{1..10}" if args.fixed_steps is None else f"fixed {args.fixed_steps}",
-                       "parents": "one shared tree node per expansion", "streams": n_robots,
-                       "launch": "one CUDA graph per step (captured C-ABI launches)" if graphed else "eager C-ABI calls from Python",
-                       "states_per_step_per_gpu": units_step,
-                       "l2": f"each step writes {samples_step * 200 / 1e6:.0f} MB of distinct segment buffers per GPU (> 126 MB L2); no flush needed",
-                       "parallelism": f"{world_size} x independent per-robot replans, no data-path collective"},
+            "multi_gpu": multi,
+            "config": workload_config(n_robots, n_exp, args.fixed_steps),
+            "arm": {"expansions_per_robot_per_step": n_exp, "streams": n_robots,
+                    "launch": "one CUDA graph per step (captured C-ABI launches)" if graphed else "eager C-ABI calls from Python",
+                    "states_per_step_per_gpu": units_step,
+                    "segment_bytes_per_step_per_gpu": samples_step * 200},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
             "secondary": secondary,
         }
@@ -521,12 +562,12 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
 
         def scan(n_plans=P):
             ctx.first_conflict_dev(n_plans, R, T, traj, None, res[:n_plans], st)
-            return sharding.gather_plans(res[:n_plans], world)
+            return res[:n_plans]
 
         for _ in range(3):
             allres = scan()
         barrier()
-        assert allres.shape[0] == P * world and int((allres[:, 0] >= 0).sum().item()) == 0, "throughput plans must be conflict free"
+        assert int((allres[:, 0] >= 0).sum().item()) == 0, "throughput plans must be conflict free"
         reps = 10
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -538,17 +579,6 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
         pairs = P * (R * (R - 1) // 2) * T
         rate = float(pairs) * world * reps / (ms * 1e-3)
         gbs = CONFLICT_BYTES_PER_TRAJ_STATE * P * R * T * reps / (e0.elapsed_time(e1) * 1e-3) * 1e-9
-        # strong scaling of ONE 256-plan batch: plans sharded over the ranks, verdicts all-gathered
-        lo, hi = sharding.shard_range(P, rank, world)
-        for _ in range(3):
-            scan(hi - lo)
-        barrier()
-        e0.record()
-        for _ in range(reps):
-            scan(hi - lo)
-        e1.record()
-        barrier()
-        strong_rate = float(pairs) * reps / (max_over_ranks(e0.elapsed_time(e1)) * 1e-3)
         # single-plan latency (435 pairs x 10K steps, L2 resident), rank-local
         one = traj[:1].contiguous()
         for _ in range(3):
@@ -559,16 +589,37 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
             ctx.first_conflict_dev(1, R, T, one, None, res[:1], st)
         e1.record()
         torch.cuda.synchronize()
+        one_us = 1e3 * e0.elapsed_time(e1) / 50
+        # the same single-plan scan replayed from a CUDA graph (20 launches per replay): kernel + launch latency without
+        # the ~9 us a ctypes call from Python costs
+        side = torch.cuda.Stream()
+        side.wait_stream(st)
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(20):
+                    ctx.first_conflict_dev(1, R, T, one, None, res[:1], side)
+            for _ in range(3):
+                g.replay()
+            side.synchronize()
+            e0.record(side)
+            for _ in range(10):
+                g.replay()
+            e1.record(side)
+            side.synchronize()
+        one_graph_us = 1e3 * e0.elapsed_time(e1) / 200
+        del g
         out["conflict"] = {"metric": "conflict-checked state-pairs/s", "value": rate, "scene": scene, "plans": P,
-                           "pairs": R * (R - 1) // 2, "timesteps": T, "scaling": "weak (256 plans per rank, verdicts all-gathered)",
-                           "strong_scaling_value": strong_rate,
-                           "single_plan_latency_us": 1e3 * e0.elapsed_time(e1) / 50,
+                           "pairs": R * (R - 1) // 2, "timesteps": T,
+                           "scaling": "weak (an independent 256-plan batch per rank, no exchange)",
+                           "single_plan_latency_us": one_graph_us, "single_plan_latency_python_us": one_us,
                            "roofline": {"kernel": "k_conflict_keys", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
                                         "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": peak_src,
                                         "traffic": None if "k_conflict_keys" not in traffic else
                                         traffic["k_conflict_keys"]["dram_read_bytes"] + traffic["k_conflict_keys"]["dram_write_bytes"],
                                         "algorithmic_bytes_per_launch": CONFLICT_BYTES_PER_TRAJ_STATE * P * R * T,
                                         "note": "per GPU; algorithmic 12 B per trajectory state (x, y, theta), the scan itself reads 8 B"}}
+    out["conflict_strong"] = run_conflict_strong(pkg, workloads, sharding, dev, rank, world, barrier, max_over_ranks)
     # ---- per-robot replans sharded over the ranks (config 4: Empty32x32 20 robots) ------------------------------
     scene = "Empty32x32_20robots"
     with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
@@ -596,17 +647,100 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
     for scene in ("Empty32x32_10robots", "Benchmark_Empty32x32_30robots"):
         with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
             starts, goals = pkg.scenes.start_states(scene), pkg.scenes.goals(scene)
-            times, ok = [], 0
+            times, ok, detail = [], 0, []
             for seed in (1, 2, 3):
+                l0 = ctx.launch_count()
                 t0 = time.perf_counter()
                 _, _, st = ctx.kcbs_solve(starts, goals, ctx.kcbs_params(low_level=ctx.rrt_params(seed=seed), time_limit_s=60.0))
                 times.append(time.perf_counter() - t0)
                 ok += int(st.solved)
+                detail.append({"nodes_expanded": int(st.nodes_expanded), "low_level_plans": int(st.low_level_calls),
+                               "plans_validated": int(st.conflict_checks), "merges": int(st.merges),
+                               "root_s": round(float(st.root_seconds), 4), "kernel_launches": int(ctx.launch_count() - l0)})
             solve[scene] = {"robots": int(starts.shape[1]), "median_s": float(np.median(times)), "runs_s": [round(t, 4) for t in times],
-                            "solved": ok, "of": 3}
+                            "solved": ok, "of": 3, "runs": detail}
     out["kcbs_solve"] = {"metric": "K-CBS solve time (Empty32x32)", "unit": "s", "higher_is_better": False, "scenes": solve,
-                         "note": "batched GPU RRT low level + K-CBS high level; reference budget is 180 s per solve (demo_*.cpp:168)"}
+                         "baseline": "none possible (the reference's planners live in the un-vendored OMPL K-CBS fork; only its "
+                                     "180 s budget per solve is known, demo_*.cpp:168)",
+                         "note": "batched GPU RRT low level + K-CBS high level"}
     return out
+
+
+def run_conflict_strong(pkg, workloads, sharding, dev, rank, world, barrier, max_over_ranks):
+    """BASELINE config 5 at N GPUs, STRONG scaling: ONE plan batch (identical on every rank = the all-gathered plans) is
+    validated by all ranks together through kcbs_first_conflict_sharded_dev -- time slabs per rank, the per-plan keys
+    exchanged inside the scan kernel over NVLink peer memory, every rank ends with every record.  Timed as CUDA-graph
+    replays of `reps` back-to-back calls (events on the launching stream, max over ranks); the ranks run in lock step
+    through the mailboxes.  L2: consecutive calls scan different batches (4 x 922 MB in rotation at P = 256; one
+    7.4 GB batch at P = 2048), so a rank's slab is never L2 resident from the previous call."""
+    import torch
+    scene = "Benchmark_Empty32x32_30robots"
+    R, T = 30, 10000
+    pairs = R * (R - 1) // 2
+    res = {"metric": "conflict-checked state-pairs/s (one batch, all ranks)", "scene": scene, "pairs": pairs, "timesteps": T,
+           "scaling": "strong", "exchange": "per-plan 8-byte keys stored into every peer's mailbox from inside the scan kernel "
+           "(NVLink P2P, CUDA IPC); no NCCL call and no second launch on the critical path"}
+    with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
+        sharding.connect_peers(ctx, rank, world, max_plans=2048)
+        st = torch.cuda.Stream()
+        for P, n_sets, reps in ((256, 4, 8), (2048, 1, 2)):
+            sets = [torch.cat([workloads.cell_plans(scene, 256, T, seed=1000 * P + 16 * q + c, xp=torch) for c in range(P // 256)])
+                    for q in range(n_sets)]
+            out = torch.empty((P, 4), dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+
+            def timed(fn, n_replays=5):
+                """fn(i) issues call i on stream st; returns microseconds per call (this rank)."""
+                with torch.cuda.stream(st):
+                    for i in range(2 * n_sets):
+                        fn(i)
+                    st.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=st):
+                        for i in range(reps * n_sets):
+                            fn(i)
+                    g.replay()
+                    st.synchronize()
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(st)
+                    for _ in range(n_replays):
+                        g.replay()
+                    e1.record(st)
+                    st.synchronize()
+                    barrier()
+                del g
+                return 1e3 * e0.elapsed_time(e1) / (n_replays * reps * n_sets)
+
+            us = max_over_ranks(timed(lambda i: ctx.first_conflict_sharded_dev(P, R, T, sets[i % n_sets], None, out, st)))
+            ctx.peer_status()
+            assert int((out[:, 0] != -1).sum().item()) == 0, "throughput plans must be conflict free on every rank"
+            entry = {"plans": P, "us_per_batch": us, "value": P * pairs * T / (us * 1e-6), "unit": "state-pairs/s",
+                     "slab_MB_per_rank": 12.0 * P * R * T / world / 1e6}
+            if world > 1:
+                # the same batch on ONE GPU (rank 0 alone, the others wait): the denominator of the speed-up, same run
+                one_us = 0.0
+                if rank == 0:
+                    with torch.cuda.stream(st):
+                        for i in range(2 * n_sets):
+                            ctx.first_conflict_dev(P, R, T, sets[i % n_sets], None, out, st)
+                        st.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(st)
+                        for i in range(reps * n_sets):
+                            ctx.first_conflict_dev(P, R, T, sets[i % n_sets], None, out, st)
+                        e1.record(st)
+                        st.synchronize()
+                    one_us = 1e3 * e0.elapsed_time(e1) / (reps * n_sets)
+                barrier()
+                one_us = max_over_ranks(one_us)
+                entry["single_gpu_us_per_batch"] = one_us
+                entry["speedup_vs_one_gpu"] = one_us / us
+            res[f"P{P}"] = entry
+            del sets, out
+        barrier()
+        ctx.peer_disconnect()
+    return res
 
 
 if __name__ == "__main__":

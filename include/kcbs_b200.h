@@ -43,8 +43,9 @@ typedef enum kcbs_status {
     KCBS_ERR_CUDA = 2,             /* CUDA runtime/driver failure; see kcbs_last_error         */
     KCBS_ERR_NO_DEVICE = 3,        /* no sm_100-class device: there is no CPU fallback         */
     KCBS_ERR_OUT_OF_MEMORY = 4,
-    KCBS_ERR_UNKNOWN_ROBOT = 5     /* mirrors unordered_map::at throwing,                       *
+    KCBS_ERR_UNKNOWN_ROBOT = 5,    /* mirrors unordered_map::at throwing,                       *
                                     * StateValidityCheckerDatabase.h:111                        */
+    KCBS_ERR_PEER_TIMEOUT = 6      /* a sharded scan waited KCBS_PEER_TIMEOUT_S for a peer      */
 } kcbs_status;
 
 /* Immutable scene description, copied by kcbs_create (mirrors the by-value copies of the robot
@@ -160,6 +161,38 @@ KCBS_API int kcbs_conflict_keys_dev(kcbs_ctx *ctx, int n_plans, int R, int T, in
 KCBS_API int kcbs_conflict_finish_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj,
                                       const int32_t *lengths, const uint64_t *keys, kcbs_conflict *out,
                                       void *stream);
+
+/* ---- (3c) plan validation sharded over the GPUs of one node (BASELINE config 5) ------------
+ * One process per GPU.  Every rank holds the same plan batch (the all-gathered planned trajectories) and calls
+ * kcbs_first_conflict_sharded_dev with the same arguments: rank r scans the r-th slab of time indices
+ * (kcbs_time_slab) of every plan -- 1 / world of the HBM traffic and of the pair tests -- and the only exchange of the
+ * path, the 8-byte packed first-conflict key per plan and rank (an unsigned-min all-reduce), happens INSIDE the scan
+ * kernel over NVLink peer memory: the last CTA of a plan on a rank stores the rank's key straight into every peer's
+ * mailbox (one tagged 64-bit store per peer, the tag is the call's epoch, so the data is its own flag), waits for the
+ * peers' keys of that plan, reduces, extends the conflict (k_end) and writes the record.  After the call `out` holds
+ * all n_plans results on EVERY rank.  No NCCL call and no second launch is on the critical path.
+ * Semantics = kcbs_first_conflict_dev (scan order of StateValidityCheckerDatabase.h:78-125 through the key order).
+ *
+ * Set-up (once per context): kcbs_peer_export allocates the mailbox and fills `out` with an opaque handle; the
+ * ranks exchange the handles (any transport; they are plain bytes) and call kcbs_peer_connect with all `world`
+ * handles in rank order.  Ranks may be processes (CUDA IPC) or contexts of one process.  A wait that sees no
+ * peer for KCBS_PEER_TIMEOUT_S gives up: the results of that plan become (-2, -2, -2, -2) and
+ * kcbs_peer_status returns KCBS_ERR_PEER_TIMEOUT -- a dead peer never hangs the GPU. */
+#define KCBS_MAX_PEERS 16
+#define KCBS_PEER_TIMEOUT_S 4
+typedef struct kcbs_peer_handle {
+    unsigned char bytes[128];
+} kcbs_peer_handle;
+KCBS_API int kcbs_peer_export(kcbs_ctx *ctx, int max_plans, kcbs_peer_handle *out);
+KCBS_API int kcbs_peer_connect(kcbs_ctx *ctx, int rank, int world, const kcbs_peer_handle *handles);
+KCBS_API int kcbs_peer_disconnect(kcbs_ctx *ctx);
+/* KCBS_OK, or KCBS_ERR_PEER_TIMEOUT when a sharded scan since the last call gave up waiting (host-visible flag, no sync). */
+KCBS_API int kcbs_peer_status(kcbs_ctx *ctx);
+/* Time indices [*k_lo, *k_hi) of a T-step plan that `rank` of `world` scans (whole tiles of the scan kernel, so every
+ * rank keeps the bulk-copy path; empty when T has fewer tiles than ranks). */
+KCBS_API int kcbs_time_slab(int T, int rank, int world, int32_t *k_lo, int32_t *k_hi);
+KCBS_API int kcbs_first_conflict_sharded_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj,
+                                             const int32_t *lengths, kcbs_conflict *out, void *stream);
 
 /* ---- (3b) merged pair (two cars planned as one 10-d system after SystemMerger::merge) -------------------
  * State q = (x1, y1, v1, phi1, theta1, x2, y2, v2, phi2, theta2), control = (a1, phidot1, a2, phidot2):

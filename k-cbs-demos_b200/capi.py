@@ -81,8 +81,11 @@ EXPORTS = [
     "kcbs_measure_fp32_peak", "kcbs_measure_fp32x2_peak", "kcbs_launch_count", "kcbs_rrt_defaults",
     "kcbs_kcbs_defaults", "kcbs_rrt_plan", "kcbs_kcbs_solve", "kcbs_propagate_pair_batch", "kcbs_propagate_pair_batch_dev",
     "kcbs_validity_pair_batch", "kcbs_validity_pair_batch_dev", "kcbs_first_conflict_groups", "kcbs_first_conflict_groups_dev",
-    "kcbs_scene_grid", "kcbs_rrt_plan_many",
+    "kcbs_scene_grid", "kcbs_rrt_plan_many", "kcbs_peer_export", "kcbs_peer_connect", "kcbs_peer_disconnect",
+    "kcbs_peer_status", "kcbs_time_slab", "kcbs_first_conflict_sharded_dev",
 ]
+KCBS_MAX_PEERS = 16
+PEER_HANDLE_BYTES = 128
 
 
 def lib_path() -> str:
@@ -141,6 +144,12 @@ def load_library() -> C.CDLL:
     lib.kcbs_first_conflict_groups.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     lib.kcbs_first_conflict_groups_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.kcbs_scene_grid.argtypes = [C.POINTER(_CWorld), C.POINTER(C.c_int32), vp]
+    lib.kcbs_peer_export.argtypes = [vp, i32, vp]
+    lib.kcbs_peer_connect.argtypes = [vp, i32, i32, vp]
+    lib.kcbs_peer_disconnect.argtypes = [vp]
+    lib.kcbs_peer_status.argtypes = [vp]
+    lib.kcbs_time_slab.argtypes = [i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.kcbs_first_conflict_sharded_dev.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     lib.kcbs_launch_count.restype = i64
     lib.kcbs_launch_count.argtypes = [vp]
     _LIB = lib
@@ -358,6 +367,37 @@ class Context:
     def conflict_finish_dev(self, P, R, T, traj, lengths, keys, out, stream=None):
         self._check(self._lib.kcbs_conflict_finish_dev(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(keys),
                                                        _ptr(out), _stream(stream)))
+
+    # -- (3c) plan validation sharded over the GPUs of a node ---------------------------------------
+    def peer_export(self, max_plans: int) -> bytes:
+        """kcbs_peer_export: allocates this context's key mailbox; returns the opaque 128-byte handle."""
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        self._check(self._lib.kcbs_peer_export(self._h, max_plans, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def peer_connect(self, rank: int, world: int, handles: Sequence[bytes]):
+        """kcbs_peer_connect with the handles of all ranks in rank order."""
+        assert len(handles) == world and all(len(h) == PEER_HANDLE_BYTES for h in handles)
+        buf = C.create_string_buffer(b"".join(handles), PEER_HANDLE_BYTES * world)
+        self._check(self._lib.kcbs_peer_connect(self._h, rank, world, C.cast(buf, C.c_void_p)))
+
+    def peer_disconnect(self):
+        self._check(self._lib.kcbs_peer_disconnect(self._h))
+
+    def peer_status(self):
+        """Raises KcbsError (status 6) when a sharded scan since the last call gave up waiting for a peer."""
+        self._check(self._lib.kcbs_peer_status(self._h))
+
+    def time_slab(self, T: int, rank: int, world: int):
+        lo, hi = C.c_int32(), C.c_int32()
+        st = self._lib.kcbs_time_slab(T, rank, world, C.byref(lo), C.byref(hi))
+        if st != 0:
+            raise KcbsError(st, "kcbs_time_slab: invalid argument")
+        return lo.value, hi.value
+
+    def first_conflict_sharded_dev(self, P, R, T, traj, lengths, out, stream=None):
+        self._check(self._lib.kcbs_first_conflict_sharded_dev(self._h, P, R, T, _ptr(traj), _ptr(lengths), _ptr(out),
+                                                              _stream(stream)))
 
     # -- (3b) merged pair ------------------------------------------------------------------------
     def propagate_pair_batch(self, robot1, robot2, parents, controls, goals, steps=None, parent_idx=None, max_steps=10,

@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>
+
 #include "ctx.h"
 
 using namespace kcbs;
@@ -261,6 +263,7 @@ const char *kcbs_status_string(int status)
         case KCBS_ERR_NO_DEVICE: return "no sm_100 device (no CPU fallback)";
         case KCBS_ERR_OUT_OF_MEMORY: return "out of device memory";
         case KCBS_ERR_UNKNOWN_ROBOT: return "unknown robot";
+        case KCBS_ERR_PEER_TIMEOUT: return "peer timeout in a sharded scan";
         default: return "unknown status";
     }
 }
@@ -363,6 +366,7 @@ void kcbs_destroy(kcbs_ctx *ctx)
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     destroy_rrt_workspace(ctx);
+    destroy_peers(ctx);
     if (ctx->scene) cudaFree(ctx->scene);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -520,7 +524,7 @@ int kcbs_conflict_keys_dev(kcbs_ctx *ctx, int n_plans, int R, int T, int k_lo, i
     KCBS_CUDA(ctx, launch_fill_keys((unsigned long long *)keys, nullptr, n_plans, s));
     ctx->launches += 1;
     if (k_hi > k_lo) {
-        ConflictArgs a;
+        ConflictArgs a = {};
         a.traj = traj; a.lengths = lengths; a.keys = (unsigned long long *)keys; a.group = nullptr; a.tickets = nullptr; a.out = nullptr;
         a.P = n_plans; a.R = R; a.T = T; a.k_lo = k_lo; a.k_hi = k_hi;
         KCBS_CUDA(ctx, launch_conflict_keys(ctx->world, a, s));
@@ -546,6 +550,22 @@ int kcbs_conflict_finish_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const flo
     return KCBS_OK;
 }
 
+// keys + tickets live in the context ([key_plans] keys, then [key_plans] tickets); the kernel leaves them clean, so
+// they are filled only when the layout changes.  The layout is decided by the PLAN COUNT it was made for, never by
+// the byte capacity (reserve() over-allocates): a call with more plans than that re-lays-out and re-fills both.
+static int ensure_keys(kcbs_ctx *ctx, int n_plans, cudaStream_t s)
+{
+    if (n_plans <= ctx->key_plans) return KCBS_OK;
+    const int cap_plans = n_plans + n_plans / 4 + 64;
+    KCBS_CUDA(ctx, cudaDeviceSynchronize());  // earlier scans (any stream) still use the old layout
+    int st = reserve(ctx, ctx->keys, (sizeof(uint64_t) + sizeof(int)) * (size_t)cap_plans);
+    if (st != KCBS_OK) return st;
+    ctx->key_plans = cap_plans;
+    KCBS_CUDA(ctx, launch_fill_keys((unsigned long long *)ctx->keys.p, (int *)((uint64_t *)ctx->keys.p + cap_plans), cap_plans, s));
+    ctx->launches += 1;
+    return KCBS_OK;
+}
+
 static int first_conflict_dev_impl(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
                                    const int *d_group, kcbs_conflict *out, void *stream)
 {
@@ -556,18 +576,7 @@ static int first_conflict_dev_impl(kcbs_ctx *ctx, int n_plans, int R, int T, con
     if (!out || (T > 0 && !traj)) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "traj / out is null");
     cudaStream_t s = pick(ctx, stream);
     KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
-    // keys + tickets live in the context ([key_plans] keys, then [key_plans] tickets); the kernel leaves them clean, so
-    // they are filled only when the layout changes.  The layout is decided by the PLAN COUNT it was made for, never by
-    // the byte capacity (reserve() over-allocates): a call with more plans than that re-lays-out and re-fills both.
-    if (n_plans > ctx->key_plans) {
-        const int cap_plans = n_plans + n_plans / 4 + 64;
-        KCBS_CUDA(ctx, cudaDeviceSynchronize());  // earlier scans (any stream) still use the old layout
-        if ((st = reserve(ctx, ctx->keys, (sizeof(uint64_t) + sizeof(int)) * (size_t)cap_plans))) return st;
-        ctx->key_plans = cap_plans;
-        KCBS_CUDA(ctx, launch_fill_keys((unsigned long long *)ctx->keys.p, (int *)((uint64_t *)ctx->keys.p + cap_plans),
-                                        cap_plans, s));
-        ctx->launches += 1;
-    }
+    if ((st = ensure_keys(ctx, n_plans, s))) return st;
     if (T == 0) {   // nothing to scan: every plan is conflict free
         FinishArgs f;
         f.traj = traj; f.lengths = lengths; f.keys = (const unsigned long long *)ctx->keys.p; f.out = out; f.P = n_plans;
@@ -576,7 +585,7 @@ static int first_conflict_dev_impl(kcbs_ctx *ctx, int n_plans, int R, int T, con
         ctx->launches += 1;
         return KCBS_OK;
     }
-    ConflictArgs a;
+    ConflictArgs a = {};
     a.traj = traj; a.lengths = lengths; a.keys = (unsigned long long *)ctx->keys.p;
     a.tickets = (int *)((uint64_t *)ctx->keys.p + ctx->key_plans); a.out = out; a.group = d_group;
     a.P = n_plans; a.R = R; a.T = T; a.k_lo = 0; a.k_hi = T;
@@ -638,6 +647,180 @@ int kcbs_first_conflict_groups(kcbs_ctx *ctx, int n_plans, int R, int T, const f
     if (st != KCBS_OK) return st;
     KCBS_CUDA(ctx, cudaMemcpyAsync(out, ctx->out0.p, b_out, cudaMemcpyDeviceToHost, s));
     KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+    return KCBS_OK;
+}
+
+/* ---- (3c) sharded plan validation over NVLink peer memory ---------------------------------------- */
+
+extern "C++" {
+namespace {
+struct PeerHandleRaw {
+    uint32_t magic;
+    int32_t pid, device, box_plans, ipc_ok;
+    uint64_t ptr;
+    cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(PeerHandleRaw) <= sizeof(kcbs_peer_handle), "handle does not fit");
+constexpr uint32_t kPeerMagic = 0x4b434250u;  // "KCBP"
+
+void peer_unmap(kcbs_ctx *ctx)
+{
+    PeerState &ps = ctx->peers;
+    for (int i = 0; i < KCBS_MAX_PEERS; ++i) {
+        if (ps.ipc_opened[i] && ps.peer[i]) cudaIpcCloseMemHandle(ps.peer[i]);
+        ps.peer[i] = nullptr;
+        ps.ipc_opened[i] = false;
+    }
+    ps.world = 0;
+    ps.rank = 0;
+}
+}  // namespace
+
+namespace kcbs {
+void destroy_peers(kcbs_ctx *ctx)
+{
+    peer_unmap(ctx);
+    PeerState &ps = ctx->peers;
+    if (ps.box) cudaFree(ps.box);
+    if (ps.epoch) cudaFree(ps.epoch);
+    if (ps.h_error) cudaFreeHost(ps.h_error);
+    ps = PeerState();
+}
+}  // namespace kcbs
+}  // extern "C++"
+
+int kcbs_peer_export(kcbs_ctx *ctx, int max_plans, kcbs_peer_handle *out)
+{
+    if (!ctx || !out) return KCBS_ERR_INVALID_ARGUMENT;
+    if (max_plans < 1 || max_plans > (1 << 24)) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "max_plans out of range");
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCBS_CUDA(ctx, cudaDeviceSynchronize());
+    destroy_peers(ctx);
+    PeerState &ps = ctx->peers;
+    const size_t bytes = sizeof(unsigned long long) * 2 * KCBS_MAX_PEERS * (size_t)max_plans;
+    // a mailbox is written by the peers from the moment its handle leaves this call: it is cleared here, never later
+    KCBS_CUDA(ctx, cudaMalloc((void **)&ps.box, bytes));
+    KCBS_CUDA(ctx, cudaMemset(ps.box, 0, bytes));
+    KCBS_CUDA(ctx, cudaMalloc((void **)&ps.epoch, 64));
+    KCBS_CUDA(ctx, cudaMemset(ps.epoch, 0, 64));
+    ps.done = (int *)(ps.epoch + 1);
+    KCBS_CUDA(ctx, cudaHostAlloc((void **)&ps.h_error, sizeof(int), cudaHostAllocMapped));
+    *ps.h_error = 0;
+    KCBS_CUDA(ctx, cudaHostGetDevicePointer((void **)&ps.d_error, ps.h_error, 0));
+    KCBS_CUDA(ctx, cudaDeviceSynchronize());
+    ps.box_plans = max_plans;
+    PeerHandleRaw h;
+    std::memset(&h, 0, sizeof h);
+    h.magic = kPeerMagic;
+    h.pid = (int32_t)getpid();
+    h.device = ctx->device;
+    h.box_plans = max_plans;
+    h.ptr = (uint64_t)(uintptr_t)ps.box;
+    h.ipc_ok = cudaIpcGetMemHandle(&h.ipc, ps.box) == cudaSuccess;
+    if (!h.ipc_ok) (void)cudaGetLastError();  // contexts of one process can still connect through the raw pointer
+    std::memset(out, 0, sizeof *out);
+    std::memcpy(out->bytes, &h, sizeof h);
+    return KCBS_OK;
+}
+
+int kcbs_peer_connect(kcbs_ctx *ctx, int rank, int world, const kcbs_peer_handle *handles)
+{
+    if (!ctx || !handles) return KCBS_ERR_INVALID_ARGUMENT;
+    if (world < 1 || world > KCBS_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "rank / world out of range");
+    PeerState &ps = ctx->peers;
+    if (!ps.box) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "kcbs_peer_export must come first");
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    peer_unmap(ctx);
+    for (int i = 0; i < world; ++i) {
+        PeerHandleRaw h;
+        std::memcpy(&h, handles[i].bytes, sizeof h);
+        if (h.magic != kPeerMagic) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "not a kcbs_peer_handle");
+        if (h.box_plans != ps.box_plans) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "ranks exported different max_plans");
+        if (i == rank) {
+            if (h.ptr != (uint64_t)(uintptr_t)ps.box || h.pid != (int32_t)getpid())
+                return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "handles[rank] is not this context's handle");
+            ps.peer[i] = ps.box;
+        } else if (h.pid == (int32_t)getpid()) {
+            // another context of this process: the pointer is valid here; another device needs peer access
+            if (h.device != ctx->device) {
+                int can = 0;
+                KCBS_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, h.device));
+                if (!can) return fail(ctx, KCBS_ERR_CUDA, "no peer access between the devices of two ranks");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, KCBS_ERR_CUDA, "cudaDeviceEnablePeerAccess", e);
+                (void)cudaGetLastError();
+            }
+            ps.peer[i] = (unsigned long long *)(uintptr_t)h.ptr;
+        } else {
+            if (!h.ipc_ok) return fail(ctx, KCBS_ERR_CUDA, "the peer could not export an IPC handle");
+            void *p = nullptr;
+            KCBS_CUDA(ctx, cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+            ps.peer[i] = (unsigned long long *)p;
+            ps.ipc_opened[i] = true;
+        }
+    }
+    ps.rank = rank;
+    ps.world = world;
+    return KCBS_OK;
+}
+
+int kcbs_peer_disconnect(kcbs_ctx *ctx)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    KCBS_CUDA(ctx, cudaDeviceSynchronize());
+    peer_unmap(ctx);
+    return KCBS_OK;
+}
+
+int kcbs_peer_status(kcbs_ctx *ctx)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    PeerState &ps = ctx->peers;
+    if (ps.h_error && *(volatile int *)ps.h_error) {
+        *(volatile int *)ps.h_error = 0;
+        return fail(ctx, KCBS_ERR_PEER_TIMEOUT, "a sharded scan gave up waiting for a peer's keys");
+    }
+    return KCBS_OK;
+}
+
+int kcbs_time_slab(int T, int rank, int world, int32_t *k_lo, int32_t *k_hi)
+{
+    if (T < 0 || world < 1 || rank < 0 || rank >= world || !k_lo || !k_hi) return KCBS_ERR_INVALID_ARGUMENT;
+    int lo, hi;
+    conflict_time_slab(T, rank, world, &lo, &hi);
+    *k_lo = lo;
+    *k_hi = hi;
+    return KCBS_OK;
+}
+
+int kcbs_first_conflict_sharded_dev(kcbs_ctx *ctx, int n_plans, int R, int T, const float *traj, const int32_t *lengths,
+                                    kcbs_conflict *out, void *stream)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    PeerState &ps = ctx->peers;
+    if (ps.world < 1) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "kcbs_peer_connect must come first");
+    // one rank, or nothing to scan: no exchange (every rank takes the same branch)
+    if (ps.world == 1 || T == 0) return first_conflict_dev_impl(ctx, n_plans, R, T, traj, lengths, nullptr, out, stream);
+    int st = check_plan_args(ctx, n_plans, R, T);
+    if (st != KCBS_OK) return st;
+    if (n_plans == 0) return KCBS_OK;
+    if (n_plans > ps.box_plans) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n_plans exceeds the exported max_plans");
+    if (!out || !traj) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "traj / out is null");
+    cudaStream_t s = pick(ctx, stream);
+    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((st = ensure_keys(ctx, n_plans, s))) return st;
+    ConflictArgs a = {};
+    a.traj = traj; a.lengths = lengths; a.keys = (unsigned long long *)ctx->keys.p;
+    a.tickets = (int *)((uint64_t *)ctx->keys.p + ctx->key_plans); a.out = out; a.group = nullptr;
+    a.P = n_plans; a.R = R; a.T = T;
+    conflict_time_slab(T, ps.rank, ps.world, &a.k_lo, &a.k_hi);
+    for (int i = 0; i < ps.world; ++i) a.box_peer[i] = ps.peer[i];
+    a.epoch = ps.epoch; a.done = ps.done; a.error = ps.d_error;
+    a.rank = ps.rank; a.world = ps.world; a.box_plans = ps.box_plans;
+    KCBS_CUDA(ctx, launch_conflict_keys(ctx->world, a, s));
+    ctx->launches += 1;
     return KCBS_OK;
 }
 

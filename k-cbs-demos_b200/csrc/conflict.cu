@@ -23,16 +23,24 @@
 //   * Reduction: the packed key (k, r1, r2) is min-reduced by warp shuffles and one 64-bit atomicMin
 //     per warp; the last CTA of a plan (ticket counter) extends the conflict while the same pair keeps
 //     colliding, writes the record and resets the plan's key and ticket for the next call.
+//   * Sharded scan (a.world > 1, kcbs_first_conflict_sharded_dev): the CTAs of a rank cover its time slab only; the
+//     last CTA of a plan then exchanges the rank's key with the peers THROUGH NVLINK PEER MEMORY from inside this
+//     kernel (one tagged 64-bit store into every rank's mailbox, then a poll of its own mailbox), reduces and finishes:
+//     the scan, the min all-reduce and the k_end extension are one launch, and the exchange of one plan overlaps with
+//     the scan of the others.
+//   * Tile size: 128 time indices per CTA for large batches; 64 when the grid would otherwise be a few waves only
+//     (one plan = 79 CTAs of 128 on 148 SMs), so a single plan spreads over every SM and the tail of a small grid is short.
 #include "kcbs_device.cuh"
 #include "kernels.h"
 
 namespace kcbs {
 
-#ifndef KCBS_CONFLICT_TILE
-#define KCBS_CONFLICT_TILE 128
+constexpr int kTile = 128;      // time indices (threads) per CTA, large grids; slabs of the sharded scan align to it
+constexpr int kTileSmall = 64;  // ... small grids
+constexpr int kATile = 8;       // robots held in registers
+#ifndef KCBS_CONFLICT_SMALL_GRID
+#define KCBS_CONFLICT_SMALL_GRID 6144   // CTAs of 128 below which the 64-index tile is used (about 6 waves)
 #endif
-constexpr int kTile = KCBS_CONFLICT_TILE;   // time indices (threads) per CTA
-constexpr int kATile = 8;    // robots held in registers
 
 __device__ __forceinline__ int clamp_k(int k, int T, const int *len, int r)
 {
@@ -138,13 +146,78 @@ __device__ __forceinline__ kcbs_conflict finish_plan(const DevWorld &w, unsigned
     return c;
 }
 
-template <bool FUSED>
-__global__ void __launch_bounds__(kTile)
+// ---- key exchange of the sharded scan (system-scope accesses to mailboxes in peer memory) -------------------------
+// A message is one 64-bit word: tag (16 bits, never 0) << 48 | key (48 bits; all ones = no conflict).  It is written
+// with a single store and is its own flag; mailboxes are double buffered by call parity (a rank cannot be two calls
+// ahead of a peer, because finishing a call needs every peer's message of that call).
+constexpr unsigned long long kKey48 = 0xffffffffffffull;
+__device__ __forceinline__ void st_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned epoch_tag(unsigned epoch) { return epoch % 65535u + 1u; }
+
+// Executed by warp 0 of the last CTA of `plan` on this rank: publishes `mine`, returns the minimum over all ranks
+// (kNoConflict - 1 after a timeout: no valid key has r1 = r2 = 255 at k = 2^31 - 1).
+constexpr unsigned long long kPeerTimeoutKey = kNoConflict - 1;
+__device__ __forceinline__ unsigned long long exchange_keys(const ConflictArgs &a, int plan, unsigned epoch,
+                                                            unsigned long long mine, int lane)
+{
+    const unsigned tag = epoch_tag(epoch);
+    const size_t slot = ((size_t)(epoch & 1u) * KCBS_MAX_PEERS) * a.box_plans + plan;
+    unsigned long long got = kNoConflict;
+    bool timed_out = false;
+    if (lane < a.world) {
+        st_sys(a.box_peer[lane] + slot + (size_t)a.rank * a.box_plans, ((unsigned long long)tag << 48) | (mine & kKey48));
+        const unsigned long long *in = a.box_peer[a.rank] + slot + (size_t)lane * a.box_plans;
+        unsigned long long v = ld_sys(in);
+        if ((unsigned)(v >> 48) != tag) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned spins = 0;
+            while ((unsigned)((v = ld_sys(in)) >> 48) != tag) {
+                if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > (unsigned long long)KCBS_PEER_TIMEOUT_S * 1000000000ull) {
+                    timed_out = true;
+                    break;
+                }
+            }
+        }
+        const unsigned long long k48 = v & kKey48;
+        got = k48 == kKey48 ? kNoConflict : k48;
+    }
+    timed_out = __any_sync(0xffffffffu, timed_out);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, got, off);
+        got = o < got ? o : got;
+    }
+    if (timed_out) {
+        if (lane == 0) *(volatile int *)a.error = 1;
+        return kPeerTimeoutKey;
+    }
+    return got;
+}
+
+template <bool FUSED, int TILE>
+__global__ void __launch_bounds__(TILE)
 k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ ConflictArgs a, int tiles_per_plan)
 {
+    constexpr int kTile = TILE;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ int s_last;
+    __shared__ unsigned s_epoch;
 
     const int R = a.R, T = a.T;
     const int plan = blockIdx.x / tiles_per_plan;
@@ -162,7 +235,8 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
 
     const int n_k = min(kTile, a.k_hi - k0);   // time indices of this tile
     // bulk path: rows 16 B aligned, sizes multiples of 16 B, no padding inside the tile
-    bool bulk = ((T & 3) == 0) && ((k0 & 3) == 0) && ((n_k & 3) == 0) && ((((size_t)a.traj) & 15) == 0);
+    // (n_k <= 0: a rank of the sharded scan whose slab is empty still runs one CTA per plan for the exchange)
+    bool bulk = (n_k > 0) && ((T & 3) == 0) && ((k0 & 3) == 0) && ((n_k & 3) == 0) && ((((size_t)a.traj) & 15) == 0);
     if (bulk && len) {
         for (int r = 0; r < R; ++r) bulk &= len[r] >= k0 + n_k;
     }
@@ -191,7 +265,7 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
     unsigned long long seen = 0;
     if ((tid & 31) == 0) seen = *(volatile const unsigned long long *)(a.keys + plan);
     seen = __shfl_sync(0xffffffffu, seen, 0);
-    const bool skip = seen != kNoConflict && (long long)(seen >> 16) < (long long)k0;
+    const bool skip = (seen != kNoConflict && (long long)(seen >> 16) < (long long)k0) || n_k <= 0;
 
     if (bulk) mbar_wait(&s_bar, 0);   // (also when skipping: the copies must land before the CTA exits)
 
@@ -285,6 +359,8 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
         // last CTA of the plan finishes it and leaves key + ticket clean for the next call
         __syncthreads();
         if (tid == 0) {
+            // (the epoch is read before the ticket is taken: it advances only after every plan's last ticket)
+            if (a.world > 1) s_epoch = *(volatile const unsigned *)a.epoch;
             __threadfence();
             const int ticket = atomicAdd(a.tickets + plan, 1);
             s_last = (ticket == tiles_per_plan - 1);
@@ -292,12 +368,24 @@ k_conflict_keys(const __grid_constant__ DevWorld w, const __grid_constant__ Conf
         __syncthreads();
         if (s_last && tid < 32) {
             __threadfence();
-            const unsigned long long best = *(volatile const unsigned long long *)(a.keys + plan);
-            const kcbs_conflict c = finish_plan(w, best, base, len, T, tid);
+            unsigned long long best = *(volatile const unsigned long long *)(a.keys + plan);
+            if (a.world > 1) best = exchange_keys(a, plan, s_epoch, best, tid);
+            kcbs_conflict c;
+            if (best == kPeerTimeoutKey)
+                c.r1 = c.r2 = c.k_start = c.k_end = -2;
+            else
+                c = finish_plan(w, best, base, len, T, tid);
             if (tid == 0) {
                 a.out[plan] = c;
                 a.keys[plan] = kNoConflict;
                 a.tickets[plan] = 0;
+                if (a.world > 1) {
+                    __threadfence();
+                    if (atomicAdd(a.done, 1) == a.P - 1) {  // last plan of the call: next call, next epoch
+                        *a.done = 0;
+                        *a.epoch = s_epoch + 1u;
+                    }
+                }
             }
         }
     }
@@ -332,18 +420,37 @@ cudaError_t launch_fill_keys(unsigned long long *keys, int *tickets, int n, cuda
     return cudaGetLastError();
 }
 
-cudaError_t launch_conflict_keys(const DevWorld &w, const ConflictArgs &a, cudaStream_t stream)
+template <int TILE>
+static cudaError_t launch_conflict_tiled(const DevWorld &w, const ConflictArgs &a, cudaStream_t stream)
 {
-    if (a.P <= 0 || a.k_hi <= a.k_lo) return cudaSuccess;
-    const int tiles = (a.k_hi - a.k_lo + kTile - 1) / kTile;
+    // an empty slab (sharded scan, fewer tiles than ranks) still runs one CTA per plan: it takes part in the exchange
+    const int tiles = a.k_hi > a.k_lo ? (a.k_hi - a.k_lo + TILE - 1) / TILE : 1;
     const int Rp = (a.R + kATile - 1) / kATile * kATile;
-    const size_t smem = (size_t)2 * Rp * kTile * sizeof(float);
+    const size_t smem = (size_t)2 * Rp * TILE * sizeof(float);
     const unsigned grid = (unsigned)((long long)tiles * a.P);
     if (a.out)
-        k_conflict_keys<true><<<grid, kTile, smem, stream>>>(w, a, tiles);
+        k_conflict_keys<true, TILE><<<grid, TILE, smem, stream>>>(w, a, tiles);
     else
-        k_conflict_keys<false><<<grid, kTile, smem, stream>>>(w, a, tiles);
+        k_conflict_keys<false, TILE><<<grid, TILE, smem, stream>>>(w, a, tiles);
     return cudaGetLastError();
+}
+
+cudaError_t launch_conflict_keys(const DevWorld &w, const ConflictArgs &a, cudaStream_t stream)
+{
+    if (a.P <= 0) return cudaSuccess;
+    if (a.k_hi <= a.k_lo && !(a.world > 1 && a.out)) return cudaSuccess;
+    const long long ctas128 = (long long)((a.k_hi - a.k_lo + kTile - 1) / kTile) * a.P;
+    if (ctas128 < KCBS_CONFLICT_SMALL_GRID) return launch_conflict_tiled<kTileSmall>(w, a, stream);
+    return launch_conflict_tiled<kTile>(w, a, stream);
+}
+
+// Time slab of `rank` (whole 128-index tiles; the 64-index tile divides them).
+void conflict_time_slab(int T, int rank, int world, int *k_lo, int *k_hi)
+{
+    const long long tiles = (T + kTile - 1) / kTile;
+    const long long lo = tiles * rank / world, hi = tiles * (rank + 1) / world;
+    *k_lo = (int)(lo * kTile < T ? lo * kTile : T);
+    *k_hi = (int)(hi * kTile < T ? hi * kTile : T);
 }
 
 cudaError_t launch_conflict_finish(const DevWorld &w, const FinishArgs &a, cudaStream_t stream)
@@ -357,9 +464,11 @@ cudaError_t launch_conflict_finish(const DevWorld &w, const FinishArgs &a, cudaS
 cudaError_t init_conflict_kernels()
 {
     const int bytes = 2 * KCBS_MAX_ROBOTS * kTile * (int)sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(k_conflict_keys<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_conflict_keys<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_conflict_keys<true, kTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_conflict_keys<false, kTile>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_conflict_keys<true, kTileSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes / 2)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_conflict_keys<false, kTileSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes / 2);
 }
 
 }  // namespace kcbs

@@ -17,6 +17,19 @@ struct DevBuf {
 
 struct RrtWorkspace;  // planner.cu
 
+// Sharded plan validation (kcbs_peer_* / kcbs_first_conflict_sharded_dev): this context's key mailbox and the peers'
+// mailboxes as mapped into this process.
+struct PeerState {
+    unsigned long long *box = nullptr;  // own mailbox [2 parities][KCBS_MAX_PEERS sources][box_plans]
+    int box_plans = 0;
+    unsigned *epoch = nullptr;          // device: call counter (message tag)
+    int *done = nullptr;                // device: plans finished in the running call
+    int *h_error = nullptr, *d_error = nullptr;  // host-mapped timeout flag
+    int rank = 0, world = 0;            // world == 0: not connected
+    unsigned long long *peer[KCBS_MAX_PEERS] = {};
+    bool ipc_opened[KCBS_MAX_PEERS] = {};
+};
+
 }  // namespace kcbs
 
 struct kcbs_ctx {
@@ -30,6 +43,7 @@ struct kcbs_ctx {
     // grow-only device workspaces for the host-buffer entry points
     kcbs::DevBuf in0, in1, in2, in3, out0, out1, out2, keys;
     int key_plans = 0;      // plans the keys/tickets workspace was laid out for
+    kcbs::PeerState peers;
     void *scene = nullptr;  // cull grid + obstacle table in device memory
     std::vector<unsigned long long> h_grid;
     std::vector<float> h_obs4;
@@ -45,6 +59,7 @@ namespace kcbs {
 int fail(kcbs_ctx *ctx, int status, const char *what, cudaError_t e = cudaSuccess);
 int reserve(kcbs_ctx *ctx, DevBuf &b, size_t bytes);
 void destroy_rrt_workspace(kcbs_ctx *ctx);
+void destroy_peers(kcbs_ctx *ctx);
 
 #define KCBS_CUDA(ctx, call)                                                                                    \
     do {                                                                                                        \

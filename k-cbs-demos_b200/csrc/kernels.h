@@ -71,6 +71,13 @@ struct ConflictArgs {
     kcbs_conflict *out;        // [P] results written by the last CTA of each plan (fused finish) or null
     int P, R, T;
     int k_lo, k_hi;            // scanned time range
+    // sharded scan (kcbs_first_conflict_sharded_dev; world <= 1 otherwise): per-plan keys are exchanged through
+    // mailboxes in peer memory, box[parity][source rank][box_plans] tagged 64-bit words
+    unsigned long long *box_peer[KCBS_MAX_PEERS];  // every rank's mailbox as mapped into this process ([rank] = own)
+    unsigned *epoch;           // device word: call counter of this context (tag of this call's messages)
+    int *done;                 // device word: plans finished in this call (the last one advances the epoch)
+    int *error;                // host-mapped word: set when a wait timed out
+    int rank, world, box_plans;
 };
 
 struct FinishArgs {
@@ -86,6 +93,7 @@ cudaError_t launch_validity(const DevWorld &w, const ValidArgs &a, cudaStream_t 
 cudaError_t launch_propagate_pair(const DevWorld &w, const PairArgs &a, cudaStream_t stream);
 cudaError_t launch_validity_pair(const DevWorld &w, const PairValidArgs &a, cudaStream_t stream);
 cudaError_t launch_conflict_keys(const DevWorld &w, const ConflictArgs &a, cudaStream_t stream);
+void conflict_time_slab(int T, int rank, int world, int *k_lo, int *k_hi);
 cudaError_t launch_conflict_finish(const DevWorld &w, const FinishArgs &a, cudaStream_t stream);
 cudaError_t launch_fill_keys(unsigned long long *keys, int *tickets, int n, cudaStream_t stream);
 // FFMA saturation probe: returns flops executed; elapsed time is measured by the caller.

@@ -44,6 +44,20 @@ def unpack_key(key: int):
     return key >> 16, (key >> 8) & 0xFF, key & 0xFF
 
 
+def connect_peers(ctx, rank: int, world: int, max_plans: int) -> None:
+    """Set-up of the sharded plan scan (kcbs_first_conflict_sharded_dev): every rank exports its key mailbox, the
+    128-byte handles are all-gathered (plain bytes; NCCL or gloo), every rank maps every peer's mailbox.  The
+    all-gather doubles as the barrier the protocol needs between export (mailbox cleared) and the first scan."""
+    handle = ctx.peer_export(max_plans)
+    handles = [handle]
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+    ctx.peer_connect(rank, world, handles)
+    if world > 1:
+        dist.barrier()  # nobody scans before everybody has mapped everybody
+
+
 def reduce_min_keys(keys: torch.Tensor) -> torch.Tensor:
     """In-place all-reduce of per-plan packed keys to the global first conflict.  Keys are unsigned 64-bit
     stored in int64 tensors (no-conflict = all ones = -1); flipping the sign bit turns the unsigned order
