@@ -127,6 +127,33 @@ KCBS_API int kcbs_propagate_batch_dev(kcbs_ctx *ctx, int robot, int64_t n, int64
                                       const int32_t *steps, int max_steps, float *seg_out, float *final_out,
                                       int32_t *valid_steps, void *stream);
 
+/* Packed (CSR) segments: the same expansion, but only VALID states are written.  The states of sample i are rows
+ * offsets_out[i] .. offsets_out[i + 1] - 1 (so valid_steps[i] = offsets_out[i + 1] - offsets_out[i]) of five planes:
+ * packed_out[c * packed_cap + row] is component c.  20 bytes leave the GPU per propagated state instead of
+ * 20 * max_steps per sample (rows past the last valid state are not padded), in sample order, deterministically.
+ *   packed_out   [5][packed_cap] floats; n * max_steps rows always suffice.  Rows that do not fit are dropped
+ *                (offsets stay exact: offsets_out[n] > packed_cap tells).
+ *   offsets_out  n + 1 ints.
+ *   max_steps    at most KCBS_PACKED_MAX_STEPS (the reference's setMinMaxControlDuration(1, 10), demo_*.cpp:118).
+ *   total_out    (host call) rows emitted = offsets_out[n]; may be NULL.
+ * The host call cuts the batch into chunks and pipelines upload / kernel / download of consecutive chunks; the
+ * download is exactly the emitted rows.  final_out / valid_steps may be NULL. */
+#define KCBS_PACKED_MAX_STEPS 10
+KCBS_API int kcbs_propagate_packed(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents, const float *parents,
+                                   const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,
+                                   float *packed_out, int64_t packed_cap, int32_t *offsets_out, float *final_out,
+                                   int32_t *valid_steps, int64_t *total_out);
+KCBS_API int kcbs_propagate_packed_dev(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents, const float *parents,
+                                       const int32_t *parent_idx, const float *controls, const int32_t *steps,
+                                       int max_steps, float *packed_out, int64_t packed_cap, int32_t *offsets_out,
+                                       float *final_out, int32_t *valid_steps, void *stream);
+/* Launch shape of the expansion kernel.  0 (default): chosen per call from n -- a launch that cannot fill the GPU on
+ * its own (up to ~110K samples, e.g. ONE 64K-control expansion) runs one packed pair per thread (twice the threads,
+ * half the critical path), larger ones two pairs per thread (balanced threads).  1 / 2 force the first / second shape:
+ * 2 is the better choice when many small expansions run concurrently on different streams.  Results are
+ * bit-identical in every shape. */
+KCBS_API int kcbs_set_expansion_mode(kcbs_ctx *ctx, int mode);
+
 /* ---- (2) batched state validity ------------------------------------------------------------
  * Replaces n calls of homogeneous2ndOrderCarSystemSVC::isValid
  * (StateValidityCheckerDatabase.h:54-75) for robot `robot`.

@@ -82,7 +82,8 @@ EXPORTS = [
     "kcbs_kcbs_defaults", "kcbs_rrt_plan", "kcbs_kcbs_solve", "kcbs_propagate_pair_batch", "kcbs_propagate_pair_batch_dev",
     "kcbs_validity_pair_batch", "kcbs_validity_pair_batch_dev", "kcbs_first_conflict_groups", "kcbs_first_conflict_groups_dev",
     "kcbs_scene_grid", "kcbs_rrt_plan_many", "kcbs_peer_export", "kcbs_peer_connect", "kcbs_peer_disconnect",
-    "kcbs_peer_status", "kcbs_time_slab", "kcbs_first_conflict_sharded_dev",
+    "kcbs_peer_status", "kcbs_time_slab", "kcbs_first_conflict_sharded_dev", "kcbs_propagate_packed",
+    "kcbs_propagate_packed_dev", "kcbs_set_expansion_mode",
 ]
 KCBS_MAX_PEERS = 16
 PEER_HANDLE_BYTES = 128
@@ -120,6 +121,10 @@ def load_library() -> C.CDLL:
     prop = [vp, i32, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.kcbs_propagate_batch.argtypes = prop
     lib.kcbs_propagate_batch_dev.argtypes = prop + [vp]
+    packed = [vp, i32, i64, i64, vp, vp, vp, vp, i32, vp, i64, vp, vp, vp]
+    lib.kcbs_propagate_packed.argtypes = packed + [C.POINTER(C.c_int64)]
+    lib.kcbs_propagate_packed_dev.argtypes = packed + [vp]
+    lib.kcbs_set_expansion_mode.argtypes = [vp, i32]
     lib.kcbs_validity_batch.argtypes = [vp, i32, i64, vp, vp]
     lib.kcbs_validity_batch_dev.argtypes = [vp, i32, i64, vp, vp, vp]
     lib.kcbs_first_conflict.argtypes = [vp, i32, i32, i32, vp, vp, vp]
@@ -327,6 +332,39 @@ class Context:
         self._check(self._lib.kcbs_propagate_batch_dev(self._h, robot, n, n_parents, _ptr(parents), _ptr(parent_idx),
                                                        _ptr(controls), _ptr(steps), max_steps, _ptr(seg), _ptr(fin),
                                                        _ptr(valid), _stream(stream)))
+
+    def propagate_packed(self, robot, parents, controls, steps=None, parent_idx=None, max_steps=10, want_final=True,
+                         out=None, packed_cap=None):
+        """Host entry point kcbs_propagate_packed.  Returns (packed [5, cap] (rows [:, :total] are valid), offsets [n + 1],
+        final [5, n] or None, valid_steps [n], total).  out = (packed, offsets, final, valid) reuses caller buffers."""
+        parents = np.ascontiguousarray(parents, dtype=np.float32)
+        controls = np.ascontiguousarray(controls, dtype=np.float32)
+        n, n_parents = controls.shape[1], parents.shape[1]
+        steps = None if steps is None else np.ascontiguousarray(steps, dtype=np.int32)
+        parent_idx = None if parent_idx is None else np.ascontiguousarray(parent_idx, dtype=np.int32)
+        if out is not None:
+            packed, offsets, fin, valid = out
+        else:
+            cap = n * max_steps if packed_cap is None else packed_cap
+            packed = np.zeros((5, cap), np.float32)
+            offsets = np.zeros(n + 1, np.int32)
+            fin = np.zeros((5, n), np.float32) if want_final else None
+            valid = np.zeros(n, np.int32)
+        total = C.c_int64()
+        self._check(self._lib.kcbs_propagate_packed(self._h, robot, n, n_parents, _ptr(parents), _ptr(parent_idx),
+                                                    _ptr(controls), _ptr(steps), max_steps, _ptr(packed), packed.shape[1],
+                                                    _ptr(offsets), _ptr(fin), _ptr(valid), C.byref(total)))
+        return packed, offsets, fin, valid, total.value
+
+    def propagate_packed_dev(self, robot, n, n_parents, parents, controls, steps, parent_idx, max_steps, packed, packed_cap,
+                             offsets, fin, valid, stream=None):
+        self._check(self._lib.kcbs_propagate_packed_dev(self._h, robot, n, n_parents, _ptr(parents), _ptr(parent_idx),
+                                                        _ptr(controls), _ptr(steps), max_steps, _ptr(packed), packed_cap,
+                                                        _ptr(offsets), _ptr(fin), _ptr(valid), _stream(stream)))
+
+    def set_expansion_mode(self, mode: int):
+        """kcbs_set_expansion_mode: 0 = launch shape from n, 1 = latency shape, 2 = throughput shape."""
+        self._check(self._lib.kcbs_set_expansion_mode(self._h, mode))
 
     # -- (2) validity ---------------------------------------------------------------------
     def validity_batch(self, robot, states, out=None):

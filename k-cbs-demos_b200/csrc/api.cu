@@ -240,6 +240,9 @@ void build_fine_grid(const kcbs_world *src, DevWorld &w, std::vector<unsigned sh
         }
 }
 
+}  // namespace
+
+namespace kcbs {
 cudaStream_t pick(kcbs_ctx *ctx, void *stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
 
 int check_robot(kcbs_ctx *ctx, int robot)
@@ -247,8 +250,7 @@ int check_robot(kcbs_ctx *ctx, int robot)
     if (robot < 0 || robot >= ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "robot index out of range");
     return KCBS_OK;
 }
-
-}  // namespace
+}  // namespace kcbs
 
 extern "C" {
 
@@ -362,9 +364,10 @@ void kcbs_destroy(kcbs_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->in0, &ctx->in1, &ctx->in2, &ctx->in3, &ctx->out0, &ctx->out1, &ctx->out2, &ctx->keys};
+    DevBuf *bufs[] = {&ctx->in0, &ctx->in1, &ctx->in2, &ctx->in3, &ctx->out0, &ctx->out1, &ctx->out2, &ctx->keys, &ctx->scanws};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
+    destroy_pipeline(ctx);
     destroy_rrt_workspace(ctx);
     destroy_peers(ctx);
     if (ctx->scene) cudaFree(ctx->scene);
@@ -395,70 +398,6 @@ int kcbs_host_free(kcbs_ctx *ctx, void *p)
 {
     if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
     if (p) KCBS_CUDA(ctx, cudaFreeHost(p));
-    return KCBS_OK;
-}
-
-/* ---- (1) propagation -------------------------------------------------------------------- */
-
-int kcbs_propagate_batch_dev(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents, const float *parents,
-                             const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,
-                             float *seg_out, float *final_out, int32_t *valid_steps, void *stream)
-{
-    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
-    int st = check_robot(ctx, robot);
-    if (st != KCBS_OK) return st;
-    if (n < 0 || n_parents < 1 || max_steps < 0 || max_steps > KCBS_MAX_STEPS)
-        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n, n_parents or max_steps out of range");
-    if (n == 0) return KCBS_OK;
-    if (!parents || !controls) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "parents / controls is null");
-    if (!parent_idx && n_parents != 1 && n_parents != n)
-        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "without parent_idx, n_parents must be 1 or n");
-    if (n > (int64_t)0x7fffffff * 256) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n too large");
-    PropArgs a;
-    a.n = n; a.n_parents = n_parents; a.parents = parents; a.parent_idx = parent_idx; a.controls = controls;
-    a.steps = steps; a.seg = seg_out; a.fin = final_out; a.valid_steps = valid_steps; a.max_steps = max_steps;
-    a.robot = robot;
-    a.parent_time = nullptr; a.cons = nullptr; a.cons_states = nullptr; a.n_cons = 0; a.cons_total = 0;
-    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
-    KCBS_CUDA(ctx, launch_propagate(ctx->world, a, pick(ctx, stream)));
-    ctx->launches += 1;
-    return KCBS_OK;
-}
-
-int kcbs_propagate_batch(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents, const float *parents,
-                         const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,
-                         float *seg_out, float *final_out, int32_t *valid_steps)
-{
-    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
-    if (n < 0 || n_parents < 1 || max_steps < 0 || max_steps > KCBS_MAX_STEPS)
-        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "n, n_parents or max_steps out of range");
-    if (n == 0) return KCBS_OK;
-    if (!parents || !controls) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "parents / controls is null");
-    KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
-    const size_t b_par = sizeof(float) * 5 * (size_t)n_parents, b_ctl = sizeof(float) * 2 * (size_t)n;
-    const size_t b_idx = sizeof(int32_t) * (size_t)n;
-    const size_t b_seg = sizeof(float) * 5 * (size_t)max_steps * (size_t)n, b_fin = sizeof(float) * 5 * (size_t)n;
-    int st;
-    if ((st = reserve(ctx, ctx->in0, b_par)) || (st = reserve(ctx, ctx->in1, b_ctl)) ||
-        (st = reserve(ctx, ctx->in2, parent_idx ? b_idx : 0)) || (st = reserve(ctx, ctx->in3, steps ? b_idx : 0)) ||
-        (st = reserve(ctx, ctx->out0, seg_out ? b_seg : 0)) || (st = reserve(ctx, ctx->out1, final_out ? b_fin : 0)) ||
-        (st = reserve(ctx, ctx->out2, b_idx)))
-        return st;
-    KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in0.p, parents, b_par, cudaMemcpyHostToDevice, s));
-    KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in1.p, controls, b_ctl, cudaMemcpyHostToDevice, s));
-    if (parent_idx) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in2.p, parent_idx, b_idx, cudaMemcpyHostToDevice, s));
-    if (steps) KCBS_CUDA(ctx, cudaMemcpyAsync(ctx->in3.p, steps, b_idx, cudaMemcpyHostToDevice, s));
-    st = kcbs_propagate_batch_dev(ctx, robot, n, n_parents, (const float *)ctx->in0.p,
-                                  parent_idx ? (const int32_t *)ctx->in2.p : nullptr, (const float *)ctx->in1.p,
-                                  steps ? (const int32_t *)ctx->in3.p : nullptr, max_steps,
-                                  seg_out ? (float *)ctx->out0.p : nullptr, final_out ? (float *)ctx->out1.p : nullptr,
-                                  (int32_t *)ctx->out2.p, s);
-    if (st != KCBS_OK) return st;
-    if (seg_out) KCBS_CUDA(ctx, cudaMemcpyAsync(seg_out, ctx->out0.p, b_seg, cudaMemcpyDeviceToHost, s));
-    if (final_out) KCBS_CUDA(ctx, cudaMemcpyAsync(final_out, ctx->out1.p, b_fin, cudaMemcpyDeviceToHost, s));
-    if (valid_steps) KCBS_CUDA(ctx, cudaMemcpyAsync(valid_steps, ctx->out2.p, b_idx, cudaMemcpyDeviceToHost, s));
-    KCBS_CUDA(ctx, cudaStreamSynchronize(s));
     return KCBS_OK;
 }
 
@@ -557,7 +496,7 @@ static int ensure_keys(kcbs_ctx *ctx, int n_plans, cudaStream_t s)
 {
     if (n_plans <= ctx->key_plans) return KCBS_OK;
     const int cap_plans = n_plans + n_plans / 4 + 64;
-    KCBS_CUDA(ctx, cudaDeviceSynchronize());  // earlier scans (any stream) still use the old layout
+    if (ctx->key_plans > 0) KCBS_CUDA(ctx, cudaDeviceSynchronize());  // earlier scans (any stream) still use the old layout
     int st = reserve(ctx, ctx->keys, (sizeof(uint64_t) + sizeof(int)) * (size_t)cap_plans);
     if (st != KCBS_OK) return st;
     ctx->key_plans = cap_plans;

@@ -16,6 +16,7 @@ struct DevBuf {
 };
 
 struct RrtWorkspace;  // planner.cu
+struct HostPipeline;  // api_propagate.cu
 
 // Sharded plan validation (kcbs_peer_* / kcbs_first_conflict_sharded_dev): this context's key mailbox and the peers'
 // mailboxes as mapped into this process.
@@ -43,6 +44,10 @@ struct kcbs_ctx {
     // grow-only device workspaces for the host-buffer entry points
     kcbs::DevBuf in0, in1, in2, in3, out0, out1, out2, keys;
     int key_plans = 0;      // plans the keys/tickets workspace was laid out for
+    kcbs::DevBuf scanws;    // look-back workspace of packed expansions: [4] control words, then one status word per CTA
+    int scan_ctas = 0;      // CTAs the workspace holds (kept zeroed by the kernel)
+    int prop_rounds = 0;    // kcbs_set_expansion_mode: 0 = from n, 1 = latency shape, 2 = throughput shape
+    kcbs::HostPipeline *pipe = nullptr;  // chunked H2D / kernel / D2H pipeline of the host entry points (api_propagate.cu)
     kcbs::PeerState peers;
     void *scene = nullptr;  // cull grid + obstacle table in device memory
     std::vector<unsigned long long> h_grid;
@@ -60,6 +65,9 @@ int fail(kcbs_ctx *ctx, int status, const char *what, cudaError_t e = cudaSucces
 int reserve(kcbs_ctx *ctx, DevBuf &b, size_t bytes);
 void destroy_rrt_workspace(kcbs_ctx *ctx);
 void destroy_peers(kcbs_ctx *ctx);
+void destroy_pipeline(kcbs_ctx *ctx);
+cudaStream_t pick(kcbs_ctx *ctx, void *stream);
+int check_robot(kcbs_ctx *ctx, int robot);
 
 #define KCBS_CUDA(ctx, call)                                                                                    \
     do {                                                                                                        \

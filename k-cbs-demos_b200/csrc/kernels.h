@@ -32,6 +32,12 @@ struct PropArgs {
     const ConsDesc *cons;      // [n_cons]
     const float *cons_states;  // [3][cons_total]
     int n_cons, cons_total;
+    int rounds;                // packed pairs per thread: 1, 2, or 0 = chosen from n (propagate.cu)
+    // packed (CSR) segment output (offsets != null): seg = [5][packed_cap] planes, offsets = [n + 1] rows
+    int *offsets;
+    long long packed_cap;
+    unsigned long long *scan;  // look-back workspace: one zeroed status word per CTA (left zeroed by the kernel)
+    unsigned *scan_ctl;        // [0] CTA ticket, [1] CTAs done; zeroed, left zeroed
 };
 
 struct ValidArgs {
@@ -89,6 +95,7 @@ struct FinishArgs {
 };
 
 cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t stream);
+int propagate_grid(const PropArgs &a);   // CTAs launch_propagate will use (size of the look-back workspace)
 cudaError_t launch_validity(const DevWorld &w, const ValidArgs &a, cudaStream_t stream);
 cudaError_t launch_propagate_pair(const DevWorld &w, const PairArgs &a, cudaStream_t stream);
 cudaError_t launch_validity_pair(const DevWorld &w, const PairValidArgs &a, cudaStream_t stream);

@@ -450,7 +450,8 @@ static int rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *g
     a.robot = robot; a.n_cons = n_cons; a.cons_total = cons_total; a.max_T = max_T;
     const int n = p.n_targets * p.n_controls;
 
-    PropArgs pa;
+    PropArgs pa = {};
+    pa.rounds = ctx->prop_rounds;
     pa.n = n; pa.n_parents = ws.max_nodes; pa.parents = ws.nodes; pa.parent_idx = ws.s_parent; pa.controls = ws.s_ctrl;
     pa.steps = ws.s_steps; pa.seg = nullptr; pa.fin = ws.s_fin; pa.valid_steps = ws.s_valid; pa.max_steps = p.max_steps;
     pa.robot = robot; pa.parent_time = ws.time; pa.cons = ws.cons; pa.cons_states = ws.cons_states; pa.n_cons = n_cons;

@@ -81,25 +81,73 @@ __device__ __forceinline__ bool constraints_clear(const DevWorld &w, const PropA
 #define KCBS_PROP_THREADS 128
 #endif
 constexpr int kPropThreads = KCBS_PROP_THREADS;  // threads per CTA
-constexpr int kPropSamples = 4 * kPropThreads;   // samples per CTA (two packed pairs per thread)
-constexpr int kPropPer = kPropSamples / kPropThreads;
-constexpr int kStagedCtasPerSm = 384 / kPropThreads;  // 12 warps per SM: what the 35 KB per 256 samples stage allows
 constexpr int kStageSteps = 10;    // segments up to this many steps are staged in shared memory
 
+// Output modes of the kernel.
+//   kDirect  x, y, theta stored straight to the sample's slot of the dense segment buffer (horizons longer than
+//            kStageSteps, final-state-only calls), v / phi and the zero rows by a coalesced epilogue
+//   kDense   segments staged in shared memory, dense [5][max_steps][n] layout with zero rows past the last valid state
+//   kPacked  segments staged in shared memory, CSR layout: the valid states of sample i are rows
+//            [offsets[i], offsets[i + 1]) of five planes; nothing but valid states is written (20 B per propagated state)
+enum PropMode { kDirect = 0, kDense = 1, kPacked = 2 };
+
+// ROUNDS = packed pairs per thread.  2: ranks (2t, 2t+1) (long) then (S-2-2t, S-1-2t) (short) -- every thread has the same
+// total work, the choice for launches that fill the GPU.  1: one pair per thread, twice the threads per sample -- the
+// choice for a launch that cannot fill the GPU on its own (one 64K-control expansion = 512 warps on 592 warp schedulers
+// with ROUNDS = 2; a thread's 10-step chain of dependent RK4 sub-steps is the critical path, so more, shorter threads win).
+template <int ROUNDS>
+struct PropGeom {
+    static constexpr int kSamples = 2 * ROUNDS * kPropThreads;   // samples per CTA
+    static constexpr int kPer = 2 * ROUNDS;                      // samples per thread
+    static constexpr int kCtasPerSm = 384 / kPropThreads;        // 12 warps per SM: what 150 registers per thread allow
+};
+
 // Shared-memory staging of one CTA's segments: x, y, theta of every (step, slot), plus the four numbers from which
-// v and phi of any step follow exactly (they are linear in time).  35 KB -> 6 CTAs per SM.
+// v and phi of any step follow exactly (they are linear in time).  70 KB per 512 samples.
+template <int SAMPLES>
 struct __align__(16) PropStage {
-    float xyt[3][kStageSteps][kPropSamples];
-    float v0[kPropSamples], ua[kPropSamples], p0[kPropSamples], uw[kPropSamples];
-    __align__(16) unsigned char nv[kPropSamples];
+    float xyt[3][kStageSteps * SAMPLES];   // kDense: [step][slot]; kPacked: [cap_off[slot] + step]
+    float v0[SAMPLES], ua[SAMPLES], p0[SAMPLES], uw[SAMPLES];
+    __align__(16) unsigned char nv[SAMPLES];
+};
+
+// Bookkeeping of the packed layout (static shared memory of the kPacked kernels).
+template <int SAMPLES>
+struct PackTables {
+    static constexpr int kWords = kStageSteps * SAMPLES / 32;
+    unsigned short cap_off[SAMPLES];   // slot -> first stage position of its run (capacity max(st, 1) positions)
+    unsigned short off[SAMPLES];       // slot -> offset of its first valid state inside the CTA's packed range
+    unsigned start[kWords];            // bit p set: a run starts at stage position p
+    unsigned short wp[kWords];         // runs that start before word w
+    int cap_total, total;              // stage positions in use / valid states of the CTA
+    long long base;                    // first packed row of the CTA
+    int vblock;                        // sample block of this CTA (arrival order, see lookback_base)
+};
+
+// Where state j of the sample in `slot` lives in the stage, and where the sort pass stashes (x0, y0, theta0): in the
+// sample's own LAST position, which the sample overwrites only when it completes its final step.
+template <int MODE, int SAMPLES>
+struct StageIndex {
+    const unsigned short *cap_off;
+    const unsigned char *steps;
+    __device__ __forceinline__ int at(int j, int slot) const
+    {
+        return MODE == kPacked ? (int)cap_off[slot] + j : j * SAMPLES + slot;
+    }
+    __device__ __forceinline__ int stash(int slot) const
+    {
+        return MODE == kPacked ? (int)cap_off[slot] + max((int)steps[slot], 1) - 1 : (kStageSteps - 1) * SAMPLES + slot;
+    }
 };
 
 // propagateWhileValid for the two samples i[0], i[1] (effective durations st[0], st[1]; st = 0 for a slot past the end
 // of the batch): writes their segments, final states and valid-step counts.
-template <bool HAS_OBS, bool HAS_CONS, bool STAGED>
+template <bool HAS_OBS, bool HAS_CONS, int MODE, int SAMPLES>
 __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs &a, const long long i[2], const int st[2],
-                                              PropStage *stage, unsigned char *s_nv, const int slot[2])
+                                              PropStage<SAMPLES> *stage, const StageIndex<MODE, SAMPLES> &six,
+                                              unsigned char *s_nv, const int slot[2])
 {
+    constexpr bool STAGED = MODE != kDirect;
     float x0[2], y0[2], v0[2], phi0[2], th0[2], ua[2], uw[2];
     int t0[2];
 #pragma unroll
@@ -107,10 +155,10 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
         const long long pi = a.parent_idx ? (long long)a.parent_idx[i[e]] : (a.n_parents == 1 ? 0 : i[e]);
         t0[e] = (HAS_CONS && a.parent_time) ? a.parent_time[pi] : 0;
         if (STAGED) {  // the sort pass left the sample's inputs in shared memory (slot -1: any slot, nothing is used)
-            const int sl = max(slot[e], 0);
-            x0[e] = stage->xyt[0][kStageSteps - 1][sl];
-            y0[e] = stage->xyt[1][kStageSteps - 1][sl];
-            th0[e] = stage->xyt[2][kStageSteps - 1][sl];
+            const int sl = max(slot[e], 0), at = six.stash(sl);
+            x0[e] = stage->xyt[0][at];
+            y0[e] = stage->xyt[1][at];
+            th0[e] = stage->xyt[2][at];
             v0[e] = stage->v0[sl];
             phi0[e] = stage->p0[sl];
             ua[e] = stage->ua[sl];
@@ -144,6 +192,12 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
     bool alive[2] = {st[0] > 0, st[1] > 0};
     const long long plane = (long long)a.max_steps * a.n;
     const int jmax = max(st[0], st[1]);
+    int at0[2] = {0, 0};
+    if (STAGED) {
+        at0[0] = six.at(0, max(slot[0], 0));
+        at0[1] = six.at(0, max(slot[1], 0));
+    }
+    constexpr int kStride = MODE == kPacked ? 1 : SAMPLES;   // stage positions between consecutive steps of a sample
 
     for (int j = 0; j < jmax && (alive[0] | alive[1]); ++j) {
         const f32x2 toff2 = w.n_sub == 10 ? car_step2<10>(k, 10, vs, Ts, ts, offx, offy)
@@ -180,9 +234,10 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
             alive[e] = ok & (j + 1 < st[e]);
             if (!ok) continue;
             if (STAGED) {
-                stage->xyt[0][j][slot[e]] = xn;
-                stage->xyt[1][j][slot[e]] = yn;
-                stage->xyt[2][j][slot[e]] = tn;
+                const int at = at0[e] + j * kStride;
+                stage->xyt[0][at] = xn;
+                stage->xyt[1][at] = yn;
+                stage->xyt[2][at] = tn;
             } else if (a.seg) {
                 // straight to the sample's own slot: the CTA's stores of a row stay inside one 1 KB window, L2 merges
                 // them (and the epilogue's) into full lines; v and phi are written by the epilogue
@@ -213,32 +268,115 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
     }
 }
 
-template <bool HAS_OBS, bool HAS_CONS, bool STAGED>
-__global__ void __launch_bounds__(kPropThreads, STAGED ? kStagedCtasPerSm : KCBS_PROP_MINB)
+// Exclusive prefix sums over the CTA's slots in slot order: thread t owns the PER consecutive slots [PER t, PER t + PER).
+// Returns the CTA total; `s_warp` is scratch for one value per warp.
+template <int PER, class Get, class Put>
+__device__ __forceinline__ int block_exclusive_scan(int tid, int *s_warp, Get get, Put put)
+{
+    int v[PER], sum = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        v[u] = get(PER * tid + u);
+        sum += v[u];
+    }
+    const int lane = tid & 31, wid = tid >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += up;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int q = 0; q < kPropThreads / 32; ++q) {
+        before += q < wid ? s_warp[q] : 0;
+        total += s_warp[q];
+    }
+    int run = before + incl - sum;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        put(PER * tid + u, run);
+        run += v[u];
+    }
+    __syncthreads();   // s_warp may be reused, and the results are visible to every thread
+    return total;
+}
+
+// First packed row of the CTA that took sample block `vblock` = sum of the valid states of all earlier blocks: a
+// decoupled look-back over one status word per block (flag << 62 | value; 1 = the block's own total, 2 = inclusive
+// prefix).  Blocks are numbered in ARRIVAL order (a ticket), so every predecessor a CTA waits for is running or done.
+// Executed by warp 0; returns the exclusive prefix in every lane.
+__device__ __forceinline__ long long lookback_base(unsigned long long *scan, int vblock, long long total, int lane)
+{
+    constexpr unsigned long long kVal = (1ull << 62) - 1;
+    volatile unsigned long long *vs = scan;
+    if (vblock == 0) {
+        if (lane == 0) vs[0] = (2ull << 62) | (unsigned long long)total;
+        return 0;
+    }
+    if (lane == 0) vs[vblock] = (1ull << 62) | (unsigned long long)total;
+    long long excl = 0;
+    for (int look = vblock - 1;; look -= 32) {
+        const int idx = look - lane;
+        unsigned long long v = 2ull << 62;   // before block 0: an inclusive prefix of zero
+        if (idx >= 0) {
+            do {
+                v = vs[idx];
+            } while ((v >> 62) == 0);
+        }
+        const unsigned incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+        const int first = incl ? __ffs(incl) - 1 : 32;   // nearest predecessor that already knows its prefix
+        long long part = lane <= first ? (long long)(v & kVal) : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        excl += part;
+        if (incl) break;
+    }
+    if (lane == 0) vs[vblock] = (2ull << 62) | (unsigned long long)(excl + total);
+    return excl;
+}
+
+template <bool HAS_OBS, bool HAS_CONS, int MODE, int ROUNDS>
+__global__ void __launch_bounds__(kPropThreads, MODE != kDirect ? PropGeom<ROUNDS>::kCtasPerSm : KCBS_PROP_MINB)
 k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs a)
 {
+    constexpr bool STAGED = MODE != kDirect;
+    constexpr int kSamples = PropGeom<ROUNDS>::kSamples, kPer = PropGeom<ROUNDS>::kPer;
+    typedef PropStage<kSamples> Stage;
     __shared__ int s_hist[KCBS_MAX_STEPS + 1], s_first[KCBS_MAX_STEPS + 1];
-    __shared__ unsigned short s_perm[kPropSamples];  // rank -> slot
-    __shared__ unsigned char s_steps[kPropSamples];  // slot -> effective duration
-    __shared__ unsigned char s_nv[kPropSamples];     // slot -> valid steps (direct path)
+    __shared__ unsigned short s_perm[kSamples];  // rank -> slot
+    __shared__ unsigned char s_steps[kSamples];  // slot -> effective duration
+    __shared__ unsigned char s_nv[MODE == kDirect ? kSamples : 4];     // slot -> valid steps (direct path)
+    __shared__ PackTables<MODE == kPacked ? kSamples : 32> s_pk;    // (a stub unless kPacked)
+    __shared__ int s_warp[kPropThreads / 32];
     extern __shared__ __align__(16) unsigned char s_dyn[];  // the stage (staged variants only)
-    PropStage *stage = STAGED ? reinterpret_cast<PropStage *>(s_dyn) : nullptr;
+    Stage *stage = STAGED ? reinterpret_cast<Stage *>(s_dyn) : nullptr;
 
     const int tid = threadIdx.x;
-    const long long b0 = (long long)blockIdx.x * kPropSamples;
+    if (tid <= KCBS_MAX_STEPS) s_hist[tid] = 0;
+    if (MODE == kPacked) {
+        // sample blocks are handed out in arrival order (see lookback_base)
+        if (tid == 0) s_pk.vblock = (int)atomicAdd(a.scan_ctl, 1u);
+        for (int q = tid; q < PackTables<kSamples>::kWords; q += kPropThreads) s_pk.start[q] = 0u;
+    }
+    __syncthreads();
+    const long long b0 = (long long)(MODE == kPacked ? s_pk.vblock : (int)blockIdx.x) * kSamples;
+    StageIndex<MODE, kSamples> six;
+    six.cap_off = s_pk.cap_off;
+    six.steps = s_steps;
 
     // ---- counting sort of the CTA's samples by effective duration (longest first) ----------------
-    if (tid <= KCBS_MAX_STEPS) s_hist[tid] = 0;
-    __syncthreads();
-    int st4[kPropPer], within[kPropPer];
+    int st4[kPer], within[kPer];
     {
-        // all global loads of the thread's four samples are issued before anything depends on them (indices clamped
+        // all global loads of the thread's samples are issued before anything depends on them (indices clamped
         // instead of branched on): one or two memory round trips per CTA instead of a dozen serialised ones
-        long long ii[kPropPer], pi[kPropPer];
-        int st_req[kPropPer];
-        float v0[kPropPer], phi0[kPropPer], ua[kPropPer], uw[kPropPer], x0[kPropPer], y0[kPropPer], th0[kPropPer];
+        long long ii[kPer], pi[kPer];
+        int st_req[kPer];
+        float v0[kPer], phi0[kPer], ua[kPer], uw[kPer], x0[kPer], y0[kPer], th0[kPer];
 #pragma unroll
-        for (int u = 0; u < kPropPer; ++u) {
+        for (int u = 0; u < kPer; ++u) {
             ii[u] = min(b0 + tid + u * kPropThreads, a.n - 1);
             pi[u] = a.parent_idx ? (long long)a.parent_idx[ii[u]] : (a.n_parents == 1 ? 0 : ii[u]);
             st_req[u] = a.steps ? a.steps[ii[u]] : a.max_steps;
@@ -246,7 +384,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             uw[u] = a.controls[a.n + ii[u]];
         }
 #pragma unroll
-        for (int u = 0; u < kPropPer; ++u) {
+        for (int u = 0; u < kPer; ++u) {
             v0[u] = a.parents[2 * a.n_parents + pi[u]];
             phi0[u] = a.parents[3 * a.n_parents + pi[u]];
             if (STAGED) {
@@ -256,7 +394,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             }
         }
 #pragma unroll
-        for (int u = 0; u < kPropPer; ++u) {
+        for (int u = 0; u < kPer; ++u) {
             const int slot = tid + u * kPropThreads;
             int st = 0;
             if (b0 + slot < a.n) {
@@ -288,15 +426,11 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 }
                 st = ok_steps;
                 if (STAGED) {
-                    // inputs of the sample for propagate_two and the write-out; x0, y0, theta0 borrow the sample's own
-                    // last stage row, which the sample overwrites only when it completes its final step
+                    // inputs of the sample for propagate_two and the write-out
                     stage->v0[slot] = v0[u];
                     stage->p0[slot] = phi0[u];
                     stage->ua[slot] = ua[u];
                     stage->uw[slot] = uw[u];
-                    stage->xyt[0][kStageSteps - 1][slot] = x0[u];
-                    stage->xyt[1][kStageSteps - 1][slot] = y0[u];
-                    stage->xyt[2][kStageSteps - 1][slot] = th0[u];
                 }
             }
             st4[u] = st;
@@ -304,6 +438,32 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             if (STAGED) stage->nv[slot] = 0;
             else s_nv[slot] = 0;
             within[u] = atomicAdd(&s_hist[st], 1);
+        }
+        if (MODE == kPacked) {
+            // stage positions: every slot gets a run of max(st, 1) positions in slot order (a run per slot, so the rank of
+            // a run start IS the slot), a bit marks each run start, a per-word count makes the rank a popcount away
+            __syncthreads();
+            const int cap_total = block_exclusive_scan<kPer>(
+                tid, s_warp, [&](int slot) { return max((int)s_steps[slot], 1); },
+                [&](int slot, int off) {
+                    s_pk.cap_off[slot] = (unsigned short)off;
+                    atomicOr(&s_pk.start[off >> 5], 1u << (off & 31));
+                });
+            if (tid == 0) s_pk.cap_total = cap_total;
+        }
+        if (STAGED) {
+            // x0, y0, theta0 borrow the sample's own last stage position, which the sample overwrites only when it
+            // completes its final step
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                const int slot = tid + u * kPropThreads;
+                if (b0 + slot < a.n) {
+                    const int at = six.stash(slot);
+                    stage->xyt[0][at] = x0[u];
+                    stage->xyt[1][at] = y0[u];
+                    stage->xyt[2][at] = th0[u];
+                }
+            }
         }
     }
     __syncthreads();
@@ -317,16 +477,39 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         }
         s_first[tid] = sum;  // hist[tid + 1] + ... + hist[32]
         if (tid == 0) s_first[KCBS_MAX_STEPS] = 0;
+        if (MODE == kPacked) {
+            // wp[w] = run starts before word w (each lane owns a contiguous chunk of words)
+            constexpr int kWords = PackTables<kSamples>::kWords, kChunk = (kWords + 31) / 32;
+            int cnt = 0;
+            for (int q = 0; q < kChunk; ++q) {
+                const int wd = tid * kChunk + q;
+                if (wd < kWords) cnt += __popc(s_pk.start[wd]);
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, off);
+                if (tid >= off) incl += up;
+            }
+            int run = incl - cnt;
+            for (int q = 0; q < kChunk; ++q) {
+                const int wd = tid * kChunk + q;
+                if (wd < kWords) {
+                    s_pk.wp[wd] = (unsigned short)run;
+                    run += __popc(s_pk.start[wd]);
+                }
+            }
+        }
     }
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < kPropPer; ++u) s_perm[s_first[st4[u]] + within[u]] = (unsigned short)(tid + u * kPropThreads);
+    for (int u = 0; u < kPer; ++u) s_perm[s_first[st4[u]] + within[u]] = (unsigned short)(tid + u * kPropThreads);
     __syncthreads();
 
-    // ---- two packed pairs per thread: ranks (2t, 2t+1) (long) and (254-2t, 255-2t) (short) -------------
+    // ---- packed pairs of neighbouring ranks: (2t, 2t+1) (long) and, with two rounds, (S-2-2t, S-1-2t) (short) ------
 #pragma unroll 1
-    for (int round = 0; round < 2; ++round) {
-        const int r0 = round == 0 ? 2 * tid : kPropSamples - 2 - 2 * tid;
+    for (int round = 0; round < ROUNDS; ++round) {
+        const int r0 = round == 0 ? 2 * tid : kSamples - 2 - 2 * tid;
         int slot[2], st[2];
         long long i[2];
 #pragma unroll
@@ -340,17 +523,18 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 slot[e] = -1;
             }
         }
-        if (slot[0] >= 0 || slot[1] >= 0) propagate_two<HAS_OBS, HAS_CONS, STAGED>(w, a, i, st, stage, s_nv, slot);
+        if (slot[0] >= 0 || slot[1] >= 0)
+            propagate_two<HAS_OBS, HAS_CONS, MODE, kSamples>(w, a, i, st, stage, six, s_nv, slot);
     }
 
-    if (!STAGED && a.seg) {
+    if (MODE == kDirect && a.seg) {
         // ---- coalesced epilogue of the direct path: every thread owns the slots it sorted; it writes v and phi of the
         // valid rows (exact linear functions of time, the very expressions the integrator tested) and zero-fills all
         // five planes of the rows past the last valid state.  Disjoint from the x / y / theta stores above.
         __syncthreads();
         const long long plane = (long long)a.max_steps * a.n;
 #pragma unroll
-        for (int u = 0; u < kPropPer; ++u) {
+        for (int u = 0; u < kPer; ++u) {
             const int slot = tid + u * kPropThreads;
             const long long i = b0 + slot;
             if (i >= a.n) continue;
@@ -372,16 +556,16 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         }
     }
 
-    if (STAGED) {
+    if (MODE == kDense) {
         // ---- coalesced write-out: every row of every plane leaves as full 128 B lines; rows past the last valid
         // state are zero, so no sector of the segment buffer is ever partially written --------------------------
         __syncthreads();
         const long long plane = (long long)a.max_steps * a.n;
         if ((a.n & 3) == 0 && (reinterpret_cast<uintptr_t>(a.seg) & 15) == 0) {
             // 16 B stores: the thread owns four consecutive slots
-            const int slot = 4 * tid;
-            const long long i = b0 + slot;
-            if (i < a.n) {
+            for (int slot = 4 * tid; slot < kSamples; slot += 4 * kPropThreads) {
+                const long long i = b0 + slot;
+                if (i >= a.n) break;
                 const uchar4 nv4 = *reinterpret_cast<const uchar4 *>(&stage->nv[slot]);
                 const int nv[4] = {nv4.x, nv4.y, nv4.z, nv4.w};
                 const float4 v0 = *reinterpret_cast<const float4 *>(&stage->v0[slot]);
@@ -392,9 +576,9 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 for (int j = 0; j < a.max_steps; ++j, o += a.n) {
                     const float t1 = (float)(j + 1) * w.step;
                     const bool l0 = j < nv[0], l1 = j < nv[1], l2 = j < nv[2], l3 = j < nv[3];
-                    const float4 X = *reinterpret_cast<const float4 *>(&stage->xyt[0][j][slot]);
-                    const float4 Y = *reinterpret_cast<const float4 *>(&stage->xyt[1][j][slot]);
-                    const float4 T = *reinterpret_cast<const float4 *>(&stage->xyt[2][j][slot]);
+                    const float4 X = *reinterpret_cast<const float4 *>(&stage->xyt[0][j * kSamples + slot]);
+                    const float4 Y = *reinterpret_cast<const float4 *>(&stage->xyt[1][j * kSamples + slot]);
+                    const float4 T = *reinterpret_cast<const float4 *>(&stage->xyt[2][j * kSamples + slot]);
                     __stcs(reinterpret_cast<float4 *>(o),
                            make_float4(l0 ? X.x : 0.0f, l1 ? X.y : 0.0f, l2 ? X.z : 0.0f, l3 ? X.w : 0.0f));
                     __stcs(reinterpret_cast<float4 *>(o + plane),
@@ -412,7 +596,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             }
         } else {
 #pragma unroll
-            for (int u = 0; u < kPropPer; ++u) {
+            for (int u = 0; u < kPer; ++u) {
                 const int slot = tid + u * kPropThreads;
                 const long long i = b0 + slot;
                 if (i >= a.n) continue;
@@ -422,54 +606,145 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 for (int j = 0; j < a.max_steps; ++j, o += a.n) {
                     const bool live = j < nv;
                     const float t1 = (float)(j + 1) * w.step;
-                    __stcs(o, live ? stage->xyt[0][j][slot] : 0.0f);
-                    __stcs(o + plane, live ? stage->xyt[1][j][slot] : 0.0f);
+                    __stcs(o, live ? stage->xyt[0][j * kSamples + slot] : 0.0f);
+                    __stcs(o + plane, live ? stage->xyt[1][j * kSamples + slot] : 0.0f);
                     __stcs(o + 2 * plane, live ? fmaf(ua, t1, v0) : 0.0f);
                     __stcs(o + 3 * plane, live ? fmaf(uw, t1, p0) : 0.0f);
-                    __stcs(o + 4 * plane, live ? stage->xyt[2][j][slot] : 0.0f);
+                    __stcs(o + 4 * plane, live ? stage->xyt[2][j * kSamples + slot] : 0.0f);
                 }
+            }
+        }
+    }
+
+    if (MODE == kPacked) {
+        // ---- packed write-out: the CTA's valid states leave as ONE contiguous range of every plane ----------------
+        __syncthreads();
+        // offsets of the samples inside the CTA's range (slot order = sample order) and the CTA's total
+        const int total = block_exclusive_scan<kPer>(
+            tid, s_warp, [&](int slot) { return (int)stage->nv[slot]; },
+            [&](int slot, int off) { s_pk.off[slot] = (unsigned short)off; });
+        if (tid < 32) {
+            const long long base = lookback_base(a.scan, s_pk.vblock, total, tid);
+            if (tid == 0) {
+                s_pk.base = base;
+                s_pk.total = total;
+            }
+        }
+        __syncthreads();
+        const long long base = s_pk.base;
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            const int slot = tid + u * kPropThreads;
+            const long long i = b0 + slot;
+            if (i < a.n) {
+                a.offsets[i] = base + s_pk.off[slot];
+                if (i == a.n - 1) a.offsets[a.n] = base + total;
+            }
+        }
+        const int cap_total = s_pk.cap_total;
+        float *out = a.seg;
+        const long long cap = a.packed_cap;
+        for (int p = tid; p < cap_total; p += kPropThreads) {
+            const int wd = p >> 5;
+            const int slot = (int)s_pk.wp[wd] + __popc(s_pk.start[wd] & (0xffffffffu >> (31 - (p & 31)))) - 1;
+            const int j = p - (int)s_pk.cap_off[slot];
+            if (j < (int)stage->nv[slot]) {
+                const long long o = base + s_pk.off[slot] + j;
+                if (o < cap) {
+                    const float t1 = (float)(j + 1) * w.step;
+                    __stcs(out + o, stage->xyt[0][p]);
+                    __stcs(out + cap + o, stage->xyt[1][p]);
+                    __stcs(out + 2 * cap + o, fmaf(stage->ua[slot], t1, stage->v0[slot]));   // the integrator's expressions
+                    __stcs(out + 3 * cap + o, fmaf(stage->uw[slot], t1, stage->p0[slot]));
+                    __stcs(out + 4 * cap + o, stage->xyt[2][p]);
+                }
+            }
+        }
+        // the last CTA to get here leaves the look-back workspace clean for the next launch (every CTA has finished its
+        // look-back before it counts itself done)
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            s_warp[0] = atomicAdd(a.scan_ctl + 1, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_warp[0]) {
+            for (unsigned q = tid; q < gridDim.x; q += kPropThreads) a.scan[q] = 0ull;
+            if (tid == 0) {
+                a.scan_ctl[0] = 0u;
+                a.scan_ctl[1] = 0u;
             }
         }
     }
 }
 
-cudaError_t init_propagate_kernels()
+template <int MODE, int ROUNDS, class F>
+static cudaError_t for_each_variant(F f)
 {
-    const int bytes = (int)sizeof(PropStage);
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_propagate<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_propagate<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_propagate<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_propagate<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if ((e = f(k_propagate<false, false, MODE, ROUNDS>)) != cudaSuccess) return e;
+    if ((e = f(k_propagate<true, false, MODE, ROUNDS>)) != cudaSuccess) return e;
+    if (MODE == kPacked) return cudaSuccess;   // the planner (the only user of constraints) keeps no segments
+    if ((e = f(k_propagate<false, true, MODE == kPacked ? kDense : MODE, ROUNDS>)) != cudaSuccess) return e;
+    return f(k_propagate<true, true, MODE == kPacked ? kDense : MODE, ROUNDS>);
 }
 
-template <bool STAGED>
-static cudaError_t launch_staged(const DevWorld &w, const PropArgs &a, cudaStream_t stream)
+cudaError_t init_propagate_kernels()
 {
-    const long long grid = (a.n + kPropSamples - 1) / kPropSamples;
-    const size_t smem = STAGED ? sizeof(PropStage) : 0;
+    cudaError_t e;
+    auto set1 = [](auto *k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PropStage<PropGeom<1>::kSamples>)); };
+    auto set2 = [](auto *k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PropStage<PropGeom<2>::kSamples>)); };
+    if ((e = for_each_variant<kDense, 1>(set1)) != cudaSuccess) return e;
+    if ((e = for_each_variant<kPacked, 1>(set1)) != cudaSuccess) return e;
+    if ((e = for_each_variant<kDense, 2>(set2)) != cudaSuccess) return e;
+    return for_each_variant<kPacked, 2>(set2);
+}
+
+template <int MODE, int ROUNDS>
+static cudaError_t launch_mode(const DevWorld &w, const PropArgs &a, cudaStream_t stream)
+{
+    constexpr int kSamples = PropGeom<ROUNDS>::kSamples;
+    const unsigned grid = (unsigned)((a.n + kSamples - 1) / kSamples);
+    const size_t smem = MODE != kDirect ? sizeof(PropStage<kSamples>) : 0;
     if (a.n_cons > 0) {
+        constexpr int M = MODE == kPacked ? kDense : MODE;   // (never launched: packed calls carry no constraints)
+        if (MODE == kPacked) return cudaErrorInvalidValue;
         if (w.n_obs > 0)
-            k_propagate<true, true, STAGED><<<(unsigned)grid, kPropThreads, smem, stream>>>(w, a);
+            k_propagate<true, true, M, ROUNDS><<<grid, kPropThreads, smem, stream>>>(w, a);
         else
-            k_propagate<false, true, STAGED><<<(unsigned)grid, kPropThreads, smem, stream>>>(w, a);
+            k_propagate<false, true, M, ROUNDS><<<grid, kPropThreads, smem, stream>>>(w, a);
     } else if (w.n_obs > 0) {
-        k_propagate<true, false, STAGED><<<(unsigned)grid, kPropThreads, smem, stream>>>(w, a);
+        k_propagate<true, false, MODE, ROUNDS><<<grid, kPropThreads, smem, stream>>>(w, a);
     } else {
-        k_propagate<false, false, STAGED><<<(unsigned)grid, kPropThreads, smem, stream>>>(w, a);
+        k_propagate<false, false, MODE, ROUNDS><<<grid, kPropThreads, smem, stream>>>(w, a);
     }
     return cudaGetLastError();
+}
+
+// Samples up to which one launch runs with one packed pair per thread: the grid of 256-sample CTAs is then a single wave
+// (148 SMs x 3 CTAs), i.e. the launch cannot fill the GPU with two pairs per thread anyway.
+constexpr long long kLatencySamples = 148ll * 3 * PropGeom<1>::kSamples;
+
+int propagate_grid(const PropArgs &a)
+{
+    const int rounds = a.rounds == 1 || a.rounds == 2 ? a.rounds : (a.n <= kLatencySamples ? 1 : 2);
+    const int samples = rounds == 1 ? PropGeom<1>::kSamples : PropGeom<2>::kSamples;
+    return (int)((a.n + samples - 1) / samples);
 }
 
 cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t stream)
 {
     if (a.n <= 0) return cudaSuccess;
+    const int rounds = a.rounds == 1 || a.rounds == 2 ? a.rounds : (a.n <= kLatencySamples ? 1 : 2);
     // whole segments of up to kStageSteps steps leave through the shared-memory stage (coalesced);
     // longer horizons and final-state-only calls write directly
-#ifndef KCBS_PROP_DIRECT  // experiment builds only: bypass the shared-memory stage
-    if (a.seg != nullptr && a.max_steps <= kStageSteps) return launch_staged<true>(w, a, stream);
-#endif
-    return launch_staged<false>(w, a, stream);
+    if (a.offsets != nullptr) {
+        if (a.max_steps > kStageSteps || a.seg == nullptr || a.scan == nullptr) return cudaErrorInvalidValue;
+        return rounds == 1 ? launch_mode<kPacked, 1>(w, a, stream) : launch_mode<kPacked, 2>(w, a, stream);
+    }
+    if (a.seg != nullptr && a.max_steps <= kStageSteps)
+        return rounds == 1 ? launch_mode<kDense, 1>(w, a, stream) : launch_mode<kDense, 2>(w, a, stream);
+    return rounds == 1 ? launch_mode<kDirect, 1>(w, a, stream) : launch_mode<kDirect, 2>(w, a, stream);
 }
 
 }  // namespace kcbs

@@ -62,6 +62,9 @@ public:
     virtual void freeState(State *state) const = 0;
     virtual void copyState(State *destination, const State *source) const = 0;
     virtual double *getValueAddressAtIndex(State *state, unsigned int index) const = 0;
+    // OMPL's bounds test (RealVector: value - eps <= high && value + eps >= low with eps = DBL_EPSILON; SO2: strictly
+    // inside (-pi - eps, pi + eps); compound: every component).  The GPU kernels use the exact float image of this test.
+    virtual bool satisfiesBounds(const State *) const { return true; }
     void copyToReals(std::vector<double> &reals, const State *source) const
     {
         reals.resize(getDimension());
@@ -106,8 +109,18 @@ public:
     State *allocState() const override
     {
         auto *s = new StateType();
-        s->values = new double[dimension_ ? dimension_ : 1]();
+        // one double of slack: the reference's TwoSecondOrderCarStatePropagator copies 5 values out of (and into) these
+        // 4-vectors (StatePropagatorDatabase.h:140, :148); with the slack that stays a benign over-read / over-write
+        s->values = new double[dimension_ + 1]();
         return s;
+    }
+    bool satisfiesBounds(const State *state) const override
+    {
+        const double *v = static_cast<const StateType *>(state)->values;
+        const double eps = std::numeric_limits<double>::epsilon();
+        for (unsigned int i = 0; i < dimension_; ++i)
+            if (v[i] - eps > bounds_.high[i] || v[i] + eps < bounds_.low[i]) return false;
+        return true;
     }
     void freeState(State *state) const override
     {
@@ -149,6 +162,12 @@ public:
     double *getValueAddressAtIndex(State *state, unsigned int index) const override
     {
         return index == 0 ? &static_cast<StateType *>(state)->value : nullptr;
+    }
+    bool satisfiesBounds(const State *state) const override
+    {
+        const double pi = 3.14159265358979323846, eps = std::numeric_limits<double>::epsilon();
+        const double v = static_cast<const StateType *>(state)->value;
+        return v < pi + eps && v > -pi - eps;
     }
     // OMPL: wraps to [-pi, pi).  Only reached through the scalar post-integration hook; batches wrap on the GPU.
     void enforceBounds(State *state) const
@@ -204,6 +223,13 @@ public:
     {
         for (size_t i = 0; i < components_.size(); ++i)
             components_[i]->copyState(static_cast<CompoundState *>(d)->components[i], static_cast<const CompoundState *>(s)->components[i]);
+    }
+    bool satisfiesBounds(const State *state) const override
+    {
+        const auto *s = static_cast<const CompoundState *>(state);
+        for (size_t i = 0; i < components_.size(); ++i)
+            if (!components_[i]->satisfiesBounds(s->components[i])) return false;
+        return true;
     }
     double *getValueAddressAtIndex(State *state, unsigned int index) const override
     {
@@ -274,6 +300,7 @@ public:
     void setStateValidityChecker(const StateValidityCheckerPtr &svc) { svc_ = svc; }
     const StateValidityCheckerPtr &getStateValidityChecker() const { return svc_; }
     bool isValid(const State *state) const { return svc_->isValid(state); }
+    bool satisfiesBounds(const State *state) const { return stateSpace_->satisfiesBounds(state); }
     State *allocState() const { return stateSpace_->allocState(); }
     void freeState(State *s) const { stateSpace_->freeState(s); }
     void copyState(State *d, const State *s) const { stateSpace_->copyState(d, s); }

@@ -318,5 +318,15 @@ def ref_partial():
         L.ref_control_bounds.argtypes = [dp, dp]
         L.ref_goal_distance.restype = C.c_double
         L.ref_goal_distance.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, dp]
+        ip = C.POINTER(C.c_int)
+        L.ref_is_valid.argtypes = [C.c_uint, C.c_uint, C.c_int, dp, C.c_double, C.c_double, C.c_int, dp, ip]
+        L.ref_are_states_valid.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, dp, dp, ip]
+        L.ref_pair_is_valid.argtypes = [C.c_uint, C.c_uint, C.c_int, dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                                        dp, ip, C.c_double, C.c_double, dp, ip]
+        L.ref_pair_propagate.argtypes = [dp, dp, dp, C.c_int, dp]
+        L.ref_car_propagate.argtypes = [dp, dp, C.c_int, dp]
+        L.ref_two_car_goal.argtypes = [dp, dp, dp]
+        L.ref_shape_constants.argtypes = [C.c_double] * 6 + [dp]
+        L.ref_merge.argtypes = [C.c_int, dp, dp, C.c_uint, C.c_int, C.c_int, C.c_char_p, C.c_int, ip, dp, dp, dp, dp, dp, ip, dp, ip]
         _REF = L
     return _REF

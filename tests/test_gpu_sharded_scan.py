@@ -51,6 +51,10 @@ def test_contexts_of_one_process(pkg, orc, workloads, world):
         d = torch.from_numpy(traj).cuda()
         streams = [torch.cuda.Stream() for _ in range(world)]
         outs = [torch.full((P, 4), 7, dtype=torch.int32, device="cuda") for _ in range(world)]
+        # ranks that share ONE process must not meet a device-wide synchronisation while a peer's scan is waiting for
+        # them: the key workspace of every context is sized up front by a plain scan
+        for r in range(world):
+            ctxs[r].first_conflict_dev(P, R, T, d, None, outs[r], streams[r])
         torch.cuda.synchronize()
         for rep in range(5):    # consecutive calls: epochs advance, mailbox parities alternate
             order = range(world) if rep % 2 == 0 else reversed(range(world))
