@@ -56,7 +56,9 @@ def workload_config(n_robots=10, n_exp=25, fixed_steps=None):
 
 def read_traffic():
     """DRAM traffic per launch from the committed ncu captures (profiles/traffic_r1.json); None when absent."""
-    path = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    path = os.path.join(ROOT, "profiles", "traffic_r2.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "traffic_r1.json")
     if not os.path.exists(path):
         return {}
     with open(path) as f:
@@ -243,6 +245,10 @@ def main():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step's launches from Python instead of replaying a CUDA graph")
+    ap.add_argument("--layout", default="packed", choices=["packed", "dense"],
+                    help="segment layout of the headline: packed = valid states only (CSR), dense = [5][10][n] zero padded")
+    ap.add_argument("--expansion-mode", type=int, default=2, choices=[0, 1, 2],
+                    help="kcbs_set_expansion_mode of the headline contexts (2 = throughput shape: ten planners launch concurrently)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -303,9 +309,15 @@ def main():
               for exps in host_in]
     # outputs: every expansion of a step has its own segment buffer (13.1 MB each), so one step writes
     # n_robots * n_exp * 13.1 MB (3.3 GB by default) >> 126 MB L2: no L2 flush needed between steps
+    # (packed layout: the same capacity per expansion, of which only the valid rows -- about 45 % -- are written)
+    packed_layout = args.layout == "packed"
+    cap = MAX_STEPS * N_CONTROLS
     seg = torch.empty((n_robots, n_exp, 5, MAX_STEPS, N_CONTROLS), dtype=torch.float32, device="cuda")
     fin = torch.empty((n_robots, n_exp, 5, N_CONTROLS), dtype=torch.float32, device="cuda")
     valid = torch.zeros((n_robots, n_exp, N_CONTROLS), dtype=torch.int32, device="cuda")
+    offsets = torch.zeros((n_robots, n_exp, N_CONTROLS + 1), dtype=torch.int32, device="cuda")
+    for c in ctxs:
+        c.set_expansion_mode(args.expansion_mode)
 
     def gpu_step():
         """One step: every robot planner issues its expansions on its own stream (fork from / join into the
@@ -318,7 +330,11 @@ def main():
             sp = streams[r].cuda_stream
             for e in range(n_exp):
                 p, c, s = dev_in[r][e]
-                ctxs[r].propagate_batch_dev(r, N_CONTROLS, 1, p, c, s, None, MAX_STEPS, seg[r, e], fin[r, e], valid[r, e], sp)
+                if packed_layout:
+                    ctxs[r].propagate_packed_dev(r, N_CONTROLS, 1, p, c, s, None, MAX_STEPS, seg[r, e], cap, offsets[r, e],
+                                                 fin[r, e], valid[r, e], sp)
+                else:
+                    ctxs[r].propagate_batch_dev(r, N_CONTROLS, 1, p, c, s, None, MAX_STEPS, seg[r, e], fin[r, e], valid[r, e], sp)
         for r in range(n_robots):
             done = torch.cuda.Event()
             done.record(streams[r])
@@ -386,7 +402,11 @@ def main():
     traffic = read_traffic()
     tp = traffic.get("k_propagate")
     # ncu capture is one launch of 655,360 samples; a bench launch is one expansion of 65,536 samples of the same mix
-    k1_traffic = None if not tp else (tp["dram_read_bytes"] + tp["segment_buffer_bytes"]) * N_CONTROLS / tp["samples"]
+    if packed_layout:
+        tp = traffic.get("k_propagate_packed")
+        k1_traffic = None if not tp else (tp["dram_read_bytes"] + tp["dram_write_bytes"]) * N_CONTROLS / tp["samples"]
+    else:
+        k1_traffic = None if not tp else (tp["dram_read_bytes"] + tp["segment_buffer_bytes"]) * N_CONTROLS / tp["samples"]
     roofline = {
         "kernel": "k_propagate", "bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": ach_tflops / fp32_peak if fp32_peak else None,
@@ -396,8 +416,9 @@ def main():
         "peak_detail": {"probe": fp32_peak, "nominal": FP32_NOMINAL_TFLOPS,
                         "note": "MEASURED_PEAKS.json has no FP32 entry: peak = FFMA saturation probe run in this process"},
         "traffic": k1_traffic,
-        "traffic_unit": "bytes per launch (ncu dram read + the whole zero-filled segment buffer written, scaled from the "
-                        "655,360-sample capture in profiles/r1_k_propagate.md)",
+        "layout": args.layout,
+        "traffic_unit": "bytes per launch (ncu dram__bytes_read + dram__bytes_write of one 655,360-sample launch, scaled to 65,536 "
+                        "samples; profiles/traffic_r2.json)",
         "algorithmic_bytes_per_launch": (BYTES_PER_STATE * written_step + BYTES_PER_SAMPLE * samples_step) / launches_per_step,
         "peak_source": "FFMA saturation probe run in this process (kcbs_measure_fp32_peak); nominal 74.4",
         "frac_of_nominal": ach_tflops / FP32_NOMINAL_TFLOPS,
@@ -418,57 +439,65 @@ def main():
             row.append((pp, pc, ps))
         pin.append(row)
     # one pinned result buffer set per robot planner: the planners are independent host threads, each driving its
-    # own context / stream through the synchronous host entry point (ctypes releases the GIL during the call), so
-    # one planner's copies overlap another's kernel
+    # own context through the synchronous host entry point (ctypes releases the GIL during the call); inside a call
+    # the batch is cut into chunks whose upload / kernel / download overlap (api_propagate.cu)
     from concurrent.futures import ThreadPoolExecutor
     outs = [(ctxs[r].pinned_empty((5, MAX_STEPS, N_CONTROLS), np.float32), ctxs[r].pinned_empty((5, N_CONTROLS), np.float32),
-             ctxs[r].pinned_empty((N_CONTROLS,), np.int32)) for r in range(n_robots)]
+             ctxs[r].pinned_empty((N_CONTROLS,), np.int32), ctxs[r].pinned_empty((N_CONTROLS + 1,), np.int32)) for r in range(n_robots)]
     pool = ThreadPoolExecutor(max_workers=n_robots)
+    rows_seen = [[0] * e2e_exp for _ in range(n_robots)]
 
-    def robot_calls(r, want_seg):
+    def robot_calls(r, kind):
         torch.cuda.set_device(local_rank)
-        seg_b, fin_b, val_b = outs[r]
+        seg_b, fin_b, val_b, off_b = outs[r]
         for e in range(e2e_exp):
             pp, pc, ps = pin[r][e]
-            ctxs[r].propagate_batch(r, pp, pc, ps, max_steps=MAX_STEPS, out=(seg_b if want_seg else None, fin_b, val_b))
+            if kind == "packed":      # whole segments, valid states only: rows + offsets are the complete result
+                res = ctxs[r].propagate_packed(r, pp, pc, ps, max_steps=MAX_STEPS, out=(seg_b.reshape(5, -1), off_b, None, None))
+                rows_seen[r][e] = res[4]
+            else:
+                ctxs[r].propagate_batch(r, pp, pc, ps, max_steps=MAX_STEPS, out=(seg_b if kind == "dense" else None, fin_b, val_b))
 
-    def e2e_step():
-        list(pool.map(lambda r: robot_calls(r, True), range(n_robots)))
+    def e2e_run(kind):
+        step = lambda: list(pool.map(lambda r: robot_calls(r, kind), range(n_robots)))  # noqa: E731
+        step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0)
 
     e2e_steps = max(2, min(args.steps, 10))
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_units = float(torch.minimum(steps_all[:, :e2e_exp], valid[:, :e2e_exp] + 1).sum().item())
-    e2e_value = sum_over_ranks(e2e_units) * e2e_steps / e2e_s
     calls = n_robots * e2e_exp
-    e2e = {"value": e2e_value, "unit": "states/s",
-           "h2d_bytes_per_step": calls * (5 * 4 + N_CONTROLS * 12),
-           "d2h_bytes_per_step": calls * (N_CONTROLS * (5 * MAX_STEPS * 4 + 5 * 4 + 4)),
-           "calls_per_step": calls, "steps": e2e_steps,
-           "pcie_d2h_gbs": calls * (N_CONTROLS * (5 * MAX_STEPS * 4 + 5 * 4 + 4)) * e2e_steps / e2e_s * 1e-9,
-           "note": "kcbs_propagate_batch with pinned host buffers, one host thread per robot planner; whole segments + "
-                   "final states + counts copied back (224 B per sample: bound by the PCIe device-to-host rate, pcie_d2h_gbs)"}
-
-    # the same calls asking only for what propagateWhileValid(state, control, steps, result) returns (the final
-    # state and the step count, 24 B per sample instead of 224 B): what a planner that does not keep intermediate
-    # states would transfer
-    def e2e_final_step():
-        list(pool.map(lambda r: robot_calls(r, False), range(n_robots)))
-
-    e2e_final_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_final_step()
-    barrier()
-    e2e_final_s = max_over_ranks(time.perf_counter() - t0)
-    e2e["final_state_only"] = {"value": sum_over_ranks(e2e_units) * e2e_steps / e2e_final_s, "unit": "states/s",
+    e2e_units = float(torch.minimum(steps_all[:, :e2e_exp], valid[:, :e2e_exp] + 1).sum().item())
+    h2d = calls * (5 * 4 + N_CONTROLS * 12)
+    e2e_s = e2e_run("packed")
+    rows = float(sum(sum(x) for x in rows_seen))
+    assert rows == float(valid[:, :e2e_exp].sum().item()), "the host call returned other rows than the device call"
+    d2h_packed = int(20 * rows + 4 * (N_CONTROLS + 4) * calls)   # rows of five planes + offsets (one extra word per chunk)
+    e2e = {"value": sum_over_ranks(e2e_units) * e2e_steps / e2e_s, "unit": "states/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_packed,
+           "calls_per_step": calls, "steps": e2e_steps, "layout": "packed (valid states only) + row offsets",
+           "pcie_d2h_gbs": d2h_packed * e2e_steps / e2e_s * 1e-9,
+           "note": "kcbs_propagate_packed with pinned host buffers, one host thread per robot planner, every call pipelined in "
+                   "chunks; whole segments = every valid state (20 B each) + 4 B of row offset per sample copied back"}
+    # the zero-padded dense layout through kcbs_propagate_batch (224 B per sample), and the same calls asking only for
+    # what propagateWhileValid(state, control, steps, result) returns (final state + step count, 24 B per sample)
+    d2h_dense = calls * (N_CONTROLS * (5 * MAX_STEPS * 4 + 5 * 4 + 4))
+    dense_s = e2e_run("dense")
+    e2e["dense_layout"] = {"value": sum_over_ranks(e2e_units) * e2e_steps / dense_s, "unit": "states/s",
+                           "d2h_bytes_per_step": d2h_dense, "pcie_d2h_gbs": d2h_dense * e2e_steps / dense_s * 1e-9}
+    final_s = e2e_run("final")
+    e2e["final_state_only"] = {"value": sum_over_ranks(e2e_units) * e2e_steps / final_s, "unit": "states/s",
                                "d2h_bytes_per_step": calls * N_CONTROLS * 24}
+    # one planner alone (one host thread, one call at a time): what the chunk pipeline inside a call buys
+    t0 = time.perf_counter()
+    for _ in range(4):
+        robot_calls(0, "packed")
+    one_s = time.perf_counter() - t0
+    e2e["single_caller"] = {"value": float(torch.minimum(steps_all[0, :e2e_exp], valid[0, :e2e_exp] + 1).sum().item()) * 4 / one_s,
+                            "unit": "states/s", "note": "one host thread, sequential kcbs_propagate_packed calls"}
 
     # ---- secondary metrics: validity (K2) and conflict scan (K3), device resident ------------------
     secondary = {}
@@ -501,10 +530,11 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "multi_gpu": multi,
             "config": workload_config(n_robots, n_exp, args.fixed_steps),
-            "arm": {"expansions_per_robot_per_step": n_exp, "streams": n_robots,
+            "arm": {"expansions_per_robot_per_step": n_exp, "streams": n_robots, "segment_layout": args.layout,
+                    "expansion_mode": args.expansion_mode,
                     "launch": "one CUDA graph per step (captured C-ABI launches)" if graphed else "eager C-ABI calls from Python",
                     "states_per_step_per_gpu": units_step,
-                    "segment_bytes_per_step_per_gpu": samples_step * 200},
+                    "segment_bytes_per_step_per_gpu": (20 * written_step + 4 * samples_step) if packed_layout else samples_step * 200},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
             "secondary": secondary,
         }

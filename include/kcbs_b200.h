@@ -295,8 +295,7 @@ typedef struct kcbs_kcbs_stats {
     double root_seconds;            /* KCBS::getRootSolveTime, Benchmark.h:166                     */
     double seconds;
     int64_t conflict_checks;        /* plans validated by kcbs_first_conflict                      */
-    int32_t merges;                 /* pairs merged into one individual (SystemMerger::merge);     *
-                                     * a merged pair without a root plan is split again            */
+    int32_t merges;                 /* pairs merged into one individual (SystemMerger::merge)      */
     int32_t reserved_;
 } kcbs_kcbs_stats;
 
@@ -318,10 +317,24 @@ KCBS_API int kcbs_rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const f
                            const float *cons_states, int max_T, float *traj_out, int32_t *T_out,
                            kcbs_rrt_stats *stats);
 
+/* The same planner for a MERGED PAIR: robots robot1 and robot2 planned as one 10-d system (what the reference plans
+ * after SystemMerger::merge, SystemMergerDatabase.h:108-156): joint tree over q = (car 1, car 2), controls (a1, w1, a2, w2),
+ * expansion through the merged propagator (TwoSecondOrderCarStatePropagator, StatePropagatorDatabase.h:119-171: a car within
+ * KCBS_PAIR_GOAL_RADIUS of its goal keeps its state) and the merged validity checker
+ * (homogeneousTwo2ndOrderCarSystemSVC, StateValidityCheckerDatabase.h:225-261: the two cars never overlap each other);
+ * the goal is GoalRegionTwo2ndOrderCars (GoalRegionDatabase.h:61-108): both cars strictly within KCBS_PAIR_GOAL_RADIUS of
+ * their goals.  start = 10 reals, goals_xy = (gx1, gy1, gx2, gy2), constraints bind both cars, traj_out = [10][max_T]. */
+#define KCBS_PAIR_GOAL_RADIUS 1.5f
+KCBS_API int kcbs_rrt_plan_pair(kcbs_ctx *ctx, int robot1, int robot2, const float *start, const float *goals_xy,
+                                const kcbs_rrt_params *params, int n_cons, const int32_t *cons_robot,
+                                const int32_t *cons_k0, const int32_t *cons_len, const int32_t *cons_offset,
+                                const float *cons_states, int max_T, float *traj_out, int32_t *T_out,
+                                kcbs_rrt_stats *stats);
+
 /* n_jobs independent, unconstrained low-level plans at once (the re-plans of different robots / constraint-tree nodes
  * that one GPU owns when they are sharded over GPUs; also what the root of kcbs_kcbs_solve does): job j plans robot
  * robots[j] from starts[(c * n_jobs) + j] (c = 0..4) to goals[2 j .. 2 j + 1] with seeds[j].  The jobs run concurrently
- * on up to 8 planner lanes of the context (host thread + stream + workspace each); results do not depend on the
+ * on up to 16 planner lanes of the context (host thread + stream + workspace each); results do not depend on the
  * interleaving.  traj_out = [n_jobs][5][max_T], T_out / stats = [n_jobs] (stats may be NULL). */
 KCBS_API int kcbs_rrt_plan_many(kcbs_ctx *ctx, int n_jobs, const int32_t *robots, const float *starts, const float *goals,
                                 const kcbs_rrt_params *params, const uint64_t *seeds, int max_T, float *traj_out,
@@ -331,9 +344,9 @@ KCBS_API int kcbs_rrt_plan_many(kcbs_ctx *ctx, int n_jobs, const int32_t *robots
  * constraint tree with kcbs_first_conflict as the plan validator; every conflict spawns two children that
  * re-plan one robot each against the other's colliding states.  starts = [5][R] planes, goals = [R][2];
  * plan_out = [R][5][max_T], lengths_out = [R].  A pair with more than merge_bound conflicts is merged (the role of
- * SystemMerger::merge, SystemMergerDatabase.h:55-168) and the search restarts with it as one individual whose bodies are
- * never tested against each other; its low level is a prioritised pair planner on the single-car kernels (first car,
- * then the second against the first car's whole path), not a 10-d RRT. */
+ * SystemMerger::merge, SystemMergerDatabase.h:55-168) and the search restarts with it as one individual, placed last,
+ * whose bodies are never tested against each other by the high level; its low level is the joint 10-d planner
+ * kcbs_rrt_plan_pair.  A merged pair is never merged again (SystemMergerDatabase.h:103-104). */
 KCBS_API int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goals,
                              const kcbs_kcbs_params *params, int max_T, float *plan_out, int32_t *lengths_out,
                              kcbs_kcbs_stats *stats);

@@ -83,7 +83,7 @@ EXPORTS = [
     "kcbs_validity_pair_batch", "kcbs_validity_pair_batch_dev", "kcbs_first_conflict_groups", "kcbs_first_conflict_groups_dev",
     "kcbs_scene_grid", "kcbs_rrt_plan_many", "kcbs_peer_export", "kcbs_peer_connect", "kcbs_peer_disconnect",
     "kcbs_peer_status", "kcbs_time_slab", "kcbs_first_conflict_sharded_dev", "kcbs_propagate_packed",
-    "kcbs_propagate_packed_dev", "kcbs_set_expansion_mode",
+    "kcbs_propagate_packed_dev", "kcbs_set_expansion_mode", "kcbs_rrt_plan_pair",
 ]
 KCBS_MAX_PEERS = 16
 PEER_HANDLE_BYTES = 128
@@ -139,6 +139,8 @@ def load_library() -> C.CDLL:
     lib.kcbs_kcbs_defaults.argtypes = [C.POINTER(KcbsParams)]
     lib.kcbs_rrt_plan.argtypes = [vp, i32, vp, vp, C.POINTER(RrtParams), i32, vp, vp, vp, vp, vp, i32, vp,
                                   C.POINTER(C.c_int32), C.POINTER(RrtStats)]
+    lib.kcbs_rrt_plan_pair.argtypes = [vp, i32, i32, vp, vp, C.POINTER(RrtParams), i32, vp, vp, vp, vp, vp, i32, vp,
+                                       C.POINTER(C.c_int32), C.POINTER(RrtStats)]
     lib.kcbs_rrt_plan_many.argtypes = [vp, i32, vp, vp, vp, C.POINTER(RrtParams), vp, i32, vp, vp, vp]
     lib.kcbs_kcbs_solve.argtypes = [vp, i32, vp, vp, C.POINTER(KcbsParams), i32, vp, vp, C.POINTER(KcbsStats)]
     pair = [vp, i32, i32, i64, i64, vp, vp, vp, vp, i32, vp, C.c_float, vp, vp, vp]
@@ -516,6 +518,32 @@ class Context:
         self._check(self._lib.kcbs_rrt_plan(self._h, robot, _ptr(start), _ptr(goal), C.byref(params), len(cons), _ptr(rob),
                                             _ptr(k0), _ptr(ln), _ptr(off), _ptr(states), max_T, _ptr(out), C.byref(T),
                                             C.byref(st)))
+        return out[:, :T.value].copy(), st
+
+    def rrt_plan_pair(self, robot1, robot2, start10, goals_xy, params=None, constraints=(), max_T=4096, persistent=None):
+        """kcbs_rrt_plan_pair: the merged pair (robot1, robot2) planned as one 10-d system.  start10 = 10 reals,
+        goals_xy = (gx1, gy1, gx2, gy2).  Returns (traj [10, T] float32, RrtStats)."""
+        start = np.ascontiguousarray(start10, dtype=np.float32)
+        goal = np.ascontiguousarray(goals_xy, dtype=np.float32)
+        assert start.size == 10 and goal.size == 4
+        params = params if params is not None else self.rrt_params()
+        cons = list(constraints)
+        total = sum(c[2].shape[1] for c in cons)
+        rob = np.array([c[0] for c in cons], np.int32)
+        k0 = np.array([c[1] for c in cons], np.int32)
+        ln = np.array([c[2].shape[1] for c in cons], np.int32)
+        off = np.concatenate([[0], np.cumsum(ln)[:-1]]).astype(np.int32) if cons else np.zeros(0, np.int32)
+        states = np.zeros((3, max(total, 1)), np.float32)
+        for c, o in zip(cons, off):
+            states[:, o:o + c[2].shape[1]] = c[2]
+        if persistent is not None:
+            ln = np.where(np.asarray(persistent, bool), -ln, ln).astype(np.int32)
+        out = np.zeros((10, max_T), np.float32)
+        T = C.c_int32()
+        st = RrtStats()
+        self._check(self._lib.kcbs_rrt_plan_pair(self._h, robot1, robot2, _ptr(start), _ptr(goal), C.byref(params), len(cons),
+                                                 _ptr(rob), _ptr(k0), _ptr(ln), _ptr(off), _ptr(states), max_T, _ptr(out),
+                                                 C.byref(T), C.byref(st)))
         return out[:, :T.value].copy(), st
 
     def rrt_plan_many(self, robots, starts, goals, params=None, seeds=None, max_T=4096):

@@ -779,7 +779,7 @@ int kcbs_propagate_pair_batch_dev(kcbs_ctx *ctx, int robot1, int robot2, int64_t
     if (!parents || !controls || !goals) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "parents / controls / goals is null");
     if (!parent_idx && n_parents != 1 && n_parents != n)
         return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "without parent_idx, n_parents must be 1 or n");
-    PairArgs a;
+    PairArgs a = {};
     a.n = n; a.n_parents = n_parents; a.parents = parents; a.parent_idx = parent_idx; a.controls = controls; a.steps = steps;
     a.seg = seg_out; a.fin = final_out; a.valid_steps = valid_steps; a.max_steps = max_steps; a.robot1 = robot1; a.robot2 = robot2;
     for (int i = 0; i < 4; ++i) a.goals[i] = goals[i];

@@ -107,8 +107,7 @@ int kcbs_set_expansion_mode(kcbs_ctx *ctx, int mode)
 {
     if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
     if (mode < 0 || mode > 2) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "mode must be 0 (auto), 1 (latency) or 2 (throughput)");
-    ctx->prop_rounds = mode;
-    for (kcbs_ctx *w : ctx->workers) w->prop_rounds = mode;
+    ctx->prop_rounds = ctx->user_prop_rounds = mode;
     return KCBS_OK;
 }
 

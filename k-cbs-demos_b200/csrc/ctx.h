@@ -46,7 +46,8 @@ struct kcbs_ctx {
     int key_plans = 0;      // plans the keys/tickets workspace was laid out for
     kcbs::DevBuf scanws;    // look-back workspace of packed expansions: [4] control words, then one status word per CTA
     int scan_ctas = 0;      // CTAs the workspace holds (kept zeroed by the kernel)
-    int prop_rounds = 0;    // kcbs_set_expansion_mode: 0 = from n, 1 = latency shape, 2 = throughput shape
+    int prop_rounds = 0;    // launch shape of the next expansion: 0 = from n, 1 = latency shape, 2 = throughput shape
+    int user_prop_rounds = 0;  // what kcbs_set_expansion_mode asked for (the planner picks per batch of jobs when 0)
     kcbs::HostPipeline *pipe = nullptr;  // chunked H2D / kernel / D2H pipeline of the host entry points (api_propagate.cu)
     kcbs::PeerState peers;
     void *scene = nullptr;  // cull grid + obstacle table in device memory

@@ -230,6 +230,43 @@ __device__ __forceinline__ bool obstacles_clear_fine(const DevWorld &w, float x,
     return obstacles_clear_code(w, code, w.obs4, x, y, th, hl, hw);
 }
 
+// One dynamic-obstacle constraint of the K-CBS low level: at absolute time index k in [k0, k0 + |len|) the planned robot must
+// not overlap robot `other` placed at cons_states[plane * total + offset + (k - k0)]; len < 0 marks a persistent
+// constraint whose last state keeps holding for every later time index.
+struct ConsDesc {
+    int other, k0, len, offset;
+};
+
+// Dynamic-obstacle constraints of the K-CBS low level (the fork tests `next` against the constraining robot's
+// state at that time through areStatesValid, StateValidityCheckerDatabase.h:78-125).
+__device__ __forceinline__ bool constraints_clear(const DevWorld &w, const ConsDesc *cons, int n_cons, const float *cons_states,
+                                                  int cons_total, int k, float x, float y, float th, float hl, float hw, float rad)
+{
+    bool ok = true, have = false;
+    float c = 1.0f, s = 0.0f;
+    for (int q = 0; q < n_cons; ++q) {
+        const ConsDesc d = cons[q];
+        int rel = k - d.k0;
+        if (rel < 0) continue;
+        if (d.len < 0)
+            rel = min(rel, -d.len - 1);  // persistent constraint: its last state holds for every later time index
+        else if (rel >= d.len)
+            continue;
+        const float *st = cons_states + d.offset + rel;
+        const float ox = st[0], oy = st[cons_total], dx = ox - x, dy = oy - y;
+        const float rs = rad + w.rob_rad[d.other];
+        if (fmaf(dy, dy, dx * dx) > rs * rs * 1.000001f) continue;
+        if (!have) {
+            sincosf(th, &s, &c);
+            have = true;
+        }
+        float oc, os;
+        sincosf(st[2 * cons_total], &os, &oc);
+        ok &= sat_gap_robots(x, y, c, s, hl, hw, ox, oy, oc, os, w.rob_hl[d.other], w.rob_hw[d.other]) > 0.0f;
+    }
+    return ok;
+}
+
 // Packed first-conflict key: lexicographic (k, r1, r2) order == integer order.
 __host__ __device__ __forceinline__ unsigned long long pack_key(int k, int r1, int r2)
 {

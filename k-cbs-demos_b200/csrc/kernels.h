@@ -10,11 +10,7 @@ namespace kcbs {
 
 struct DevWorld;
 
-// One dynamic-obstacle constraint of the K-CBS low level: at absolute time index k in [k0, k0 + len) the robot
-// must not overlap robot `other` placed at cons_states[plane * total + offset + (k - k0)].
-struct ConsDesc {
-    int other, k0, len, offset;
-};
+struct ConsDesc;   // kcbs_device.cuh
 
 struct PropArgs {
     long long n, n_parents;
@@ -59,6 +55,12 @@ struct PairArgs {              // merged pair: 10-d states, 4-d controls
     int max_steps, robot1, robot2;
     float goals[4];            // gx1, gy1, gx2, gy2
     float hold_radius;         // 1.5, StatePropagatorDatabase.h:170
+    // dynamic-obstacle constraints (planner only; n_cons == 0 otherwise): they bind BOTH cars, as the merged
+    // individual's areStatesValid does (StateValidityCheckerDatabase.h:264-287)
+    const int *parent_time;
+    const ConsDesc *cons;
+    const float *cons_states;
+    int n_cons, cons_total;
 };
 
 struct PairValidArgs {

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(128) k_propagate_pair(const __grid_constant__ 
         k[c] = car_consts(w, u[c][0], u[c][1]);
     }
     const float hold2 = a.hold_radius * a.hold_radius;
+    const int t0 = (a.n_cons > 0 && a.parent_time) ? a.parent_time[pi] : 0;
     const long long plane = (long long)a.max_steps * a.n;
     int nv = 0;
     for (int j = 0; j < st; ++j) {
@@ -78,6 +79,14 @@ __global__ void __launch_bounds__(128) k_propagate_pair(const __grid_constant__ 
             }
         }
         if (!pair_state_valid(w, a.robot1, a.robot2, nxt[0], nxt[1])) break;
+        if (a.n_cons > 0) {
+            const int k = t0 + j + 1;
+            if (!constraints_clear(w, a.cons, a.n_cons, a.cons_states, a.cons_total, k, nxt[0][0], nxt[0][1], nxt[0][4], w.rob_hl[a.robot1],
+                                   w.rob_hw[a.robot1], w.rob_rad[a.robot1]) ||
+                !constraints_clear(w, a.cons, a.n_cons, a.cons_states, a.cons_total, k, nxt[1][0], nxt[1][1], nxt[1][4], w.rob_hl[a.robot2],
+                                   w.rob_hw[a.robot2], w.rob_rad[a.robot2]))
+                break;
+        }
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll

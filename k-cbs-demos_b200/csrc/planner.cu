@@ -30,32 +30,41 @@
 
 namespace kcbs {
 
+constexpr int kRrtDepth = 4;   // RRT iterations in flight on the stream before the host looks at the oldest one's outcome
+
+// What the host sees of one finished iteration (host-mapped memory, written by k_rrt_append).
+struct RrtProgress {
+    unsigned long long goal;   // packed (time << 32 | node) of the best goal node, ~0 when none yet
+    int nodes, rounds;
+};
+
 struct RrtWorkspace {
-    int max_nodes = 0, n_samples = 0, n_targets = 0, cons_cap = 0, cons_desc_cap = 0, path_cap = 0;
-    float *nodes = nullptr;        // [5][max_nodes] states
+    int max_nodes = 0, n_samples = 0, n_targets = 0, cons_cap = 0, cons_desc_cap = 0, path_cap = 0, dim = 0;
+    float *nodes = nullptr;        // [dim][max_nodes] states (dim = 5 per car)
     int *parent = nullptr;         // [max_nodes]
     int *time = nullptr;           // [max_nodes] absolute time index (propagation steps from the root)
-    float *ctrl = nullptr;         // [2][max_nodes] control of the edge into the node
+    float *ctrl = nullptr;         // [2 per car][max_nodes] control of the edge into the node
     int *steps = nullptr;          // [max_nodes] duration of the edge into the node
-    float *targets = nullptr;      // [5][n_targets]
-    unsigned long long *nn = nullptr;  // [n_targets] packed (distance bits << 32 | node)
+    float *targets = nullptr;      // [dim][n_targets]
+    unsigned long long *nn = nullptr;  // [n_targets] packed (distance bits << 32 | node); ~0 between rounds
     int *s_parent = nullptr;       // [n_samples]
-    float *s_ctrl = nullptr;       // [2][n_samples]
+    float *s_ctrl = nullptr;       // [2 per car][n_samples]
     int *s_steps = nullptr;        // [n_samples]
-    float *s_fin = nullptr;        // [5][n_samples]
+    float *s_fin = nullptr;        // [dim][n_samples]
     int *s_valid = nullptr;        // [n_samples]
     int *sel = nullptr;            // [n_targets] sample chosen for each target this round, or -1
-    int *counters = nullptr;       // [0] = node count, [1] = (unused)
+    int *counters = nullptr;       // [0] = node count, [1] = rounds completed, [2] = edges of the extracted path
     unsigned long long *goal_key = nullptr;  // packed (time << 32 | node) of the best goal node
     ConsDesc *cons = nullptr;
     float *cons_states = nullptr;
     // path extraction
     int *path_nodes = nullptr;     // [path_cap]
-    float *path_ctrl = nullptr;    // [2][path_cap]
+    float *path_ctrl = nullptr;    // [2 per car][path_cap]
     int *path_steps = nullptr, *path_parent = nullptr, *path_valid = nullptr;
-    float *path_seg = nullptr;     // [5][KCBS_MAX_STEPS][path_cap]
-    unsigned long long *h_goal = nullptr;  // pinned
-    int *h_counters = nullptr;             // pinned
+    float *path_seg = nullptr;     // [dim][KCBS_MAX_STEPS][path_cap]
+    RrtProgress *h_progress = nullptr, *d_progress = nullptr;   // [kRrtDepth] host-mapped ring
+    int *h_counters = nullptr;                                  // pinned
+    cudaEvent_t ev[kRrtDepth] = {};
 };
 
 namespace {
@@ -78,87 +87,109 @@ __device__ __forceinline__ float urand(unsigned long long seed, unsigned round, 
 
 struct RrtArgs {
     RrtWorkspace ws;
-    float goal_x, goal_y, goal_radius, goal_bias;
+    float goal[4];             // (gx, gy) per car
+    float goal_radius;         // one car: distanceGoal <= radius (GoalRegionDatabase.h:48-55); merged pair: both < radius (:61-108)
+    float goal_bias;
     float lo[4], hi[4];
     unsigned long long seed;
     unsigned round;
-    int n_targets, n_controls, min_steps, max_steps, robot;
+    int n_targets, n_controls, min_steps, max_steps, robot[2];
     int n_cons, cons_total;
     int max_T;  // states the caller's trajectory buffer holds: a goal node must have time index < max_T
 };
 
-__global__ void k_rrt_init(RrtArgs a, float x, float y, float v, float phi, float th)
+// Every kernel of an iteration starts with this test: once a goal node exists the remaining iterations already queued
+// on the stream do nothing, so the outcome is that of the first iteration that found one -- however far the host ran ahead.
+__device__ __forceinline__ bool rrt_done(const RrtArgs &a) { return *(volatile const unsigned long long *)a.ws.goal_key != ~0ull; }
+
+template <int NC>
+__global__ void k_rrt_init(RrtArgs a, const float *start)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const int M = a.ws.max_nodes;
-        a.ws.nodes[0] = x; a.ws.nodes[M] = y; a.ws.nodes[2 * M] = v; a.ws.nodes[3 * M] = phi; a.ws.nodes[4 * M] = th;
+        for (int c = 0; c < 5 * NC; ++c) a.ws.nodes[c * M] = start[c];
+        for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M] = 0.f;
         a.ws.parent[0] = -1; a.ws.time[0] = 0; a.ws.steps[0] = 0;
-        a.ws.ctrl[0] = 0.f; a.ws.ctrl[M] = 0.f;
         a.ws.counters[0] = 1;
+        a.ws.counters[1] = 0;
         *a.ws.goal_key = ~0ull;
     }
-}
-
-// Random target states: uniform over the state bounds, or the goal position with random v, phi, theta.
-__global__ void k_rrt_targets(RrtArgs a)
-{
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n_targets) return;
-    const int B = a.n_targets;
-    float q[5];
-    for (int c = 0; c < 4; ++c) q[c] = a.lo[c] + (a.hi[c] - a.lo[c]) * urand(a.seed, a.round, t, c);
-    q[4] = -kPi + kTwoPi * urand(a.seed, a.round, t, 4);
-    if (urand(a.seed, a.round, t, 5) < a.goal_bias) {
-        q[0] = a.goal_x;
-        q[1] = a.goal_y;
-    }
-    for (int c = 0; c < 5; ++c) a.ws.targets[c * B + t] = q[c];
-    a.ws.nn[t] = ~0ull;
+    if (t < a.n_targets) a.ws.nn[t] = ~0ull;
 }
 
-// ob::CompoundStateSpace::distance with unit weights: L2 over (x, y, v, phi) + SO2 arc length.
-__device__ __forceinline__ float state_distance(float x, float y, float v, float p, float th, float tx, float ty,
-                                                float tv, float tp, float tth)
+// ob::CompoundStateSpace::distance with unit weights, per car: L2 over (x, y, v, phi) + SO2 arc length.
+__device__ __forceinline__ float car_distance(const float *a, const float *b)
 {
-    const float dx = x - tx, dy = y - ty, dv = v - tv, dp = p - tp;
-    float d = fabsf(th - tth);
+    const float dx = a[0] - b[0], dy = a[1] - b[1], dv = a[2] - b[2], dp = a[3] - b[3];
+    float d = fabsf(a[4] - b[4]);
     d = d > kPi ? kTwoPi - d : d;
     return sqrtf(fmaf(dx, dx, fmaf(dy, dy, fmaf(dv, dv, dp * dp)))) + d;
+}
+
+// Random target state of round a.round: uniform over the state bounds, or (goal bias) the goal positions with random
+// v, phi, theta.  A pure function of (seed, round, t), so any kernel can recompute it.
+template <int NC>
+__device__ __forceinline__ void rrt_target(const RrtArgs &a, int t, float q[5 * NC])
+{
+    const bool to_goal = urand(a.seed, a.round, t, 5) < a.goal_bias;
+#pragma unroll
+    for (int car = 0; car < NC; ++car) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q[5 * car + c] = a.lo[c] + (a.hi[c] - a.lo[c]) * urand(a.seed, a.round, t, 16 * car + c);
+        q[5 * car + 4] = -kPi + kTwoPi * urand(a.seed, a.round, t, 16 * car + 4);
+        if (to_goal) {
+            q[5 * car + 0] = a.goal[2 * car];
+            q[5 * car + 1] = a.goal[2 * car + 1];
+        }
+    }
 }
 
 constexpr int kNNThreads = 256;
 constexpr int kNNChunk = 256;   // nodes per CTA (small: the grid must fill 148 SMs while the tree is still small)
 
-// grid = (ceil(n_targets / 256), ceil(n_nodes / kNNChunk)): every thread owns one target and scans one chunk
-// of nodes staged through shared memory.
-__global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a, int n_nodes)
+// grid = (ceil(n_targets / 256), chunks of the largest tree this round can have): every thread owns one target and scans
+// one chunk of nodes staged through shared memory; the node count is read on the device (the host does not know it).
+template <int NC>
+__global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a)
 {
-    __shared__ float s[5][kNNThreads];
+    constexpr int D = 5 * NC;
+    __shared__ float s[D][kNNThreads];
+    if (rrt_done(a)) return;
+    const int n_nodes = min(a.ws.counters[0], a.ws.max_nodes);
+    const int n0 = blockIdx.y * kNNChunk, n1 = min(n0 + kNNChunk, n_nodes);
+    if (n0 >= n_nodes) return;
     const int B = a.n_targets, M = a.ws.max_nodes;
     const int t = blockIdx.x * kNNThreads + threadIdx.x;
     const bool live = t < B;
-    float q[5] = {0, 0, 0, 0, 0};
-    if (live)
-        for (int c = 0; c < 5; ++c) q[c] = a.ws.targets[c * B + t];
-    const int n0 = blockIdx.y * kNNChunk, n1 = min(n0 + kNNChunk, n_nodes);
+    float q[D];
+    rrt_target<NC>(a, min(t, B - 1), q);
+    if (live && blockIdx.y == 0)
+        for (int c = 0; c < D; ++c) a.ws.targets[c * B + t] = q[c];
     float best = 3.0e38f;
     int best_i = 0;
     for (int base = n0; base < n1; base += kNNThreads) {
         const int i = base + threadIdx.x;
         __syncthreads();
         if (i < n1)
-            for (int c = 0; c < 5; ++c) s[c][threadIdx.x] = a.ws.nodes[c * M + i];
+            for (int c = 0; c < D; ++c) s[c][threadIdx.x] = a.ws.nodes[c * M + i];
         __syncthreads();
         const int m = min(kNNThreads, n1 - base);
         for (int j = 0; j < m; ++j) {
-            // the real-vector part alone already bounds the distance from below: most nodes are rejected on the
-            // squared L2 without the square root and the SO2 term
+            // the real-vector part of the first car alone already bounds the distance from below: most nodes are rejected
+            // on the squared L2 without the square root and the SO2 term
             const float dx = s[0][j] - q[0], dy = s[1][j] - q[1], dv = s[2][j] - q[2], dp = s[3][j] - q[3];
             const float l2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dv, dv, dp * dp)));
             if (l2 < best * best) {
                 float dth = fabsf(s[4][j] - q[4]);
                 dth = dth > kPi ? kTwoPi - dth : dth;
-                const float d = sqrtf(l2) + dth;
+                float d = sqrtf(l2) + dth;
+                if (NC == 2) {
+                    float o[5];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) o[c] = s[5 * (NC - 1) + c][j];
+                    d += car_distance(o, q + 5 * (NC - 1));
+                }
                 if (d < best) {
                     best = d;
                     best_i = base + j;
@@ -166,28 +197,32 @@ __global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a, int n_nod
             }
         }
     }
-    if (live && n1 > n0)
-        atomicMin(a.ws.nn + t, ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)best_i);
+    if (live) atomicMin(a.ws.nn + t, ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)best_i);
 }
 
 // (parent, control, duration) for every sample: sample s belongs to target s / n_controls.
+template <int NC>
 __global__ void k_rrt_samples(RrtArgs a)
 {
+    if (rrt_done(a)) return;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = a.n_targets * a.n_controls;
     if (s >= n) return;
     const int t = s / a.n_controls;
     a.ws.s_parent[s] = (int)(a.ws.nn[t] & 0xffffffffu);
-    a.ws.s_ctrl[s] = -1.0f + 2.0f * urand(a.seed, a.round, s, 8);       // ControlSpaceDatabase.h:48-51
-    a.ws.s_ctrl[n + s] = -1.0f + 2.0f * urand(a.seed, a.round, s, 9);
+#pragma unroll
+    for (int car = 0; car < NC; ++car) {
+        a.ws.s_ctrl[(2 * car) * n + s] = -1.0f + 2.0f * urand(a.seed, a.round, s, 8 + 16 * car);       // ControlSpaceDatabase.h:48-51
+        a.ws.s_ctrl[(2 * car + 1) * n + s] = -1.0f + 2.0f * urand(a.seed, a.round, s, 9 + 16 * car);
+    }
     const int span = a.max_steps - a.min_steps + 1;
     a.ws.s_steps[s] = a.min_steps + min(span - 1, (int)(urand(a.seed, a.round, s, 10) * (float)span));
 }
 
 // A robot waiting at its final state must also respect the constraints that come later.
-__device__ bool parked_state_clear(const DevWorld &w, const RrtArgs &a, int t_node, float x, float y, float th)
+__device__ bool parked_state_clear(const DevWorld &w, const RrtArgs &a, int robot, int t_node, float x, float y, float th)
 {
-    const float hl = w.rob_hl[a.robot], hw = w.rob_hw[a.robot], rad = w.rob_rad[a.robot];
+    const float hl = w.rob_hl[robot], hw = w.rob_hw[robot], rad = w.rob_rad[robot];
     float s, c;
     sincosf(th, &s, &c);
     for (int q = 0; q < a.n_cons; ++q) {
@@ -210,20 +245,25 @@ __device__ bool parked_state_clear(const DevWorld &w, const RrtArgs &a, int t_no
 }
 
 // One warp per target: the valid sample that ends closest to the target becomes a tree node.
-__global__ void __launch_bounds__(256) k_rrt_select(const __grid_constant__ DevWorld w, RrtArgs a)
+template <int NC>
+__global__ void __launch_bounds__(256) k_rrt_select(RrtArgs a)
 {
+    constexpr int D = 5 * NC;
+    if (rrt_done(a)) return;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.n_targets) return;
-    const int B = a.n_targets, C = a.n_controls, n = B * C, M = a.ws.max_nodes;
-    float q[5];
-    for (int c = 0; c < 5; ++c) q[c] = a.ws.targets[c * B + warp];
+    const int B = a.n_targets, C = a.n_controls, n = B * C;
+    float q[D];
+    for (int c = 0; c < D; ++c) q[c] = a.ws.targets[c * B + warp];
     float best = 3.0e38f;
     int best_s = -1;
     for (int j = lane; j < C; j += 32) {
         const int s = warp * C + j;
         if (a.ws.s_valid[s] >= a.min_steps) {
-            const float d = state_distance(a.ws.s_fin[s], a.ws.s_fin[n + s], a.ws.s_fin[2 * n + s], a.ws.s_fin[3 * n + s],
-                                           a.ws.s_fin[4 * n + s], q[0], q[1], q[2], q[3], q[4]);
+            float f[D];
+            for (int c = 0; c < D; ++c) f[c] = a.ws.s_fin[c * n + s];
+            float d = car_distance(f, q);
+            if (NC == 2) d += car_distance(f + 5 * (NC - 1), q + 5 * (NC - 1));
             if (d < best) {
                 best = d;
                 best_s = s;
@@ -239,18 +279,33 @@ __global__ void __launch_bounds__(256) k_rrt_select(const __grid_constant__ DevW
             best_s = os;
         }
     }
-    if (lane == 0) a.ws.sel[warp] = best_s;
+    if (lane == 0) {
+        a.ws.sel[warp] = best_s;
+        a.ws.nn[warp] = ~0ull;   // consumed by k_rrt_samples of this round: clean for the next round's atomicMin
+    }
 }
 
 // Appends the chosen samples to the tree in TARGET ORDER (one CTA, block-wide prefix sum of the "found one" flags), so
 // that node indices -- and with them nearest-neighbour ties, the goal node and the whole plan -- depend only on the
-// seed, never on the order in which warps of k_rrt_select happen to finish.
+// seed, never on the order in which warps of k_rrt_select happen to finish.  Reports the round to the host.
+template <int NC>
 __global__ void __launch_bounds__(1024) k_rrt_append(const __grid_constant__ DevWorld w, RrtArgs a)
 {
+    constexpr int D = 5 * NC;
     __shared__ int s_warp[32];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int B = a.n_targets, C = a.n_controls, n = B * C, M = a.ws.max_nodes;
+    RrtProgress *slot = a.ws.d_progress + (a.round % kRrtDepth);
+    if (rrt_done(a)) {   // (uniform: nobody has written the key yet in this launch)
+        if (tid == 0) {
+            slot->goal = *a.ws.goal_key;
+            slot->nodes = a.ws.counters[0];
+            slot->rounds = a.ws.counters[1];
+        }
+        return;
+    }
+    __syncthreads();     // every thread has read the key before anybody may set it below
     if (tid == 0) s_base = a.ws.counters[0];
     __syncthreads();
     for (int t0 = 0; t0 < B; t0 += 1024) {
@@ -267,34 +322,49 @@ __global__ void __launch_bounds__(1024) k_rrt_append(const __grid_constant__ Dev
         const int idx = s_base + before + __popc(bal & ((1u << lane) - 1u));
         if (s >= 0 && idx < M) {
             const int par = a.ws.s_parent[s], nv = a.ws.s_valid[s];
-            const float x = a.ws.s_fin[s], y = a.ws.s_fin[n + s], th = a.ws.s_fin[4 * n + s];
-            a.ws.nodes[idx] = x;
-            a.ws.nodes[M + idx] = y;
-            a.ws.nodes[2 * M + idx] = a.ws.s_fin[2 * n + s];
-            a.ws.nodes[3 * M + idx] = a.ws.s_fin[3 * n + s];
-            a.ws.nodes[4 * M + idx] = th;
+            float f[D];
+            for (int c = 0; c < D; ++c) {
+                f[c] = a.ws.s_fin[c * n + s];
+                a.ws.nodes[c * M + idx] = f[c];
+            }
             a.ws.parent[idx] = par;
             const int t_node = a.ws.time[par] + nv;
             a.ws.time[idx] = t_node;
-            a.ws.ctrl[idx] = a.ws.s_ctrl[s];
-            a.ws.ctrl[M + idx] = a.ws.s_ctrl[n + s];
+            for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M + idx] = a.ws.s_ctrl[c * n + s];
             a.ws.steps[idx] = nv;
-            // GoalRegion2ndOrderCar::distanceGoal <= threshold (GoalRegionDatabase.h:48-55)
-            const float gx = x - a.goal_x, gy = y - a.goal_y;
             // (a path that would not fit the caller's buffer is never a solution: it would come back truncated)
-            if (t_node < a.max_T && sqrtf(fmaf(gx, gx, gy * gy)) <= a.goal_radius) {
-                if (a.n_cons == 0 || parked_state_clear(w, a, t_node, x, y, th))
-                    atomicMin(a.ws.goal_key, ((unsigned long long)(unsigned)t_node << 32) | (unsigned)idx);
+            bool in_goal = t_node < a.max_T;
+#pragma unroll
+            for (int car = 0; car < NC; ++car) {
+                const float gx = f[5 * car] - a.goal[2 * car], gy = f[5 * car + 1] - a.goal[2 * car + 1];
+                const float d = sqrtf(fmaf(gx, gx, gy * gy));
+                // GoalRegion2ndOrderCar: distanceGoal <= threshold (GoalRegionDatabase.h:48-55);
+                // GoalRegionTwo2ndOrderCars: both distances < threshold (:61-108)
+                in_goal &= NC == 1 ? d <= a.goal_radius : d < a.goal_radius;
             }
+            if (in_goal && a.n_cons > 0) {
+#pragma unroll
+                for (int car = 0; car < NC; ++car)
+                    in_goal = in_goal && parked_state_clear(w, a, a.robot[car], t_node, f[5 * car], f[5 * car + 1], f[5 * car + 4]);
+            }
+            if (in_goal) atomicMin(a.ws.goal_key, ((unsigned long long)(unsigned)t_node << 32) | (unsigned)idx);
         }
         __syncthreads();
         if (tid == 0) s_base = min(s_base + total, M);
         __syncthreads();
     }
-    if (tid == 0) a.ws.counters[0] = s_base;
+    if (tid == 0) {
+        a.ws.counters[0] = s_base;
+        a.ws.counters[1] = (int)a.round + 1;
+        __threadfence();
+        slot->goal = *(volatile unsigned long long *)a.ws.goal_key;
+        slot->nodes = s_base;
+        slot->rounds = (int)a.round + 1;
+    }
 }
 
-// Walks goal -> root (one thread) and emits the edges root -> goal as k_propagate inputs.
+// Walks goal -> root (one thread) and emits the edges root -> goal as propagation inputs.
+template <int NC>
 __global__ void k_rrt_path(RrtArgs a, int goal_node, int path_cap, int *n_edges_out)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -304,8 +374,7 @@ __global__ void k_rrt_path(RrtArgs a, int goal_node, int path_cap, int *n_edges_
     for (int e = 0; e < n; ++e) {
         const int i = a.ws.path_nodes[n - 1 - e];
         a.ws.path_parent[e] = a.ws.parent[i];
-        a.ws.path_ctrl[e] = a.ws.ctrl[i];
-        a.ws.path_ctrl[path_cap + e] = a.ws.ctrl[M + i];
+        for (int c = 0; c < 2 * NC; ++c) a.ws.path_ctrl[c * n + e] = a.ws.ctrl[c * M + i];   // planes of stride n = the edge count
         a.ws.path_steps[e] = a.ws.steps[i];
     }
     *n_edges_out = n;
@@ -325,37 +394,42 @@ void free_workspace(RrtWorkspace &ws)
                  ws.path_steps, ws.path_parent, ws.path_valid, ws.path_seg};
     for (void *p : d)
         if (p) cudaFree(p);
-    if (ws.h_goal) cudaFreeHost(ws.h_goal);
+    if (ws.h_progress) cudaFreeHost(ws.h_progress);
     if (ws.h_counters) cudaFreeHost(ws.h_counters);
+    for (cudaEvent_t e : ws.ev)
+        if (e) cudaEventDestroy(e);
     ws = RrtWorkspace();
 }
 
-int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int cons_total, int n_cons)
+int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int cons_total, int n_cons)
 {
     if (!ctx->rrt) ctx->rrt = new RrtWorkspace();
     RrtWorkspace &ws = *ctx->rrt;
-    const int n_samples = p.n_targets * p.n_controls;
-    if (ws.max_nodes != p.max_nodes || ws.n_samples != n_samples || ws.n_targets != p.n_targets) {
+    const int n_samples = p.n_targets * p.n_controls, dim = 5 * n_cars;
+    if (ws.max_nodes != p.max_nodes || ws.n_samples != n_samples || ws.n_targets != p.n_targets || ws.dim < dim) {
         KCBS_CUDA(ctx, cudaDeviceSynchronize());
         free_workspace(ws);
         int st;
-        const size_t M = (size_t)p.max_nodes, S = (size_t)n_samples, B = (size_t)p.n_targets;
+        const size_t M = (size_t)p.max_nodes, S = (size_t)n_samples, B = (size_t)p.n_targets, D = (size_t)dim, U = (size_t)2 * n_cars;
         ws.path_cap = 8192;
         const size_t PC = (size_t)ws.path_cap;
-        if ((st = dev_alloc(ctx, ws.nodes, 5 * M)) || (st = dev_alloc(ctx, ws.parent, M)) || (st = dev_alloc(ctx, ws.time, M)) ||
-            (st = dev_alloc(ctx, ws.ctrl, 2 * M)) || (st = dev_alloc(ctx, ws.steps, M)) || (st = dev_alloc(ctx, ws.targets, 5 * B)) ||
-            (st = dev_alloc(ctx, ws.nn, B)) || (st = dev_alloc(ctx, ws.s_parent, S)) || (st = dev_alloc(ctx, ws.s_ctrl, 2 * S)) ||
-            (st = dev_alloc(ctx, ws.s_steps, S)) || (st = dev_alloc(ctx, ws.s_fin, 5 * S)) || (st = dev_alloc(ctx, ws.s_valid, S)) || (st = dev_alloc(ctx, ws.sel, B)) ||
+        if ((st = dev_alloc(ctx, ws.nodes, D * M)) || (st = dev_alloc(ctx, ws.parent, M)) || (st = dev_alloc(ctx, ws.time, M)) ||
+            (st = dev_alloc(ctx, ws.ctrl, U * M)) || (st = dev_alloc(ctx, ws.steps, M)) || (st = dev_alloc(ctx, ws.targets, D * B)) ||
+            (st = dev_alloc(ctx, ws.nn, B)) || (st = dev_alloc(ctx, ws.s_parent, S)) || (st = dev_alloc(ctx, ws.s_ctrl, U * S)) ||
+            (st = dev_alloc(ctx, ws.s_steps, S)) || (st = dev_alloc(ctx, ws.s_fin, D * S)) || (st = dev_alloc(ctx, ws.s_valid, S)) || (st = dev_alloc(ctx, ws.sel, B)) ||
             (st = dev_alloc(ctx, ws.counters, 4)) || (st = dev_alloc(ctx, ws.goal_key, 1)) || (st = dev_alloc(ctx, ws.path_nodes, PC)) ||
-            (st = dev_alloc(ctx, ws.path_ctrl, 2 * PC)) || (st = dev_alloc(ctx, ws.path_steps, PC)) ||
+            (st = dev_alloc(ctx, ws.path_ctrl, U * PC)) || (st = dev_alloc(ctx, ws.path_steps, PC)) ||
             (st = dev_alloc(ctx, ws.path_parent, PC)) || (st = dev_alloc(ctx, ws.path_valid, PC)) ||
-            (st = dev_alloc(ctx, ws.path_seg, 5 * (size_t)KCBS_MAX_STEPS * PC)))
+            (st = dev_alloc(ctx, ws.path_seg, D * (size_t)KCBS_MAX_STEPS * PC)))
             return st;
-        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_goal, sizeof(unsigned long long), cudaHostAllocDefault));
+        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_progress, sizeof(RrtProgress) * kRrtDepth, cudaHostAllocMapped));
+        KCBS_CUDA(ctx, cudaHostGetDevicePointer((void **)&ws.d_progress, ws.h_progress, 0));
         KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_counters, 4 * sizeof(int), cudaHostAllocDefault));
+        for (cudaEvent_t &e : ws.ev) KCBS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ws.max_nodes = p.max_nodes;
         ws.n_samples = n_samples;
         ws.n_targets = p.n_targets;
+        ws.dim = dim;
     }
     if (cons_total > ws.cons_cap) {
         KCBS_CUDA(ctx, cudaDeviceSynchronize());
@@ -409,16 +483,23 @@ void destroy_rrt_workspace(kcbs_ctx *ctx)
     }
 }
 
-// The low-level planner proper (host orchestration; every arithmetic step is a kernel).
-static int rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *goal_xy, const kcbs_rrt_params &p,
+// The low-level planner proper for NC cars planned as one system (NC = 1: a robot; NC = 2: a merged pair, the 10-d
+// system of SystemMergerDatabase.h:108-156).  Host orchestration only; every arithmetic step is a kernel.  The host
+// queues iterations without waiting for them: each round reports (goal, node count) into a host-mapped ring, the host
+// looks at round i - kRrtDepth before it queues round i, and rounds queued after the goal was found cancel themselves on
+// the device.  start = 5 NC reals, goal_xy = 2 NC, traj_out = [5 NC][max_T].
+template <int NC>
+static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const float *goal_xy, const kcbs_rrt_params &p,
                     int n_cons, const int32_t *cons_robot, const int32_t *cons_k0, const int32_t *cons_len,
                     const int32_t *cons_offset, const float *cons_states, int max_T, float *traj_out, int32_t *T_out,
                     kcbs_rrt_stats *stats)
 {
+    constexpr int D = 5 * NC, U = 2 * NC;
     const double t_begin = now_s();
     int st = check_rrt_params(ctx, p);
     if (st) return st;
-    if (robot < 0 || robot >= ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "robot index out of range");
+    for (int c = 0; c < NC; ++c)
+        if (robots[c] < 0 || robots[c] >= ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "robot index out of range");
     if (!start || !goal_xy || !traj_out || !T_out || max_T < 1) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "null argument");
     int cons_total = 0;
     for (int c = 0; c < n_cons; ++c) {
@@ -427,91 +508,133 @@ static int rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *g
         cons_total = std::max(cons_total, cons_offset[c] + std::abs(cons_len[c]));
     }
     KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
-    if ((st = ensure_workspace(ctx, p, cons_total, n_cons))) return st;
+    if ((st = ensure_workspace(ctx, p, NC, cons_total, n_cons))) return st;
     RrtWorkspace &ws = *ctx->rrt;
     cudaStream_t s = ctx->stream;
 
+    std::vector<ConsDesc> desc(n_cons);
     if (n_cons > 0) {
-        std::vector<ConsDesc> desc(n_cons);
         for (int c = 0; c < n_cons; ++c) desc[c] = ConsDesc{cons_robot[c], cons_k0[c], cons_len[c], cons_offset[c]};
         KCBS_CUDA(ctx, cudaMemcpyAsync(ws.cons, desc.data(), sizeof(ConsDesc) * n_cons, cudaMemcpyHostToDevice, s));
         // host planes have stride cons_total; keep the same stride on the device
         KCBS_CUDA(ctx, cudaMemcpyAsync(ws.cons_states, cons_states, sizeof(float) * 3 * (size_t)cons_total, cudaMemcpyHostToDevice, s));
-        KCBS_CUDA(ctx, cudaStreamSynchronize(s));  // desc is a local
     }
+    // the start state travels through the (not yet used) target buffer
+    KCBS_CUDA(ctx, cudaMemcpyAsync(ws.targets, start, sizeof(float) * D, cudaMemcpyHostToDevice, s));
 
     RrtArgs a;
     a.ws = ws;
-    a.goal_x = goal_xy[0]; a.goal_y = goal_xy[1]; a.goal_radius = p.goal_radius; a.goal_bias = p.goal_bias;
+    for (int c = 0; c < 2 * NC; ++c) a.goal[c] = goal_xy[c];
+    for (int c = 2 * NC; c < 4; ++c) a.goal[c] = 0.0f;
+    a.goal_radius = NC == 1 ? p.goal_radius : KCBS_PAIR_GOAL_RADIUS;
+    a.goal_bias = p.goal_bias;
     // sampling box = the state bounds the validity test uses (thresholds are within one ulp of them)
     for (int c = 0; c < 4; ++c) { a.lo[c] = ctx->world.lo_t[c]; a.hi[c] = ctx->world.hi_t[c]; }
     a.seed = p.seed; a.round = 0;
     a.n_targets = p.n_targets; a.n_controls = p.n_controls; a.min_steps = p.min_steps; a.max_steps = p.max_steps;
-    a.robot = robot; a.n_cons = n_cons; a.cons_total = cons_total; a.max_T = max_T;
+    a.robot[0] = robots[0]; a.robot[1] = robots[NC - 1]; a.n_cons = n_cons; a.cons_total = cons_total; a.max_T = max_T;
     const int n = p.n_targets * p.n_controls;
 
     PropArgs pa = {};
-    pa.rounds = ctx->prop_rounds;
-    pa.n = n; pa.n_parents = ws.max_nodes; pa.parents = ws.nodes; pa.parent_idx = ws.s_parent; pa.controls = ws.s_ctrl;
-    pa.steps = ws.s_steps; pa.seg = nullptr; pa.fin = ws.s_fin; pa.valid_steps = ws.s_valid; pa.max_steps = p.max_steps;
-    pa.robot = robot; pa.parent_time = ws.time; pa.cons = ws.cons; pa.cons_states = ws.cons_states; pa.n_cons = n_cons;
-    pa.cons_total = cons_total;
+    PairArgs qa = {};
+    if (NC == 1) {
+        pa.rounds = ctx->prop_rounds;
+        pa.n = n; pa.n_parents = ws.max_nodes; pa.parents = ws.nodes; pa.parent_idx = ws.s_parent; pa.controls = ws.s_ctrl;
+        pa.steps = ws.s_steps; pa.seg = nullptr; pa.fin = ws.s_fin; pa.valid_steps = ws.s_valid; pa.max_steps = p.max_steps;
+        pa.robot = robots[0]; pa.parent_time = ws.time; pa.cons = ws.cons; pa.cons_states = ws.cons_states; pa.n_cons = n_cons;
+        pa.cons_total = cons_total;
+    } else {
+        qa.n = n; qa.n_parents = ws.max_nodes; qa.parents = ws.nodes; qa.parent_idx = ws.s_parent; qa.controls = ws.s_ctrl;
+        qa.steps = ws.s_steps; qa.seg = nullptr; qa.fin = ws.s_fin; qa.valid_steps = ws.s_valid; qa.max_steps = p.max_steps;
+        qa.robot1 = robots[0]; qa.robot2 = robots[NC - 1];
+        for (int c = 0; c < 4; ++c) qa.goals[c] = a.goal[c];
+        qa.hold_radius = KCBS_PAIR_GOAL_RADIUS;   // StatePropagatorDatabase.h:170
+        qa.parent_time = ws.time; qa.cons = ws.cons; qa.cons_states = ws.cons_states; qa.n_cons = n_cons; qa.cons_total = cons_total;
+    }
 
-    k_rrt_init<<<1, 32, 0, s>>>(a, start[0], start[1], start[2], start[3], start[4]);
+    for (int q = 0; q < kRrtDepth; ++q) ws.h_progress[q] = RrtProgress{~0ull, 1, 0};
+    k_rrt_init<NC><<<(p.n_targets + 255) / 256, 256, 0, s>>>(a, ws.targets);
     ctx->launches += 1;
-    int n_nodes = 1, iters = 0;
+    int n_nodes = 1, iters = 0, queued = 0;
     unsigned long long goal = ~0ull;
     // the start itself may already satisfy the goal
     {
-        const float gx = start[0] - goal_xy[0], gy = start[1] - goal_xy[1];
-        if (std::sqrt(gx * gx + gy * gy) <= p.goal_radius && n_cons == 0) goal = 0;
+        bool in = n_cons == 0;
+        for (int c = 0; c < NC; ++c) {
+            const float gx = start[5 * c] - goal_xy[2 * c], gy = start[5 * c + 1] - goal_xy[2 * c + 1];
+            const float d = std::sqrt(gx * gx + gy * gy);
+            in = in && (NC == 1 ? d <= a.goal_radius : d < a.goal_radius);
+        }
+        if (in) goal = 0;
     }
-    while (goal == ~0ull && iters < p.max_iterations && n_nodes < p.max_nodes) {
+    while (goal == ~0ull && queued < p.max_iterations) {
+        if (queued >= kRrtDepth) {   // outcome of the round that used this ring slot last
+            KCBS_CUDA(ctx, cudaEventSynchronize(ws.ev[queued % kRrtDepth]));
+            const RrtProgress pr = ws.h_progress[queued % kRrtDepth];
+            if (pr.goal != ~0ull || pr.nodes >= p.max_nodes) break;
+        }
         if (p.time_limit_s > 0 && now_s() - t_begin > p.time_limit_s) break;
-        a.round = (unsigned)iters;
-        k_rrt_targets<<<(p.n_targets + 255) / 256, 256, 0, s>>>(a);
-        dim3 g((p.n_targets + kNNThreads - 1) / kNNThreads, (n_nodes + kNNChunk - 1) / kNNChunk);
-        k_rrt_nearest<<<g, kNNThreads, 0, s>>>(a, n_nodes);
-        k_rrt_samples<<<(n + 255) / 256, 256, 0, s>>>(a);
-        KCBS_CUDA(ctx, launch_propagate(ctx->world, pa, s));
-        k_rrt_select<<<(p.n_targets * 32 + 255) / 256, 256, 0, s>>>(ctx->world, a);
-        k_rrt_append<<<1, 1024, 0, s>>>(ctx->world, a);
-        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters, ws.counters, sizeof(int), cudaMemcpyDeviceToHost, s));
-        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_goal, ws.goal_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        a.round = (unsigned)queued;
+        // the tree has at most 1 + round * n_targets nodes when this round starts
+        const long long bound = std::min<long long>(p.max_nodes, 1 + (long long)queued * p.n_targets);
+        dim3 g((p.n_targets + kNNThreads - 1) / kNNThreads, (unsigned)((bound + kNNChunk - 1) / kNNChunk));
+        k_rrt_nearest<NC><<<g, kNNThreads, 0, s>>>(a);
+        k_rrt_samples<NC><<<(n + 255) / 256, 256, 0, s>>>(a);
+        if (NC == 1)
+            KCBS_CUDA(ctx, launch_propagate(ctx->world, pa, s));
+        else
+            KCBS_CUDA(ctx, launch_propagate_pair(ctx->world, qa, s));
+        k_rrt_select<NC><<<(p.n_targets * 32 + 255) / 256, 256, 0, s>>>(a);
+        k_rrt_append<NC><<<1, 1024, 0, s>>>(ctx->world, a);
+        KCBS_CUDA(ctx, cudaEventRecord(ws.ev[queued % kRrtDepth], s));
+        ctx->launches += 5;
+        ++queued;
+    }
+    if (goal == ~0ull) {
+        // drain: the final word is on the device (rounds queued after the goal was found did nothing)
+        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters, ws.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        KCBS_CUDA(ctx, cudaMemcpyAsync(&ws.h_progress[0].goal, ws.goal_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         KCBS_CUDA(ctx, cudaStreamSynchronize(s));
-        ctx->launches += 6;
+        goal = ws.h_progress[0].goal;
         n_nodes = std::min(ws.h_counters[0], p.max_nodes);
-        goal = *ws.h_goal;
-        ++iters;
+        iters = ws.h_counters[1];
+    } else {
+        KCBS_CUDA(ctx, cudaStreamSynchronize(s));   // `desc` and the start state were still in flight
     }
 
     int T = 0;
     if (goal != ~0ull) {
-        // states of the path: start, then every edge re-expanded by k_propagate (same arithmetic as the search)
+        // states of the path: start, then every edge re-expanded by the propagation kernel (same arithmetic as the search)
         const int goal_node = (int)(goal & 0xffffffffu);
-        for (int c = 0; c < 5; ++c) traj_out[(size_t)c * max_T] = start[c];
+        for (int c = 0; c < D; ++c) traj_out[(size_t)c * max_T] = start[c];
         T = 1;
         if (goal_node != 0) {
             int *d_n = ws.counters + 2;
-            k_rrt_path<<<1, 32, 0, s>>>(a, goal_node, ws.path_cap, d_n);
+            // (edge count first: the control planes of the path are written with exactly that stride)
+            k_rrt_path<NC><<<1, 32, 0, s>>>(a, goal_node, ws.path_cap, d_n);
             KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters + 2, d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
             KCBS_CUDA(ctx, cudaStreamSynchronize(s));
             const int E = ws.h_counters[2];
-            PropArgs pe = pa;
-            pe.n = E; pe.parent_idx = ws.path_parent; pe.controls = ws.path_ctrl; pe.steps = ws.path_steps;
-            pe.seg = ws.path_seg; pe.fin = nullptr; pe.valid_steps = ws.path_valid; pe.max_steps = p.max_steps;
-            // controls planes of the path have stride path_cap: compact them to stride E for the kernel
-            KCBS_CUDA(ctx, cudaMemcpyAsync(ws.path_ctrl + E, ws.path_ctrl + ws.path_cap, sizeof(float) * E, cudaMemcpyDeviceToDevice, s));
-            KCBS_CUDA(ctx, launch_propagate(ctx->world, pe, s));
+            if (NC == 1) {
+                PropArgs pe = pa;
+                pe.n = E; pe.parent_idx = ws.path_parent; pe.controls = ws.path_ctrl; pe.steps = ws.path_steps;
+                pe.seg = ws.path_seg; pe.fin = nullptr; pe.valid_steps = ws.path_valid; pe.max_steps = p.max_steps;
+                KCBS_CUDA(ctx, launch_propagate(ctx->world, pe, s));
+            } else {
+                PairArgs qe = qa;
+                qe.n = E; qe.parent_idx = ws.path_parent; qe.controls = ws.path_ctrl; qe.steps = ws.path_steps;
+                qe.seg = ws.path_seg; qe.fin = nullptr; qe.valid_steps = ws.path_valid; qe.max_steps = p.max_steps;
+                KCBS_CUDA(ctx, launch_propagate_pair(ctx->world, qe, s));
+            }
             ctx->launches += 2;
-            std::vector<float> seg((size_t)5 * p.max_steps * E);
+            std::vector<float> seg((size_t)D * p.max_steps * E);
             std::vector<int> valid(E);
             KCBS_CUDA(ctx, cudaMemcpyAsync(seg.data(), ws.path_seg, sizeof(float) * seg.size(), cudaMemcpyDeviceToHost, s));
             KCBS_CUDA(ctx, cudaMemcpyAsync(valid.data(), ws.path_valid, sizeof(int) * E, cudaMemcpyDeviceToHost, s));
             KCBS_CUDA(ctx, cudaStreamSynchronize(s));
             for (int e = 0; e < E; ++e)
                 for (int j = 0; j < valid[e] && T < max_T; ++j, ++T)
-                    for (int c = 0; c < 5; ++c) traj_out[(size_t)c * max_T + T] = seg[((size_t)c * p.max_steps + j) * E + e];
+                    for (int c = 0; c < D; ++c) traj_out[(size_t)c * max_T + T] = seg[((size_t)c * p.max_steps + j) * E + e];
         }
     }
     *T_out = T;
@@ -568,8 +691,26 @@ int kcbs_rrt_plan(kcbs_ctx *ctx, int robot, const float *start, const float *goa
         kcbs_rrt_defaults(&p);
     if (n_cons < 0 || (n_cons > 0 && (!cons_robot || !cons_k0 || !cons_len || !cons_offset || !cons_states)))
         return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "constraint arrays are null");
-    return rrt_plan(ctx, robot, start, goal_xy, p, n_cons, cons_robot, cons_k0, cons_len, cons_offset, cons_states, max_T,
-                    traj_out, T_out, stats);
+    return rrt_plan<1>(ctx, &robot, start, goal_xy, p, n_cons, cons_robot, cons_k0, cons_len, cons_offset, cons_states, max_T,
+                       traj_out, T_out, stats);
+}
+
+int kcbs_rrt_plan_pair(kcbs_ctx *ctx, int robot1, int robot2, const float *start, const float *goals_xy, const kcbs_rrt_params *params,
+                       int n_cons, const int32_t *cons_robot, const int32_t *cons_k0, const int32_t *cons_len,
+                       const int32_t *cons_offset, const float *cons_states, int max_T, float *traj_out, int32_t *T_out,
+                       kcbs_rrt_stats *stats)
+{
+    if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
+    kcbs_rrt_params p;
+    if (params)
+        p = *params;
+    else
+        kcbs_rrt_defaults(&p);
+    if (n_cons < 0 || (n_cons > 0 && (!cons_robot || !cons_k0 || !cons_len || !cons_offset || !cons_states)))
+        return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "constraint arrays are null");
+    const int robots[2] = {robot1, robot2};
+    return rrt_plan<2>(ctx, robots, start, goals_xy, p, n_cons, cons_robot, cons_k0, cons_len, cons_offset, cons_states, max_T,
+                       traj_out, T_out, stats);
 }
 
 // ---- K-CBS high level ------------------------------------------------------------------------------------
@@ -626,6 +767,10 @@ int run_planner_jobs(kcbs_ctx *ctx, int n_jobs, int max_lanes, Job job)
     std::vector<kcbs_ctx *> lane_ctx(lanes);
     for (int i = 0; i < lanes; ++i)
         if (!(lane_ctx[i] = planner_lane(ctx, i))) return fail(ctx, KCBS_ERR_CUDA, "planner worker creation failed");
+    // launch shape of the lanes' expansions (kcbs_set_expansion_mode of the caller's context wins): a handful of lanes
+    // cannot fill the GPU, so each expansion takes the latency shape; many concurrent lanes take the throughput shape
+    const int user_mode = ctx->user_prop_rounds;
+    for (int i = 0; i < lanes; ++i) lane_ctx[i]->prop_rounds = user_mode ? user_mode : (lanes > 4 ? 2 : 1);
     std::atomic<int> next(0);
     std::vector<int> status(lanes, KCBS_OK);
     auto body = [&](int lane) {
@@ -639,6 +784,7 @@ int run_planner_jobs(kcbs_ctx *ctx, int n_jobs, int max_lanes, Job job)
     for (int i = 1; i < lanes; ++i) threads.emplace_back(body, i);
     body(0);
     for (auto &t : threads) t.join();
+    ctx->prop_rounds = user_mode;
     for (int i = 0; i < lanes; ++i) {
         if (i > 0) {
             ctx->launches += lane_ctx[i]->launches;
@@ -652,8 +798,30 @@ int run_planner_jobs(kcbs_ctx *ctx, int n_jobs, int max_lanes, Job job)
     return KCBS_OK;
 }
 
-constexpr int kPlannerLanes = 8;
+constexpr int kPlannerLanes = 16;
 }  // extern "C++"
+
+// flat constraint arrays of the C ABI from the constraint objects of a tree node
+struct FlatConstraints {
+    std::vector<int32_t> robot, k0, ln, off;
+    std::vector<float> states;
+    explicit FlatConstraints(const std::vector<std::shared_ptr<Constraint>> &cons)
+    {
+        int total = 0;
+        for (const auto &c : cons) {
+            robot.push_back(c->other); k0.push_back(c->k0); off.push_back(total);
+            ln.push_back(c->persistent ? -(int)c->x.size() : (int)c->x.size());
+            total += (int)c->x.size();
+        }
+        states.assign((size_t)3 * std::max(total, 1), 0.0f);
+        for (size_t q = 0; q < cons.size(); ++q)
+            for (size_t j = 0; j < cons[q]->x.size(); ++j) {
+                states[off[q] + j] = cons[q]->x[j];
+                states[(size_t)total + off[q] + j] = cons[q]->y[j];
+                states[(size_t)2 * total + off[q] + j] = cons[q]->th[j];
+            }
+    }
+};
 
 int plan_robot(kcbs_ctx *ctx, int r, const float *starts, const float *goals, int R, const kcbs_rrt_params &p,
                const std::vector<std::shared_ptr<Constraint>> &cons, int max_T, std::vector<float> &traj, int &len,
@@ -661,29 +829,45 @@ int plan_robot(kcbs_ctx *ctx, int r, const float *starts, const float *goals, in
 {
     float start[5];
     for (int c = 0; c < 5; ++c) start[c] = starts[(size_t)c * R + r];
-    std::vector<int32_t> robot, k0, ln, off;
-    int total = 0;
-    for (const auto &c : cons) {
-        robot.push_back(c->other); k0.push_back(c->k0); off.push_back(total);
-        ln.push_back(c->persistent ? -(int)c->x.size() : (int)c->x.size());
-        total += (int)c->x.size();
-    }
-    std::vector<float> states((size_t)3 * std::max(total, 1));
-    for (size_t q = 0; q < cons.size(); ++q)
-        for (size_t j = 0; j < cons[q]->x.size(); ++j) {
-            states[off[q] + j] = cons[q]->x[j];
-            states[(size_t)total + off[q] + j] = cons[q]->y[j];
-            states[(size_t)2 * total + off[q] + j] = cons[q]->th[j];
-        }
+    FlatConstraints fc(cons);
     std::vector<float> out((size_t)5 * max_T);
     int32_t T = 0;
-    const int st = kcbs_rrt_plan(ctx, r, start, goals + 2 * r, &p, (int)cons.size(), robot.data(), k0.data(), ln.data(),
-                                 off.data(), states.data(), max_T, out.data(), &T, &rs);
+    const int st = kcbs_rrt_plan(ctx, r, start, goals + 2 * r, &p, (int)cons.size(), fc.robot.data(), fc.k0.data(), fc.ln.data(),
+                                 fc.off.data(), fc.states.data(), max_T, out.data(), &T, &rs);
     if (st != KCBS_OK) return st;
     len = T;
     traj.assign((size_t)5 * std::max(T, 1), 0.0f);
     for (int c = 0; c < 5; ++c)
         for (int k = 0; k < T; ++k) traj[(size_t)c * T + k] = out[(size_t)c * max_T + k];
+    return KCBS_OK;
+}
+
+// A merged pair planned as ONE 10-d system (SystemMergerDatabase.h:108-156): joint RRT over both cars' states and
+// controls through k_propagate_pair (freeze-at-goal rule, the two cars kept apart by the merged isValid), goal = both cars
+// within 1.5 of their goals.  Both trajectories come back with the same length.
+int plan_pair(kcbs_ctx *ctx, int r1, int r2, const float *starts, const float *goals, int R, const kcbs_rrt_params &p,
+              const std::vector<std::shared_ptr<Constraint>> &cons, int max_T, std::vector<float> &traj1, std::vector<float> &traj2,
+              int &len, kcbs_rrt_stats &rs)
+{
+    float start[10], goal[4] = {goals[2 * r1], goals[2 * r1 + 1], goals[2 * r2], goals[2 * r2 + 1]};
+    for (int c = 0; c < 5; ++c) {
+        start[c] = starts[(size_t)c * R + r1];
+        start[5 + c] = starts[(size_t)c * R + r2];
+    }
+    FlatConstraints fc(cons);
+    std::vector<float> out((size_t)10 * max_T);
+    int32_t T = 0;
+    const int st = kcbs_rrt_plan_pair(ctx, r1, r2, start, goal, &p, (int)cons.size(), fc.robot.data(), fc.k0.data(), fc.ln.data(),
+                                      fc.off.data(), fc.states.data(), max_T, out.data(), &T, &rs);
+    if (st != KCBS_OK) return st;
+    len = T;
+    traj1.assign((size_t)5 * std::max(T, 1), 0.0f);
+    traj2.assign((size_t)5 * std::max(T, 1), 0.0f);
+    for (int c = 0; c < 5; ++c)
+        for (int k = 0; k < T; ++k) {
+            traj1[(size_t)c * T + k] = out[(size_t)c * max_T + k];
+            traj2[(size_t)c * T + k] = out[(size_t)(5 + c) * max_T + k];
+        }
     return KCBS_OK;
 }
 
@@ -708,8 +892,9 @@ int kcbs_rrt_plan_many(kcbs_ctx *ctx, int n_jobs, const int32_t *robots, const f
         float start[5];
         for (int c = 0; c < 5; ++c) start[c] = starts[(size_t)c * n_jobs + j];
         kcbs_rrt_stats rs;
-        const int st = rrt_plan(lane, robots[j], start, goals + 2 * (size_t)j, lp, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                max_T, traj_out + (size_t)j * 5 * max_T, T_out + j, &rs);
+        const int robot = robots[j];
+        const int st = rrt_plan<1>(lane, &robot, start, goals + 2 * (size_t)j, lp, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   max_T, traj_out + (size_t)j * 5 * max_T, T_out + j, &rs);
         if (stats) stats[j] = rs;
         return st;
     });
@@ -730,60 +915,41 @@ struct Search {
     kcbs_kcbs_stats *S;
     std::vector<std::vector<int>> ind;  // robots of every individual
     std::vector<int> ind_of;            // robot -> individual
-    std::vector<char> no_merge;         // [R * R] pairs whose merged low level found no root plan: never merged again
 };
 
-// Low-level plan of one individual into `node`: its robots one after the other, each against the individual's
-// constraints plus the whole paths (padded with the parked final state up to the horizon) of the members planned before
-// it.  Returns KCBS_OK and sets `solved`.
-int plan_individual_ordered(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsigned long long seed, bool reversed,
-                            bool &solved)
+// Low-level plan of one individual into `node`: a single robot through the 5-d RRT, a merged pair through the joint 10-d
+// RRT (a few seeds are tried before a merged pair is given up: the joint space is large).  Returns KCBS_OK and sets `solved`.
+int plan_individual(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsigned long long seed, bool &solved)
 {
-    solved = true;
-    std::vector<std::shared_ptr<Constraint>> cons = node.cons[I];
-    const size_t n = q.ind[I].size();
-    for (size_t m = 0; m < n; ++m) {
-        const int r = q.ind[I][reversed ? n - 1 - m : m];
-        kcbs_rrt_params lp = q.P.low_level;
+    const std::vector<int> &members = q.ind[I];
+    kcbs_rrt_params lp = q.P.low_level;
+    kcbs_rrt_stats rs;
+    if (members.size() == 1) {
+        const int r = members[0];
         lp.seed = q.P.low_level.seed * 1000003ull + seed * 131ull + (unsigned long long)r;  // seed = salt of this plan
-        kcbs_rrt_stats rs;
-        const int st = plan_robot(lane, r, q.starts, q.goals, q.R, lp, cons, q.max_T, node.traj[r], node.len[r], rs);
+        const int st = plan_robot(lane, r, q.starts, q.goals, q.R, lp, node.cons[I], q.max_T, node.traj[r], node.len[r], rs);
+        solved = st == KCBS_OK && rs.solved;
+        return st;
+    }
+    const int r1 = members[0], r2 = members[1];
+    solved = false;
+    for (int attempt = 0; attempt < 3 && !solved; ++attempt) {
+        lp.seed = q.P.low_level.seed * 1000003ull + (seed + 7ull * attempt) * 131ull + (unsigned long long)(64 * r1 + r2 + 4096);
+        int len = 0;
+        const int st = plan_pair(lane, r1, r2, q.starts, q.goals, q.R, lp, node.cons[I], q.max_T, node.traj[r1], node.traj[r2], len, rs);
         if (st != KCBS_OK) return st;
-        if (!rs.solved) {
-            solved = false;
-            return KCBS_OK;
-        }
-        if (m + 1 < n) {  // the next member must avoid this one everywhere, also where it is parked
-            auto c = std::make_shared<Constraint>();
-            c->other = r;
-            c->k0 = 0;
-            c->persistent = true;
-            const int L = node.len[r];
-            for (int k = 0; k < L; ++k) {
-                c->x.push_back(node.traj[r][(size_t)0 * L + k]);
-                c->y.push_back(node.traj[r][(size_t)1 * L + k]);
-                c->th.push_back(node.traj[r][(size_t)4 * L + k]);
-            }
-            cons.push_back(c);
-        }
+        node.len[r1] = node.len[r2] = len;
+        solved = rs.solved != 0;
+        if (q.P.time_limit_s > 0 && now_s() - q.t_begin > q.P.time_limit_s) break;
     }
     return KCBS_OK;
 }
 
-int plan_individual(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsigned long long seed, bool &solved)
-{
-    int st = plan_individual_ordered(lane, q, node, I, seed, false, solved);
-    // a merged pair whose second car finds no way around the first is tried once more in the other order
-    if (st == KCBS_OK && !solved && q.ind[I].size() > 1) st = plan_individual_ordered(lane, q, node, I, seed + 1, true, solved);
-    return st;
-}
-
 // Best-first search of the constraint tree.  Returns KCBS_OK with `solution` set, or with merge_a >= 0 when a pair of
 // single-robot individuals exceeded the merge bound (the caller merges and restarts), or with neither (time / node
-// budget exhausted, or the root has no plan: failed_root names a merged individual without a root plan, if any).
-int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int &merge_b, int &failed_root)
+// budget exhausted, or the root has no plan).
+int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int &merge_b)
 {
-    failed_root = -1;
     kcbs_ctx *ctx = q.ctx;
     kcbs_kcbs_stats &S = *q.S;
     const int R = q.R, NI = (int)q.ind.size();
@@ -807,10 +973,7 @@ int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int
         if (st != KCBS_OK) return st;
         for (int I = 0; I < NI; ++I) {
             S.low_level_calls += (int)q.ind[I].size();
-            if (!ok[I]) {
-                root_ok = false;
-                if (q.ind[I].size() > 1) failed_root = I;
-            }
+            if (!ok[I]) root_ok = false;
         }
         for (int r = 0; r < R; ++r) root->cost += root->len[r];
     }
@@ -859,8 +1022,8 @@ int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int
         // merge bound (KCBS::setMergeBound): a pair of single robots that keeps colliding becomes one individual
         const int I1 = q.ind_of[cf.r1], I2 = q.ind_of[cf.r2];
         const int n_conf = ++pair_conflicts[(size_t)std::min(I1, I2) * NI + std::max(I1, I2)];
-        if (n_conf > q.P.merge_bound && q.ind[I1].size() == 1 && q.ind[I2].size() == 1 &&
-            !q.no_merge[(size_t)std::min(cf.r1, cf.r2) * R + std::max(cf.r1, cf.r2)]) {
+        // (merging something that is already a merged pair is not supported, SystemMergerDatabase.h:103-104)
+        if (n_conf > q.P.merge_bound && q.ind[I1].size() == 1 && q.ind[I2].size() == 1) {
             merge_a = std::min(I1, I2);
             merge_b = std::max(I1, I2);
             return KCBS_OK;
@@ -928,28 +1091,20 @@ int kcbs_kcbs_solve(kcbs_ctx *ctx, int R, const float *starts, const float *goal
         q.ind_of[r] = r;
     }
 
-    q.no_merge.assign((size_t)R * R, 0);
     std::shared_ptr<CbsNode> solution;
     for (;;) {
-        int ma = -1, mb = -1, failed = -1;
-        const int st = search_tree(q, solution, ma, mb, failed);
+        int ma = -1, mb = -1;
+        const int st = search_tree(q, solution, ma, mb);
         if (st != KCBS_OK) return st;
-        if (solution) break;
-        if (ma >= 0) {
-            // SystemMerger::merge(ma, mb): the pair becomes one individual and the search starts over (as the fork does)
-            q.ind[ma].insert(q.ind[ma].end(), q.ind[mb].begin(), q.ind[mb].end());
-            q.ind.erase(q.ind.begin() + mb);
-            ++S.merges;
-        } else if (failed >= 0) {
-            // the prioritised pair planner found no root plan for this merged pair (e.g. two cars that must swap places
-            // in a corridor): split it again, never merge these two again, and let the constraint tree handle them
-            const int a = q.ind[failed][0], b = q.ind[failed][1];
-            q.no_merge[(size_t)std::min(a, b) * R + std::max(a, b)] = 1;
-            q.ind[failed] = {a};
-            q.ind.push_back({b});
-        } else {
-            break;
-        }
+        if (solution || ma < 0) break;
+        // SystemMerger::merge(ma, mb): the pair becomes one individual, placed last, and the search starts over (as the
+        // fork does); from now on it is planned as one 10-d system
+        std::vector<int> merged = q.ind[ma];
+        merged.insert(merged.end(), q.ind[mb].begin(), q.ind[mb].end());
+        q.ind.erase(q.ind.begin() + mb);
+        q.ind.erase(q.ind.begin() + ma);
+        q.ind.push_back(merged);
+        ++S.merges;
         for (size_t I = 0; I < q.ind.size(); ++I)
             for (int r : q.ind[I]) q.ind_of[r] = (int)I;
         if (q.P.time_limit_s > 0 && now_s() - q.t_begin > q.P.time_limit_s) break;

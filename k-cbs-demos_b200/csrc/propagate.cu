@@ -44,36 +44,6 @@
 
 namespace kcbs {
 
-// Dynamic-obstacle constraints of the K-CBS low level (the fork tests `next` against the constraining robot's
-// state at that time through areStatesValid, StateValidityCheckerDatabase.h:78-125).
-__device__ __forceinline__ bool constraints_clear(const DevWorld &w, const PropArgs &a, int k, float x, float y,
-                                                  float th, float hl, float hw, float rad)
-{
-    bool ok = true, have = false;
-    float c = 1.0f, s = 0.0f;
-    for (int q = 0; q < a.n_cons; ++q) {
-        const ConsDesc d = a.cons[q];
-        int rel = k - d.k0;
-        if (rel < 0) continue;
-        if (d.len < 0)
-            rel = min(rel, -d.len - 1);  // persistent constraint: its last state holds for every later time index
-        else if (rel >= d.len)
-            continue;
-        const float *st = a.cons_states + d.offset + rel;
-        const float ox = st[0], oy = st[a.cons_total], dx = ox - x, dy = oy - y;
-        const float rs = rad + w.rob_rad[d.other];
-        if (fmaf(dy, dy, dx * dx) > rs * rs * 1.000001f) continue;
-        if (!have) {
-            sincosf(th, &s, &c);
-            have = true;
-        }
-        float oc, os;
-        sincosf(st[2 * a.cons_total], &os, &oc);
-        ok &= sat_gap_robots(x, y, c, s, hl, hw, ox, oy, oc, os, w.rob_hl[d.other], w.rob_hw[d.other]) > 0.0f;
-    }
-    return ok;
-}
-
 #ifndef KCBS_PROP_MINB
 #define KCBS_PROP_MINB 4
 #endif
@@ -222,7 +192,7 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
                 if (ok) ok = obstacles_clear_fine(w, xn, yn, tn, hl, hw);
             }
             if (HAS_CONS) {
-                if (ok) ok = constraints_clear(w, a, t0[e] + j + 1, xn, yn, tn, hl, hw, w.rob_rad[a.robot]);
+                if (ok) ok = constraints_clear(w, a.cons, a.n_cons, a.cons_states, a.cons_total, t0[e] + j + 1, xn, yn, tn, hl, hw, w.rob_rad[a.robot]);
             }
             xs[e] = ok ? xn : xs[e];
             ys[e] = ok ? yn : ys[e];

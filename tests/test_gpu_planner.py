@@ -138,8 +138,14 @@ def test_kcbs_merges_when_the_bound_is_exceeded(pkg, orc, gpu_ctx_factory, scene
         traj[r, :, :L] = plan[r][[0, 1, 4], :L]
     res, _, _ = oracle.first_conflict(traj, lengths=lengths)
     assert res[0] == -1, f"conflict {res} in a merged plan"
-    for r in (0, R - 1):
-        check_path(oracle, plan[r][:, :int(lengths[r])], starts[:, r], goals[r], r)
+    for r in range(R):
+        # (a car of a merged pair stops within 1.5 of its goal and stands still from then on: its path is checked state by
+        # state here, the joint dynamics in test_pair_rrt_plans_two_cars_as_one_system)
+        L = int(lengths[r])
+        assert np.hypot(plan[r][0, L - 1] - goals[r][0], plan[r][1, L - 1] - goals[r][1]) < 1.5 + 1e-4
+        for k in range(0, L, 7):
+            valid, margin = oracle.is_valid(plan[r][:, k].astype(np.float64), r)
+            assert valid or abs(margin) < 2e-5
     if scene != "Empty32x32_10robots":
         assert st.merges >= 1     # these scenes do conflict at the root
 
@@ -183,3 +189,69 @@ def test_rrt_persistent_constraint(pkg, orc, gpu_ctx_factory):
     # (or at least the plans differ), so the flag is what made the difference
     free, st2 = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=5), constraints=[(1, 0, other)])
     assert st2.solved == 1
+
+
+def check_pair_path(oracle, traj, start10, goals, r1=0, r2=1):
+    """traj [10, T]: every transition is one step of the reference's merged propagator (freeze rule included) under
+    admissible controls, every state valid for the merged system, both cars end within 1.5 of their goals."""
+    T = traj.shape[1]
+    assert (traj[:, 0] == np.asarray(start10, np.float32)).all()
+    for c, g in ((0, goals[:2]), (5, goals[2:])):
+        assert np.hypot(traj[c, -1] - g[0], traj[c + 1, -1] - g[1]) < 1.5 + 1e-4
+    for k in range(T - 1):
+        q, qn = traj[:, k].astype(np.float64), traj[:, k + 1].astype(np.float64)
+        u = np.array([(qn[2] - q[2]) / 0.1, (qn[3] - q[3]) / 0.1, (qn[7] - q[7]) / 0.1, (qn[8] - q[8]) / 0.1])
+        assert np.abs(u).max() <= 1.0 + 1e-3
+        ref = oracle.pair_propagate(q, np.clip(u, -1, 1), goals)
+        for c in (0, 5):
+            ok, d = state_close(qn[c:c + 5].astype(np.float32)[:, None], ref[c:c + 5][:, None])
+            assert ok.all(), f"step {k} car {c // 5}: {d.ravel()}"
+        valid, margin = oracle.pair_is_valid(qn, r1, r2)
+        assert valid or abs(margin) < 2e-5, f"state {k + 1} invalid (margin {margin})"
+
+
+def test_pair_rrt_plans_two_cars_as_one_system(pkg, orc, gpu_ctx_factory):
+    # two cars that have to cross each other's straight line, planned jointly in the 10-d space
+    scene = "Empty32x32_10robots"
+    ctx = gpu_ctx_factory(scene)
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    start = np.array([10, 16, 0, 0, 0, 16, 10, 0, 0, np.pi / 2], np.float32)
+    goals = np.array([22, 16, 16, 22], np.float32)
+    traj, st = ctx.rrt_plan_pair(0, 1, start, goals, ctx.rrt_params(seed=4, time_limit_s=30.0))
+    assert st.solved == 1 and traj.shape[0] == 10 and traj.shape[1] == st.path_steps + 1
+    check_pair_path(oracle, traj, start, goals)
+    # a third robot parked for ever on car 1's straight line: both cars of the pair avoid it at all times
+    K = 5
+    block = np.zeros((3, K), np.float32)
+    block[0], block[1], block[2] = 16.0, 16.0, 0.3
+    traj2, st2 = ctx.rrt_plan_pair(0, 1, start, goals, ctx.rrt_params(seed=4, time_limit_s=30.0), constraints=[(2, 0, block)],
+                                   persistent=[True])
+    assert st2.solved == 1
+    check_pair_path(oracle, traj2, start, goals)
+    for k in range(traj2.shape[1]):
+        for c in (0, 5):
+            ok, _ = oracle.pair_valid(c // 5, traj2[[c, c + 1, c + 4], k], 2, block[:, -1])
+            assert ok, f"constraint violated by car {c // 5} at step {k}"
+
+
+def test_kcbs_plans_the_merged_pair_jointly(pkg, orc, gpu_ctx_factory):
+    # merge bound 0: the first conflicting pair is merged at once and from then on planned as ONE 10-d system (no car-by-car
+    # fallback, no split); Robot 1 and Robot 3 of the corridor scene have to swap places in a passage two robots wide
+    scene = "Corridor10x10_4robots"
+    ctx = gpu_ctx_factory(scene)
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    starts, goals = pkg.scenes.start_states(scene), pkg.scenes.goals(scene)
+    params = ctx.kcbs_params(low_level=ctx.rrt_params(seed=3, time_limit_s=20.0), time_limit_s=170.0, merge_bound=0)
+    plan, lengths, st = ctx.kcbs_solve(starts, goals, params, max_T=2048)
+    assert st.solved == 1 and st.merges >= 1
+    R = starts.shape[1]
+    T = int(lengths.max())
+    traj = np.zeros((R, 3, T), np.float32)
+    for r in range(R):
+        L = int(lengths[r])
+        traj[r, :, :L] = plan[r][[0, 1, 4], :L]
+    res, _, _ = oracle.first_conflict(traj, lengths=lengths)
+    assert res[0] == -1, f"conflict {res} in the merged plan"
+    # merged cars stop within 1.5 of their goals (the merged goal region), the others within 0.5
+    within = [float(np.hypot(plan[r][0, lengths[r] - 1] - goals[r][0], plan[r][1, lengths[r] - 1] - goals[r][1])) for r in range(R)]
+    assert sum(d <= 0.5 + 1e-4 for d in within) >= R - 2 * st.merges and max(within) < 1.5 + 1e-4

@@ -51,6 +51,10 @@ if what in ("propagate", "all"):
             units = float(torch.minimum(ds, val + 1).sum().item())
             print(f"propagate {scene} n={n} steps={'U' if fixed is None else fixed}: {ms * 1e3:.1f} us  {units / ms / 1e-3:.3e} states/s "
                   f"({980 * units / ms / 1e-3 / 1e12:.1f} TFLOP/s algorithmic)")
+            off = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+            ms = timed(lambda: ctx.propagate_packed_dev(0, n, p.shape[1], dp, dc, ds, None, 10, seg, 10 * n, off, fin, val, stream), 5)
+            print(f"propagate PACKED {scene} n={n} steps={'U' if fixed is None else fixed}: {ms * 1e3:.1f} us  {units / ms / 1e-3:.3e} states/s "
+                  f"({980 * units / ms / 1e-3 / 1e12:.1f} TFLOP/s algorithmic); rows {int(off[n])}")
         ctx.close()
 
 if what in ("validity", "all"):

@@ -18,34 +18,51 @@ stream = torch.cuda.Stream()
 
 
 def timed(fn, reps=20):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    """Microseconds per call: `reps` calls captured into one CUDA graph (the C-ABI launches themselves; no Python between
+    them, a ctypes call costs ~9 us) and replayed; CUDA events on the replay stream."""
     with torch.cuda.stream(stream):
-        e0.record()
-        for _ in range(reps):
+        for _ in range(3):
             fn()
-        e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps * 1e3  # us
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        stream.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(5):
+            g.replay()
+        e1.record(stream)
+        stream.synchronize()
+    return e0.elapsed_time(e1) / (5 * reps) * 1e3  # us
 
 
-print("# Size sweep, round 1 (B200; one launch at a time, device-resident buffers, CUDA events)\n")
+print("# Size sweep, round 2 (B200; back-to-back launches of ONE stream replayed from a CUDA graph, device-resident buffers, CUDA events)\n")
 print("## K1 k_propagate — Empty32x32, one shared parent, durations U{1..10}\n")
 print("| control samples | us per launch | propagated states/s | algorithmic TFLOP/s |\n|---|---|---|---|")
 scene = "Empty32x32_10robots"
 ctx = pkg.Context(pkg.scenes.world(scene))
-for n in (4096, 16384, 65536, 262144, 1048576, 4194304):
+print("(columns: launch shape forced to one pair per thread / two pairs per thread / chosen from n; dense and packed segments)\n")
+print("| control samples | dense, 1 pair us | dense, 2 pairs us | dense, auto us | packed, auto us | final only, auto us | states/s (dense auto) | TFLOP/s |\n|---|---|---|---|---|---|---|---|")
+for n in (4096, 16384, 65536, 131072, 262144, 1048576, 4194304):
     p, c, s = workloads.expansion_batch(scene, n, seed=3, shared_parent=True, interior=1.5)
     dp, dc, ds = torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(s).cuda()
     seg = torch.empty((5, 10, n), device="cuda")
     fin = torch.empty((5, n), device="cuda")
     val = torch.zeros(n, dtype=torch.int32, device="cuda")
-    us = timed(lambda: ctx.propagate_batch_dev(0, n, 1, dp, dc, ds, None, 10, seg, fin, val, stream))
+    off = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
+    row = []
+    for mode in (1, 2, 0):
+        ctx.set_expansion_mode(mode)
+        row.append(timed(lambda: ctx.propagate_batch_dev(0, n, 1, dp, dc, ds, None, 10, seg, fin, val, stream)))
+    us = row[2]
     units = float(torch.minimum(ds, val + 1).sum().item())
-    print(f"| {n} | {us:.1f} | {units / us * 1e6:.3e} | {980 * units / us * 1e6 / 1e12:.1f} |")
-    del seg, fin, val
+    row.append(timed(lambda: ctx.propagate_packed_dev(0, n, 1, dp, dc, ds, None, 10, seg, 10 * n, off, fin, val, stream)))
+    row.append(timed(lambda: ctx.propagate_batch_dev(0, n, 1, dp, dc, ds, None, 10, None, fin, val, stream)))
+    print(f"| {n} | " + " | ".join(f"{x:.1f}" for x in row) + f" | {units / us * 1e6:.3e} | {980 * units / us * 1e6 / 1e12:.1f} |")
+    del seg, fin, val, off
 ctx.close()
 
 print("\n## K2 k_validity — Congested10x10 (9 obstacles) and Empty32x32\n")
