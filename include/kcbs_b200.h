@@ -127,17 +127,21 @@ KCBS_API int kcbs_propagate_batch_dev(kcbs_ctx *ctx, int robot, int64_t n, int64
                                       const int32_t *steps, int max_steps, float *seg_out, float *final_out,
                                       int32_t *valid_steps, void *stream);
 
-/* Packed (CSR) segments: the same expansion, but only VALID states are written.  The states of sample i are rows
- * offsets_out[i] .. offsets_out[i + 1] - 1 (so valid_steps[i] = offsets_out[i + 1] - offsets_out[i]) of five planes:
- * packed_out[c * packed_cap + row] is component c.  20 bytes leave the GPU per propagated state instead of
- * 20 * max_steps per sample (rows past the last valid state are not padded), in sample order, deterministically.
- *   packed_out   [5][packed_cap] floats; n * max_steps rows always suffice.  Rows that do not fit are dropped
- *                (offsets stay exact: offsets_out[n] > packed_cap tells).
+/* Packed (CSR) segments: the same expansion, without the padding of the dense layout.  Sample i owns rows
+ * offsets_out[i] .. offsets_out[i + 1] - 1 of five planes (packed_out[c * packed_cap + row] is component c); the first
+ * valid_steps[i] of them are its states, in step order.  A sample owns as many rows as it can have valid states at all:
+ * its requested duration cut where v or phi leave their bounds (both are linear in time, so that is known before
+ * anything is integrated); rows it owns but did not reach -- it left the workspace or hit an obstacle earlier -- are
+ * zero, as are the up to 3 rows that round a block of samples up to a 16-byte boundary.  On the Empty32x32 expansion
+ * workload that is 1.05 rows per valid state: ~21 bytes leave the GPU per propagated state instead of 20 * max_steps per
+ * sample.  Rows are in sample order and do not depend on how the GPU schedules the work.
+ *   packed_out   [5][packed_cap] floats; n * max_steps + 4 * (n / 256 + 1) rows always suffice.  Rows that do not fit
+ *                are dropped (offsets stay exact: offsets_out[n] > packed_cap tells).
  *   offsets_out  n + 1 ints.
  *   max_steps    at most KCBS_PACKED_MAX_STEPS (the reference's setMinMaxControlDuration(1, 10), demo_*.cpp:118).
  *   total_out    (host call) rows emitted = offsets_out[n]; may be NULL.
  * The host call cuts the batch into chunks and pipelines upload / kernel / download of consecutive chunks; the
- * download is exactly the emitted rows.  final_out / valid_steps may be NULL. */
+ * download is exactly the emitted rows.  final_out may be NULL; valid_steps may be NULL in the device call. */
 #define KCBS_PACKED_MAX_STEPS 10
 KCBS_API int kcbs_propagate_packed(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents, const float *parents,
                                    const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,

@@ -11,9 +11,9 @@ using namespace kcbs;
 
 namespace kcbs {
 
-constexpr int kPipeSlots = 3;            // chunks in flight
-constexpr int64_t kPipeMinChunk = 8192;  // samples; below this a chunk's kernel is mostly launch latency
-constexpr int kPipeChunks = 4;           // chunks a large call is cut into at least
+constexpr int kPipeSlots = 3;             // chunks in flight
+constexpr int64_t kPipeMinChunk = 32768;  // samples; smaller chunks cost more in launches and copy set-up than they hide
+constexpr int kPipeChunks = 4;            // chunks a large call is cut into at least
 
 struct PipeSlot {
     cudaStream_t stream = nullptr;
@@ -195,6 +195,8 @@ static int propagate_host(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents
         d_parents = (const float *)ctx->in0.p;
     }
 
+    // rows a chunk of cn samples can emit at most: its requested steps + the rows that align every block of samples
+    auto chunk_rows = [&](int64_t cn) { return ((cn * max_steps + 4 * (cn / 256 + 2)) + 3) & ~(int64_t)3; };
     struct Pending {
         int slot = -1;
         int64_t c0 = 0, cn = 0;
@@ -209,7 +211,7 @@ static int propagate_host(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents
         const int64_t room = std::max<int64_t>(0, std::min<int64_t>(total, packed_cap - running));
         if (room > 0)
             KCBS_CUDA(ctx, cudaMemcpy2DAsync(packed_out + running, sizeof(float) * (size_t)packed_cap, S.seg.p,
-                                             sizeof(float) * (size_t)q.cn * max_steps, sizeof(float) * (size_t)room, 5,
+                                             sizeof(float) * (size_t)chunk_rows(q.cn), sizeof(float) * (size_t)room, 5,
                                              cudaMemcpyDeviceToHost, S.stream));
         running += total;
         return KCBS_OK;
@@ -228,7 +230,8 @@ static int propagate_host(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents
             }
         }
         const size_t b_ctl = sizeof(float) * 2 * (size_t)cn, b_idx = sizeof(int32_t) * (size_t)cn;
-        const size_t b_fin = sizeof(float) * 5 * (size_t)cn, b_seg = sizeof(float) * 5 * (size_t)max_steps * (size_t)cn;
+        const size_t b_fin = sizeof(float) * 5 * (size_t)cn;
+        const size_t b_seg = packed ? sizeof(float) * 5 * (size_t)chunk_rows(cn) : sizeof(float) * 5 * (size_t)max_steps * (size_t)cn;
         if ((st = reserve(ctx, S.ctl, b_ctl)) || (st = reserve(ctx, S.idx, parent_idx ? b_idx : 0)) ||
             (st = reserve(ctx, S.steps, steps ? b_idx : 0)) || (st = reserve(ctx, S.par, par_chunked ? b_fin : 0)) ||
             (st = reserve(ctx, S.seg, (seg_out || packed) ? b_seg : 0)) || (st = reserve(ctx, S.fin, final_out ? b_fin : 0)) ||
@@ -261,7 +264,7 @@ static int propagate_host(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents
                                (int32_t *)S.valid.p);
         if (packed) {
             a.offsets = (int32_t *)S.offsets.p;
-            a.packed_cap = cn * max_steps;
+            a.packed_cap = chunk_rows(cn);
             if ((st = ensure_scan(ctx, S.scan, S.scan_ctas, propagate_grid(a), s))) return st;
             a.scan_ctl = (unsigned *)S.scan.p;
             a.scan = (unsigned long long *)((char *)S.scan.p + 16);

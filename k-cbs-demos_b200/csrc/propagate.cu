@@ -57,8 +57,11 @@ constexpr int kStageSteps = 10;    // segments up to this many steps are staged 
 //   kDirect  x, y, theta stored straight to the sample's slot of the dense segment buffer (horizons longer than
 //            kStageSteps, final-state-only calls), v / phi and the zero rows by a coalesced epilogue
 //   kDense   segments staged in shared memory, dense [5][max_steps][n] layout with zero rows past the last valid state
-//   kPacked  segments staged in shared memory, CSR layout: the valid states of sample i are rows
-//            [offsets[i], offsets[i + 1]) of five planes; nothing but valid states is written (20 B per propagated state)
+//   kPacked  segments staged in shared memory, CSR layout: sample i owns rows [offsets[i], offsets[i + 1]) of five planes,
+//            as many as it can have valid states at all (its effective duration, known before anything is integrated); the
+//            first valid_steps[i] of them hold its states, the rest (a sample that left the workspace early) are zero.
+//            Because the row count does not depend on the integration, a CTA learns its first row (a look-back over the
+//            CTAs before it) while it integrates, and the write-out is a straight, 16-byte vectorised copy of the stage.
 enum PropMode { kDirect = 0, kDense = 1, kPacked = 2 };
 
 // ROUNDS = packed pairs per thread.  2: ranks (2t, 2t+1) (long) then (S-2-2t, S-1-2t) (short) -- every thread has the same
@@ -85,13 +88,13 @@ struct __align__(16) PropStage {
 template <int SAMPLES>
 struct PackTables {
     static constexpr int kWords = kStageSteps * SAMPLES / 32;
-    unsigned short cap_off[SAMPLES];   // slot -> first stage position of its run (capacity max(st, 1) positions)
-    unsigned short off[SAMPLES];       // slot -> offset of its first valid state inside the CTA's packed range
-    unsigned start[kWords];            // bit p set: a run starts at stage position p
-    unsigned short wp[kWords];         // runs that start before word w
-    int cap_total, total;              // stage positions in use / valid states of the CTA
-    long long base;                    // first packed row of the CTA
-    int vblock;                        // sample block of this CTA (arrival order, see lookback_base)
+    unsigned short cap_off[SAMPLES];       // slot -> first stage position (= first row inside the CTA's range) of its run
+    unsigned short slot_of_run[SAMPLES];   // k-th non-empty run (in slot order) -> slot
+    unsigned start[kWords];                // bit p set: a run starts at stage position p
+    unsigned short wp[kWords];             // runs that start before word w
+    int cap_total;                         // stage positions in use = rows of the CTA (before rounding up to 4)
+    volatile long long base;               // first packed row of the CTA, -1 until the look-back has it
+    int vblock;                            // sample block of this CTA (arrival order, see lookback_base)
 };
 
 // Where state j of the sample in `slot` lives in the stage, and where the sort pass stashes (x0, y0, theta0): in the
@@ -106,7 +109,7 @@ struct StageIndex {
     }
     __device__ __forceinline__ int stash(int slot) const
     {
-        return MODE == kPacked ? (int)cap_off[slot] + max((int)steps[slot], 1) - 1 : (kStageSteps - 1) * SAMPLES + slot;
+        return MODE == kPacked ? (int)cap_off[slot] + (int)steps[slot] - 1 : (kStageSteps - 1) * SAMPLES + slot;
     }
 };
 
@@ -125,10 +128,18 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
         const long long pi = a.parent_idx ? (long long)a.parent_idx[i[e]] : (a.n_parents == 1 ? 0 : i[e]);
         t0[e] = (HAS_CONS && a.parent_time) ? a.parent_time[pi] : 0;
         if (STAGED) {  // the sort pass left the sample's inputs in shared memory (slot -1: any slot, nothing is used)
-            const int sl = max(slot[e], 0), at = six.stash(sl);
-            x0[e] = stage->xyt[0][at];
-            y0[e] = stage->xyt[1][at];
-            th0[e] = stage->xyt[2][at];
+            const int sl = max(slot[e], 0);
+            if (MODE == kPacked && st[e] == 0) {
+                // a sample without a single admissible step owns no stage position: its parent comes from global memory
+                x0[e] = a.parents[0 * a.n_parents + pi];
+                y0[e] = a.parents[1 * a.n_parents + pi];
+                th0[e] = a.parents[4 * a.n_parents + pi];
+            } else {
+                const int at = six.stash(sl);
+                x0[e] = stage->xyt[0][at];
+                y0[e] = stage->xyt[1][at];
+                th0[e] = stage->xyt[2][at];
+            }
             v0[e] = stage->v0[sl];
             phi0[e] = stage->p0[sl];
             ua[e] = stage->ua[sl];
@@ -222,6 +233,14 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         if (slot[e] < 0) continue;  // past the end of the batch
+        if (MODE == kPacked) {
+            // rows the sample owns but did not reach (it left the workspace / hit an obstacle early) leave as zeros
+            for (int j = nv[e]; j < st[e]; ++j) {
+                stage->xyt[0][at0[e] + j] = 0.0f;
+                stage->xyt[1][at0[e] + j] = 0.0f;
+                stage->xyt[2][at0[e] + j] = 0.0f;
+            }
+        }
         if (STAGED) {
             stage->nv[slot[e]] = (unsigned char)nv[e];
         } else {
@@ -410,16 +429,21 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             within[u] = atomicAdd(&s_hist[st], 1);
         }
         if (MODE == kPacked) {
-            // stage positions: every slot gets a run of max(st, 1) positions in slot order (a run per slot, so the rank of
-            // a run start IS the slot), a bit marks each run start, a per-word count makes the rank a popcount away
+            // stage positions = rows: every slot gets a run of st positions in slot order; a bit marks the start of each
+            // non-empty run and a per-word count makes "which run holds position p" a popcount away.  One scan carries
+            // both the positions (low half) and the number of non-empty runs (high half).
             __syncthreads();
-            const int cap_total = block_exclusive_scan<kPer>(
-                tid, s_warp, [&](int slot) { return max((int)s_steps[slot], 1); },
-                [&](int slot, int off) {
+            const int both = block_exclusive_scan<kPer>(
+                tid, s_warp, [&](int slot) { const int st = s_steps[slot]; return st | ((st > 0) << 16); },
+                [&](int slot, int pre) {
+                    const int off = pre & 0xffff, run = pre >> 16;
                     s_pk.cap_off[slot] = (unsigned short)off;
-                    atomicOr(&s_pk.start[off >> 5], 1u << (off & 31));
+                    if (s_steps[slot] > 0) {
+                        s_pk.slot_of_run[run] = (unsigned short)slot;
+                        atomicOr(&s_pk.start[off >> 5], 1u << (off & 31));
+                    }
                 });
-            if (tid == 0) s_pk.cap_total = cap_total;
+            if (tid == 0) s_pk.cap_total = both & 0xffff;
         }
         if (STAGED) {
             // x0, y0, theta0 borrow the sample's own last stage position, which the sample overwrites only when it
@@ -427,7 +451,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
 #pragma unroll
             for (int u = 0; u < kPer; ++u) {
                 const int slot = tid + u * kPropThreads;
-                if (b0 + slot < a.n) {
+                if (b0 + slot < a.n && (MODE != kPacked || st4[u] > 0)) {
                     const int at = six.stash(slot);
                     stage->xyt[0][at] = x0[u];
                     stage->xyt[1][at] = y0[u];
@@ -474,7 +498,14 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < kPer; ++u) s_perm[s_first[st4[u]] + within[u]] = (unsigned short)(tid + u * kPropThreads);
+    if (MODE == kPacked && tid == 0) s_pk.base = -1;
     __syncthreads();
+    if (MODE == kPacked && tid >= kPropThreads - 32) {
+        // the CTA's first row, while the other warps already integrate: the rows of a CTA (rounded up to 4, so that every
+        // CTA starts 16-byte aligned) are known now.  The last warp does it: it holds the shortest durations.
+        const long long base = lookback_base(a.scan, s_pk.vblock, (long long)((s_pk.cap_total + 3) & ~3), tid & 31);
+        if ((tid & 31) == 0) s_pk.base = base;
+    }
 
     // ---- packed pairs of neighbouring ranks: (2t, 2t+1) (long) and, with two rounds, (S-2-2t, S-1-2t) (short) ------
 #pragma unroll 1
@@ -587,47 +618,60 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
     }
 
     if (MODE == kPacked) {
-        // ---- packed write-out: the CTA's valid states leave as ONE contiguous range of every plane ----------------
+        // ---- packed write-out: the CTA's rows leave as ONE contiguous, 16-byte aligned range of every plane -----------
         __syncthreads();
-        // offsets of the samples inside the CTA's range (slot order = sample order) and the CTA's total
-        const int total = block_exclusive_scan<kPer>(
-            tid, s_warp, [&](int slot) { return (int)stage->nv[slot]; },
-            [&](int slot, int off) { s_pk.off[slot] = (unsigned short)off; });
-        if (tid < 32) {
-            const long long base = lookback_base(a.scan, s_pk.vblock, total, tid);
-            if (tid == 0) {
-                s_pk.base = base;
-                s_pk.total = total;
-            }
-        }
-        __syncthreads();
-        const long long base = s_pk.base;
+        const long long base = s_pk.base;   // (published by the last warp long ago; the barrier orders the read)
+        const int cap_total = s_pk.cap_total, rows4 = (cap_total + 3) & ~3;
 #pragma unroll
         for (int u = 0; u < kPer; ++u) {
             const int slot = tid + u * kPropThreads;
             const long long i = b0 + slot;
             if (i < a.n) {
-                a.offsets[i] = base + s_pk.off[slot];
-                if (i == a.n - 1) a.offsets[a.n] = base + total;
+                a.offsets[i] = (int)(base + s_pk.cap_off[slot]);
+                if (i == a.n - 1) a.offsets[a.n] = (int)(base + rows4);
             }
         }
-        const int cap_total = s_pk.cap_total;
         float *out = a.seg;
         const long long cap = a.packed_cap;
-        for (int p = tid; p < cap_total; p += kPropThreads) {
-            const int wd = p >> 5;
-            const int slot = (int)s_pk.wp[wd] + __popc(s_pk.start[wd] & (0xffffffffu >> (31 - (p & 31)))) - 1;
-            const int j = p - (int)s_pk.cap_off[slot];
-            if (j < (int)stage->nv[slot]) {
-                const long long o = base + s_pk.off[slot] + j;
-                if (o < cap) {
-                    const float t1 = (float)(j + 1) * w.step;
-                    __stcs(out + o, stage->xyt[0][p]);
-                    __stcs(out + cap + o, stage->xyt[1][p]);
-                    __stcs(out + 2 * cap + o, fmaf(stage->ua[slot], t1, stage->v0[slot]));   // the integrator's expressions
-                    __stcs(out + 3 * cap + o, fmaf(stage->uw[slot], t1, stage->p0[slot]));
-                    __stcs(out + 4 * cap + o, stage->xyt[2][p]);
+        const bool vec = (cap & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && base + rows4 <= cap;
+        for (int p4 = 4 * tid; p4 < rows4; p4 += 4 * kPropThreads) {
+            float X[4], Y[4], V[4], P[4], T[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int p = p4 + e;
+                X[e] = Y[e] = V[e] = P[e] = T[e] = 0.0f;
+                if (p < cap_total) {
+                    const int wd = p >> 5;
+                    const int run = (int)s_pk.wp[wd] + __popc(s_pk.start[wd] & (0xffffffffu >> (31 - (p & 31)))) - 1;
+                    const int slot = s_pk.slot_of_run[run];
+                    const int j = p - (int)s_pk.cap_off[slot];
+                    if (j < (int)stage->nv[slot]) {
+                        const float t1 = (float)(j + 1) * w.step;
+                        X[e] = stage->xyt[0][p];
+                        Y[e] = stage->xyt[1][p];
+                        T[e] = stage->xyt[2][p];
+                        V[e] = fmaf(stage->ua[slot], t1, stage->v0[slot]);   // the integrator's expressions
+                        P[e] = fmaf(stage->uw[slot], t1, stage->p0[slot]);
+                    }
                 }
+            }
+            const long long o = base + p4;
+            if (vec) {
+                __stcs(reinterpret_cast<float4 *>(out + o), make_float4(X[0], X[1], X[2], X[3]));
+                __stcs(reinterpret_cast<float4 *>(out + cap + o), make_float4(Y[0], Y[1], Y[2], Y[3]));
+                __stcs(reinterpret_cast<float4 *>(out + 2 * cap + o), make_float4(V[0], V[1], V[2], V[3]));
+                __stcs(reinterpret_cast<float4 *>(out + 3 * cap + o), make_float4(P[0], P[1], P[2], P[3]));
+                __stcs(reinterpret_cast<float4 *>(out + 4 * cap + o), make_float4(T[0], T[1], T[2], T[3]));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (o + e < cap) {
+                        __stcs(out + o + e, X[e]);
+                        __stcs(out + cap + o + e, Y[e]);
+                        __stcs(out + 2 * cap + o + e, V[e]);
+                        __stcs(out + 3 * cap + o + e, P[e]);
+                        __stcs(out + 4 * cap + o + e, T[e]);
+                    }
             }
         }
         // the last CTA to get here leaves the look-back workspace clean for the next launch (every CTA has finished its
