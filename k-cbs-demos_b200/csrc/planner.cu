@@ -53,7 +53,8 @@ struct RrtWorkspace {
     float *s_fin = nullptr;        // [dim][n_samples]
     int *s_valid = nullptr;        // [n_samples]
     int *sel = nullptr;            // [n_targets] sample chosen for each target this round, or -1
-    int *counters = nullptr;       // [0] = node count, [1] = rounds completed, [2] = edges of the extracted path
+    int *counters = nullptr;       // [0], [1] = node count (ring by round parity), [2] = rounds completed, [3] = append ticket,
+                                   // [4] = edges of the extracted path
     unsigned long long *goal_key = nullptr;  // packed (time << 32 | node) of the best goal node
     ConsDesc *cons = nullptr;
     float *cons_states = nullptr;
@@ -110,8 +111,10 @@ __global__ void k_rrt_init(RrtArgs a, const float *start)
         for (int c = 0; c < 5 * NC; ++c) a.ws.nodes[c * M] = start[c];
         for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M] = 0.f;
         a.ws.parent[0] = -1; a.ws.time[0] = 0; a.ws.steps[0] = 0;
-        a.ws.counters[0] = 1;
-        a.ws.counters[1] = 0;
+        a.ws.counters[0] = 1;   // node count seen by round 0 (parity ring, see rrt_node_count)
+        a.ws.counters[1] = 1;
+        a.ws.counters[2] = 0;   // rounds completed
+        a.ws.counters[3] = 0;   // CTA ticket of k_rrt_append
         *a.ws.goal_key = ~0ull;
     }
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -146,18 +149,32 @@ __device__ __forceinline__ void rrt_target(const RrtArgs &a, int t, float q[5 * 
 }
 
 constexpr int kNNThreads = 256;
-constexpr int kNNChunk = 256;   // nodes per CTA (small: the grid must fill 148 SMs while the tree is still small)
+constexpr int kNNChunkMax = 256;   // nodes per CTA at most (the chunk shrinks while the tree is small, so that the grid fills 148 SMs)
+
+// nodes per CTA for a tree of at most `bound` nodes: about 64 chunks, multiples of 32, within [32, kNNChunkMax]
+inline int nn_chunk(long long bound)
+{
+    long long c = (bound / 64 + 31) / 32 * 32;
+    return (int)std::max<long long>(32, std::min<long long>(kNNChunkMax, c));
+}
+
+// node count of the tree at the start of `round`: counters live in a two-entry ring indexed by the round's parity, so a
+// round's kernels read one entry while k_rrt_append writes the other
+__device__ __forceinline__ int rrt_node_count(const RrtArgs &a) { return min(a.ws.counters[a.round & 1u], a.ws.max_nodes); }
 
 // grid = (ceil(n_targets / 256), chunks of the largest tree this round can have): every thread owns one target and scans
-// one chunk of nodes staged through shared memory; the node count is read on the device (the host does not know it).
+// one chunk of nodes staged through shared memory (car 0 as float4 + heading; the node count is read on the device: the
+// host does not know it).  Four independent running minima keep four nodes in flight per thread.
 template <int NC>
-__global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a)
+__global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a, int chunk)
 {
     constexpr int D = 5 * NC;
-    __shared__ float s[D][kNNThreads];
+    __shared__ float4 s_r[kNNChunkMax];             // x, y, v, phi of car 0
+    __shared__ float s_t[kNNChunkMax];              // theta of car 0
+    __shared__ float s_o[NC == 2 ? 5 : 1][kNNChunkMax];   // car 1 (merged pair only)
     if (rrt_done(a)) return;
-    const int n_nodes = min(a.ws.counters[0], a.ws.max_nodes);
-    const int n0 = blockIdx.y * kNNChunk, n1 = min(n0 + kNNChunk, n_nodes);
+    const int n_nodes = rrt_node_count(a);
+    const int n0 = blockIdx.y * chunk, n1 = min(n0 + chunk, n_nodes);
     if (n0 >= n_nodes) return;
     const int B = a.n_targets, M = a.ws.max_nodes;
     const int t = blockIdx.x * kNNThreads + threadIdx.x;
@@ -166,38 +183,53 @@ __global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a)
     rrt_target<NC>(a, min(t, B - 1), q);
     if (live && blockIdx.y == 0)
         for (int c = 0; c < D; ++c) a.ws.targets[c * B + t] = q[c];
-    float best = 3.0e38f;
-    int best_i = 0;
-    for (int base = n0; base < n1; base += kNNThreads) {
-        const int i = base + threadIdx.x;
-        __syncthreads();
-        if (i < n1)
-            for (int c = 0; c < D; ++c) s[c][threadIdx.x] = a.ws.nodes[c * M + i];
-        __syncthreads();
-        const int m = min(kNNThreads, n1 - base);
-        for (int j = 0; j < m; ++j) {
-            // the real-vector part of the first car alone already bounds the distance from below: most nodes are rejected
-            // on the squared L2 without the square root and the SO2 term
-            const float dx = s[0][j] - q[0], dy = s[1][j] - q[1], dv = s[2][j] - q[2], dp = s[3][j] - q[3];
-            const float l2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dv, dv, dp * dp)));
-            if (l2 < best * best) {
-                float dth = fabsf(s[4][j] - q[4]);
-                dth = dth > kPi ? kTwoPi - dth : dth;
-                float d = sqrtf(l2) + dth;
-                if (NC == 2) {
-                    float o[5];
+    const int m = n1 - n0;
+    for (int j = threadIdx.x; j < m; j += kNNThreads) {
+        const int i = n0 + j;
+        s_r[j] = make_float4(a.ws.nodes[i], a.ws.nodes[M + i], a.ws.nodes[2 * M + i], a.ws.nodes[3 * M + i]);
+        s_t[j] = a.ws.nodes[4 * M + i];
+        if (NC == 2)
+            for (int c = 0; c < 5; ++c) s_o[c][j] = a.ws.nodes[(5 + c) * M + i];
+    }
+    __syncthreads();
+    float best[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+    int best_j[4] = {0, 0, 0, 0};
+    auto visit = [&](int j, int k) {
+        // the real-vector part of the first car alone already bounds the distance from below: most nodes are rejected
+        // on the squared L2 without the square root and the SO2 term
+        const float4 r = s_r[j];
+        const float dx = r.x - q[0], dy = r.y - q[1], dv = r.z - q[2], dp = r.w - q[3];
+        const float l2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dv, dv, dp * dp)));
+        if (l2 < best[k] * best[k]) {
+            float dth = fabsf(s_t[j] - q[4]);
+            dth = dth > kPi ? kTwoPi - dth : dth;
+            float d = sqrtf(l2) + dth;
+            if (NC == 2) {
+                float o[5];
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) o[c] = s[5 * (NC - 1) + c][j];
-                    d += car_distance(o, q + 5 * (NC - 1));
-                }
-                if (d < best) {
-                    best = d;
-                    best_i = base + j;
-                }
+                for (int c = 0; c < 5; ++c) o[c] = s_o[c][j];
+                d += car_distance(o, q + 5 * (NC - 1));
+            }
+            if (d < best[k]) {
+                best[k] = d;
+                best_j[k] = j;
             }
         }
+    };
+    int j = 0;
+    for (; j + 4 <= m; j += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) visit(j + k, k);
     }
-    if (live) atomicMin(a.ws.nn + t, ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)best_i);
+    for (; j < m; ++j) visit(j, 0);
+    // smallest distance, ties to the smallest node index (what a sequential scan with `<` finds)
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+        if (best[k] < best[0] || (best[k] == best[0] && best_j[k] < best_j[0])) {
+            best[0] = best[k];
+            best_j[0] = best_j[k];
+        }
+    if (live) atomicMin(a.ws.nn + t, ((unsigned long long)__float_as_uint(best[0]) << 32) | (unsigned)(n0 + best_j[0]));
 }
 
 // (parent, control, duration) for every sample: sample s belongs to target s / n_controls.
@@ -285,80 +317,109 @@ __global__ void __launch_bounds__(256) k_rrt_select(RrtArgs a)
     }
 }
 
-// Appends the chosen samples to the tree in TARGET ORDER (one CTA, block-wide prefix sum of the "found one" flags), so
-// that node indices -- and with them nearest-neighbour ties, the goal node and the whole plan -- depend only on the
-// seed, never on the order in which warps of k_rrt_select happen to finish.  Reports the round to the host.
+// Appends the chosen samples to the tree in TARGET ORDER, so that node indices -- and with them nearest-neighbour ties,
+// the goal node and the whole plan -- depend only on the seed, never on the order in which warps of k_rrt_select happen
+// to finish.  CTA b owns targets [256 b, 256 b + 256); the position of a target's node is the node count plus the number of
+// chosen samples before it, which every CTA counts for itself over the (tiny) selection array.  The last CTA to finish
+// publishes the new node count (other parity, see rrt_node_count) and reports the round to the host.
+constexpr int kAppendThreads = 256;
 template <int NC>
-__global__ void __launch_bounds__(1024) k_rrt_append(const __grid_constant__ DevWorld w, RrtArgs a)
+__global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_constant__ DevWorld w, RrtArgs a)
 {
     constexpr int D = 5 * NC;
-    __shared__ int s_warp[32];
-    __shared__ int s_base;
+    __shared__ int s_warp[kAppendThreads / 32], s_wtot[kAppendThreads / 32];
+    __shared__ int s_before, s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int B = a.n_targets, C = a.n_controls, n = B * C, M = a.ws.max_nodes;
     RrtProgress *slot = a.ws.d_progress + (a.round % kRrtDepth);
-    if (rrt_done(a)) {   // (uniform: nobody has written the key yet in this launch)
-        if (tid == 0) {
+    if (rrt_done(a)) {   // (uniform: the key cannot change while cancelled rounds run)
+        if (tid == 0 && blockIdx.x == 0) {
             slot->goal = *a.ws.goal_key;
-            slot->nodes = a.ws.counters[0];
-            slot->rounds = a.ws.counters[1];
+            slot->nodes = a.ws.counters[a.round & 1u];
+            slot->rounds = a.ws.counters[2];
+            a.ws.counters[(a.round + 1u) & 1u] = a.ws.counters[a.round & 1u];
         }
         return;
     }
-    __syncthreads();     // every thread has read the key before anybody may set it below
-    if (tid == 0) s_base = a.ws.counters[0];
-    __syncthreads();
-    for (int t0 = 0; t0 < B; t0 += 1024) {
+    const int n_nodes = rrt_node_count(a);
+    // chosen samples before this CTA's targets, and in all targets
+    int before = 0, total = 0;
+    for (int t0 = 0; t0 < B; t0 += kAppendThreads) {
         const int t = t0 + tid;
-        const int s = t < B ? a.ws.sel[t] : -1;
-        const unsigned bal = __ballot_sync(0xffffffffu, s >= 0);
-        if (lane == 0) s_warp[wid] = __popc(bal);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int q = 0; q < 32; ++q) {
-            before += q < wid ? s_warp[q] : 0;
-            total += s_warp[q];
+        const int cnt = __popc(__ballot_sync(0xffffffffu, t < B && a.ws.sel[t] >= 0));
+        if (lane == 0) {
+            total += cnt;
+            if (t0 + wid * 32 < (int)blockIdx.x * kAppendThreads) before += cnt;
         }
-        const int idx = s_base + before + __popc(bal & ((1u << lane) - 1u));
-        if (s >= 0 && idx < M) {
-            const int par = a.ws.s_parent[s], nv = a.ws.s_valid[s];
-            float f[D];
-            for (int c = 0; c < D; ++c) {
-                f[c] = a.ws.s_fin[c * n + s];
-                a.ws.nodes[c * M + idx] = f[c];
-            }
-            a.ws.parent[idx] = par;
-            const int t_node = a.ws.time[par] + nv;
-            a.ws.time[idx] = t_node;
-            for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M + idx] = a.ws.s_ctrl[c * n + s];
-            a.ws.steps[idx] = nv;
-            // (a path that would not fit the caller's buffer is never a solution: it would come back truncated)
-            bool in_goal = t_node < a.max_T;
-#pragma unroll
-            for (int car = 0; car < NC; ++car) {
-                const float gx = f[5 * car] - a.goal[2 * car], gy = f[5 * car + 1] - a.goal[2 * car + 1];
-                const float d = sqrtf(fmaf(gx, gx, gy * gy));
-                // GoalRegion2ndOrderCar: distanceGoal <= threshold (GoalRegionDatabase.h:48-55);
-                // GoalRegionTwo2ndOrderCars: both distances < threshold (:61-108)
-                in_goal &= NC == 1 ? d <= a.goal_radius : d < a.goal_radius;
-            }
-            if (in_goal && a.n_cons > 0) {
-#pragma unroll
-                for (int car = 0; car < NC; ++car)
-                    in_goal = in_goal && parked_state_clear(w, a, a.robot[car], t_node, f[5 * car], f[5 * car + 1], f[5 * car + 4]);
-            }
-            if (in_goal) atomicMin(a.ws.goal_key, ((unsigned long long)(unsigned)t_node << 32) | (unsigned)idx);
-        }
-        __syncthreads();
-        if (tid == 0) s_base = min(s_base + total, M);
-        __syncthreads();
     }
+    if (lane == 0) {
+        s_warp[wid] = before;
+        s_wtot[wid] = total;
+    }
+    __syncthreads();
     if (tid == 0) {
-        a.ws.counters[0] = s_base;
-        a.ws.counters[1] = (int)a.round + 1;
+        int bsum = 0;
+        for (int q = 0; q < kAppendThreads / 32; ++q) bsum += s_warp[q];
+        s_before = bsum;
+    }
+    int tsum = 0;
+    for (int q = 0; q < kAppendThreads / 32; ++q) tsum += s_wtot[q];
+    __syncthreads();
+    // this CTA's targets
+    const int t = blockIdx.x * kAppendThreads + tid;
+    const int s_idx = t < B ? a.ws.sel[t] : -1;
+    const unsigned bal = __ballot_sync(0xffffffffu, s_idx >= 0);
+    __syncthreads();
+    if (lane == 0) s_warp[wid] = __popc(bal);
+    __syncthreads();
+    int in_cta = 0;
+    for (int q = 0; q < wid; ++q) in_cta += s_warp[q];
+    const int idx = n_nodes + s_before + in_cta + __popc(bal & ((1u << lane) - 1u));
+    if (s_idx >= 0 && idx < M) {
+        const int s = s_idx;
+        const int par = a.ws.s_parent[s], nv = a.ws.s_valid[s];
+        float f[D];
+        for (int c = 0; c < D; ++c) {
+            f[c] = a.ws.s_fin[c * n + s];
+            a.ws.nodes[c * M + idx] = f[c];
+        }
+        a.ws.parent[idx] = par;
+        const int t_node = a.ws.time[par] + nv;
+        a.ws.time[idx] = t_node;
+        for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M + idx] = a.ws.s_ctrl[c * n + s];
+        a.ws.steps[idx] = nv;
+        // (a path that would not fit the caller's buffer is never a solution: it would come back truncated)
+        bool in_goal = t_node < a.max_T;
+#pragma unroll
+        for (int car = 0; car < NC; ++car) {
+            const float gx = f[5 * car] - a.goal[2 * car], gy = f[5 * car + 1] - a.goal[2 * car + 1];
+            const float d = sqrtf(fmaf(gx, gx, gy * gy));
+            // GoalRegion2ndOrderCar: distanceGoal <= threshold (GoalRegionDatabase.h:48-55);
+            // GoalRegionTwo2ndOrderCars: both distances < threshold (:61-108)
+            in_goal &= NC == 1 ? d <= a.goal_radius : d < a.goal_radius;
+        }
+        if (in_goal && a.n_cons > 0) {
+#pragma unroll
+            for (int car = 0; car < NC; ++car)
+                in_goal = in_goal && parked_state_clear(w, a, a.robot[car], t_node, f[5 * car], f[5 * car + 1], f[5 * car + 4]);
+        }
+        if (in_goal) atomicMin(a.ws.goal_key, ((unsigned long long)(unsigned)t_node << 32) | (unsigned)idx);
+    }
+    // the last CTA of the round publishes the node count and reports to the host
+    __syncthreads();
+    if (tid == 0) {
         __threadfence();
+        s_last = atomicAdd(a.ws.counters + 3, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        const int count = min(n_nodes + tsum, M);
+        a.ws.counters[(a.round + 1u) & 1u] = count;
+        a.ws.counters[2] = (int)a.round + 1;
+        a.ws.counters[3] = 0;
         slot->goal = *(volatile unsigned long long *)a.ws.goal_key;
-        slot->nodes = s_base;
+        slot->nodes = count;
         slot->rounds = (int)a.round + 1;
     }
 }
@@ -417,14 +478,14 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
             (st = dev_alloc(ctx, ws.ctrl, U * M)) || (st = dev_alloc(ctx, ws.steps, M)) || (st = dev_alloc(ctx, ws.targets, D * B)) ||
             (st = dev_alloc(ctx, ws.nn, B)) || (st = dev_alloc(ctx, ws.s_parent, S)) || (st = dev_alloc(ctx, ws.s_ctrl, U * S)) ||
             (st = dev_alloc(ctx, ws.s_steps, S)) || (st = dev_alloc(ctx, ws.s_fin, D * S)) || (st = dev_alloc(ctx, ws.s_valid, S)) || (st = dev_alloc(ctx, ws.sel, B)) ||
-            (st = dev_alloc(ctx, ws.counters, 4)) || (st = dev_alloc(ctx, ws.goal_key, 1)) || (st = dev_alloc(ctx, ws.path_nodes, PC)) ||
+            (st = dev_alloc(ctx, ws.counters, 8)) || (st = dev_alloc(ctx, ws.goal_key, 1)) || (st = dev_alloc(ctx, ws.path_nodes, PC)) ||
             (st = dev_alloc(ctx, ws.path_ctrl, U * PC)) || (st = dev_alloc(ctx, ws.path_steps, PC)) ||
             (st = dev_alloc(ctx, ws.path_parent, PC)) || (st = dev_alloc(ctx, ws.path_valid, PC)) ||
             (st = dev_alloc(ctx, ws.path_seg, D * (size_t)KCBS_MAX_STEPS * PC)))
             return st;
         KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_progress, sizeof(RrtProgress) * kRrtDepth, cudaHostAllocMapped));
         KCBS_CUDA(ctx, cudaHostGetDevicePointer((void **)&ws.d_progress, ws.h_progress, 0));
-        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_counters, 4 * sizeof(int), cudaHostAllocDefault));
+        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_counters, 8 * sizeof(int), cudaHostAllocDefault));
         for (cudaEvent_t &e : ws.ev) KCBS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ws.max_nodes = p.max_nodes;
         ws.n_samples = n_samples;
@@ -494,7 +555,7 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
                     const int32_t *cons_offset, const float *cons_states, int max_T, float *traj_out, int32_t *T_out,
                     kcbs_rrt_stats *stats)
 {
-    constexpr int D = 5 * NC, U = 2 * NC;
+    constexpr int D = 5 * NC;
     const double t_begin = now_s();
     int st = check_rrt_params(ctx, p);
     if (st) return st;
@@ -577,27 +638,28 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         a.round = (unsigned)queued;
         // the tree has at most 1 + round * n_targets nodes when this round starts
         const long long bound = std::min<long long>(p.max_nodes, 1 + (long long)queued * p.n_targets);
-        dim3 g((p.n_targets + kNNThreads - 1) / kNNThreads, (unsigned)((bound + kNNChunk - 1) / kNNChunk));
-        k_rrt_nearest<NC><<<g, kNNThreads, 0, s>>>(a);
+        const int chunk = nn_chunk(bound);
+        dim3 g((p.n_targets + kNNThreads - 1) / kNNThreads, (unsigned)((bound + chunk - 1) / chunk));
+        k_rrt_nearest<NC><<<g, kNNThreads, 0, s>>>(a, chunk);
         k_rrt_samples<NC><<<(n + 255) / 256, 256, 0, s>>>(a);
         if (NC == 1)
             KCBS_CUDA(ctx, launch_propagate(ctx->world, pa, s));
         else
             KCBS_CUDA(ctx, launch_propagate_pair(ctx->world, qa, s));
         k_rrt_select<NC><<<(p.n_targets * 32 + 255) / 256, 256, 0, s>>>(a);
-        k_rrt_append<NC><<<1, 1024, 0, s>>>(ctx->world, a);
+        k_rrt_append<NC><<<(p.n_targets + kAppendThreads - 1) / kAppendThreads, kAppendThreads, 0, s>>>(ctx->world, a);
         KCBS_CUDA(ctx, cudaEventRecord(ws.ev[queued % kRrtDepth], s));
         ctx->launches += 5;
         ++queued;
     }
     if (goal == ~0ull) {
         // drain: the final word is on the device (rounds queued after the goal was found did nothing)
-        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters, ws.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters, ws.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
         KCBS_CUDA(ctx, cudaMemcpyAsync(&ws.h_progress[0].goal, ws.goal_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         KCBS_CUDA(ctx, cudaStreamSynchronize(s));
         goal = ws.h_progress[0].goal;
-        n_nodes = std::min(ws.h_counters[0], p.max_nodes);
-        iters = ws.h_counters[1];
+        iters = ws.h_counters[2];
+        n_nodes = std::min(ws.h_counters[iters & 1], p.max_nodes);   // the entry the next round would have read
     } else {
         KCBS_CUDA(ctx, cudaStreamSynchronize(s));   // `desc` and the start state were still in flight
     }
@@ -609,12 +671,12 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         for (int c = 0; c < D; ++c) traj_out[(size_t)c * max_T] = start[c];
         T = 1;
         if (goal_node != 0) {
-            int *d_n = ws.counters + 2;
+            int *d_n = ws.counters + 4;
             // (edge count first: the control planes of the path are written with exactly that stride)
             k_rrt_path<NC><<<1, 32, 0, s>>>(a, goal_node, ws.path_cap, d_n);
-            KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters + 2, d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
+            KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters + 4, d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
             KCBS_CUDA(ctx, cudaStreamSynchronize(s));
-            const int E = ws.h_counters[2];
+            const int E = ws.h_counters[4];
             if (NC == 1) {
                 PropArgs pe = pa;
                 pe.n = E; pe.parent_idx = ws.path_parent; pe.controls = ws.path_ctrl; pe.steps = ws.path_steps;

@@ -350,8 +350,9 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         if (tid == 0) s_pk.vblock = (int)atomicAdd(a.scan_ctl, 1u);
         for (int q = tid; q < PackTables<kSamples>::kWords; q += kPropThreads) s_pk.start[q] = 0u;
     }
-    __syncthreads();
-    const long long b0 = (long long)(MODE == kPacked ? s_pk.vblock : (int)blockIdx.x) * kSamples;
+    // (kPacked: the block of samples is the ticket's, which is blockIdx.x unless CTAs started out of order; the loads
+    // below are issued for that guess while the ticket is still on its way and repeated in the rare other case)
+    long long b0 = (long long)blockIdx.x * kSamples;
     StageIndex<MODE, kSamples> six;
     six.cap_off = s_pk.cap_off;
     six.steps = s_steps;
@@ -364,23 +365,31 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         long long ii[kPer], pi[kPer];
         int st_req[kPer];
         float v0[kPer], phi0[kPer], ua[kPer], uw[kPer], x0[kPer], y0[kPer], th0[kPer];
+        auto load_samples = [&]() {
 #pragma unroll
-        for (int u = 0; u < kPer; ++u) {
-            ii[u] = min(b0 + tid + u * kPropThreads, a.n - 1);
-            pi[u] = a.parent_idx ? (long long)a.parent_idx[ii[u]] : (a.n_parents == 1 ? 0 : ii[u]);
-            st_req[u] = a.steps ? a.steps[ii[u]] : a.max_steps;
-            ua[u] = a.controls[ii[u]];
-            uw[u] = a.controls[a.n + ii[u]];
-        }
-#pragma unroll
-        for (int u = 0; u < kPer; ++u) {
-            v0[u] = a.parents[2 * a.n_parents + pi[u]];
-            phi0[u] = a.parents[3 * a.n_parents + pi[u]];
-            if (STAGED) {
-                x0[u] = a.parents[0 * a.n_parents + pi[u]];
-                y0[u] = a.parents[1 * a.n_parents + pi[u]];
-                th0[u] = a.parents[4 * a.n_parents + pi[u]];
+            for (int u = 0; u < kPer; ++u) {
+                ii[u] = min(b0 + tid + u * kPropThreads, a.n - 1);
+                pi[u] = a.parent_idx ? (long long)a.parent_idx[ii[u]] : (a.n_parents == 1 ? 0 : ii[u]);
+                st_req[u] = a.steps ? a.steps[ii[u]] : a.max_steps;
+                ua[u] = a.controls[ii[u]];
+                uw[u] = a.controls[a.n + ii[u]];
             }
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+                v0[u] = a.parents[2 * a.n_parents + pi[u]];
+                phi0[u] = a.parents[3 * a.n_parents + pi[u]];
+                if (STAGED) {
+                    x0[u] = a.parents[0 * a.n_parents + pi[u]];
+                    y0[u] = a.parents[1 * a.n_parents + pi[u]];
+                    th0[u] = a.parents[4 * a.n_parents + pi[u]];
+                }
+            }
+        };
+        load_samples();
+        __syncthreads();   // the histogram is clear (and, kPacked, the ticket is in)
+        if (MODE == kPacked && s_pk.vblock != (int)blockIdx.x) {
+            b0 = (long long)s_pk.vblock * kSamples;
+            load_samples();
         }
 #pragma unroll
         for (int u = 0; u < kPer; ++u) {
@@ -503,8 +512,21 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
     if (MODE == kPacked && tid >= kPropThreads - 32) {
         // the CTA's first row, while the other warps already integrate: the rows of a CTA (rounded up to 4, so that every
         // CTA starts 16-byte aligned) are known now.  The last warp does it: it holds the shortest durations.
-        const long long base = lookback_base(a.scan, s_pk.vblock, (long long)((s_pk.cap_total + 3) & ~3), tid & 31);
-        if ((tid & 31) == 0) s_pk.base = base;
+        const int lane = tid & 31;
+        const long long base = lookback_base(a.scan, s_pk.vblock, (long long)((s_pk.cap_total + 3) & ~3), lane);
+        if (lane == 0) s_pk.base = base;
+        // this CTA is through with the look-back workspace; the last CTA of the grid to get here leaves it clean for the
+        // next launch (also off the critical path: that CTA still has its integration ahead)
+        unsigned done = 0;
+        if (lane == 0) done = atomicAdd(a.scan_ctl + 1, 1u);
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done == gridDim.x - 1) {
+            for (unsigned q = lane; q < gridDim.x; q += 32) a.scan[q] = 0ull;
+            if (lane == 0) {
+                a.scan_ctl[0] = 0u;
+                a.scan_ctl[1] = 0u;
+            }
+        }
     }
 
     // ---- packed pairs of neighbouring ranks: (2t, 2t+1) (long) and, with two rounds, (S-2-2t, S-1-2t) (short) ------
@@ -672,21 +694,6 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                         __stcs(out + 3 * cap + o + e, P[e]);
                         __stcs(out + 4 * cap + o + e, T[e]);
                     }
-            }
-        }
-        // the last CTA to get here leaves the look-back workspace clean for the next launch (every CTA has finished its
-        // look-back before it counts itself done)
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            s_warp[0] = atomicAdd(a.scan_ctl + 1, 1u) == gridDim.x - 1;
-        }
-        __syncthreads();
-        if (s_warp[0]) {
-            for (unsigned q = tid; q < gridDim.x; q += kPropThreads) a.scan[q] = 0ull;
-            if (tid == 0) {
-                a.scan_ctl[0] = 0u;
-                a.scan_ctl[1] = 0u;
             }
         }
     }

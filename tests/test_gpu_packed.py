@@ -37,7 +37,7 @@ def check_packed(ctx, robot, parents, controls, steps, parent_idx=None, max_step
     req = np.full(n, max_steps) if steps is None else np.clip(steps, 0, max_steps)
     cap = np.diff(offsets)
     assert (cap >= valid).all() and (cap <= req + 3).all()      # (+3: a block of samples starts 16-byte aligned)
-    assert total <= valid.sum() * 1.6 + 4 * (n // 256 + 2)
+    assert total <= req.sum() + 4 * (n // 256 + 2)
     want = dense_rows(seg, valid)
     got, live = packed_rows(packed, offsets, valid)
     assert (got.view(np.uint32) == want.view(np.uint32)).all(), "packed rows differ from the dense segments"
