@@ -229,11 +229,34 @@ def run_reference(args):
         "note": "reference = CPU oracle port (OMPL K-CBS fork + Boost are not installable here); the reference is "
                 "single-threaded, this arm uses every host thread",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line.  Libraries print banners there (NCCL's version line, for one), so file
+    descriptor 1 is pointed at stderr for the whole run and the line goes to a private duplicate of the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -540,7 +563,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": int(launches),
             "secondary": secondary,
         }
-        print(json.dumps(line))
+        emit(line)
     pool.shutdown()
     for c in ctxs:
         c.close()
