@@ -2,6 +2,7 @@
 // calls, and the host-buffer calls as a chunked pipeline (H2D of chunk k+1 and the kernel of chunk k run while chunk
 // k-1 is copied back), dense or packed (CSR) segments.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -12,15 +13,25 @@ using namespace kcbs;
 namespace kcbs {
 
 constexpr int kPipeSlots = 3;             // chunks in flight
-constexpr int64_t kPipeMinChunk = 32768;  // samples; smaller chunks cost more in launches and copy set-up than they hide
 constexpr int kPipeChunks = 4;            // chunks a large call is cut into at least
+// samples per chunk at least: smaller chunks cost more in launches and copy set-up than they hide (KCBS_PIPE_MIN_CHUNK
+// overrides it for experiments)
+static int64_t pipe_min_chunk()
+{
+    static const int64_t v = [] {
+        const char *e = std::getenv("KCBS_PIPE_MIN_CHUNK");
+        const long long x = e ? std::atoll(e) : 0;
+        return (int64_t)(x >= 2048 ? x : 32768);
+    }();
+    return v;
+}
 
 struct PipeSlot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     DevBuf par, ctl, idx, steps, seg, fin, valid, offsets, scan;
     int scan_ctas = 0;
-    int32_t *h_offsets = nullptr;  // pinned: chunk-local offsets (packed mode)
+    int32_t *h_offsets = nullptr;  // pinned: chunk-local offsets [cn + 1], then the valid counts [cn] (packed mode: one copy)
     size_t h_offsets_cap = 0;
 };
 
@@ -181,7 +192,7 @@ static int propagate_host(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents
     HostPipeline &P = *ctx->pipe;
 
     // chunks: multiples of 2048 samples (whole CTAs of either shape, 16-byte aligned planes)
-    int64_t chunk = std::max<int64_t>(kPipeMinChunk, (n + kPipeChunks - 1) / kPipeChunks);
+    int64_t chunk = std::max<int64_t>(pipe_min_chunk(), (n + kPipeChunks - 1) / kPipeChunks);
     chunk = (chunk + 2047) / 2048 * 2048;
     const int n_chunks = (int)((n + chunk - 1) / chunk);
     const bool par_chunked = !parent_idx && n_parents == n && n_parents != 1;   // sample i starts at parent i
@@ -208,6 +219,7 @@ static int propagate_host(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents
         const int64_t total = S.h_offsets[q.cn];
         for (int64_t i = 0; i < q.cn; ++i) offsets_out[q.c0 + i] = (int32_t)(running + S.h_offsets[i]);
         offsets_out[q.c0 + q.cn] = (int32_t)(running + total);
+        if (valid_steps) std::memcpy(valid_steps + q.c0, S.h_offsets + q.cn + 1, sizeof(int32_t) * (size_t)q.cn);
         const int64_t room = std::max<int64_t>(0, std::min<int64_t>(total, packed_cap - running));
         if (room > 0)
             KCBS_CUDA(ctx, cudaMemcpy2DAsync(packed_out + running, sizeof(float) * (size_t)packed_cap, S.seg.p,
@@ -235,13 +247,13 @@ static int propagate_host(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents
         if ((st = reserve(ctx, S.ctl, b_ctl)) || (st = reserve(ctx, S.idx, parent_idx ? b_idx : 0)) ||
             (st = reserve(ctx, S.steps, steps ? b_idx : 0)) || (st = reserve(ctx, S.par, par_chunked ? b_fin : 0)) ||
             (st = reserve(ctx, S.seg, (seg_out || packed) ? b_seg : 0)) || (st = reserve(ctx, S.fin, final_out ? b_fin : 0)) ||
-            (st = reserve(ctx, S.valid, b_idx)) || (st = reserve(ctx, S.offsets, packed ? b_idx + sizeof(int32_t) : 0)))
+            (st = reserve(ctx, S.valid, packed ? 0 : b_idx)) || (st = reserve(ctx, S.offsets, packed ? 2 * b_idx + sizeof(int32_t) : 0)))
             return st;
-        if (packed && S.h_offsets_cap < (size_t)cn + 1) {
+        if (packed && S.h_offsets_cap < 2 * (size_t)cn + 1) {
             if (S.h_offsets) KCBS_CUDA(ctx, cudaFreeHost(S.h_offsets));
             S.h_offsets = nullptr;
-            KCBS_CUDA(ctx, cudaHostAlloc((void **)&S.h_offsets, sizeof(int32_t) * ((size_t)chunk + 1), cudaHostAllocDefault));
-            S.h_offsets_cap = (size_t)chunk + 1;
+            KCBS_CUDA(ctx, cudaHostAlloc((void **)&S.h_offsets, sizeof(int32_t) * (2 * (size_t)chunk + 1), cudaHostAllocDefault));
+            S.h_offsets_cap = 2 * (size_t)chunk + 1;
         }
         // inputs of the chunk: planes of the host batch have stride n, planes of the chunk stride cn
         KCBS_CUDA(ctx, cudaMemcpy2DAsync(S.ctl.p, sizeof(float) * (size_t)cn, controls + c0, sizeof(float) * (size_t)n,
@@ -261,7 +273,7 @@ static int propagate_host(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents
         PropArgs a = make_args(ctx, robot, cn, np, dp, parent_idx ? (const int32_t *)S.idx.p : nullptr, (const float *)S.ctl.p,
                                steps ? (const int32_t *)S.steps.p : nullptr, max_steps,
                                (seg_out || packed) ? (float *)S.seg.p : nullptr, final_out ? (float *)S.fin.p : nullptr,
-                               (int32_t *)S.valid.p);
+                               packed ? (int32_t *)S.offsets.p + cn + 1 : (int32_t *)S.valid.p);
         if (packed) {
             a.offsets = (int32_t *)S.offsets.p;
             a.packed_cap = chunk_rows(cn);
@@ -272,12 +284,13 @@ static int propagate_host(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents
         KCBS_CUDA(ctx, launch_propagate(ctx->world, a, s));
         ctx->launches += 1;
         // results of the chunk
-        if (valid_steps) KCBS_CUDA(ctx, cudaMemcpyAsync(valid_steps + c0, S.valid.p, b_idx, cudaMemcpyDeviceToHost, s));
+        if (valid_steps && !packed) KCBS_CUDA(ctx, cudaMemcpyAsync(valid_steps + c0, S.valid.p, b_idx, cudaMemcpyDeviceToHost, s));
         if (final_out)
             KCBS_CUDA(ctx, cudaMemcpy2DAsync(final_out + c0, sizeof(float) * (size_t)n, S.fin.p, sizeof(float) * (size_t)cn,
                                              sizeof(float) * (size_t)cn, 5, cudaMemcpyDeviceToHost, s));
         if (packed) {
-            KCBS_CUDA(ctx, cudaMemcpyAsync(S.h_offsets, S.offsets.p, b_idx + sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            // offsets and (right behind them) the valid counts come down in one copy
+            KCBS_CUDA(ctx, cudaMemcpyAsync(S.h_offsets, S.offsets.p, (valid_steps ? 2 : 1) * b_idx + sizeof(int32_t), cudaMemcpyDeviceToHost, s));
             KCBS_CUDA(ctx, cudaEventRecord(S.done, s));
             if (pending.slot >= 0 && (st = finish_packed_chunk(pending))) return st;
             pending.slot = c % kPipeSlots;
