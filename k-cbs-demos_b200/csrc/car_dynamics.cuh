@@ -139,120 +139,143 @@ __device__ __forceinline__ f32x2 rcp2(f32x2 a)
     return pk(rcp_approx(lo), rcp_approx(hi));
 }
 
+// negation of both halves (ptxas folds it into the operand modifier of the consuming FFMA2)
+__device__ __forceinline__ f32x2 neg2(f32x2 a)
+{
+    float lo, hi;
+    upk(a, lo, hi);
+    return pk(-lo, -hi);
+}
+
 // Per-pair constants of the packed integrator.
 struct CarConsts2 {
-    f32x2 td, ntd;   // +-tan((h/2) w)
-    f32x2 tf, ntf;   // +-tan(h w)
-    f32x2 dU;        // increment of U = (h/2)(v / L) per sub-step
-    f32x2 dW, dW2;   // increments of W = (h/6) v and of W2 = 2 W(half step) per sub-step
-    f32x2 dWs;       // increment of Ws = W1 + 2 W2 + W4
-    float tstep[2];  // tan(step * w): advances tan(phi) from one propagation step to the next
-    float kscale, h6, hh_ua_k[2], hh_ua_w[2];
+    f32x2 td, ntd;          // +-tan((h/2) w): advances tan(phi) by half a sub-step
+    f32x2 tf, ntf;          // +-tan(h w): by a whole sub-step
+    f32x2 tstep, ntstep;    // +-tan(step * w): from one propagation step to the next
+    f32x2 dU, dUh, dU6;     // increments of U = (h/2)(v / L) per sub-step / half sub-step, and a sixth of the former
+    f32x2 ua, v0;           // acceleration and the parent's speed (v is an exact linear function of time)
+    float kscale;           // (h/2) / L
+    float cpos;             // L / 3: position offsets are accumulated in units of this (see car_step2)
 };
 
-__device__ __forceinline__ CarConsts2 car_consts2(const DevWorld &w, const float ua[2], const float uw[2])
+__device__ __forceinline__ float tan_small(float d)   // |d| <= 0.1: the series is exact to 1e-10
+{
+    const float d2 = d * d;
+    return d * fmaf(d2, fmaf(d2, fmaf(d2, 17.0f / 315.0f, 2.0f / 15.0f), 1.0f / 3.0f), 1.0f);
+}
+
+__device__ __forceinline__ CarConsts2 car_consts2(const DevWorld &w, const float ua[2], const float uw[2], const float v0[2])
 {
     CarConsts2 k;
     const float h = w.h, hh = 0.5f * w.h;
-    k.h6 = w.h * (1.0f / 6.0f);
     k.kscale = hh * w.inv_len;
-    float td[2];
+    k.cpos = __fdividef(1.0f / 3.0f, w.inv_len);
+    float td[2], tf[2], tp[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-        const float dl = hh * uw[e], dl2 = dl * dl;
-        td[e] = dl * fmaf(dl2, fmaf(dl2, 2.0f / 15.0f, 1.0f / 3.0f), 1.0f);
-        const float ds = w.step * uw[e], ds2 = ds * ds;  // |ds| <= 0.1: the series is exact to 1e-10
-        k.tstep[e] = ds * fmaf(ds2, fmaf(ds2, fmaf(ds2, 17.0f / 315.0f, 2.0f / 15.0f), 1.0f / 3.0f), 1.0f);
-        k.hh_ua_k[e] = k.kscale * hh * ua[e];   // U at the half sub-step = U1 + this
-        k.hh_ua_w[e] = 2.0f * k.h6 * hh * ua[e];  // W2 = 2 W1 + this
+        td[e] = tan_small(hh * uw[e]);
+        tf[e] = tan_small(h * uw[e]);
+        tp[e] = tan_small(w.step * uw[e]);
     }
     k.td = pk(td[0], td[1]);
     k.ntd = pk(-td[0], -td[1]);
-    {
-        float tf[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float df = h * uw[e], df2 = df * df;
-            tf[e] = df * fmaf(df2, fmaf(df2, 2.0f / 15.0f, 1.0f / 3.0f), 1.0f);
-        }
-        k.tf = pk(tf[0], tf[1]);
-        k.ntf = pk(-tf[0], -tf[1]);
-    }
-    k.dU = pk(k.kscale * h * ua[0], k.kscale * h * ua[1]);
-    k.dW = pk(k.h6 * h * ua[0], k.h6 * h * ua[1]);
-    k.dW2 = pk(2.0f * k.h6 * h * ua[0], 2.0f * k.h6 * h * ua[1]);
-    k.dWs = pk(6.0f * k.h6 * h * ua[0], 6.0f * k.h6 * h * ua[1]);
+    k.tf = pk(tf[0], tf[1]);
+    k.ntf = pk(-tf[0], -tf[1]);
+    k.tstep = pk(tp[0], tp[1]);
+    k.ntstep = pk(-tp[0], -tp[1]);
+    const float du0 = k.kscale * h * ua[0], du1 = k.kscale * h * ua[1];
+    k.dU = pk(du0, du1);
+    k.dUh = pk(0.5f * du0, 0.5f * du1);
+    k.dU6 = pk(du0 * (1.0f / 6.0f), du1 * (1.0f / 6.0f));
+    k.ua = pk(ua[0], ua[1]);
+    k.v0 = pk(v0[0], v0[1]);
     return k;
 }
 
-// One propagation step of two samples at once (same RK4 stages as car_step).  With K1, K2, K4 the (h/2)-scaled heading
-// rates at the stages, the stage headings are theta1 + {0, K1, K2, 2 K2}, so
-//   sum_i w_i cos(theta_i) = c1 A - s1 B,  sum_i w_i sin(theta_i) = s1 A + c1 B,
-//   A = W1 + W2 (cos K1 + cos K2) + W4 cos 2K2,  B = W2 (sin K1 + sin K2) + W4 sin 2K2   (|K| <= 0.035:
-//   cos d = 1 - d^2/2, sin d = d to the accuracy of car_step's second-order rotations),
-// and stage 1 of the next sub-step takes (c1, s1) of theta + the accumulated dtheta = (K1 + 4 K2 + K4) / 3 from MUFU.
-// 34 packed instructions + 8 MUFU (4 RCP, 2 SIN, 2 COS) per sub-step of two samples.
+// Sub-steps (of the ten per propagation step) whose two reciprocals -- 1 / (1 - T td) and 1 / (1 - T tf) -- are taken
+// from ONE reciprocal of their product (+3 packed multiplies, -2 MUFU per sub-step of two samples): the knob that balances
+// the FMA pipe against the MUFU pipe.
+#ifndef KCBS_RCP_SHARE_MASK
+#define KCBS_RCP_SHARE_MASK 0x3ff
+#endif
+
+// State of two samples carried from one propagation step to the next.
+struct CarPair2 {
+    f32x2 T;           // tan(phi) at the start of the step
+    f32x2 TH;          // heading at the start of the step (wrapped)
+    f32x2 offx, offy;  // position offsets from the parents in units of CarConsts2::cpos
+};
+
+// One propagation step of two samples at once: n_sub classical RK4 sub-steps with the reference's stages (car_step is the
+// scalar form).  U = (h/2) v / L is an exact linear sequence, K = U tan(phi) the (h/2)-scaled heading rate.  With K1, K2,
+// K4 at the stages, the stage headings are theta1 + {0, K1, K2, 2 K2} and (h/6) v = (L/3) U, so in complex form
+//   (h/6) sum_i w_i v_i e^{i theta_i} = (L/3) e^{i (theta1 + K2)} [U1 e^{-i K2} + 2 U2 e^{i (K1 - K2)} + 2 U2 + U4 e^{i K2}]
+//     = (L/3) e^{i (theta1 + K2)} (A + i B),   A = U2 (6 - K2^2),   B = dU K2 + 2 U2 (K1 - K2)
+// (U1 + U4 = 2 U2, U4 - U1 = dU exactly; |K2| <= 0.0175 and |K1 - K2| ~ 1e-4: the neglected terms are below 4e-8 A), and
+// because B / A = dU tan(phi2) / 6 + (K1 - K2) / 3 is ~1e-4, A + i B = A e^{i B / A} to 1e-8: the four stages collapse to
+//   A (cos, sin)(theta*),   theta* = theta1 + (K1 + 2 K2) / 3 + (dU / 6) tan(phi2)
+// with ONE MUFU sin / cos per sample and sub-step (its 5e-7 error enters the position with weight h v and does not
+// accumulate).  The heading advances by (K1 + 4 K2 + K4) / 3.  tan(phi) at the half and the full sub-step both follow
+// from the start of the sub-step by the addition formula (independent reciprocals: no chain through the half step).
+// 21 packed instructions + 2 FMUL + 8 MUFU (4 RCP, 2 SIN, 2 COS) per sub-step of two samples; an FFMA2 with three
+// register operands occupies the FMA pipe for 3 cycles, every other packed instruction for 2 (tools/ubench/pipes.cu).
+// `t_start` = time of the step's start (v there = v0 + ua t_start).  Returns the heading at the end of the step (not
+// wrapped); p.T, p.offx, p.offy are advanced, p.TH is left to the caller (it wraps).
 template <int N_SUB>
-__device__ __forceinline__ f32x2 car_step2(const CarConsts2 &k, int n_sub, const float vs[2], const float T0[2],
-                                           const float ts[2], f32x2 &offx, f32x2 &offy)
+__device__ __forceinline__ f32x2 car_step2(const CarConsts2 &k, int n_sub, float t_start, CarPair2 &p)
 {
-    float s1[2], c1[2], U0[2], W0[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        __sincosf(ts[e], &s1[e], &c1[e]);
-        U0[e] = k.kscale * vs[e];
-        W0[e] = k.h6 * vs[e];
-    }
-    const f32x2 ONE = pk1(1.0f), NHALF = pk1(-0.5f), FOUR = pk1(4.0f), THIRD = pk1(1.0f / 3.0f);
-    f32x2 T = pk(T0[0], T0[1]);
-    f32x2 U1 = pk(U0[0], U0[1]), U2 = pk(U0[0] + k.hh_ua_k[0], U0[1] + k.hh_ua_k[1]);
-    f32x2 W1 = pk(W0[0], W0[1]), W2 = pk(fmaf(2.0f, W0[0], k.hh_ua_w[0]), fmaf(2.0f, W0[1], k.hh_ua_w[1]));
-    f32x2 C = pk(c1[0], c1[1]), S = pk(s1[0], s1[1]);
+    const f32x2 ONE = pk1(1.0f), NEG1 = pk1(-1.0f), TWO = pk1(2.0f), FOUR = pk1(4.0f), SIX = pk1(6.0f), THIRD = pk1(1.0f / 3.0f);
+    f32x2 T = p.T;
+    // tan(phi) at the end of the step straight from its start (one rounding-level error per step, off the sub-steps'
+    // dependency chain)
+    p.T = mul2(add2(T, k.tstep), rcp2(fma2(T, k.ntstep, ONE)));
+    const f32x2 V = fma2(k.ua, pk1(t_start), k.v0);
+    const f32x2 U1 = mul2(pk1(k.kscale), V);
+    f32x2 U2 = add2(U1, k.dUh);
     f32x2 K1 = mul2(U1, T);
-    f32x2 Ws = add2(add2(W1, add2(W1, k.dW)), add2(W2, W2));
-    f32x2 toff = pk1(0.0f);
-    const f32x2 TS = pk(ts[0], ts[1]);
+    f32x2 toff3 = pk1(0.0f);     // 3 x the heading offset from p.TH
+    f32x2 offx = p.offx, offy = p.offy;
 
 #pragma unroll kPropUnroll
     for (int n = 0; n < (N_SUB > 0 ? N_SUB : n_sub); ++n) {
-        // tan(phi) at the half and the full sub-step
-        const f32x2 T2 = mul2(add2(T, k.td), rcp2(fma2(T, k.ntd, ONE)));
-        // tan(phi) at the full sub-step straight from the start of the sub-step (addition formula with tan(h w)): the two
-        // reciprocals of a sub-step are independent, which halves the loop-carried dependency chain (4 % faster and a
-        // slightly smaller error than chaining T2 -> T)
-        T = mul2(add2(T, k.tf), rcp2(fma2(T, k.ntf, ONE)));
-        const f32x2 U4 = add2(U1, k.dU), W4 = add2(W1, k.dW);
+        const f32x2 D2 = fma2(T, k.ntd, ONE), N2 = add2(T, k.td);
+        const f32x2 D4 = fma2(T, k.ntf, ONE), N4 = add2(T, k.tf);
+        f32x2 T2;
+#ifdef KCBS_EXP_NORCP
+        // timing experiment only (inaccurate): 1 / (1 - e) ~ 1 + e, no MUFU
+        if (true) {
+            T2 = mul2(N2, fma2(T, k.td, ONE));
+            T = mul2(N4, fma2(T, k.tf, ONE));
+        } else
+#endif
+        if (N_SUB > 0 && ((KCBS_RCP_SHARE_MASK >> (n % 10)) & 1)) {
+            const f32x2 R = rcp2(mul2(D2, D4));
+            T2 = mul2(mul2(N2, D4), R);
+            T = mul2(mul2(N4, D2), R);
+        } else {
+            T2 = mul2(N2, rcp2(D2));
+            T = mul2(N4, rcp2(D4));
+        }
+        const f32x2 U4 = add2(U2, k.dUh);
         const f32x2 K2 = mul2(U2, T2), K4 = mul2(U4, T);
-        const f32x2 K22 = add2(K2, K2);
-        // A = (W1 + 2 W2 + W4) - (W2 (K1^2 + K2^2) + W4 (2 K2)^2) / 2
-        const f32x2 sq = fma2(K2, K2, mul2(K1, K1));
-        const f32x2 m = fma2(W4, mul2(K22, K22), mul2(W2, sq));
-        const f32x2 A = fma2(NHALF, m, Ws);
-        const f32x2 B = fma2(W4, K22, mul2(W2, add2(K1, K2)));
-        offx = sub2(fma2(C, A, offx), mul2(S, B));
-        offy = fma2(C, B, fma2(S, A, offy));
-        // heading
-        const f32x2 dth = mul2(fma2(FOUR, K2, add2(K1, K4)), THIRD);
-        toff = add2(toff, dth);
+        const f32x2 A = mul2(U2, fma2(mul2(K2, K2), NEG1, SIX));
+        const f32x2 z = add2(toff3, K1);
+        const f32x2 ang = fma2(fma2(K2, TWO, z), THIRD, fma2(k.dU6, T2, p.TH));   // theta*
         {
-            // stage-1 heading of the next sub-step straight from the angle: the MUFU pipe has room (4 RCP per sub-step
-            // of two samples), the FMA pipe is the one that binds, and a rotation of (C, S) costs it ten instructions;
-            // the MUFU error (5e-7) enters the position with weight W = (h/6) v and does not accumulate
             float a0, a1, c0, c1, s0, s1;
-            upk(add2(TS, toff), a0, a1);
+            upk(ang, a0, a1);
             __sincosf(a0, &s0, &c0);
             __sincosf(a1, &s1, &c1);
-            C = pk(c0, c1);
-            S = pk(s0, s1);
+            offx = fma2(pk(c0, c1), A, offx);
+            offy = fma2(pk(s0, s1), A, offy);
         }
+        toff3 = fma2(K2, FOUR, add2(z, K4));
         K1 = K4;
-        U1 = U4;
         U2 = add2(U2, k.dU);
-        W1 = W4;
-        W2 = add2(W2, k.dW2);
-        Ws = add2(Ws, k.dWs);
     }
-    return toff;
+    p.offx = offx;
+    p.offy = offy;
+    return fma2(toff3, THIRD, p.TH);
 }
 
 }  // namespace kcbs

@@ -155,20 +155,24 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
         uw[e] = a.controls[a.n + i[e]];
     }
     const float hl = w.rob_hl[a.robot], hw = w.rob_hw[a.robot];
-    const CarConsts2 k = car_consts2(w, ua, uw);
+    const CarConsts2 k = car_consts2(w, ua, uw, v0);
 
-    f32x2 offx = pk1(0.0f), offy = pk1(0.0f);  // position offsets from the parents
-    float xs[2] = {x0[0], x0[1]}, ys[2] = {y0[0], y0[1]}, vs[2] = {v0[0], v0[1]};   // last valid states
-    float ps[2] = {phi0[0], phi0[1]}, ts[2] = {th0[0], th0[1]};
-    // tan(phi) at the start of the current step: accurate once per sample, then advanced step by step with the
-    // addition formula and tan(step * w) (one rounding-level error per step instead of one sincosf per step)
-    float Ts[2];
+    // tan(phi) at the parent: accurate once per sample; from then on it advances step by step with the addition formula
+    CarPair2 p;
+    {
+        float Ts[2];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        float sp, cp;
-        sincosf(phi0[e], &sp, &cp);
-        Ts[e] = __fdividef(sp, cp);
+        for (int e = 0; e < 2; ++e) {
+            float sp, cp;
+            sincosf(phi0[e], &sp, &cp);
+            Ts[e] = __fdividef(sp, cp);
+        }
+        p.T = pk(Ts[0], Ts[1]);
+        p.TH = pk(th0[0], th0[1]);
+        p.offx = p.offy = pk1(0.0f);   // position offsets from the parents (in units of k.cpos)
     }
+    const f32x2 X0 = pk(x0[0], x0[1]), Y0 = pk(y0[0], y0[1]), CP = pk1(k.cpos);
+    float xl[2] = {x0[0], x0[1]}, yl[2] = {y0[0], y0[1]}, tl[2] = {th0[0], th0[1]};   // last valid state (direct path only)
     int nv[2] = {0, 0};
     bool alive[2] = {st[0] > 0, st[1] > 0};
     const long long plane = (long long)a.max_steps * a.n;
@@ -181,58 +185,74 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
     constexpr int kStride = MODE == kPacked ? 1 : SAMPLES;   // stage positions between consecutive steps of a sample
 
     for (int j = 0; j < jmax && (alive[0] | alive[1]); ++j) {
-        const f32x2 toff2 = w.n_sub == 10 ? car_step2<10>(k, 10, vs, Ts, ts, offx, offy)
-                                          : car_step2<0>(k, w.n_sub, vs, Ts, ts, offx, offy);
-        float ox[2], oy[2], toff[2];
-        upk(offx, ox[0], ox[1]);
-        upk(offy, oy[0], oy[1]);
-        upk(toff2, toff[0], toff[1]);
-        const float t1 = (float)(j + 1) * w.step;
+        const float ts = (float)j * w.step;
+        const f32x2 ang = w.n_sub == 10 ? car_step2<10>(k, 10, ts, p) : car_step2<0>(k, w.n_sub, ts, p);
+        float xn[2], yn[2], tn[2];
+        upk(fma2(CP, p.offx, X0), xn[0], xn[1]);
+        upk(fma2(CP, p.offy, Y0), yn[0], yn[1]);
+        upk(ang, tn[0], tn[1]);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            // straight-line code with predicated commits, so that the two halves interleave; a finished half keeps
-            // integrating from its last state and nothing of it is used
-            const float xn = x0[e] + ox[e], yn = y0[e] + oy[e];
-            const float vn = fmaf(ua[e], t1, v0[e]), pn = fmaf(uw[e], t1, phi0[e]);
-            const float tn = wrap_angle(ts[e] + toff[e]);
-            const float Tn = __fdividef(Ts[e] + k.tstep[e], fmaf(-Ts[e], k.tstep[e], 1.0f));
+            // straight-line code with predicated commits, so that the two halves interleave; a half that has failed keeps
+            // integrating from whatever it holds and nothing of it is used again
+            tn[e] = wrap_angle(tn[e]);
             // v and phi of every step below st were tested when st was derived (same expressions): x, y, theta remain
-            bool ok = alive[e] & (xn >= w.lo_t[0]) & (xn <= w.hi_t[0]) & (yn >= w.lo_t[1]) & (yn <= w.hi_t[1]) &
-                      (tn >= w.th_lo_t) & (tn <= w.th_hi_t);
+            bool ok = alive[e] & (xn[e] >= w.lo_t[0]) & (xn[e] <= w.hi_t[0]) & (yn[e] >= w.lo_t[1]) & (yn[e] <= w.hi_t[1]) &
+                      (tn[e] >= w.th_lo_t) & (tn[e] <= w.th_hi_t);
             if (HAS_OBS) {
-                if (ok) ok = obstacles_clear_fine(w, xn, yn, tn, hl, hw);
+                if (ok) ok = obstacles_clear_fine(w, xn[e], yn[e], tn[e], hl, hw);
             }
             if (HAS_CONS) {
-                if (ok) ok = constraints_clear(w, a.cons, a.n_cons, a.cons_states, a.cons_total, t0[e] + j + 1, xn, yn, tn, hl, hw, w.rob_rad[a.robot]);
+                if (ok) ok = constraints_clear(w, a.cons, a.n_cons, a.cons_states, a.cons_total, t0[e] + j + 1, xn[e], yn[e], tn[e], hl, hw, w.rob_rad[a.robot]);
             }
-            xs[e] = ok ? xn : xs[e];
-            ys[e] = ok ? yn : ys[e];
-            vs[e] = ok ? vn : vs[e];
-            ps[e] = ok ? pn : ps[e];
-            ts[e] = ok ? tn : ts[e];
-            Ts[e] = ok ? Tn : Ts[e];
             nv[e] = ok ? j + 1 : nv[e];
             alive[e] = ok & (j + 1 < st[e]);
+            if (!STAGED) {
+                xl[e] = ok ? xn[e] : xl[e];
+                yl[e] = ok ? yn[e] : yl[e];
+                tl[e] = ok ? tn[e] : tl[e];
+            }
             if (!ok) continue;
             if (STAGED) {
                 const int at = at0[e] + j * kStride;
-                stage->xyt[0][at] = xn;
-                stage->xyt[1][at] = yn;
-                stage->xyt[2][at] = tn;
+                stage->xyt[0][at] = xn[e];
+                stage->xyt[1][at] = yn[e];
+                stage->xyt[2][at] = tn[e];
             } else if (a.seg) {
                 // straight to the sample's own slot: the CTA's stores of a row stay inside one 1 KB window, L2 merges
                 // them (and the epilogue's) into full lines; v and phi are written by the epilogue
                 float *o = a.seg + (long long)j * a.n + i[e];
-                __stcs(o, xn);
-                __stcs(o + plane, yn);
-                __stcs(o + 4 * plane, tn);
+                __stcs(o, xn[e]);
+                __stcs(o + plane, yn[e]);
+                __stcs(o + 4 * plane, tn[e]);
             }
         }
+        p.TH = pk(tn[0], tn[1]);
     }
 
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         if (slot[e] < 0) continue;  // past the end of the batch
+        if (a.fin) {
+            // the last valid state: x, y, theta as staged (or tracked, direct path), v and phi from their linear form
+            float xf = xl[e], yf = yl[e], tf = tl[e];
+            if (STAGED) {
+                // (a sample that never moved reads back its parent: x0, y0, theta0 still sit in its stash; the packed
+                // layout has no stage position for a sample without a single admissible step)
+                const int at = nv[e] > 0 ? at0[e] + (nv[e] - 1) * kStride : six.stash(slot[e]);
+                if (!(MODE == kPacked && st[e] == 0)) {
+                    xf = stage->xyt[0][at];
+                    yf = stage->xyt[1][at];
+                    tf = stage->xyt[2][at];
+                }
+            }
+            const float tfin = (float)nv[e] * w.step;
+            a.fin[i[e]] = xf;
+            a.fin[a.n + i[e]] = yf;
+            a.fin[2 * a.n + i[e]] = nv[e] > 0 ? fmaf(ua[e], tfin, v0[e]) : v0[e];
+            a.fin[3 * a.n + i[e]] = nv[e] > 0 ? fmaf(uw[e], tfin, phi0[e]) : phi0[e];
+            a.fin[4 * a.n + i[e]] = tf;
+        }
         if (MODE == kPacked) {
             // rows the sample owns but did not reach (it left the workspace / hit an obstacle early) leave as zeros
             for (int j = nv[e]; j < st[e]; ++j) {
@@ -247,13 +267,6 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
             s_nv[slot[e]] = (unsigned char)nv[e];
         }
         if (a.valid_steps) a.valid_steps[i[e]] = nv[e];
-        if (a.fin) {
-            a.fin[i[e]] = xs[e];
-            a.fin[a.n + i[e]] = ys[e];
-            a.fin[2 * a.n + i[e]] = vs[e];
-            a.fin[3 * a.n + i[e]] = ps[e];
-            a.fin[4 * a.n + i[e]] = ts[e];
-        }
     }
 }
 
