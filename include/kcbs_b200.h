@@ -127,21 +127,24 @@ KCBS_API int kcbs_propagate_batch_dev(kcbs_ctx *ctx, int robot, int64_t n, int64
                                       const int32_t *steps, int max_steps, float *seg_out, float *final_out,
                                       int32_t *valid_steps, void *stream);
 
-/* Packed (CSR) segments: the same expansion, without the padding of the dense layout.  Sample i owns rows
- * offsets_out[i] .. offsets_out[i + 1] - 1 of five planes (packed_out[c * packed_cap + row] is component c); the first
- * valid_steps[i] of them are its states, in step order.  A sample owns as many rows as it can have valid states at all:
- * its requested duration cut where v or phi leave their bounds (both are linear in time, so that is known before
+/* Packed (CSR) segments: the same expansion, without the padding of the dense layout.  Sample i owns a run of rows
+ * that starts at offsets_out[i], in five planes (packed_out[c * packed_cap + row] is component c); the first
+ * valid_steps[i] rows of the run are its states, in step order.  A sample owns as many rows as it can have valid states
+ * at all: its requested duration cut where v or phi leave their bounds (both are linear in time, so that is known before
  * anything is integrated); rows it owns but did not reach -- it left the workspace or hit an obstacle earlier -- are
  * zero, as are the up to 3 rows that round a block of samples up to a 16-byte boundary.  On the Empty32x32 expansion
  * workload that is 1.05 rows per valid state: ~21 bytes leave the GPU per propagated state instead of 20 * max_steps per
- * sample.  Rows are in sample order and do not depend on how the GPU schedules the work.
+ * sample.  The runs of a block of 256 / 512 consecutive samples follow each other in sample order; the blocks themselves
+ * are placed first come, first served (one atomic per block, no block waits for another), so offsets_out is NOT
+ * monotone across blocks and the placement may differ from call to call; the states do not.
  *   packed_out   [5][packed_cap] floats; n * max_steps + 4 * (n / 256 + 1) rows always suffice.  Rows that do not fit
  *                are dropped (offsets stay exact: offsets_out[n] > packed_cap tells).
- *   offsets_out  n + 1 ints.
+ *   offsets_out  n + 1 ints: the first row of every sample, and in offsets_out[n] the number of rows emitted.
  *   max_steps    at most KCBS_PACKED_MAX_STEPS (the reference's setMinMaxControlDuration(1, 10), demo_*.cpp:118).
  *   total_out    (host call) rows emitted = offsets_out[n]; may be NULL.
  * The host call cuts the batch into chunks and pipelines upload / kernel / download of consecutive chunks; the
- * download is exactly the emitted rows.  final_out may be NULL; valid_steps may be NULL in the device call. */
+ * download is exactly the emitted rows.  final_out may be NULL; valid_steps may be NULL in the device call.  One context
+ * runs one packed call at a time (the row allocator lives in the context). */
 #define KCBS_PACKED_MAX_STEPS 10
 KCBS_API int kcbs_propagate_packed(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents, const float *parents,
                                    const int32_t *parent_idx, const float *controls, const int32_t *steps, int max_steps,

@@ -32,8 +32,8 @@ struct PropArgs {
     // packed (CSR) segment output (offsets != null): seg = [5][packed_cap] planes, offsets = [n + 1] rows
     int *offsets;
     long long packed_cap;
-    unsigned long long *scan;  // look-back workspace: one zeroed status word per CTA (left zeroed by the kernel)
-    unsigned *scan_ctl;        // [0] CTA ticket, [1] CTAs done; zeroed, left zeroed
+    unsigned long long *scan;  // (spare workspace words behind scan_ctl)
+    unsigned *scan_ctl;        // 8-byte aligned row allocator (CTAs served << 40 | rows handed out); zeroed, left zeroed
 };
 
 struct ValidArgs {

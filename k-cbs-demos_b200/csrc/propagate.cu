@@ -38,6 +38,7 @@
 // coalesced pass that also zero-fills the rows past the last valid state: every 32 B sector is written
 // completely (no partial-sector traffic at L2, no read-modify-write at HBM).
 #include <cstddef>
+#include <type_traits>
 
 #include "car_dynamics.cuh"
 #include "kernels.h"
@@ -57,11 +58,12 @@ constexpr int kStageSteps = 10;    // segments up to this many steps are staged 
 //   kDirect  x, y, theta stored straight to the sample's slot of the dense segment buffer (horizons longer than
 //            kStageSteps, final-state-only calls), v / phi and the zero rows by a coalesced epilogue
 //   kDense   segments staged in shared memory, dense [5][max_steps][n] layout with zero rows past the last valid state
-//   kPacked  segments staged in shared memory, CSR layout: sample i owns rows [offsets[i], offsets[i + 1]) of five planes,
-//            as many as it can have valid states at all (its effective duration, known before anything is integrated); the
+//   kPacked  segments staged in shared memory, CSR layout: sample i owns a run of rows from offsets[i] in five planes, as
+//            many as it can have valid states at all (its effective duration, known before anything is integrated); the
 //            first valid_steps[i] of them hold its states, the rest (a sample that left the workspace early) are zero.
-//            Because the row count does not depend on the integration, a CTA learns its first row (a look-back over the
-//            CTAs before it) while it integrates, and the write-out is a straight, 16-byte vectorised copy of the stage.
+//            Because the row count does not depend on the integration, a CTA gets its rows from the allocator (one
+//            atomic, first come, first served) while it integrates, and the write-out is a straight, 16-byte vectorised
+//            copy of the stage.
 enum PropMode { kDirect = 0, kDense = 1, kPacked = 2 };
 
 // ROUNDS = packed pairs per thread.  2: ranks (2t, 2t+1) (long) then (S-2-2t, S-1-2t) (short) -- every thread has the same
@@ -87,22 +89,26 @@ struct __align__(16) PropStage {
 // Bookkeeping of the packed layout (static shared memory of the kPacked kernels).
 template <int SAMPLES>
 struct PackTables {
-    static constexpr int kWords = kStageSteps * SAMPLES / 32;
-    unsigned short cap_off[SAMPLES];       // slot -> first stage position (= first row inside the CTA's range) of its run
-    unsigned short slot_of_run[SAMPLES];   // k-th non-empty run (in slot order) -> slot
-    unsigned start[kWords];                // bit p set: a run starts at stage position p
-    unsigned short wp[kWords];             // runs that start before word w
+    unsigned short cap_off[SAMPLES + 4];   // slot -> first stage position (= first row inside the CTA's range) of its run
     int cap_total;                         // stage positions in use = rows of the CTA (before rounding up to 4)
-    volatile long long base;               // first packed row of the CTA, -1 until the look-back has it
-    int vblock;                            // sample block of this CTA (arrival order, see lookback_base)
+    long long base;                        // first packed row of the CTA
 };
 
 // Where state j of the sample in `slot` lives in the stage, and where the sort pass stashes (x0, y0, theta0): in the
-// sample's own LAST position, which the sample overwrites only when it completes its final step.
+// sample's own LAST position, which the sample overwrites only when it completes its final step.  Component c of stage
+// position p is flat[c * pstride + p].  kDense: three planes (x, y, theta) of kStageSteps * SAMPLES positions.  kPacked:
+// when the CTA's rows fit into 3/5 of that (U{1..10} durations: 55 % on average) the same memory holds FIVE planes and
+// v, phi are staged too (`five`), so the write-out is one straight copy; otherwise three planes, and v, phi are laid out
+// in a second pass.
 template <int MODE, int SAMPLES>
 struct StageIndex {
+    static constexpr int kPositions = kStageSteps * SAMPLES;
+    static constexpr int kFivePositions = kPositions * 3 / 5;   // (a multiple of 4)
     const unsigned short *cap_off;
     const unsigned char *steps;
+    float *flat;
+    int pstride;
+    bool five;
     __device__ __forceinline__ int at(int j, int slot) const
     {
         return MODE == kPacked ? (int)cap_off[slot] + j : j * SAMPLES + slot;
@@ -111,6 +117,7 @@ struct StageIndex {
     {
         return MODE == kPacked ? (int)cap_off[slot] + (int)steps[slot] - 1 : (kStageSteps - 1) * SAMPLES + slot;
     }
+    __device__ __forceinline__ float &ref(int c, int pos) const { return flat[c * pstride + pos]; }
 };
 
 // propagateWhileValid for the two samples i[0], i[1] (effective durations st[0], st[1]; st = 0 for a slot past the end
@@ -136,9 +143,9 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
                 th0[e] = a.parents[4 * a.n_parents + pi];
             } else {
                 const int at = six.stash(sl);
-                x0[e] = stage->xyt[0][at];
-                y0[e] = stage->xyt[1][at];
-                th0[e] = stage->xyt[2][at];
+                x0[e] = six.ref(0, at);
+                y0[e] = six.ref(1, at);
+                th0[e] = six.ref(2, at);
             }
             v0[e] = stage->v0[sl];
             phi0[e] = stage->p0[sl];
@@ -185,7 +192,7 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
     constexpr int kStride = MODE == kPacked ? 1 : SAMPLES;   // stage positions between consecutive steps of a sample
 
     for (int j = 0; j < jmax && (alive[0] | alive[1]); ++j) {
-        const float ts = (float)j * w.step;
+        const float ts = (float)j * w.step, t1 = (float)(j + 1) * w.step;
         const f32x2 ang = w.n_sub == 10 ? car_step2<10>(k, 10, ts, p) : car_step2<0>(k, w.n_sub, ts, p);
         float xn[2], yn[2], tn[2];
         upk(fma2(CP, p.offx, X0), xn[0], xn[1]);
@@ -215,9 +222,13 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
             if (!ok) continue;
             if (STAGED) {
                 const int at = at0[e] + j * kStride;
-                stage->xyt[0][at] = xn[e];
-                stage->xyt[1][at] = yn[e];
-                stage->xyt[2][at] = tn[e];
+                six.ref(0, at) = xn[e];
+                six.ref(1, at) = yn[e];
+                six.ref(2, at) = tn[e];
+                if (MODE == kPacked && six.five) {   // the expressions st was derived with (and the dense write-out's)
+                    six.ref(3, at) = fmaf(ua[e], t1, v0[e]);
+                    six.ref(4, at) = fmaf(uw[e], t1, phi0[e]);
+                }
             } else if (a.seg) {
                 // straight to the sample's own slot: the CTA's stores of a row stay inside one 1 KB window, L2 merges
                 // them (and the epilogue's) into full lines; v and phi are written by the epilogue
@@ -233,40 +244,95 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
         if (slot[e] < 0) continue;  // past the end of the batch
-        if (a.fin) {
-            // the last valid state: x, y, theta as staged (or tracked, direct path), v and phi from their linear form
-            float xf = xl[e], yf = yl[e], tf = tl[e];
-            if (STAGED) {
-                // (a sample that never moved reads back its parent: x0, y0, theta0 still sit in its stash; the packed
-                // layout has no stage position for a sample without a single admissible step)
-                const int at = nv[e] > 0 ? at0[e] + (nv[e] - 1) * kStride : six.stash(slot[e]);
-                if (!(MODE == kPacked && st[e] == 0)) {
-                    xf = stage->xyt[0][at];
-                    yf = stage->xyt[1][at];
-                    tf = stage->xyt[2][at];
-                }
-            }
-            const float tfin = (float)nv[e] * w.step;
-            a.fin[i[e]] = xf;
-            a.fin[a.n + i[e]] = yf;
-            a.fin[2 * a.n + i[e]] = nv[e] > 0 ? fmaf(ua[e], tfin, v0[e]) : v0[e];
-            a.fin[3 * a.n + i[e]] = nv[e] > 0 ? fmaf(uw[e], tfin, phi0[e]) : phi0[e];
-            a.fin[4 * a.n + i[e]] = tf;
-        }
         if (MODE == kPacked) {
             // rows the sample owns but did not reach (it left the workspace / hit an obstacle early) leave as zeros
             for (int j = nv[e]; j < st[e]; ++j) {
-                stage->xyt[0][at0[e] + j] = 0.0f;
-                stage->xyt[1][at0[e] + j] = 0.0f;
-                stage->xyt[2][at0[e] + j] = 0.0f;
+                six.ref(0, at0[e] + j) = 0.0f;
+                six.ref(1, at0[e] + j) = 0.0f;
+                six.ref(2, at0[e] + j) = 0.0f;
+                if (six.five) {
+                    six.ref(3, at0[e] + j) = 0.0f;
+                    six.ref(4, at0[e] + j) = 0.0f;
+                }
             }
         }
         if (STAGED) {
+            // final states and valid counts leave with the write-out (coalesced, from the stage)
             stage->nv[slot[e]] = (unsigned char)nv[e];
-        } else {
-            s_nv[slot[e]] = (unsigned char)nv[e];
+            continue;
         }
+        s_nv[slot[e]] = (unsigned char)nv[e];
         if (a.valid_steps) a.valid_steps[i[e]] = nv[e];
+        if (a.fin) {
+            // the last valid state: x, y, theta as tracked, v and phi from their linear form
+            const float tfin = (float)nv[e] * w.step;
+            a.fin[i[e]] = xl[e];
+            a.fin[a.n + i[e]] = yl[e];
+            a.fin[2 * a.n + i[e]] = nv[e] > 0 ? fmaf(ua[e], tfin, v0[e]) : v0[e];
+            a.fin[3 * a.n + i[e]] = nv[e] > 0 ? fmaf(uw[e], tfin, phi0[e]) : phi0[e];
+            a.fin[4 * a.n + i[e]] = tl[e];
+        }
+    }
+}
+
+// Final states and valid counts of the CTA's samples, from the stage (staged variants): thread t owns the four consecutive
+// slots 4 t .. 4 t + 3, so every plane leaves as 16-byte stores.  (x, y, theta) = the sample's last valid row (`row`
+// gives its stage position), v and phi from their linear form; a sample that never moved returns its parent.
+template <int SAMPLES, class Stage, class Row, class Ref>
+__device__ __forceinline__ void write_final_states(const DevWorld &w, const PropArgs &a, const Stage *stage, long long b0, int tid, Row row,
+                                                   Ref ref)
+{
+    if (!a.fin && !a.valid_steps) return;
+    for (int slot = 4 * tid; slot < SAMPLES; slot += 4 * kPropThreads) {
+        const long long i0 = b0 + slot;
+        if (i0 >= a.n) break;
+        float f[5][4];
+        int nvs[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long i = min(i0 + e, a.n - 1);
+            const int sl = slot + e;
+            const int nv = i0 + e < a.n ? (int)stage->nv[sl] : 0;
+            nvs[e] = nv;
+            if (!a.fin) continue;
+            if (nv > 0) {
+                const int at = row(sl, nv - 1);
+                const float tfin = (float)nv * w.step;
+                f[0][e] = ref(0, at);
+                f[1][e] = ref(1, at);
+                f[2][e] = fmaf(stage->ua[sl], tfin, stage->v0[sl]);
+                f[3][e] = fmaf(stage->uw[sl], tfin, stage->p0[sl]);
+                f[4][e] = ref(2, at);
+            } else {
+                const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
+#pragma unroll
+                for (int c = 0; c < 5; ++c) f[c][e] = a.parents[c * a.n_parents + pi];
+            }
+        }
+        const bool vec = i0 + 3 < a.n && (a.n & 3) == 0;
+        if (a.fin) {
+            if (vec && (reinterpret_cast<uintptr_t>(a.fin) & 15) == 0) {
+#pragma unroll
+                for (int c = 0; c < 5; ++c)
+                    *reinterpret_cast<float4 *>(a.fin + c * a.n + i0) = make_float4(f[c][0], f[c][1], f[c][2], f[c][3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (i0 + e < a.n) {
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) a.fin[c * a.n + i0 + e] = f[c][e];
+                    }
+            }
+        }
+        if (a.valid_steps) {
+            if (i0 + 3 < a.n && (reinterpret_cast<uintptr_t>(a.valid_steps + i0) & 15) == 0) {
+                *reinterpret_cast<int4 *>(a.valid_steps + i0) = make_int4(nvs[0], nvs[1], nvs[2], nvs[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (i0 + e < a.n) a.valid_steps[i0 + e] = nvs[e];
+            }
+        }
     }
 }
 
@@ -306,40 +372,6 @@ __device__ __forceinline__ int block_exclusive_scan(int tid, int *s_warp, Get ge
     return total;
 }
 
-// First packed row of the CTA that took sample block `vblock` = sum of the valid states of all earlier blocks: a
-// decoupled look-back over one status word per block (flag << 62 | value; 1 = the block's own total, 2 = inclusive
-// prefix).  Blocks are numbered in ARRIVAL order (a ticket), so every predecessor a CTA waits for is running or done.
-// Executed by warp 0; returns the exclusive prefix in every lane.
-__device__ __forceinline__ long long lookback_base(unsigned long long *scan, int vblock, long long total, int lane)
-{
-    constexpr unsigned long long kVal = (1ull << 62) - 1;
-    volatile unsigned long long *vs = scan;
-    if (vblock == 0) {
-        if (lane == 0) vs[0] = (2ull << 62) | (unsigned long long)total;
-        return 0;
-    }
-    if (lane == 0) vs[vblock] = (1ull << 62) | (unsigned long long)total;
-    long long excl = 0;
-    for (int look = vblock - 1;; look -= 32) {
-        const int idx = look - lane;
-        unsigned long long v = 2ull << 62;   // before block 0: an inclusive prefix of zero
-        if (idx >= 0) {
-            do {
-                v = vs[idx];
-            } while ((v >> 62) == 0);
-        }
-        const unsigned incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-        const int first = incl ? __ffs(incl) - 1 : 32;   // nearest predecessor that already knows its prefix
-        long long part = lane <= first ? (long long)(v & kVal) : 0;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-        excl += part;
-        if (incl) break;
-    }
-    if (lane == 0) vs[vblock] = (2ull << 62) | (unsigned long long)(excl + total);
-    return excl;
-}
-
 template <bool HAS_OBS, bool HAS_CONS, int MODE, int ROUNDS>
 __global__ void __launch_bounds__(kPropThreads, MODE != kDirect ? PropGeom<ROUNDS>::kCtasPerSm : KCBS_PROP_MINB)
 k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs a)
@@ -358,17 +390,14 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
 
     const int tid = threadIdx.x;
     if (tid <= KCBS_MAX_STEPS) s_hist[tid] = 0;
-    if (MODE == kPacked) {
-        // sample blocks are handed out in arrival order (see lookback_base)
-        if (tid == 0) s_pk.vblock = (int)atomicAdd(a.scan_ctl, 1u);
-        for (int q = tid; q < PackTables<kSamples>::kWords; q += kPropThreads) s_pk.start[q] = 0u;
-    }
-    // (kPacked: the block of samples is the ticket's, which is blockIdx.x unless CTAs started out of order; the loads
-    // below are issued for that guess while the ticket is still on its way and repeated in the rare other case)
-    long long b0 = (long long)blockIdx.x * kSamples;
+    const long long b0 = (long long)blockIdx.x * kSamples;
     StageIndex<MODE, kSamples> six;
     six.cap_off = s_pk.cap_off;
     six.steps = s_steps;
+    six.flat = STAGED ? &stage->xyt[0][0] : nullptr;
+    six.pstride = StageIndex<MODE, kSamples>::kPositions;
+    six.five = false;
+    unsigned long long alloc = 0;   // (kPacked, thread 0) the row allocator's answer, see below
 
     // ---- counting sort of the CTA's samples by effective duration (longest first) ----------------
     int st4[kPer], within[kPer];
@@ -399,11 +428,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             }
         };
         load_samples();
-        __syncthreads();   // the histogram is clear (and, kPacked, the ticket is in)
-        if (MODE == kPacked && s_pk.vblock != (int)blockIdx.x) {
-            b0 = (long long)s_pk.vblock * kSamples;
-            load_samples();
-        }
+        __syncthreads();   // the histogram is clear
 #pragma unroll
         for (int u = 0; u < kPer; ++u) {
             const int slot = tid + u * kPropThreads;
@@ -451,21 +476,22 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             within[u] = atomicAdd(&s_hist[st], 1);
         }
         if (MODE == kPacked) {
-            // stage positions = rows: every slot gets a run of st positions in slot order; a bit marks the start of each
-            // non-empty run and a per-word count makes "which run holds position p" a popcount away.  One scan carries
-            // both the positions (low half) and the number of non-empty runs (high half).
+            // stage positions = rows: every slot gets a run of st positions in slot order
             __syncthreads();
-            const int both = block_exclusive_scan<kPer>(
-                tid, s_warp, [&](int slot) { const int st = s_steps[slot]; return st | ((st > 0) << 16); },
-                [&](int slot, int pre) {
-                    const int off = pre & 0xffff, run = pre >> 16;
-                    s_pk.cap_off[slot] = (unsigned short)off;
-                    if (s_steps[slot] > 0) {
-                        s_pk.slot_of_run[run] = (unsigned short)slot;
-                        atomicOr(&s_pk.start[off >> 5], 1u << (off & 31));
-                    }
-                });
-            if (tid == 0) s_pk.cap_total = both & 0xffff;
+            const int total = block_exclusive_scan<kPer>(
+                tid, s_warp, [&](int slot) { return (int)s_steps[slot]; },
+                [&](int slot, int pre) { s_pk.cap_off[slot] = (unsigned short)pre; });
+            if (tid == 0) {
+                s_pk.cap_total = total;
+                s_pk.cap_off[kSamples] = (unsigned short)total;
+                // The CTA's rows are allocated first come, first served: one atomic on (CTAs served << 40 | rows handed
+                // out); nobody waits for anybody.  The answer stays in a register until the write-out, so thread 0 does
+                // not wait for it here.
+                alloc = atomicAdd(reinterpret_cast<unsigned long long *>(a.scan_ctl), (1ull << 40) | (unsigned long long)((total + 3) & ~3));
+            }
+            // rows of the CTA fit into 3/5 of the stage: five planes, v and phi are staged too
+            six.five = total <= StageIndex<MODE, kSamples>::kFivePositions;
+            if (six.five) six.pstride = StageIndex<MODE, kSamples>::kFivePositions;
         }
         if (STAGED) {
             // x0, y0, theta0 borrow the sample's own last stage position, which the sample overwrites only when it
@@ -475,9 +501,9 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 const int slot = tid + u * kPropThreads;
                 if (b0 + slot < a.n && (MODE != kPacked || st4[u] > 0)) {
                     const int at = six.stash(slot);
-                    stage->xyt[0][at] = x0[u];
-                    stage->xyt[1][at] = y0[u];
-                    stage->xyt[2][at] = th0[u];
+                    six.ref(0, at) = x0[u];
+                    six.ref(1, at) = y0[u];
+                    six.ref(2, at) = th0[u];
                 }
             }
         }
@@ -493,54 +519,11 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
         }
         s_first[tid] = sum;  // hist[tid + 1] + ... + hist[32]
         if (tid == 0) s_first[KCBS_MAX_STEPS] = 0;
-        if (MODE == kPacked) {
-            // wp[w] = run starts before word w (each lane owns a contiguous chunk of words)
-            constexpr int kWords = PackTables<kSamples>::kWords, kChunk = (kWords + 31) / 32;
-            int cnt = 0;
-            for (int q = 0; q < kChunk; ++q) {
-                const int wd = tid * kChunk + q;
-                if (wd < kWords) cnt += __popc(s_pk.start[wd]);
-            }
-            int incl = cnt;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, incl, off);
-                if (tid >= off) incl += up;
-            }
-            int run = incl - cnt;
-            for (int q = 0; q < kChunk; ++q) {
-                const int wd = tid * kChunk + q;
-                if (wd < kWords) {
-                    s_pk.wp[wd] = (unsigned short)run;
-                    run += __popc(s_pk.start[wd]);
-                }
-            }
-        }
     }
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < kPer; ++u) s_perm[s_first[st4[u]] + within[u]] = (unsigned short)(tid + u * kPropThreads);
-    if (MODE == kPacked && tid == 0) s_pk.base = -1;
     __syncthreads();
-    if (MODE == kPacked && tid >= kPropThreads - 32) {
-        // the CTA's first row, while the other warps already integrate: the rows of a CTA (rounded up to 4, so that every
-        // CTA starts 16-byte aligned) are known now.  The last warp does it: it holds the shortest durations.
-        const int lane = tid & 31;
-        const long long base = lookback_base(a.scan, s_pk.vblock, (long long)((s_pk.cap_total + 3) & ~3), lane);
-        if (lane == 0) s_pk.base = base;
-        // this CTA is through with the look-back workspace; the last CTA of the grid to get here leaves it clean for the
-        // next launch (also off the critical path: that CTA still has its integration ahead)
-        unsigned done = 0;
-        if (lane == 0) done = atomicAdd(a.scan_ctl + 1, 1u);
-        done = __shfl_sync(0xffffffffu, done, 0);
-        if (done == gridDim.x - 1) {
-            for (unsigned q = lane; q < gridDim.x; q += 32) a.scan[q] = 0ull;
-            if (lane == 0) {
-                a.scan_ctl[0] = 0u;
-                a.scan_ctl[1] = 0u;
-            }
-        }
-    }
 
     // ---- packed pairs of neighbouring ranks: (2t, 2t+1) (long) and, with two rounds, (S-2-2t, S-1-2t) (short) ------
 #pragma unroll 1
@@ -609,6 +592,8 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 const float4 p0 = *reinterpret_cast<const float4 *>(&stage->p0[slot]);
                 const float4 uw = *reinterpret_cast<const float4 *>(&stage->uw[slot]);
                 float *o = a.seg + i;
+                // (every lane runs all rows: a loop bound that differs between the lanes would split the row stores of
+                // the warp into partial sectors)
                 for (int j = 0; j < a.max_steps; ++j, o += a.n) {
                     const float t1 = (float)(j + 1) * w.step;
                     const bool l0 = j < nv[0], l1 = j < nv[1], l2 = j < nv[2], l3 = j < nv[3];
@@ -650,64 +635,99 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 }
             }
         }
+        write_final_states<kSamples>(w, a, stage, b0, tid, [&](int sl, int j) { return j * kSamples + sl; },
+                                     [&](int c, int at) { return six.ref(c, at); });
     }
 
     if (MODE == kPacked) {
-        // ---- packed write-out: the CTA's rows leave as ONE contiguous, 16-byte aligned range of every plane -----------
-        __syncthreads();
-        const long long base = s_pk.base;   // (published by the last warp long ago; the barrier orders the read)
+        // ---- packed write-out: the CTA's rows leave as ONE contiguous, 16-byte aligned range of every plane, a straight
+        // copy of the stage (row order already).  With three stage planes (the CTA's rows did not fit five), v and phi
+        // are laid out in the freed stage by the threads that own the samples and leave the same way ------------------
         const int cap_total = s_pk.cap_total, rows4 = (cap_total + 3) & ~3;
-#pragma unroll
-        for (int u = 0; u < kPer; ++u) {
-            const int slot = tid + u * kPropThreads;
-            const long long i = b0 + slot;
-            if (i < a.n) {
-                a.offsets[i] = (int)(base + s_pk.cap_off[slot]);
-                if (i == a.n - 1) a.offsets[a.n] = (int)(base + rows4);
+        if (tid == 0) {
+            // the allocator's answer is needed now; the last CTA served also reports the total and leaves the
+            // allocator zeroed for the next launch (every other CTA of this launch has been served)
+            const long long first = (long long)(alloc & ((1ull << 40) - 1));
+            s_pk.base = first;
+            if ((unsigned)(alloc >> 40) == gridDim.x - 1) {
+                a.offsets[a.n] = (int)(first + rows4);
+                *reinterpret_cast<unsigned long long *>(a.scan_ctl) = 0ull;
             }
         }
+        __syncthreads();
+        const long long base = s_pk.base;
         float *out = a.seg;
         const long long cap = a.packed_cap;
         const bool vec = (cap & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && base + rows4 <= cap;
-        for (int p4 = 4 * tid; p4 < rows4; p4 += 4 * kPropThreads) {
-            float X[4], Y[4], V[4], P[4], T[4];
+        // copies stage planes s[0..NP) to the output planes o[0..NP); positions past cap_total (the round-up) are zero
+        auto copy_planes = [&](auto np, const int (&sp)[5], const int (&op)[5]) {
+            constexpr int NP = decltype(np)::value;
+            for (int p4 = 4 * tid; p4 < rows4; p4 += 4 * kPropThreads) {
+                float4 q[NP];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int p = p4 + e;
-                X[e] = Y[e] = V[e] = P[e] = T[e] = 0.0f;
-                if (p < cap_total) {
-                    const int wd = p >> 5;
-                    const int run = (int)s_pk.wp[wd] + __popc(s_pk.start[wd] & (0xffffffffu >> (31 - (p & 31)))) - 1;
-                    const int slot = s_pk.slot_of_run[run];
-                    const int j = p - (int)s_pk.cap_off[slot];
-                    if (j < (int)stage->nv[slot]) {
-                        const float t1 = (float)(j + 1) * w.step;
-                        X[e] = stage->xyt[0][p];
-                        Y[e] = stage->xyt[1][p];
-                        T[e] = stage->xyt[2][p];
-                        V[e] = fmaf(stage->ua[slot], t1, stage->v0[slot]);   // the integrator's expressions
-                        P[e] = fmaf(stage->uw[slot], t1, stage->p0[slot]);
+                for (int c = 0; c < NP; ++c) q[c] = *reinterpret_cast<const float4 *>(&six.ref(sp[c], p4));
+                if (p4 + 4 > cap_total) {
+#pragma unroll
+                    for (int c = 0; c < NP; ++c) {
+                        if (p4 + 1 >= cap_total) q[c].y = 0.0f;
+                        if (p4 + 2 >= cap_total) q[c].z = 0.0f;
+                        q[c].w = 0.0f;
+                    }
+                }
+                const long long o = base + p4;
+#pragma unroll
+                for (int c = 0; c < NP; ++c) {
+                    float *dst = out + op[c] * cap + o;
+                    if (vec) {
+                        __stcs(reinterpret_cast<float4 *>(dst), q[c]);
+                    } else {
+                        const float e4[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (o + e < cap) __stcs(dst + e, e4[e]);
                     }
                 }
             }
-            const long long o = base + p4;
-            if (vec) {
-                __stcs(reinterpret_cast<float4 *>(out + o), make_float4(X[0], X[1], X[2], X[3]));
-                __stcs(reinterpret_cast<float4 *>(out + cap + o), make_float4(Y[0], Y[1], Y[2], Y[3]));
-                __stcs(reinterpret_cast<float4 *>(out + 2 * cap + o), make_float4(V[0], V[1], V[2], V[3]));
-                __stcs(reinterpret_cast<float4 *>(out + 3 * cap + o), make_float4(P[0], P[1], P[2], P[3]));
-                __stcs(reinterpret_cast<float4 *>(out + 4 * cap + o), make_float4(T[0], T[1], T[2], T[3]));
+        };
+        if (six.five) {
+            copy_planes(std::integral_constant<int, 5>(), {0, 1, 2, 3, 4}, {0, 1, 4, 2, 3});
+        } else {
+            copy_planes(std::integral_constant<int, 3>(), {0, 1, 2, 0, 0}, {0, 1, 4, 0, 0});
+        }
+        // row offsets (16-byte stores: the thread owns four consecutive slots), final states, valid counts
+        for (int slot = 4 * tid; slot < kSamples; slot += 4 * kPropThreads) {
+            const long long i0 = b0 + slot;
+            if (i0 >= a.n) break;
+            const int o4[4] = {(int)(base + s_pk.cap_off[slot]), (int)(base + s_pk.cap_off[slot + 1]),
+                               (int)(base + s_pk.cap_off[slot + 2]), (int)(base + s_pk.cap_off[slot + 3])};
+            if (i0 + 3 < a.n && (reinterpret_cast<uintptr_t>(a.offsets + i0) & 15) == 0) {
+                *reinterpret_cast<int4 *>(a.offsets + i0) = make_int4(o4[0], o4[1], o4[2], o4[3]);
             } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (o + e < cap) {
-                        __stcs(out + o + e, X[e]);
-                        __stcs(out + cap + o + e, Y[e]);
-                        __stcs(out + 2 * cap + o + e, V[e]);
-                        __stcs(out + 3 * cap + o + e, P[e]);
-                        __stcs(out + 4 * cap + o + e, T[e]);
-                    }
+                    if (i0 + e < a.n) a.offsets[i0 + e] = o4[e];
             }
+        }
+        write_final_states<kSamples>(w, a, stage, b0, tid, [&](int sl, int j) { return (int)s_pk.cap_off[sl] + j; },
+                                     [&](int c, int at) { return six.ref(c, at); });
+        if (!six.five) {
+            __syncthreads();   // x, y, theta have left the stage
+            for (int slot = 4 * tid; slot < kSamples; slot += 4 * kPropThreads) {
+                if (b0 + slot >= a.n) break;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int sl = slot + e;
+                    const int at = s_pk.cap_off[sl], st = (int)s_pk.cap_off[sl + 1] - at, nv = stage->nv[sl];
+                    const float v0 = stage->v0[sl], ua = stage->ua[sl], p0 = stage->p0[sl], uw = stage->uw[sl];
+                    for (int j = 0; j < st; ++j) {
+                        const float t1 = (float)(j + 1) * w.step;
+                        six.ref(0, at + j) = j < nv ? fmaf(ua, t1, v0) : 0.0f;   // the integrator's expressions
+                        six.ref(1, at + j) = j < nv ? fmaf(uw, t1, p0) : 0.0f;
+                    }
+                }
+            }
+            __syncthreads();
+            copy_planes(std::integral_constant<int, 2>(), {0, 1, 0, 0, 0}, {2, 3, 0, 0, 0});
         }
     }
 }

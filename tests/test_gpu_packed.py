@@ -1,8 +1,9 @@
 """GPU tests of the packed (CSR) segment output of the expansion kernel (kcbs_propagate_packed[_dev]) and of the launch
 shapes (kcbs_set_expansion_mode).  The dense output is gated against the oracle in test_gpu_propagate.py /
 test_gpu_fullsize.py; here the packed rows must equal the dense rows BIT FOR BIT (same kernel arithmetic, other
-layout), in sample order, for every size, parent layout and launch shape.  A sample owns as many rows as it can have
-valid states at all (its effective duration); the rows it did not reach are zero."""
+layout) for every size, parent layout and launch shape.  A sample owns as many rows as it can have valid states at all
+(its effective duration), starting at offsets[i]; the rows it did not reach are zero.  Blocks of samples are placed
+first come, first served, so the offsets are not monotone across blocks: the runs must be disjoint and tight."""
 import numpy as np
 import pytest
 
@@ -19,8 +20,7 @@ def dense_rows(seg, valid):
 def packed_rows(packed, offsets, valid):
     """The valid rows of a packed result in (sample, step) order, and a mask of the rows that hold a state."""
     n = len(valid)
-    cap = np.diff(offsets)
-    assert (cap >= valid).all() and (cap >= 0).all()
+    assert (offsets[:n] >= 0).all()
     live = np.zeros(packed.shape[1], bool)
     idx = np.repeat(offsets[:n], valid) + (np.arange(valid.sum()) - np.repeat(np.cumsum(valid) - valid, valid))
     live[idx] = True
@@ -32,11 +32,14 @@ def check_packed(ctx, robot, parents, controls, steps, parent_idx=None, max_step
     packed, offsets, pfin, pvalid, total = ctx.propagate_packed(robot, parents, controls, steps, parent_idx=parent_idx,
                                                                 max_steps=max_steps)
     n = controls.shape[1]
-    assert offsets[0] == 0 and total == offsets[n] and (pvalid == valid).all() and (pfin == fin).all()
-    # sample i owns rows offsets[i] .. offsets[i + 1] - 1: at least its valid states, at most its requested duration
+    assert total == offsets[n] and (pvalid == valid).all() and (pfin == fin).all()
+    assert total == 0 or offsets[:n].min() == 0
+    # sample i owns a run of rows from offsets[i] that holds its valid states: the runs of different samples are disjoint,
+    # and all rows together are no more than the requested durations (+3 per block of samples: 16-byte alignment)
     req = np.full(n, max_steps) if steps is None else np.clip(steps, 0, max_steps)
-    cap = np.diff(offsets)
-    assert (cap >= valid).all() and (cap <= req + 3).all()      # (+3: a block of samples starts 16-byte aligned)
+    moved = np.flatnonzero(valid > 0)
+    order = moved[np.argsort(offsets[moved], kind="stable")]
+    assert (np.diff(np.append(offsets[order], total)) >= valid[order]).all()
     assert total <= req.sum() + 4 * (n // 256 + 2)
     want = dense_rows(seg, valid)
     got, live = packed_rows(packed, offsets, valid)
@@ -59,7 +62,7 @@ def test_packed_equals_dense(pkg, workloads, scene, mode):
 
 @pytest.mark.parametrize("n", [1, 2, 7, 255, 256, 257, 511, 512, 513, 2047, 2049, 8191, 8193, 33000, 200000, 1 << 20])
 def test_packed_sizes(pkg, workloads, n):
-    # CTA boundaries of both launch shapes, pipeline chunk boundaries, many-window look-backs (2048+ CTAs)
+    # CTA boundaries of both launch shapes, pipeline chunk boundaries, grids of several waves
     scene = "Empty32x32_10robots"
     with pkg.Context(pkg.scenes.world(scene), device=0) as ctx:
         parents, controls, steps = workloads.expansion_batch(scene, n, seed=n, interior=0.2)
@@ -103,13 +106,13 @@ def test_packed_dev_repeated_launches_and_small_capacity(pkg, workloads):
             offsets = torch.full((n + 1,), -1, dtype=torch.int32, device="cuda")
             dfin = torch.empty((5, n), device="cuda")
             dval = torch.empty(n, dtype=torch.int32, device="cuda")
-            for rep in range(3):    # the look-back workspace must come back clean from every launch
+            for rep in range(3):    # the row allocator must come back clean from every launch
                 ctx.propagate_packed_dev(0, n, n, dp, dc, ds, None, 10, packed, cap, offsets, dfin, dval, st)
             torch.cuda.synchronize()
             off = offsets.cpu().numpy()
             if ref_off is None:
                 ref_off = off
-            assert off[0] == 0 and (off == ref_off).all() and (np.diff(off) >= valid).all()     # offsets never depend on the capacity
+            assert off[n] == ref_off[n]     # the rows a launch needs never depend on the capacity
             got = packed.cpu().numpy()
             fits = off[:n] + valid <= cap       # samples whose rows all fit
             rows, live = packed_rows(got, off, np.where(fits, valid, 0))
@@ -120,7 +123,7 @@ def test_packed_dev_repeated_launches_and_small_capacity(pkg, workloads):
             assert (got[:, ~used] == -7.0).all()      # nothing past the emitted rows, nothing past the capacity
             assert (dval.cpu().numpy() == valid).all() and (dfin.cpu().numpy() == fin).all()
         total = int(ref_off[n])
-        # graph replay of packed launches (ticket / status words are reset on the device)
+        # graph replay of packed launches (the row allocator is reset on the device)
         packed = torch.zeros((5, n * 10), device="cuda")
         offsets = torch.zeros(n + 1, dtype=torch.int32, device="cuda")
         side = torch.cuda.Stream()
