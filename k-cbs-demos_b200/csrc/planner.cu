@@ -11,7 +11,8 @@
 //
 // Low level, per round (all state in HBM, one stream):
 //   k_rrt_targets   n_targets random states (goal biased), packed (distance, index) keys reset
-//   k_rrt_nearest   tiled all-pairs nearest tree node per target, 64-bit atomicMin on (distance bits, index)
+//   k_rrt_nearest   tiled all-pairs nearest tree node per target (four targets per thread in packed FP32 pairs, nodes
+//                   broadcast from shared memory), 64-bit atomicMin on (distance bits, index)
 //   k_rrt_samples   n_targets x n_controls (parent index, control, duration) triples
 //   k_propagate     the K1 expansion kernel with dynamic-obstacle constraints and per-parent time indices
 //   k_rrt_select    per target the sample that ends closest to it becomes a tree node; goal test
@@ -53,6 +54,8 @@ struct RrtWorkspace {
     float *s_fin = nullptr;        // [dim][n_samples]
     int *s_valid = nullptr;        // [n_samples]
     int *sel = nullptr;            // [n_targets] sample chosen for each target this round, or -1
+    float4 *nn_r = nullptr;        // [max_nodes] (x, y, v, phi) of the first car: what the nearest-neighbour scan streams
+    float *nn_t = nullptr;         // [max_nodes] its heading
     int *counters = nullptr;       // [0], [1] = node count (ring by round parity), [2] = rounds completed, [3] = append ticket,
                                    // [4] = edges of the extracted path
     unsigned long long *goal_key = nullptr;  // packed (time << 32 | node) of the best goal node
@@ -109,6 +112,8 @@ __global__ void k_rrt_init(RrtArgs a, const float *start)
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const int M = a.ws.max_nodes;
         for (int c = 0; c < 5 * NC; ++c) a.ws.nodes[c * M] = start[c];
+        a.ws.nn_r[0] = make_float4(start[0], start[1], start[2], start[3]);
+        a.ws.nn_t[0] = start[4];
         for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M] = 0.f;
         a.ws.parent[0] = -1; a.ws.time[0] = 0; a.ws.steps[0] = 0;
         a.ws.counters[0] = 1;   // node count seen by round 0 (parity ring, see rrt_node_count)
@@ -148,13 +153,17 @@ __device__ __forceinline__ void rrt_target(const RrtArgs &a, int t, float q[5 * 
     }
 }
 
-constexpr int kNNThreads = 256;
-constexpr int kNNChunkMax = 256;   // nodes per CTA at most (the chunk shrinks while the tree is small, so that the grid fills 148 SMs)
+constexpr int kNNThreads = 128;
+constexpr int kNNPer = 4;                            // targets per thread (two packed pairs)
+constexpr int kNNTile = kNNThreads * kNNPer;         // targets per CTA
+constexpr int kNNChunkMax = 512;   // nodes per CTA at most (the chunk shrinks while the tree is small, so that the grid fills 148 SMs)
 
-// nodes per CTA for a tree of at most `bound` nodes: about 64 chunks, multiples of 32, within [32, kNNChunkMax]
-inline int nn_chunk(long long bound)
+// nodes per CTA for a tree of at most `bound` nodes and `tiles` target tiles: about 600 CTAs, multiples of 32, within
+// [32, kNNChunkMax]
+inline int nn_chunk(long long bound, int tiles)
 {
-    long long c = (bound / 64 + 31) / 32 * 32;
+    const long long chunks = std::max(1, 600 / std::max(tiles, 1));
+    long long c = (bound / chunks + 31) / 32 * 32;
     return (int)std::max<long long>(32, std::min<long long>(kNNChunkMax, c));
 }
 
@@ -162,74 +171,117 @@ inline int nn_chunk(long long bound)
 // round's kernels read one entry while k_rrt_append writes the other
 __device__ __forceinline__ int rrt_node_count(const RrtArgs &a) { return min(a.ws.counters[a.round & 1u], a.ws.max_nodes); }
 
-// grid = (ceil(n_targets / 256), chunks of the largest tree this round can have): every thread owns one target and scans
-// one chunk of nodes staged through shared memory (car 0 as float4 + heading; the node count is read on the device: the
-// host does not know it).  Four independent running minima keep four nodes in flight per thread.
+typedef unsigned long long nn_f32x2;
+__device__ __forceinline__ nn_f32x2 nn_pk(float lo, float hi)
+{
+    nn_f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ nn_f32x2 nn_sub2(nn_f32x2 a, nn_f32x2 b)
+{
+    nn_f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ nn_f32x2 nn_mul2(nn_f32x2 a, nn_f32x2 b)
+{
+    nn_f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ nn_f32x2 nn_fma2(nn_f32x2 a, nn_f32x2 b, nn_f32x2 c)
+{
+    nn_f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float nn_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// grid = (ceil(n_targets / 512), chunks of the largest tree this round can have): every thread owns FOUR targets (two
+// packed FP32 pairs) and scans one chunk of nodes broadcast from shared memory (car 0 with every component duplicated, so
+// that a node is a packed operand as it stands; the node count is read on the device: the host does not know it).
+// Straight-line code per node -- squared L2 over (x, y, v, phi), MUFU square root, SO2 arc -- and one unsigned minimum on
+// (distance bits with the low 9 bits replaced by the node's place in the chunk): the distance is compared to 2^-14
+// relative, ties go to the smallest index, nothing diverges.
 template <int NC>
 __global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a, int chunk)
 {
     constexpr int D = 5 * NC;
-    __shared__ float4 s_r[kNNChunkMax];             // x, y, v, phi of car 0
-    __shared__ float s_t[kNNChunkMax];              // theta of car 0
+    static_assert(kNNChunkMax <= 512, "the node's place in the chunk takes 9 bits of the key");
+    __shared__ float2 s_n[5][kNNChunkMax];             // (c, c) for c = x, y, v, phi, theta of car 0
     __shared__ float s_o[NC == 2 ? 5 : 1][kNNChunkMax];   // car 1 (merged pair only)
     if (rrt_done(a)) return;
     const int n_nodes = rrt_node_count(a);
     const int n0 = blockIdx.y * chunk, n1 = min(n0 + chunk, n_nodes);
     if (n0 >= n_nodes) return;
     const int B = a.n_targets, M = a.ws.max_nodes;
-    const int t = blockIdx.x * kNNThreads + threadIdx.x;
-    const bool live = t < B;
-    float q[D];
-    rrt_target<NC>(a, min(t, B - 1), q);
-    if (live && blockIdx.y == 0)
-        for (int c = 0; c < D; ++c) a.ws.targets[c * B + t] = q[c];
     const int m = n1 - n0;
     for (int j = threadIdx.x; j < m; j += kNNThreads) {
-        const int i = n0 + j;
-        s_r[j] = make_float4(a.ws.nodes[i], a.ws.nodes[M + i], a.ws.nodes[2 * M + i], a.ws.nodes[3 * M + i]);
-        s_t[j] = a.ws.nodes[4 * M + i];
+        const float4 r = a.ws.nn_r[n0 + j];
+        const float th = a.ws.nn_t[n0 + j];
+        s_n[0][j] = make_float2(r.x, r.x);
+        s_n[1][j] = make_float2(r.y, r.y);
+        s_n[2][j] = make_float2(r.z, r.z);
+        s_n[3][j] = make_float2(r.w, r.w);
+        s_n[4][j] = make_float2(th, th);
         if (NC == 2)
-            for (int c = 0; c < 5; ++c) s_o[c][j] = a.ws.nodes[(5 + c) * M + i];
+            for (int c = 0; c < 5; ++c) s_o[c][j] = a.ws.nodes[(5 + c) * M + n0 + j];
     }
+    // the thread's targets: t0 + {0, 1, 2, 3} * kNNThreads (coalesced stores of the target planes)
+    const int t0 = blockIdx.x * kNNTile + threadIdx.x;
+    float q[kNNPer][D];
+#pragma unroll
+    for (int u = 0; u < kNNPer; ++u) {
+        const int t = t0 + u * kNNThreads;
+        rrt_target<NC>(a, min(t, B - 1), q[u]);
+        if (t < B && blockIdx.y == 0)
+            for (int c = 0; c < D; ++c) a.ws.targets[c * B + t] = q[u][c];
+    }
+    nn_f32x2 Q[2][5];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) Q[h][c] = nn_pk(q[2 * h][c], q[2 * h + 1][c]);
     __syncthreads();
-    float best[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
-    int best_j[4] = {0, 0, 0, 0};
-    auto visit = [&](int j, int k) {
-        // the real-vector part of the first car alone already bounds the distance from below: most nodes are rejected
-        // on the squared L2 without the square root and the SO2 term
-        const float4 r = s_r[j];
-        const float dx = r.x - q[0], dy = r.y - q[1], dv = r.z - q[2], dp = r.w - q[3];
-        const float l2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dv, dv, dp * dp)));
-        if (l2 < best[k] * best[k]) {
-            float dth = fabsf(s_t[j] - q[4]);
-            dth = dth > kPi ? kTwoPi - dth : dth;
-            float d = sqrtf(l2) + dth;
-            if (NC == 2) {
-                float o[5];
+    unsigned best[kNNPer] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll 4
+    for (int j = 0; j < m; ++j) {
+        nn_f32x2 N[5];
 #pragma unroll
-                for (int c = 0; c < 5; ++c) o[c] = s_o[c][j];
-                d += car_distance(o, q + 5 * (NC - 1));
-            }
-            if (d < best[k]) {
-                best[k] = d;
-                best_j[k] = j;
+        for (int c = 0; c < 5; ++c) N[c] = *reinterpret_cast<const nn_f32x2 *>(&s_n[c][j]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const nn_f32x2 dx = nn_sub2(N[0], Q[h][0]), dy = nn_sub2(N[1], Q[h][1]), dv = nn_sub2(N[2], Q[h][2]), dp = nn_sub2(N[3], Q[h][3]);
+            const nn_f32x2 l2 = nn_fma2(dx, dx, nn_fma2(dy, dy, nn_fma2(dv, dv, nn_mul2(dp, dp))));
+            const nn_f32x2 dt = nn_sub2(N[4], Q[h][4]);
+            float l[2], t[2];
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(l[0]), "=f"(l[1]) : "l"(l2));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(t[0]), "=f"(t[1]) : "l"(dt));
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float at = fabsf(t[e]);
+                float d = nn_sqrt(l[e]) + fminf(at, kTwoPi - at);
+                if (NC == 2) {
+                    float o[5];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) o[c] = s_o[c][j];
+                    d += car_distance(o, q[2 * h + e] + 5 * (NC - 1));
+                }
+                best[2 * h + e] = min(best[2 * h + e], (__float_as_uint(d) & 0xfffffe00u) | (unsigned)j);
             }
         }
-    };
-    int j = 0;
-    for (; j + 4 <= m; j += 4) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) visit(j + k, k);
     }
-    for (; j < m; ++j) visit(j, 0);
-    // smallest distance, ties to the smallest node index (what a sequential scan with `<` finds)
 #pragma unroll
-    for (int k = 1; k < 4; ++k)
-        if (best[k] < best[0] || (best[k] == best[0] && best_j[k] < best_j[0])) {
-            best[0] = best[k];
-            best_j[0] = best_j[k];
-        }
-    if (live) atomicMin(a.ws.nn + t, ((unsigned long long)__float_as_uint(best[0]) << 32) | (unsigned)(n0 + best_j[0]));
+    for (int u = 0; u < kNNPer; ++u) {
+        const int t = t0 + u * kNNThreads;
+        if (t < B) atomicMin(a.ws.nn + t, ((unsigned long long)(best[u] & 0xfffffe00u) << 32) | (unsigned)(n0 + (int)(best[u] & 0x1ffu)));
+    }
 }
 
 // (parent, control, duration) for every sample: sample s belongs to target s / n_controls.
@@ -388,6 +440,8 @@ __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_cons
         a.ws.time[idx] = t_node;
         for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M + idx] = a.ws.s_ctrl[c * n + s];
         a.ws.steps[idx] = nv;
+        a.ws.nn_r[idx] = make_float4(f[0], f[1], f[2], f[3]);
+        a.ws.nn_t[idx] = f[4];
         // (a path that would not fit the caller's buffer is never a solution: it would come back truncated)
         bool in_goal = t_node < a.max_T;
 #pragma unroll
@@ -452,7 +506,7 @@ void free_workspace(RrtWorkspace &ws)
 {
     void *d[] = {ws.nodes, ws.parent, ws.time, ws.ctrl, ws.steps, ws.targets, ws.nn, ws.s_parent, ws.s_ctrl, ws.s_steps,
                  ws.s_fin, ws.s_valid, ws.sel, ws.counters, ws.goal_key, ws.cons, ws.cons_states, ws.path_nodes, ws.path_ctrl,
-                 ws.path_steps, ws.path_parent, ws.path_valid, ws.path_seg};
+                 ws.path_steps, ws.path_parent, ws.path_valid, ws.path_seg, ws.nn_r, ws.nn_t};
     for (void *p : d)
         if (p) cudaFree(p);
     if (ws.h_progress) cudaFreeHost(ws.h_progress);
@@ -481,7 +535,8 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
             (st = dev_alloc(ctx, ws.counters, 8)) || (st = dev_alloc(ctx, ws.goal_key, 1)) || (st = dev_alloc(ctx, ws.path_nodes, PC)) ||
             (st = dev_alloc(ctx, ws.path_ctrl, U * PC)) || (st = dev_alloc(ctx, ws.path_steps, PC)) ||
             (st = dev_alloc(ctx, ws.path_parent, PC)) || (st = dev_alloc(ctx, ws.path_valid, PC)) ||
-            (st = dev_alloc(ctx, ws.path_seg, D * (size_t)KCBS_MAX_STEPS * PC)))
+            (st = dev_alloc(ctx, ws.path_seg, D * (size_t)KCBS_MAX_STEPS * PC)) || (st = dev_alloc(ctx, ws.nn_r, M)) ||
+            (st = dev_alloc(ctx, ws.nn_t, M)))
             return st;
         KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_progress, sizeof(RrtProgress) * kRrtDepth, cudaHostAllocMapped));
         KCBS_CUDA(ctx, cudaHostGetDevicePointer((void **)&ws.d_progress, ws.h_progress, 0));
@@ -638,8 +693,9 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         a.round = (unsigned)queued;
         // the tree has at most 1 + round * n_targets nodes when this round starts
         const long long bound = std::min<long long>(p.max_nodes, 1 + (long long)queued * p.n_targets);
-        const int chunk = nn_chunk(bound);
-        dim3 g((p.n_targets + kNNThreads - 1) / kNNThreads, (unsigned)((bound + chunk - 1) / chunk));
+        const int tiles = (p.n_targets + kNNTile - 1) / kNNTile;
+        const int chunk = nn_chunk(bound, tiles);
+        dim3 g((unsigned)tiles, (unsigned)((bound + chunk - 1) / chunk));
         k_rrt_nearest<NC><<<g, kNNThreads, 0, s>>>(a, chunk);
         k_rrt_samples<NC><<<(n + 255) / 256, 256, 0, s>>>(a);
         if (NC == 1)
