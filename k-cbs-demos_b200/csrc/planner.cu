@@ -15,7 +15,8 @@
 //                   broadcast from shared memory), 64-bit atomicMin on (distance bits, index)
 //   k_rrt_samples   n_targets x n_controls (parent index, control, duration) triples
 //   k_propagate     the K1 expansion kernel with dynamic-obstacle constraints and per-parent time indices
-//   k_rrt_select    per target the sample that ends closest to it becomes a tree node; goal test
+//   k_rrt_select    per target the sample that ends closest to it is chosen
+//   k_rrt_append    the chosen samples become tree nodes in target order (goal test, report to the host)
 // A found path is re-expanded edge by edge with k_propagate (identical arithmetic) to emit every 0.1 s state.
 #include <algorithm>
 #include <atomic>
@@ -57,7 +58,7 @@ struct RrtWorkspace {
     float4 *nn_r = nullptr;        // [max_nodes] (x, y, v, phi) of the first car: what the nearest-neighbour scan streams
     float *nn_t = nullptr;         // [max_nodes] its heading
     int *counters = nullptr;       // [0], [1] = node count (ring by round parity), [2] = rounds completed, [3] = append ticket,
-                                   // [4] = edges of the extracted path
+                                   // [4] = edges of the extracted path, [5] = a goal node exists (set between rounds)
     unsigned long long *goal_key = nullptr;  // packed (time << 32 | node) of the best goal node
     ConsDesc *cons = nullptr;
     float *cons_states = nullptr;
@@ -104,7 +105,10 @@ struct RrtArgs {
 
 // Every kernel of an iteration starts with this test: once a goal node exists the remaining iterations already queued
 // on the stream do nothing, so the outcome is that of the first iteration that found one -- however far the host ran ahead.
-__device__ __forceinline__ bool rrt_done(const RrtArgs &a) { return *(volatile const unsigned long long *)a.ws.goal_key != ~0ull; }
+// The flag is raised by the last CTA of the round that found a goal node (k_rrt_append), never while a kernel that
+// tests it is running: every thread of every kernel of a round sees the same answer (the goal key itself changes while
+// k_rrt_append runs).
+__device__ __forceinline__ bool rrt_done(const RrtArgs &a) { return *(volatile const int *)(a.ws.counters + 5) != 0; }
 
 template <int NC>
 __global__ void k_rrt_init(RrtArgs a, const float *start)
@@ -120,6 +124,7 @@ __global__ void k_rrt_init(RrtArgs a, const float *start)
         a.ws.counters[1] = 1;
         a.ws.counters[2] = 0;   // rounds completed
         a.ws.counters[3] = 0;   // CTA ticket of k_rrt_append
+        a.ws.counters[5] = 0;   // a goal node exists (rrt_done)
         *a.ws.goal_key = ~0ull;
     }
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -371,20 +376,23 @@ __global__ void __launch_bounds__(256) k_rrt_select(RrtArgs a)
 
 // Appends the chosen samples to the tree in TARGET ORDER, so that node indices -- and with them nearest-neighbour ties,
 // the goal node and the whole plan -- depend only on the seed, never on the order in which warps of k_rrt_select happen
-// to finish.  CTA b owns targets [256 b, 256 b + 256); the position of a target's node is the node count plus the number of
-// chosen samples before it, which every CTA counts for itself over the (tiny) selection array.  The last CTA to finish
-// publishes the new node count (other parity, see rrt_node_count) and reports the round to the host.
-constexpr int kAppendThreads = 256;
+// to finish.  CTA b owns targets [128 b, 128 b + 128); the position of a target's node is the node count plus the number of
+// chosen samples before it, which every CTA counts for itself over the (tiny) selection array.  The kernel is latency
+// bound (a few thousand scattered nodes), so every level of loads is issued for all of a thread's work before anything
+// waits: the selection array, then the chosen sample, then the parent's time index.  The last CTA to finish publishes the
+// new node count (other parity, see rrt_node_count) and reports the round to the host.
+constexpr int kAppendThreads = 128;
+constexpr int kAppendScan = 16;   // selection entries a thread counts per pass (in flight together)
 template <int NC>
 __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_constant__ DevWorld w, RrtArgs a)
 {
-    constexpr int D = 5 * NC;
-    __shared__ int s_warp[kAppendThreads / 32], s_wtot[kAppendThreads / 32];
-    __shared__ int s_before, s_last;
+    constexpr int D = 5 * NC, U = 2 * NC, kWarps = kAppendThreads / 32;
+    __shared__ int s_before[kWarps], s_total[kWarps], s_own[kWarps];
+    __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int B = a.n_targets, C = a.n_controls, n = B * C, M = a.ws.max_nodes;
     RrtProgress *slot = a.ws.d_progress + (a.round % kRrtDepth);
-    if (rrt_done(a)) {   // (uniform: the key cannot change while cancelled rounds run)
+    if (rrt_done(a)) {   // (uniform, see rrt_done)
         if (tid == 0 && blockIdx.x == 0) {
             slot->goal = *a.ws.goal_key;
             slot->nodes = a.ws.counters[a.round & 1u];
@@ -394,54 +402,65 @@ __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_cons
         return;
     }
     const int n_nodes = rrt_node_count(a);
+    const int first = blockIdx.x * kAppendThreads;   // this CTA's first target
+    const int t = first + tid;
+    const int s_idx = t < B ? a.ws.sel[t] : -1;
     // chosen samples before this CTA's targets, and in all targets
     int before = 0, total = 0;
-    for (int t0 = 0; t0 < B; t0 += kAppendThreads) {
-        const int t = t0 + tid;
-        const int cnt = __popc(__ballot_sync(0xffffffffu, t < B && a.ws.sel[t] >= 0));
-        if (lane == 0) {
-            total += cnt;
-            if (t0 + wid * 32 < (int)blockIdx.x * kAppendThreads) before += cnt;
+    for (int j0 = 0; j0 < B; j0 += kAppendScan * kAppendThreads) {
+        int v[kAppendScan];
+#pragma unroll
+        for (int q = 0; q < kAppendScan; ++q) {
+            const int j = j0 + q * kAppendThreads + tid;
+            v[q] = j < B ? a.ws.sel[j] : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < kAppendScan; ++q) {
+            const int j = j0 + q * kAppendThreads + tid;
+            total += v[q] >= 0;
+            before += v[q] >= 0 && j < first;
         }
     }
-    if (lane == 0) {
-        s_warp[wid] = before;
-        s_wtot[wid] = total;
+    // the chosen sample, while the counts are reduced
+    const int s = max(s_idx, 0);
+    const int par = a.ws.s_parent[s], nv = a.ws.s_valid[s];
+    float f[D], u[U];
+#pragma unroll
+    for (int c = 0; c < D; ++c) f[c] = a.ws.s_fin[c * n + s];
+#pragma unroll
+    for (int c = 0; c < U; ++c) u[c] = a.ws.s_ctrl[c * n + s];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, off);
+        total += __shfl_xor_sync(0xffffffffu, total, off);
     }
-    __syncthreads();
-    if (tid == 0) {
-        int bsum = 0;
-        for (int q = 0; q < kAppendThreads / 32; ++q) bsum += s_warp[q];
-        s_before = bsum;
-    }
-    int tsum = 0;
-    for (int q = 0; q < kAppendThreads / 32; ++q) tsum += s_wtot[q];
-    __syncthreads();
-    // this CTA's targets
-    const int t = blockIdx.x * kAppendThreads + tid;
-    const int s_idx = t < B ? a.ws.sel[t] : -1;
     const unsigned bal = __ballot_sync(0xffffffffu, s_idx >= 0);
+    if (lane == 0) {
+        s_before[wid] = before;
+        s_total[wid] = total;
+        s_own[wid] = __popc(bal);
+    }
+    const int t_par = a.ws.time[par];
     __syncthreads();
-    if (lane == 0) s_warp[wid] = __popc(bal);
-    __syncthreads();
-    int in_cta = 0;
-    for (int q = 0; q < wid; ++q) in_cta += s_warp[q];
-    const int idx = n_nodes + s_before + in_cta + __popc(bal & ((1u << lane) - 1u));
+    int bsum = 0, tsum = 0, in_cta = 0;
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) {
+        bsum += s_before[q];
+        tsum += s_total[q];
+        in_cta += q < wid ? s_own[q] : 0;
+    }
+    const int idx = n_nodes + bsum + in_cta + __popc(bal & ((1u << lane) - 1u));
     if (s_idx >= 0 && idx < M) {
-        const int s = s_idx;
-        const int par = a.ws.s_parent[s], nv = a.ws.s_valid[s];
-        float f[D];
-        for (int c = 0; c < D; ++c) {
-            f[c] = a.ws.s_fin[c * n + s];
-            a.ws.nodes[c * M + idx] = f[c];
-        }
-        a.ws.parent[idx] = par;
-        const int t_node = a.ws.time[par] + nv;
-        a.ws.time[idx] = t_node;
-        for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M + idx] = a.ws.s_ctrl[c * n + s];
-        a.ws.steps[idx] = nv;
+#pragma unroll
+        for (int c = 0; c < D; ++c) a.ws.nodes[c * M + idx] = f[c];
         a.ws.nn_r[idx] = make_float4(f[0], f[1], f[2], f[3]);
         a.ws.nn_t[idx] = f[4];
+        a.ws.parent[idx] = par;
+        const int t_node = t_par + nv;
+        a.ws.time[idx] = t_node;
+#pragma unroll
+        for (int c = 0; c < U; ++c) a.ws.ctrl[c * M + idx] = u[c];
+        a.ws.steps[idx] = nv;
         // (a path that would not fit the caller's buffer is never a solution: it would come back truncated)
         bool in_goal = t_node < a.max_T;
 #pragma unroll
@@ -472,6 +491,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_cons
         a.ws.counters[(a.round + 1u) & 1u] = count;
         a.ws.counters[2] = (int)a.round + 1;
         a.ws.counters[3] = 0;
+        a.ws.counters[5] = *(volatile unsigned long long *)a.ws.goal_key != ~0ull;
         slot->goal = *(volatile unsigned long long *)a.ws.goal_key;
         slot->nodes = count;
         slot->rounds = (int)a.round + 1;
