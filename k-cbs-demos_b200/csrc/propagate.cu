@@ -120,12 +120,20 @@ struct StageIndex {
     __device__ __forceinline__ float &ref(int c, int pos) const { return flat[c * pstride + pos]; }
 };
 
+// tan(phi) of a parent state: accurate (it seeds a hundred sub-steps of the addition formula).
+__device__ __forceinline__ float tan_phi(float phi)
+{
+    float sp, cp;
+    sincosf(phi, &sp, &cp);
+    return __fdividef(sp, cp);
+}
+
 // propagateWhileValid for the two samples i[0], i[1] (effective durations st[0], st[1]; st = 0 for a slot past the end
 // of the batch): writes their segments, final states and valid-step counts.
 template <bool HAS_OBS, bool HAS_CONS, int MODE, int SAMPLES>
 __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs &a, const long long i[2], const int st[2],
                                               PropStage<SAMPLES> *stage, const StageIndex<MODE, SAMPLES> &six,
-                                              unsigned char *s_nv, const int slot[2])
+                                              unsigned char *s_nv, const int slot[2], float tan_shared)
 {
     constexpr bool STAGED = MODE != kDirect;
     float x0[2], y0[2], v0[2], phi0[2], th0[2], ua[2], uw[2];
@@ -167,15 +175,15 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
     // tan(phi) at the parent: accurate once per sample; from then on it advances step by step with the addition formula
     CarPair2 p;
     {
-        float Ts[2];
+        float Ts[2] = {tan_shared, tan_shared};
+        if (a.n_parents != 1) {   // (one shared parent: the thread took its tangent once, tan_phi)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            float sp, cp;
-            sincosf(phi0[e], &sp, &cp);
-            Ts[e] = __fdividef(sp, cp);
+            for (int e = 0; e < 2; ++e) Ts[e] = tan_phi(phi0[e]);
         }
         p.T = pk(Ts[0], Ts[1]);
-        p.TH = pk(th0[0], th0[1]);
+        // the heading enters wrapped (the general wrap, once per sample): every step then moves it by less than pi, so
+        // the per-step wrap is two compares
+        p.TH = pk(wrap_angle(th0[0]), wrap_angle(th0[1]));
         p.offx = p.offy = pk1(0.0f);   // position offsets from the parents (in units of k.cpos)
     }
     const f32x2 X0 = pk(x0[0], x0[1]), Y0 = pk(y0[0], y0[1]), CP = pk1(k.cpos);
@@ -191,8 +199,9 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
     }
     constexpr int kStride = MODE == kPacked ? 1 : SAMPLES;   // stage positions between consecutive steps of a sample
 
-    for (int j = 0; j < jmax && (alive[0] | alive[1]); ++j) {
-        const float ts = (float)j * w.step, t1 = (float)(j + 1) * w.step;
+    float jf = 0.0f;   // (float)j: small integers are exact
+    for (int j = 0; j < jmax && (alive[0] | alive[1]); ++j, jf += 1.0f) {
+        const float ts = jf * w.step, t1 = (jf + 1.0f) * w.step;
         const f32x2 ang = w.n_sub == 10 ? car_step2<10>(k, 10, ts, p) : car_step2<0>(k, w.n_sub, ts, p);
         float xn[2], yn[2], tn[2];
         upk(fma2(CP, p.offx, X0), xn[0], xn[1]);
@@ -202,7 +211,8 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
         for (int e = 0; e < 2; ++e) {
             // straight-line code with predicated commits, so that the two halves interleave; a half that has failed keeps
             // integrating from whatever it holds and nothing of it is used again
-            tn[e] = wrap_angle(tn[e]);
+            tn[e] = tn[e] >= kPi ? tn[e] - kTwoPi : tn[e];     // wrap_angle for |theta| < 3 pi
+            tn[e] = tn[e] < -kPi ? tn[e] + kTwoPi : tn[e];
             // v and phi of every step below st were tested when st was derived (same expressions): x, y, theta remain
             bool ok = alive[e] & (xn[e] >= w.lo_t[0]) & (xn[e] <= w.hi_t[0]) & (yn[e] >= w.lo_t[1]) & (yn[e] <= w.hi_t[1]) &
                       (tn[e] >= w.th_lo_t) & (tn[e] <= w.th_hi_t);
@@ -526,6 +536,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
     __syncthreads();
 
     // ---- packed pairs of neighbouring ranks: (2t, 2t+1) (long) and, with two rounds, (S-2-2t, S-1-2t) (short) ------
+    const float tan_shared = a.n_parents == 1 ? tan_phi(a.parents[3]) : 0.0f;
 #pragma unroll 1
     for (int round = 0; round < ROUNDS; ++round) {
         const int r0 = round == 0 ? 2 * tid : kSamples - 2 - 2 * tid;
@@ -543,7 +554,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             }
         }
         if (slot[0] >= 0 || slot[1] >= 0)
-            propagate_two<HAS_OBS, HAS_CONS, MODE, kSamples>(w, a, i, st, stage, six, s_nv, slot);
+            propagate_two<HAS_OBS, HAS_CONS, MODE, kSamples>(w, a, i, st, stage, six, s_nv, slot, tan_shared);
     }
 
     if (MODE == kDirect && a.seg) {
