@@ -427,7 +427,7 @@ def main():
     # ncu capture is one launch of 655,360 samples; a bench launch is one expansion of 65,536 samples of the same mix
     if packed_layout:
         tp = traffic.get("k_propagate_packed")
-        k1_traffic = None if not tp else (tp["dram_read_bytes"] + tp["dram_write_bytes"]) * N_CONTROLS / tp["samples"]
+        k1_traffic = None if not tp else (tp["dram_read_bytes"] + max(tp["dram_write_bytes"], tp.get("output_bytes", 0))) * N_CONTROLS / tp["samples"]
     else:
         k1_traffic = None if not tp else (tp["dram_read_bytes"] + tp["segment_buffer_bytes"]) * N_CONTROLS / tp["samples"]
     roofline = {
@@ -440,14 +440,19 @@ def main():
                         "note": "MEASURED_PEAKS.json has no FP32 entry: peak = FFMA saturation probe run in this process"},
         "traffic": k1_traffic,
         "layout": args.layout,
-        "traffic_unit": "bytes per launch (ncu dram__bytes_read + dram__bytes_write of one 655,360-sample launch, scaled to 65,536 "
-                        "samples; profiles/traffic_r2.json)",
+        "traffic_unit": "bytes per launch: ncu dram__bytes_read of one 655,360-sample launch + the bytes that launch writes (ncu's write "
+                        "counter stops while most of them are still dirty in L2), scaled to 65,536 samples; profiles/traffic_r2.json",
         "algorithmic_bytes_per_launch": (BYTES_PER_STATE * written_step + BYTES_PER_SAMPLE * samples_step) / launches_per_step,
+        # the call also returns the final state (20 B) and, packed, the row offset (4 B) of every sample
+        "algorithmic_bytes_with_per_sample_outputs": (BYTES_PER_STATE * written_step + (BYTES_PER_SAMPLE + 24) * samples_step) / launches_per_step,
         "peak_source": "FFMA saturation probe run in this process (kcbs_measure_fp32_peak); nominal 74.4",
         "frac_of_nominal": ach_tflops / FP32_NOMINAL_TFLOPS,
         "algorithmic_flops_per_state": FLOPS_PER_STATE, "avg_launch_ms": kern_ms,
         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src},
     }
+    if k1_traffic:
+        roofline["traffic_over_algorithmic"] = k1_traffic / roofline["algorithmic_bytes_per_launch"]
+        roofline["traffic_over_algorithmic_with_per_sample_outputs"] = k1_traffic / roofline["algorithmic_bytes_with_per_sample_outputs"]
 
     # ---- e2e: host buffers through the reference-facing host entry point --------------------------
     e2e_exp = min(n_exp, 4)
@@ -516,6 +521,24 @@ def main():
     final_s = e2e_run("final")
     e2e["final_state_only"] = {"value": sum_over_ranks(e2e_units) * e2e_steps / final_s, "unit": "states/s",
                                "d2h_bytes_per_step": calls * N_CONTROLS * 24}
+    # the ceiling of the e2e leg: plain pinned copies of 256 MB, all ranks at once (at N > 1 the ranks share the host's memory
+    # system and root complex: the box is one NUMA node, there is nothing to pin to)
+    probe_dev = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    probe_host = torch.empty(64 << 20, dtype=torch.float32).pin_memory()
+    probe = {}
+    for name, dst, src in (("d2h_gbs", probe_host, probe_dev), ("h2d_gbs", probe_dev, probe_host)):
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        probe[name] = 4 * probe_dev.numel() * 4 / (max_over_ranks(c0.elapsed_time(c1)) * 1e-3) * 1e-9
+    del probe_dev, probe_host
+    e2e["pcie_probe"] = dict(probe, note="per GPU, 256 MB pinned cudaMemcpyAsync, all ranks concurrently")
+    e2e["d2h_fraction_of_probe"] = e2e["pcie_d2h_gbs"] / probe["d2h_gbs"]
     # one planner alone (one host thread, one call at a time): what the chunk pipeline inside a call buys
     t0 = time.perf_counter()
     for _ in range(4):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """ncu target for K1 alone: a warm-up launch and `reps` timed launches of k_propagate on one batch.
-Usage: python tools/profile_k1.py [n] [fixed_steps|0] [dense|packed|final] [scene] [reps]
+Usage: python tools/profile_k1.py [n] [fixed_steps|0] [dense|packed|final] [scene] [reps] [expansion mode 0|1|2]
 Under ncu: -k regex:k_propagate -s 1 -c 1"""
 import os
 import sys
@@ -19,8 +19,10 @@ fixed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 layout = sys.argv[3] if len(sys.argv) > 3 else "dense"
 scene = sys.argv[4] if len(sys.argv) > 4 else "Empty32x32_10robots"
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+mode = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 stream = torch.cuda.Stream()
 ctx = pkg.Context(pkg.scenes.world(scene))
+ctx.set_expansion_mode(mode)
 p, c, s = workloads.expansion_batch(scene, n, seed=3, shared_parent=(n <= 65536), interior=1.5, fixed_steps=fixed or None)
 dp, dc, ds = torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(s).cuda()
 seg = torch.empty((5, 10, n), device="cuda")
