@@ -2,6 +2,7 @@
 // calls, and the host-buffer calls as a chunked pipeline (H2D of chunk k+1 and the kernel of chunk k run while chunk
 // k-1 is copied back), dense or packed (CSR) segments.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -25,6 +26,16 @@ static int64_t pipe_min_chunk()
     }();
     return v;
 }
+
+// Host calls of the process in flight (all contexts): see propagate_host.
+static std::atomic<int> g_host_calls{0};
+constexpr int kCrowdedCallers = 3;
+constexpr int64_t kCrowdedChunk = 131072;
+struct ActiveHostCall {
+    int others;
+    ActiveHostCall() : others(g_host_calls.fetch_add(1, std::memory_order_relaxed)) {}
+    ~ActiveHostCall() { g_host_calls.fetch_sub(1, std::memory_order_relaxed); }
+};
 
 struct PipeSlot {
     cudaStream_t stream = nullptr;
@@ -191,8 +202,13 @@ static int propagate_host(kcbs_ctx *ctx, int robot, int64_t n, int64_t n_parents
     if ((st = ensure_pipeline(ctx))) return st;
     HostPipeline &P = *ctx->pipe;
 
-    // chunks: multiples of 2048 samples (whole CTAs of either shape, 16-byte aligned planes)
-    int64_t chunk = std::max<int64_t>(pipe_min_chunk(), (n + kPipeChunks - 1) / kPipeChunks);
+    // chunks: multiples of 2048 samples (whole CTAs of either shape, 16-byte aligned planes).  The pipeline inside a call
+    // pays when the call has the PCIe link to itself; when other host threads of the process are inside host calls of
+    // their own contexts (one planner thread per robot), their calls overlap each other and bigger copies use the link
+    // better (measured: 43 -> 46 GB/s device to host with ten callers), so such a call goes up and down in one piece
+    ActiveHostCall active_call;
+    const bool crowded = active_call.others >= kCrowdedCallers;
+    int64_t chunk = std::max<int64_t>(crowded ? kCrowdedChunk : pipe_min_chunk(), (n + kPipeChunks - 1) / kPipeChunks);
     chunk = (chunk + 2047) / 2048 * 2048;
     const int n_chunks = (int)((n + chunk - 1) / chunk);
     const bool par_chunked = !parent_idx && n_parents == n && n_parents != 1;   // sample i starts at parent i
