@@ -6,37 +6,28 @@
 //   SecondOrderCarODEPostIntegration       StatePropagatorDatabase.h:67-74 (theta wrap per step)
 //   homogeneous2ndOrderCarSystemSVC::isValid  StateValidityCheckerDatabase.h:54-75
 //
-// The kernel is classical RK4 with the reference's stages, evaluated with what the ODE's structure
-// gives for free:
-//   * vdot = a and phidot = w are constant: the v / phi stage values are exact linear functions of
-//     time, stages 2 and 3 share v, phi, tan(phi) and k_theta, and stage 4 of a sub-step is stage 1
-//     of the next one.
-//   * phi advances by the constant delta = (h/2) w per half sub-step, so tan(phi) follows the addition
-//     formula tan(phi + delta) = (T + t) / (1 - T t) (FADD + FFMA + MUFU.RCP + FMUL); re-anchored by an
-//     accurate sincosf every propagation step.
-//   * the four stage headings of a sub-step differ by at most h*|k_theta| <= 0.035 rad, so their
-//     (cos, sin) follow from the previous stage by a 2nd-order rotation (FFMA only, truncation
-//     < 1e-6 which enters the position with weight h/6); re-anchored by MUFU sincos every step.
-//     This moves the kernel off the MUFU pipe (10 -> 2 MUFU per sub-step) onto the FMA pipe.
-//   * k_theta is carried pre-scaled by h/2 and v pre-scaled by h/6, both as exact linear sequences, so a
-//     sub-step is ~45 FMA-pipe instructions + 2 MUFU.
-//   * positions and the heading are accumulated as small offsets from the parent / the step start,
-//     so FP32 rounding at |x| ~ 32 happens once per written state, not once per sub-step.
+// The kernel is classical RK4 with the reference's stages, evaluated with what the ODE's structure gives for free
+// (car_dynamics.cuh, car_step2, has the derivation and the cost model):
+//   * vdot = a and phidot = w are constant: the v / phi stage values are exact linear functions of time, stages 2 and
+//     3 share v, phi, tan(phi) and k_theta, and stage 4 of a sub-step is stage 1 of the next one.
+//   * tan(phi) at the half and the full sub-step follows from the start of the sub-step by the addition formula
+//     tan(phi + d) = (T + t) / (1 - T t); the two denominators share one MUFU.RCP.  Re-anchored every propagation step.
+//   * the four stage headings of a sub-step differ by at most 0.035 rad, so the weighted sum of the four stage velocities
+//     collapses to ONE amplitude times (cos, sin) of ONE heading: one MUFU sin / cos per sample and sub-step.
+//   * positions are accumulated as offsets from the parent and the heading as an offset from the step start, so FP32
+//     rounding at |x| ~ 32 happens once per written state, not once per sub-step.
+//   * every thread integrates TWO samples at once in packed FP32 pairs (fma / mul / add .f32x2, SASS FFMA2 ...):
+//     21 packed instructions + 2 FMUL + 6 MUFU per sub-step of two samples.
 //
-//   * every thread integrates TWO samples at once in packed FP32 pairs (fma / mul / add .f32x2, SASS FFMA2 ...): the
-//     kernel is bound by issue slots, and a packed instruction does two samples' worth of FMA-pipe work in one
-//     slot (car_step2 in car_dynamics.cuh: 34 packed instructions + 8 MUFU per sub-step of two samples).
-//
-// Work distribution: requested durations are U{1..10} (SimpleDirectedControlSampler), which would
-// idle 45 % of the lanes of a warp; and because v, phi are linear in time, the step at which a sample
-// leaves the v / phi bounds is known up front, so its effective duration is too (the doomed step is never
-// integrated).  Each CTA (64 threads) therefore counting-sorts its 256 samples by duration in shared memory and every
-// thread runs two packed pairs of neighbouring ranks: ranks (2t, 2t+1) (long) and then (254-2t, 255-2t) (short).
-// Both halves of a pair and the lanes of a warp then hold (almost) equal durations in both rounds and every thread
-// of the CTA has the same total work, so neither lanes nor warps idle.  Segments are staged in shared memory at their original
-// slots (x, y, theta per step; v and phi are recomputed from their exact linear form) and leave in one
-// coalesced pass that also zero-fills the rows past the last valid state: every 32 B sector is written
-// completely (no partial-sector traffic at L2, no read-modify-write at HBM).
+// Work distribution: requested durations are U{1..10} (SimpleDirectedControlSampler), which would idle 45 % of the
+// lanes of a warp; and because v, phi are linear in time, the step at which a sample leaves the v / phi bounds is known
+// up front, so its effective duration is too (the doomed step is never integrated).  Each CTA (128 threads) therefore
+// counting-sorts its 512 samples by effective duration in shared memory and every thread runs two packed pairs of
+// neighbouring ranks: ranks (2t, 2t+1) (long) and then (510-2t, 511-2t) (short).  Both halves of a pair and the lanes
+// of a warp then hold (almost) equal durations in both rounds and every thread of the CTA has the same total work, so
+// neither lanes nor warps idle.  (Launches that cannot fill the GPU run one pair per thread, 256 samples per CTA.)
+// Segments are staged in shared memory (x, y, theta per step; v and phi are recomputed from their exact linear form, or
+// staged too when the packed layout leaves room) and leave in one coalesced pass: see the output modes below.
 #include <cstddef>
 #include <type_traits>
 
@@ -78,7 +69,7 @@ struct PropGeom {
 };
 
 // Shared-memory staging of one CTA's segments: x, y, theta of every (step, slot), plus the four numbers from which
-// v and phi of any step follow exactly (they are linear in time).  70 KB per 512 samples.
+// v and phi of any step follow exactly (they are linear in time).  70 KB per 512 samples: three CTAs per SM.
 template <int SAMPLES>
 struct __align__(16) PropStage {
     float xyt[3][kStageSteps * SAMPLES];   // kDense: [step][slot]; kPacked: [cap_off[slot] + step]

@@ -1,7 +1,9 @@
 """world_size-2 CPU (gloo) tests of the host-side multi-GPU logic: time-slab partitioning of the conflict
 scan with the unsigned-min key reduction, plan sharding + all-gather, and replan round-robin.  The per-rank
-scan is played by the CPU oracle here (no GPU in this container); on the GPU box the same sharding functions
-drive kcbs_conflict_keys_dev / kcbs_conflict_finish_dev (tests/test_gpu_conflict.py, bench.py)."""
+scan is played by the CPU oracle here (no GPU in this container).  On the GPU box the keys path is exercised by
+tests/test_gpu_conflict.py (kcbs_conflict_keys_dev + kcbs_conflict_finish_dev on one GPU) and the production
+multi-GPU scan -- keys exchanged inside the kernel over peer memory, kcbs_first_conflict_sharded_dev -- by
+tests/test_gpu_sharded_scan.py (2 ranks under torchrun) and bench.py's strong-scaling section."""
 import os
 import socket
 import sys
