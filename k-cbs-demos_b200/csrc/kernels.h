@@ -29,6 +29,9 @@ struct PropArgs {
     const float *cons_states;  // [3][cons_total]
     int n_cons, cons_total;
     int rounds;                // packed pairs per thread: 1, 2, or 0 = chosen from n (propagate.cu)
+    // parent of sample i = parent_idx[(i / parent_group) * parent_stride] (0 = 1: one entry per sample).  The planner hands
+    // over its nearest-neighbour keys as they stand: one 64-bit key per target, node index in the low word
+    int parent_group, parent_stride;
     // packed (CSR) segment output (offsets != null): seg = [5][packed_cap] planes, offsets = [n + 1] rows
     int *offsets;
     long long packed_cap;
@@ -53,6 +56,7 @@ struct PairArgs {              // merged pair: 10-d states, 4-d controls
     float *fin;                // [10][n] or null
     int *valid_steps;
     int max_steps, robot1, robot2;
+    int parent_group, parent_stride;   // as in PropArgs
     float goals[4];            // gx1, gy1, gx2, gy2
     float hold_radius;         // 1.5, StatePropagatorDatabase.h:170
     // dynamic-obstacle constraints (planner only; n_cons == 0 otherwise): they bind BOTH cars, as the merged
@@ -95,6 +99,15 @@ struct FinishArgs {
     kcbs_conflict *out;
     int P, R, T;
 };
+
+// index of the parent state of sample i (PropArgs / PairArgs)
+template <class A>
+__host__ __device__ inline long long parent_of(const A &a, long long i)
+{
+    if (!a.parent_idx) return a.n_parents == 1 ? 0 : i;
+    const long long g = a.parent_group > 1 ? i / a.parent_group : i;
+    return (long long)a.parent_idx[a.parent_stride > 1 ? g * a.parent_stride : g];
+}
 
 cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t stream);
 int propagate_grid(const PropArgs &a);   // CTAs launch_propagate will use (size of the look-back workspace)

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) k_propagate_pair(const __grid_constant__ 
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
+    const long long pi = parent_of(a, i);
     int st = a.steps ? a.steps[i] : a.max_steps;
     st = min(max(st, 0), a.max_steps);
 

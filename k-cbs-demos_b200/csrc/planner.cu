@@ -9,13 +9,14 @@
 // (StateSpaceDatabase.h:45-46: L2 over (x, y, v, phi) + SO2 arc, weights 1), goal = disc of 0.5 around the goal
 // position (GoalRegionDatabase.h:48-55), conflicts = kcbs_first_conflict.
 //
-// Low level, per round (all state in HBM, one stream):
+// Low level, per round (all state in HBM, one stream, four launches):
 //   k_rrt_targets   n_targets random states (goal biased), packed (distance, index) keys reset
 //   k_rrt_nearest   tiled all-pairs nearest tree node per target (four targets per thread in packed FP32 pairs, nodes
 //                   broadcast from shared memory), 64-bit atomicMin on (distance bits, index)
-//   k_rrt_samples   n_targets x n_controls (parent index, control, duration) triples
-//   k_propagate     the K1 expansion kernel with dynamic-obstacle constraints and per-parent time indices
-//   k_rrt_select    per target the sample that ends closest to it is chosen
+//   k_propagate     the K1 expansion kernel with dynamic-obstacle constraints and per-parent time indices; the parent of a
+//                   sample is its target's nearest node (the keys of k_rrt_nearest as they stand), its control and
+//                   duration were drawn one round ahead
+//   k_rrt_select    per target the sample that ends closest to it is chosen; the next round's controls and durations
 //   k_rrt_append    the chosen samples become tree nodes in target order (goal test, report to the host)
 // A found path is re-expanded edge by edge with k_propagate (identical arithmetic) to emit every 0.1 s state.
 #include <algorithm>
@@ -48,10 +49,9 @@ struct RrtWorkspace {
     float *ctrl = nullptr;         // [2 per car][max_nodes] control of the edge into the node
     int *steps = nullptr;          // [max_nodes] duration of the edge into the node
     float *targets = nullptr;      // [dim][n_targets]
-    unsigned long long *nn = nullptr;  // [n_targets] packed (distance bits << 32 | node); ~0 between rounds
-    int *s_parent = nullptr;       // [n_samples]
-    float *s_ctrl = nullptr;       // [2 per car][n_samples]
-    int *s_steps = nullptr;        // [n_samples]
+    unsigned long long *nn = nullptr;  // [n_targets] packed (distance bits << 32 | node); kNNEmpty between rounds
+    float *s_ctrl = nullptr;       // [2 rounds (parity)][2 per car][n_samples]: drawn one round ahead (k_rrt_select)
+    int *s_steps = nullptr;        // [2 rounds (parity)][n_samples]
     float *s_fin = nullptr;        // [dim][n_samples]
     int *s_valid = nullptr;        // [n_samples]
     int *sel = nullptr;            // [n_targets] sample chosen for each target this round, or -1
@@ -90,6 +90,10 @@ __device__ __forceinline__ float urand(unsigned long long seed, unsigned round, 
     return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 
+// "No neighbour yet": larger than every real key, and its low word is a valid node index (the root), so a cancelled round's
+// propagation -- the only kernel of a round that cannot test rrt_done -- still reads a parent that exists.
+constexpr unsigned long long kNNEmpty = 0xffffffff00000000ull;
+
 struct RrtArgs {
     RrtWorkspace ws;
     float goal[4];             // (gx, gy) per car
@@ -109,27 +113,6 @@ struct RrtArgs {
 // tests it is running: every thread of every kernel of a round sees the same answer (the goal key itself changes while
 // k_rrt_append runs).
 __device__ __forceinline__ bool rrt_done(const RrtArgs &a) { return *(volatile const int *)(a.ws.counters + 5) != 0; }
-
-template <int NC>
-__global__ void k_rrt_init(RrtArgs a, const float *start)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const int M = a.ws.max_nodes;
-        for (int c = 0; c < 5 * NC; ++c) a.ws.nodes[c * M] = start[c];
-        a.ws.nn_r[0] = make_float4(start[0], start[1], start[2], start[3]);
-        a.ws.nn_t[0] = start[4];
-        for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M] = 0.f;
-        a.ws.parent[0] = -1; a.ws.time[0] = 0; a.ws.steps[0] = 0;
-        a.ws.counters[0] = 1;   // node count seen by round 0 (parity ring, see rrt_node_count)
-        a.ws.counters[1] = 1;
-        a.ws.counters[2] = 0;   // rounds completed
-        a.ws.counters[3] = 0;   // CTA ticket of k_rrt_append
-        a.ws.counters[5] = 0;   // a goal node exists (rrt_done)
-        *a.ws.goal_key = ~0ull;
-    }
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < a.n_targets) a.ws.nn[t] = ~0ull;
-}
 
 // ob::CompoundStateSpace::distance with unit weights, per car: L2 over (x, y, v, phi) + SO2 arc length.
 __device__ __forceinline__ float car_distance(const float *a, const float *b)
@@ -289,23 +272,42 @@ __global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a, int chunk
     }
 }
 
-// (parent, control, duration) for every sample: sample s belongs to target s / n_controls.
+// Control and duration of sample s of round `round` (sample s belongs to target s / n_controls; its parent is that
+// target's nearest node): a pure function of (seed, round, s), written into the buffer of the round's parity.
 template <int NC>
-__global__ void k_rrt_samples(RrtArgs a)
+__device__ __forceinline__ void rrt_write_sample(const RrtArgs &a, unsigned round, int s)
 {
-    if (rrt_done(a)) return;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = a.n_targets * a.n_controls;
-    if (s >= n) return;
-    const int t = s / a.n_controls;
-    a.ws.s_parent[s] = (int)(a.ws.nn[t] & 0xffffffffu);
+    float *ctrl = a.ws.s_ctrl + (size_t)(round & 1u) * 2 * NC * n;
 #pragma unroll
     for (int car = 0; car < NC; ++car) {
-        a.ws.s_ctrl[(2 * car) * n + s] = -1.0f + 2.0f * urand(a.seed, a.round, s, 8 + 16 * car);       // ControlSpaceDatabase.h:48-51
-        a.ws.s_ctrl[(2 * car + 1) * n + s] = -1.0f + 2.0f * urand(a.seed, a.round, s, 9 + 16 * car);
+        ctrl[(2 * car) * n + s] = -1.0f + 2.0f * urand(a.seed, round, s, 8 + 16 * car);       // ControlSpaceDatabase.h:48-51
+        ctrl[(2 * car + 1) * n + s] = -1.0f + 2.0f * urand(a.seed, round, s, 9 + 16 * car);
     }
     const int span = a.max_steps - a.min_steps + 1;
-    a.ws.s_steps[s] = a.min_steps + min(span - 1, (int)(urand(a.seed, a.round, s, 10) * (float)span));
+    a.ws.s_steps[(size_t)(round & 1u) * n + s] = a.min_steps + min(span - 1, (int)(urand(a.seed, round, s, 10) * (float)span));
+}
+
+template <int NC>
+__global__ void k_rrt_init(RrtArgs a, const float *start)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int M = a.ws.max_nodes;
+        for (int c = 0; c < 5 * NC; ++c) a.ws.nodes[c * M] = start[c];
+        a.ws.nn_r[0] = make_float4(start[0], start[1], start[2], start[3]);
+        a.ws.nn_t[0] = start[4];
+        for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M] = 0.f;
+        a.ws.parent[0] = -1; a.ws.time[0] = 0; a.ws.steps[0] = 0;
+        a.ws.counters[0] = 1;   // node count seen by round 0 (parity ring, see rrt_node_count)
+        a.ws.counters[1] = 1;
+        a.ws.counters[2] = 0;   // rounds completed
+        a.ws.counters[3] = 0;   // CTA ticket of k_rrt_append
+        a.ws.counters[5] = 0;   // a goal node exists (rrt_done)
+        *a.ws.goal_key = ~0ull;
+    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < a.n_targets) a.ws.nn[t] = kNNEmpty;
+    if (t < a.n_targets * a.n_controls) rrt_write_sample<NC>(a, 0u, t);   // (grid = one thread per sample)
 }
 
 // A robot waiting at its final state must also respect the constraints that come later.
@@ -368,10 +370,9 @@ __global__ void __launch_bounds__(256) k_rrt_select(RrtArgs a)
             best_s = os;
         }
     }
-    if (lane == 0) {
-        a.ws.sel[warp] = best_s;
-        a.ws.nn[warp] = ~0ull;   // consumed by k_rrt_samples of this round: clean for the next round's atomicMin
-    }
+    if (lane == 0) a.ws.sel[warp] = best_s;
+    // the controls and durations of the next round's samples of this target (other parity: this round's are still needed)
+    for (int j = lane; j < C; j += 32) rrt_write_sample<NC>(a, a.round + 1u, warp * C + j);
 }
 
 // Appends the chosen samples to the tree in TARGET ORDER, so that node indices -- and with them nearest-neighbour ties,
@@ -423,12 +424,15 @@ __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_cons
     }
     // the chosen sample, while the counts are reduced
     const int s = max(s_idx, 0);
-    const int par = a.ws.s_parent[s], nv = a.ws.s_valid[s];
+    // (the parent of a target's samples = the node index in the low word of its nearest-neighbour key)
+    const int par = t < B ? (int)(a.ws.nn[t] & 0xffffffffu) : 0, nv = a.ws.s_valid[s];
+    const float *ctrl = a.ws.s_ctrl + (size_t)(a.round & 1u) * U * n;
     float f[D], u[U];
 #pragma unroll
     for (int c = 0; c < D; ++c) f[c] = a.ws.s_fin[c * n + s];
 #pragma unroll
-    for (int c = 0; c < U; ++c) u[c] = a.ws.s_ctrl[c * n + s];
+    for (int c = 0; c < U; ++c) u[c] = ctrl[c * n + s];
+    if (t < B) a.ws.nn[t] = kNNEmpty;   // clean for the next round's atomicMin
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         before += __shfl_xor_sync(0xffffffffu, before, off);
@@ -524,7 +528,7 @@ int dev_alloc(kcbs_ctx *ctx, T *&p, size_t n)
 
 void free_workspace(RrtWorkspace &ws)
 {
-    void *d[] = {ws.nodes, ws.parent, ws.time, ws.ctrl, ws.steps, ws.targets, ws.nn, ws.s_parent, ws.s_ctrl, ws.s_steps,
+    void *d[] = {ws.nodes, ws.parent, ws.time, ws.ctrl, ws.steps, ws.targets, ws.nn, ws.s_ctrl, ws.s_steps,
                  ws.s_fin, ws.s_valid, ws.sel, ws.counters, ws.goal_key, ws.cons, ws.cons_states, ws.path_nodes, ws.path_ctrl,
                  ws.path_steps, ws.path_parent, ws.path_valid, ws.path_seg, ws.nn_r, ws.nn_t};
     for (void *p : d)
@@ -550,8 +554,8 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
         const size_t PC = (size_t)ws.path_cap;
         if ((st = dev_alloc(ctx, ws.nodes, D * M)) || (st = dev_alloc(ctx, ws.parent, M)) || (st = dev_alloc(ctx, ws.time, M)) ||
             (st = dev_alloc(ctx, ws.ctrl, U * M)) || (st = dev_alloc(ctx, ws.steps, M)) || (st = dev_alloc(ctx, ws.targets, D * B)) ||
-            (st = dev_alloc(ctx, ws.nn, B)) || (st = dev_alloc(ctx, ws.s_parent, S)) || (st = dev_alloc(ctx, ws.s_ctrl, U * S)) ||
-            (st = dev_alloc(ctx, ws.s_steps, S)) || (st = dev_alloc(ctx, ws.s_fin, D * S)) || (st = dev_alloc(ctx, ws.s_valid, S)) || (st = dev_alloc(ctx, ws.sel, B)) ||
+            (st = dev_alloc(ctx, ws.nn, B)) || (st = dev_alloc(ctx, ws.s_ctrl, 2 * U * S)) ||
+            (st = dev_alloc(ctx, ws.s_steps, 2 * S)) || (st = dev_alloc(ctx, ws.s_fin, D * S)) || (st = dev_alloc(ctx, ws.s_valid, S)) || (st = dev_alloc(ctx, ws.sel, B)) ||
             (st = dev_alloc(ctx, ws.counters, 8)) || (st = dev_alloc(ctx, ws.goal_key, 1)) || (st = dev_alloc(ctx, ws.path_nodes, PC)) ||
             (st = dev_alloc(ctx, ws.path_ctrl, U * PC)) || (st = dev_alloc(ctx, ws.path_steps, PC)) ||
             (st = dev_alloc(ctx, ws.path_parent, PC)) || (st = dev_alloc(ctx, ws.path_valid, PC)) ||
@@ -675,12 +679,14 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
     PairArgs qa = {};
     if (NC == 1) {
         pa.rounds = ctx->prop_rounds;
-        pa.n = n; pa.n_parents = ws.max_nodes; pa.parents = ws.nodes; pa.parent_idx = ws.s_parent; pa.controls = ws.s_ctrl;
+        pa.n = n; pa.n_parents = ws.max_nodes; pa.parents = ws.nodes; pa.parent_idx = reinterpret_cast<const int *>(ws.nn); pa.controls = ws.s_ctrl;
+        pa.parent_group = p.n_controls; pa.parent_stride = 2;   // the low words of the nearest-neighbour keys (little endian)
         pa.steps = ws.s_steps; pa.seg = nullptr; pa.fin = ws.s_fin; pa.valid_steps = ws.s_valid; pa.max_steps = p.max_steps;
         pa.robot = robots[0]; pa.parent_time = ws.time; pa.cons = ws.cons; pa.cons_states = ws.cons_states; pa.n_cons = n_cons;
         pa.cons_total = cons_total;
     } else {
-        qa.n = n; qa.n_parents = ws.max_nodes; qa.parents = ws.nodes; qa.parent_idx = ws.s_parent; qa.controls = ws.s_ctrl;
+        qa.n = n; qa.n_parents = ws.max_nodes; qa.parents = ws.nodes; qa.parent_idx = reinterpret_cast<const int *>(ws.nn); qa.controls = ws.s_ctrl;
+        qa.parent_group = p.n_controls; qa.parent_stride = 2;
         qa.steps = ws.s_steps; qa.seg = nullptr; qa.fin = ws.s_fin; qa.valid_steps = ws.s_valid; qa.max_steps = p.max_steps;
         qa.robot1 = robots[0]; qa.robot2 = robots[NC - 1];
         for (int c = 0; c < 4; ++c) qa.goals[c] = a.goal[c];
@@ -689,7 +695,7 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
     }
 
     for (int q = 0; q < kRrtDepth; ++q) ws.h_progress[q] = RrtProgress{~0ull, 1, 0};
-    k_rrt_init<NC><<<(p.n_targets + 255) / 256, 256, 0, s>>>(a, ws.targets);
+    k_rrt_init<NC><<<(n + 255) / 256, 256, 0, s>>>(a, ws.targets);
     ctx->launches += 1;
     int n_nodes = 1, iters = 0, queued = 0;
     unsigned long long goal = ~0ull;
@@ -717,7 +723,9 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         const int chunk = nn_chunk(bound, tiles);
         dim3 g((unsigned)tiles, (unsigned)((bound + chunk - 1) / chunk));
         k_rrt_nearest<NC><<<g, kNNThreads, 0, s>>>(a, chunk);
-        k_rrt_samples<NC><<<(n + 255) / 256, 256, 0, s>>>(a);
+        // this round's controls and durations (drawn one round ahead) sit in the buffer of the round's parity
+        pa.controls = qa.controls = ws.s_ctrl + (size_t)(queued & 1) * 2 * NC * n;
+        pa.steps = qa.steps = ws.s_steps + (size_t)(queued & 1) * n;
         if (NC == 1)
             KCBS_CUDA(ctx, launch_propagate(ctx->world, pa, s));
         else
@@ -725,7 +733,7 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         k_rrt_select<NC><<<(p.n_targets * 32 + 255) / 256, 256, 0, s>>>(a);
         k_rrt_append<NC><<<(p.n_targets + kAppendThreads - 1) / kAppendThreads, kAppendThreads, 0, s>>>(ctx->world, a);
         KCBS_CUDA(ctx, cudaEventRecord(ws.ev[queued % kRrtDepth], s));
-        ctx->launches += 5;
+        ctx->launches += 4;
         ++queued;
     }
     if (goal == ~0ull) {
@@ -755,12 +763,12 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
             const int E = ws.h_counters[4];
             if (NC == 1) {
                 PropArgs pe = pa;
-                pe.n = E; pe.parent_idx = ws.path_parent; pe.controls = ws.path_ctrl; pe.steps = ws.path_steps;
+                pe.n = E; pe.parent_idx = ws.path_parent; pe.parent_group = pe.parent_stride = 1; pe.controls = ws.path_ctrl; pe.steps = ws.path_steps;
                 pe.seg = ws.path_seg; pe.fin = nullptr; pe.valid_steps = ws.path_valid; pe.max_steps = p.max_steps;
                 KCBS_CUDA(ctx, launch_propagate(ctx->world, pe, s));
             } else {
                 PairArgs qe = qa;
-                qe.n = E; qe.parent_idx = ws.path_parent; qe.controls = ws.path_ctrl; qe.steps = ws.path_steps;
+                qe.n = E; qe.parent_idx = ws.path_parent; qe.parent_group = qe.parent_stride = 1; qe.controls = ws.path_ctrl; qe.steps = ws.path_steps;
                 qe.seg = ws.path_seg; qe.fin = nullptr; qe.valid_steps = ws.path_valid; qe.max_steps = p.max_steps;
                 KCBS_CUDA(ctx, launch_propagate_pair(ctx->world, qe, s));
             }

@@ -131,7 +131,7 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
     int t0[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-        const long long pi = a.parent_idx ? (long long)a.parent_idx[i[e]] : (a.n_parents == 1 ? 0 : i[e]);
+        const long long pi = parent_of(a, i[e]);
         t0[e] = (HAS_CONS && a.parent_time) ? a.parent_time[pi] : 0;
         if (STAGED) {  // the sort pass left the sample's inputs in shared memory (slot -1: any slot, nothing is used)
             const int sl = max(slot[e], 0);
@@ -305,7 +305,7 @@ __device__ __forceinline__ void write_final_states(const DevWorld &w, const Prop
                 f[3][e] = fmaf(stage->uw[sl], tfin, stage->p0[sl]);
                 f[4][e] = ref(2, at);
             } else {
-                const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
+                const long long pi = parent_of(a, i);
 #pragma unroll
                 for (int c = 0; c < 5; ++c) f[c][e] = a.parents[c * a.n_parents + pi];
             }
@@ -412,7 +412,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
 #pragma unroll
             for (int u = 0; u < kPer; ++u) {
                 ii[u] = min(b0 + tid + u * kPropThreads, a.n - 1);
-                pi[u] = a.parent_idx ? (long long)a.parent_idx[ii[u]] : (a.n_parents == 1 ? 0 : ii[u]);
+                pi[u] = parent_of(a, ii[u]);
                 st_req[u] = a.steps ? a.steps[ii[u]] : a.max_steps;
                 ua[u] = a.controls[ii[u]];
                 uw[u] = a.controls[a.n + ii[u]];
@@ -560,7 +560,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             const long long i = b0 + slot;
             if (i >= a.n) continue;
             const int nv = s_nv[slot];
-            const long long pi = a.parent_idx ? (long long)a.parent_idx[i] : (a.n_parents == 1 ? 0 : i);
+            const long long pi = parent_of(a, i);
             const float v0 = a.parents[2 * a.n_parents + pi], p0 = a.parents[3 * a.n_parents + pi];
             const float ua = a.controls[i], uw = a.controls[a.n + i];
             for (int j = 0; j < a.max_steps; ++j) {
