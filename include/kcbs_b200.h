@@ -268,7 +268,8 @@ typedef struct kcbs_rrt_params {
     int32_t n_targets;      /* tree nodes expanded per iteration                  (default 2048)   */
     int32_t n_controls;     /* sampled controls per expanded node                 (default 32)     *
                              * n_targets * n_controls = 65,536 controls per expansion round        */
-    int32_t max_nodes;      /* tree capacity                                      (default 1<<18)  */
+    int32_t max_nodes;      /* tree capacity; 0 = from the workspace: 1.5 x the rounds a path across it needs,
+                               32 .. 128 rounds of n_targets nodes                 (default 0)     */
     int32_t max_iterations; /*                                                    (default 512)    */
     int32_t min_steps;      /* setMinMaxControlDuration(1, 10), demo_*.cpp:118                      */
     int32_t max_steps;

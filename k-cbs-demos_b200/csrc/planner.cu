@@ -598,7 +598,7 @@ double now_s()
 
 int check_rrt_params(kcbs_ctx *ctx, const kcbs_rrt_params &p)
 {
-    if (p.n_targets < 1 || p.n_controls < 1 || p.max_nodes < 2 || p.max_iterations < 1 || p.min_steps < 1 ||
+    if (p.n_targets < 1 || p.n_controls < 1 || (p.max_nodes != 0 && p.max_nodes < 2) || p.max_iterations < 1 || p.min_steps < 1 ||
         p.max_steps < p.min_steps || p.max_steps > KCBS_MAX_STEPS || !(p.goal_radius > 0) ||
         (long long)p.n_targets * p.n_controls > (1ll << 26))
         return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "kcbs_rrt_params out of range");
@@ -628,16 +628,32 @@ void destroy_rrt_workspace(kcbs_ctx *ctx)
 // queues iterations without waiting for them: each round reports (goal, node count) into a host-mapped ring, the host
 // looks at round i - kRrtDepth before it queues round i, and rounds queued after the goal was found cancel themselves on
 // the device.  start = 5 NC reals, goal_xy = 2 NC, traj_out = [5 NC][max_T].
+// Tree capacity when the caller leaves it to the planner (max_nodes = 0): the rounds a path across the workspace needs at
+// full speed (one round extends the tree by at most max_steps * step seconds of driving) with 50 % slack, between 32 and
+// 128 rounds.  A re-plan that cannot succeed -- K-CBS produces them: a constraint can park another robot on the goal --
+// costs the whole capacity (the nearest-neighbour scan grows with the tree), so the capacity is what bounds a failure.
+static int auto_max_nodes(const kcbs_ctx *ctx, const kcbs_rrt_params &p)
+{
+    const DevWorld &w = ctx->world;
+    const float dx = w.hi_t[0] - w.lo_t[0], dy = w.hi_t[1] - w.lo_t[1];
+    const float v_max = std::max(std::fabs(w.lo_t[2]), std::fabs(w.hi_t[2]));
+    const float per_round = std::max(1e-3f, v_max * w.step * (float)p.max_steps);
+    const int rounds = std::min(128, std::max(32, (int)std::ceil(1.5f * std::sqrt(dx * dx + dy * dy) / per_round)));
+    return (int)std::min<long long>((long long)rounds * p.n_targets + 1, 1ll << 22);
+}
+
 template <int NC>
-static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const float *goal_xy, const kcbs_rrt_params &p,
+static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const float *goal_xy, const kcbs_rrt_params &p_in,
                     int n_cons, const int32_t *cons_robot, const int32_t *cons_k0, const int32_t *cons_len,
                     const int32_t *cons_offset, const float *cons_states, int max_T, float *traj_out, int32_t *T_out,
                     kcbs_rrt_stats *stats)
 {
     constexpr int D = 5 * NC;
     const double t_begin = now_s();
-    int st = check_rrt_params(ctx, p);
+    int st = check_rrt_params(ctx, p_in);
     if (st) return st;
+    kcbs_rrt_params p = p_in;
+    if (p.max_nodes == 0) p.max_nodes = auto_max_nodes(ctx, p);
     for (int c = 0; c < NC; ++c)
         if (robots[c] < 0 || robots[c] >= ctx->n_robots) return fail(ctx, KCBS_ERR_UNKNOWN_ROBOT, "robot index out of range");
     if (!start || !goal_xy || !traj_out || !T_out || max_T < 1) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "null argument");
@@ -805,7 +821,7 @@ void kcbs_rrt_defaults(kcbs_rrt_params *p)
     if (!p) return;
     p->n_targets = 2048;
     p->n_controls = 32;
-    p->max_nodes = 1 << 18;
+    p->max_nodes = 0;       // chosen from the workspace, see auto_max_nodes
     p->max_iterations = 512;
     p->min_steps = 1;    // demo_*.cpp:118
     p->max_steps = 10;

@@ -13,12 +13,13 @@ pkg = graft.load_package()
 scene = sys.argv[1] if len(sys.argv) > 1 else "Benchmark_Empty32x32_30robots"
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+max_nodes = int(sys.argv[4]) if len(sys.argv) > 4 else None   # low-level tree size (default of kcbs_rrt_defaults when absent)
 with pkg.Context(pkg.scenes.world(scene), device=0) as ctx:
     starts, goals = pkg.scenes.start_states(scene), pkg.scenes.goals(scene)
     for rep in range(reps):
         l0 = ctx.launch_count()
         t0 = time.perf_counter()
-        _, lengths, st = ctx.kcbs_solve(starts, goals, ctx.kcbs_params(low_level=ctx.rrt_params(seed=seed + rep), time_limit_s=60.0))
+        _, lengths, st = ctx.kcbs_solve(starts, goals, ctx.kcbs_params(low_level=ctx.rrt_params(seed=seed + rep, **({} if max_nodes is None else {'max_nodes': max_nodes})), time_limit_s=60.0))
         dt = time.perf_counter() - t0
         print(f"{scene} seed {seed + rep}: solved={st.solved} {dt * 1e3:.1f} ms, root {st.root_seconds * 1e3:.1f} ms, nodes {st.nodes_expanded}, "
               f"low-level plans {st.low_level_calls}, validations {st.conflict_checks}, merges {st.merges}, "
