@@ -342,7 +342,7 @@ def main():
     for c in ctxs:
         c.set_expansion_mode(args.expansion_mode)
 
-    def gpu_step():
+    def gpu_step(packed_layout=packed_layout):
         """One step: every robot planner issues its expansions on its own stream (fork from / join into the
         current stream, so the whole step can be captured into one CUDA graph)."""
         cur = torch.cuda.current_stream()
@@ -415,6 +415,28 @@ def main():
     elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
     total_units = sum_over_ranks(units_step) * args.steps
     value = total_units / (elapsed_ms * 1e-3)
+    # the other segment layout through the same loop (a few steps), for the record: dense = zero-padded [5][10][n] segments
+    # (2.2 x the bytes, no row bookkeeping), packed = valid rows only
+    other = {}
+    if not args.no_graph:
+        other_packed = not packed_layout
+        og = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(og):
+            gpu_step(other_packed)
+        for _ in range(3):
+            og.replay()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o_steps = max(3, min(args.steps, 5))
+        o0.record(main_stream)
+        for _ in range(o_steps):
+            og.replay()
+        o1.record(main_stream)
+        barrier()
+        o_ms = max_over_ranks(o0.elapsed_time(o1))
+        other = {"layout": "packed" if other_packed else "dense", "steps": o_steps,
+                 "value": sum_over_ranks(units_step) * o_steps / (o_ms * 1e-3), "ms_per_step": o_ms / o_steps}
+        del og
     fp32_peak_after = ctxs[0].measure_fp32_peak()
     fp32_peak = max(fp32_peak_before, fp32_peak_after)
 
@@ -450,6 +472,9 @@ def main():
         "algorithmic_flops_per_state": FLOPS_PER_STATE, "avg_launch_ms": kern_ms,
         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak, "peak_source": peak_src},
     }
+    if other:
+        other["frac"] = FLOPS_PER_STATE * units_step / (other["ms_per_step"] * 1e-3) * 1e-12 / fp32_peak if fp32_peak else None
+        roofline["other_layout"] = other
     if k1_traffic:
         roofline["traffic_over_algorithmic"] = k1_traffic / roofline["algorithmic_bytes_per_launch"]
         roofline["traffic_over_algorithmic_with_per_sample_outputs"] = k1_traffic / roofline["algorithmic_bytes_with_per_sample_outputs"]
