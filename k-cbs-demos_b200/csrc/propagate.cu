@@ -121,12 +121,17 @@ __device__ __forceinline__ float tan_phi(float phi)
 
 // propagateWhileValid for the two samples i[0], i[1] (effective durations st[0], st[1]; st = 0 for a slot past the end
 // of the batch): writes their segments, final states and valid-step counts.
-template <bool HAS_OBS, bool HAS_CONS, int MODE, int SAMPLES>
+// FIVE (packed layout only): the CTA's rows fit five stage planes; the plane stride is a compile-time constant either way,
+// so that a store into plane c is the position plus an immediate.
+template <bool HAS_OBS, bool HAS_CONS, int MODE, int SAMPLES, bool FIVE>
 __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs &a, const long long i[2], const int st[2],
                                               PropStage<SAMPLES> *stage, const StageIndex<MODE, SAMPLES> &six,
                                               unsigned char *s_nv, const int slot[2], float tan_shared)
 {
     constexpr bool STAGED = MODE != kDirect;
+    constexpr int kPlane = FIVE ? StageIndex<MODE, SAMPLES>::kFivePositions : StageIndex<MODE, SAMPLES>::kPositions;
+    float *const flat = six.flat;
+    auto ref = [&](int c, int pos) -> float & { return flat[c * kPlane + pos]; };
     float x0[2], y0[2], v0[2], phi0[2], th0[2], ua[2], uw[2];
     int t0[2];
 #pragma unroll
@@ -142,9 +147,9 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
                 th0[e] = a.parents[4 * a.n_parents + pi];
             } else {
                 const int at = six.stash(sl);
-                x0[e] = six.ref(0, at);
-                y0[e] = six.ref(1, at);
-                th0[e] = six.ref(2, at);
+                x0[e] = ref(0, at);
+                y0[e] = ref(1, at);
+                th0[e] = ref(2, at);
             }
             v0[e] = stage->v0[sl];
             phi0[e] = stage->p0[sl];
@@ -223,12 +228,12 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
             if (!ok) continue;
             if (STAGED) {
                 const int at = at0[e] + j * kStride;
-                six.ref(0, at) = xn[e];
-                six.ref(1, at) = yn[e];
-                six.ref(2, at) = tn[e];
-                if (MODE == kPacked && six.five) {   // the expressions st was derived with (and the dense write-out's)
-                    six.ref(3, at) = fmaf(ua[e], t1, v0[e]);
-                    six.ref(4, at) = fmaf(uw[e], t1, phi0[e]);
+                ref(0, at) = xn[e];
+                ref(1, at) = yn[e];
+                ref(2, at) = tn[e];
+                if (FIVE) {   // the expressions st was derived with (and the dense write-out's)
+                    ref(3, at) = fmaf(ua[e], t1, v0[e]);
+                    ref(4, at) = fmaf(uw[e], t1, phi0[e]);
                 }
             } else if (a.seg) {
                 // straight to the sample's own slot: the CTA's stores of a row stay inside one 1 KB window, L2 merges
@@ -248,12 +253,12 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
         if (MODE == kPacked) {
             // rows the sample owns but did not reach (it left the workspace / hit an obstacle early) leave as zeros
             for (int j = nv[e]; j < st[e]; ++j) {
-                six.ref(0, at0[e] + j) = 0.0f;
-                six.ref(1, at0[e] + j) = 0.0f;
-                six.ref(2, at0[e] + j) = 0.0f;
-                if (six.five) {
-                    six.ref(3, at0[e] + j) = 0.0f;
-                    six.ref(4, at0[e] + j) = 0.0f;
+                ref(0, at0[e] + j) = 0.0f;
+                ref(1, at0[e] + j) = 0.0f;
+                ref(2, at0[e] + j) = 0.0f;
+                if (FIVE) {
+                    ref(3, at0[e] + j) = 0.0f;
+                    ref(4, at0[e] + j) = 0.0f;
                 }
             }
         }
@@ -544,8 +549,12 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 slot[e] = -1;
             }
         }
-        if (slot[0] >= 0 || slot[1] >= 0)
-            propagate_two<HAS_OBS, HAS_CONS, MODE, kSamples>(w, a, i, st, stage, six, s_nv, slot, tan_shared);
+        if (slot[0] >= 0 || slot[1] >= 0) {
+            if (MODE == kPacked && six.five)
+                propagate_two<HAS_OBS, HAS_CONS, MODE, kSamples, MODE == kPacked>(w, a, i, st, stage, six, s_nv, slot, tan_shared);
+            else
+                propagate_two<HAS_OBS, HAS_CONS, MODE, kSamples, false>(w, a, i, st, stage, six, s_nv, slot, tan_shared);
+        }
     }
 
     if (MODE == kDirect && a.seg) {
