@@ -128,6 +128,36 @@ def test_invalid_parent_direction(pkg, orc, gpu_ctx_factory):
     assert (fin[:, 0] == p[:, 0]).all()
 
 
+def test_parent_headings_at_and_beyond_the_wrap(pkg, orc, gpu_ctx_factory):
+    # the reference wraps the heading after every step (SO2 enforceBounds, StatePropagatorDatabase.h:67-74), whatever the
+    # parent's heading was: parents at +-pi, just inside, and several turns away must give the oracle's segments
+    scene = "Empty32x32_10robots"
+    ctx = gpu_ctx_factory(scene)
+    o = orc.Oracle(pkg.scenes.world(scene))
+    pi32 = np.float32(np.pi)
+    headings = np.array([-pi32, np.nextafter(pi32, np.float32(0)), np.nextafter(-pi32, np.float32(0)), 3.0, -3.1, 3.5, -4.0,
+                         7.0, -9.5, 12.0, 40.0, -55.5], np.float32)
+    rng = np.random.default_rng(7)
+    n = len(headings) * 32
+    parents = np.empty((5, n), np.float32)
+    parents[0], parents[1] = 16.0 + rng.uniform(-3, 3, n), 16.0 + rng.uniform(-3, 3, n)
+    parents[2], parents[3] = rng.uniform(-0.9, 0.9, n), rng.uniform(-0.9, 0.9, n)
+    parents[4] = np.repeat(headings, 32)
+    controls = rng.uniform(-1, 1, (2, n)).astype(np.float32)
+    steps = rng.integers(1, 11, n).astype(np.int32)
+    seg, fin, valid = ctx.propagate_batch(0, parents, controls, steps)
+    for i in range(n):
+        nv, oseg, ofin = o.propagate_while_valid(parents[:, i], controls[:, i], int(steps[i]))
+        assert nv == valid[i], f"sample {i} (heading {parents[4, i]}): {valid[i]} vs {nv} valid steps"
+        for j in range(nv):
+            ok, d = state_close(seg[:, j, i:i + 1], np.asarray(oseg[j], np.float64)[:, None])
+            assert ok.all(), f"sample {i} (heading {parents[4, i]}) step {j}: {d.ravel()}"
+            assert -np.pi <= seg[4, j, i] < np.pi
+    # packed layout, same arithmetic
+    packed, offsets, pfin, pvalid, total = ctx.propagate_packed(0, parents, controls, steps)
+    assert (pvalid == valid).all() and (pfin.view(np.uint32) == fin.view(np.uint32)).all()
+
+
 def test_errors(pkg, gpu_ctx_factory):
     ctx = gpu_ctx_factory("Empty32x32_10robots")
     p = np.zeros((5, 3), np.float32)
