@@ -337,8 +337,10 @@ class Context:
 
     def propagate_packed(self, robot, parents, controls, steps=None, parent_idx=None, max_steps=10, want_final=True,
                          out=None, packed_cap=None):
-        """Host entry point kcbs_propagate_packed.  Returns (packed [5, cap] (rows [:, :total] are valid), offsets [n + 1],
-        final [5, n] or None, valid_steps [n], total).  out = (packed, offsets, final, valid) reuses caller buffers."""
+        """Host entry point kcbs_propagate_packed.  Returns (packed [5, cap] (rows [:, :total] are in use), offsets [n + 1],
+        final [5, n] or None, valid_steps [n], total).  Sample i's states are rows offsets[i] .. offsets[i] + valid_steps[i] - 1;
+        blocks of samples are placed first come, first served, so offsets is not monotone across blocks (offsets[n] = total).
+        out = (packed, offsets, final, valid) reuses caller buffers."""
         parents = np.ascontiguousarray(parents, dtype=np.float32)
         controls = np.ascontiguousarray(controls, dtype=np.float32)
         n, n_parents = controls.shape[1], parents.shape[1]
