@@ -445,26 +445,29 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
                 // before integrating anything: that step would fail isValid, so the segment ends just before
                 // it (same result as propagating it and testing).  Sorting by this effective duration keeps
                 // warps uniform even when many samples leave the v / phi bounds early.
-                // fmaf(u, t, v0) is monotonic in t, so the valid steps form a prefix; when the first and the last
-                // requested step are inside, all of them are (the common case: two evaluations instead of a loop)
+                // fmaf(u, t, v0) is monotonic in t, so the valid steps form a prefix.  The crossing estimated from
+                // the linear form is right to within one step, so five independent evaluations of the exact test
+                // (no data-dependent branch: the four samples of a thread interleave) settle it; anything they do
+                // not settle (a degenerate estimate) falls back to counting the prefix.
                 auto inside = [&](int j) {
                     const float t1 = (float)(j + 1) * w.step;
                     const float vn = fmaf(ua[u], t1, v0[u]), pn = fmaf(uw[u], t1, phi0[u]);
                     return (vn >= w.lo_t[2]) & (vn <= w.hi_t[2]) & (pn >= w.lo_t[3]) & (pn <= w.hi_t[3]);
                 };
-                int ok_steps = 0;
-                if (st > 0 && inside(0)) {
-                    if (inside(st - 1)) {
-                        ok_steps = st;
-                    } else {
-                        // estimate the crossing from the linear form, then settle it with the exact test (0-1 moves)
-                        const float cv = __fdividef((ua[u] > 0.0f ? w.hi_t[2] : w.lo_t[2]) - v0[u], ua[u] * w.step);
-                        const float cp = __fdividef((uw[u] > 0.0f ? w.hi_t[3] : w.lo_t[3]) - phi0[u], uw[u] * w.step);
-                        const float c = fminf(ua[u] != 0.0f ? cv : 1.0e9f, uw[u] != 0.0f ? cp : 1.0e9f);
-                        ok_steps = min(max((int)c, 1), st - 1);
-                        while (ok_steps < st - 1 && inside(ok_steps)) ++ok_steps;
-                        while (ok_steps > 1 && !inside(ok_steps - 1)) --ok_steps;
-                    }
+                const float cv = __fdividef((ua[u] > 0.0f ? w.hi_t[2] : w.lo_t[2]) - v0[u], ua[u] * w.step);
+                const float cp = __fdividef((uw[u] > 0.0f ? w.hi_t[3] : w.lo_t[3]) - phi0[u], uw[u] * w.step);
+                const float c = fminf(ua[u] != 0.0f ? cv : 1.0e9f, uw[u] != 0.0f ? cp : 1.0e9f);
+                const int k = min(max((int)c, 1), st);
+                const bool e0 = inside(0), em2 = inside(k - 2), em1 = inside(k - 1), ek = inside(k),
+                           ek1 = inside(k + 1);
+                int ok_steps = k + 1;
+                bool unsettled = !(k + 1 == st || !ek1);
+                if (k == st || !ek) { ok_steps = k; unsettled = false; }
+                if (!em1) { ok_steps = k - 1; unsettled = !em2; }
+                if (st == 0 || !e0) { ok_steps = 0; unsettled = false; }
+                if (unsettled) {
+                    ok_steps = 0;
+                    while (ok_steps < st && inside(ok_steps)) ++ok_steps;
                 }
                 st = ok_steps;
                 if (STAGED) {
