@@ -12,6 +12,21 @@ struct DevWorld;
 
 struct ConsDesc;   // kcbs_device.cuh
 
+// What changes from one low-level plan to the next, and from one RRT round to the next, lives on the DEVICE (one 128-byte
+// block per planner workspace, uploaded once per plan): the kernels of a round read it instead of taking it as launch
+// arguments, so the same launches -- a CUDA graph with a device-driven loop -- serve every round of every plan.
+struct RrtPlan {
+    // (the first 16 bytes are what the propagation kernels read, as one word)
+    int round;                 // index of the current round = rounds completed (kept by k_rrt_append)
+    int robot[2];              // robot of car 0 / car 1 (merged pair; = robot[0] for one car)
+    int n_cons;
+    int cons_total, max_T, max_iterations, node_cap;
+    float goal[4];             // (gx, gy) per car
+    float goal_radius, goal_bias;
+    unsigned long long seed;
+    unsigned long long limit_ns, t_start;   // time limit of the device-driven loop (0 = none); start stamp (k_rrt_init)
+};
+
 struct PropArgs {
     long long n, n_parents;
     const float *parents;      // [5][n_parents]
@@ -37,6 +52,10 @@ struct PropArgs {
     long long packed_cap;
     unsigned long long *scan;  // (spare workspace words behind scan_ctl)
     unsigned *scan_ctl;        // 8-byte aligned row allocator (CTAs served << 40 | rows handed out); zeroed, left zeroed
+    // planner rounds (null otherwise): robot, n_cons, cons_total come from the plan block, and controls / steps are the
+    // buffers of the round's parity: controls + (round & 1) * parity_ctrl, steps + (round & 1) * parity_steps
+    const RrtPlan *plan;
+    long long parity_ctrl, parity_steps;
 };
 
 struct ValidArgs {
@@ -65,6 +84,9 @@ struct PairArgs {              // merged pair: 10-d states, 4-d controls
     const ConsDesc *cons;
     const float *cons_states;
     int n_cons, cons_total;
+    // planner rounds (null otherwise): robots, goals, n_cons, cons_total and the round's parity come from the plan block
+    const RrtPlan *plan;
+    long long parity_ctrl, parity_steps;
 };
 
 struct PairValidArgs {

@@ -35,10 +35,24 @@ __device__ __forceinline__ bool pair_state_valid(const DevWorld &w, int r1, int 
     return true;
 }
 
-__global__ void __launch_bounds__(128) k_propagate_pair(const __grid_constant__ DevWorld w, const __grid_constant__ PairArgs a)
+__global__ void __launch_bounds__(128) k_propagate_pair(const __grid_constant__ DevWorld w, const __grid_constant__ PairArgs a_in)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    if (i >= a_in.n) return;
+    // planner rounds: robots, goals, constraint counts and the round's parity come from the plan block (kernels.h)
+    PairArgs a = a_in;
+    if (a_in.plan) {
+        const RrtPlan &p = *a_in.plan;
+        const int round = __ldcg(&p.round);
+        a.robot1 = __ldcg(&p.robot[0]);
+        a.robot2 = __ldcg(&p.robot[1]);
+        a.n_cons = __ldcg(&p.n_cons);
+        a.cons_total = __ldcg(&p.cons_total);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a.goals[c] = __ldcg(&p.goal[c]);
+        a.controls = a_in.controls + (round & 1) * a_in.parity_ctrl;
+        if (a_in.steps) a.steps = a_in.steps + (round & 1) * a_in.parity_steps;
+    }
     const long long pi = parent_of(a, i);
     int st = a.steps ? a.steps[i] : a.max_steps;
     st = min(max(st, 0), a.max_steps);

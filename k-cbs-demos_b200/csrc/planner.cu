@@ -23,6 +23,8 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <queue>
@@ -70,6 +72,12 @@ struct RrtWorkspace {
     RrtProgress *h_progress = nullptr, *d_progress = nullptr;   // [kRrtDepth] host-mapped ring
     int *h_counters = nullptr;                                  // pinned
     cudaEvent_t ev[kRrtDepth] = {};
+    RrtPlan *plan = nullptr, *h_plan = nullptr;   // the plan block on the device (kernels.h) and its pinned staging copy
+    // device-driven rounds: one instantiated graph per (cars, constrained or not), rebuilt when the launch shape changes
+    struct Loop {
+        cudaGraphExec_t exec = nullptr;
+        int key[5] = {0, 0, 0, 0, 0};   // n_targets, n_controls, min_steps, max_steps, expansion shape
+    } loop[2][2];
 };
 
 namespace {
@@ -94,18 +102,47 @@ __device__ __forceinline__ float urand(unsigned long long seed, unsigned round, 
 // propagation -- the only kernel of a round that cannot test rrt_done -- still reads a parent that exists.
 constexpr unsigned long long kNNEmpty = 0xffffffff00000000ull;
 
+// Launch arguments of the planner kernels.  Everything from `goal` on is NOT filled by the host: it is loaded from the
+// plan block on the device at the top of every kernel (rrt_load_plan), see RrtPlan.
 struct RrtArgs {
     RrtWorkspace ws;
+    float lo[4], hi[4];
+    int n_targets, n_controls, min_steps, max_steps;
+    cudaGraphConditionalHandle loop;   // the WHILE node of the device-driven loop (in_loop != 0), set by k_rrt_append
+    int in_loop;
     float goal[4];             // (gx, gy) per car
     float goal_radius;         // one car: distanceGoal <= radius (GoalRegionDatabase.h:48-55); merged pair: both < radius (:61-108)
     float goal_bias;
-    float lo[4], hi[4];
     unsigned long long seed;
     unsigned round;
-    int n_targets, n_controls, min_steps, max_steps, robot[2];
+    int robot[2];
     int n_cons, cons_total;
     int max_T;  // states the caller's trajectory buffer holds: a goal node must have time index < max_T
+    int max_iterations;
+    unsigned long long limit_ns, t_start;
 };
+
+static_assert(offsetof(RrtPlan, goal) == 32 && offsetof(RrtPlan, goal_radius) == 48 && offsetof(RrtPlan, seed) == 56 &&
+                  offsetof(RrtPlan, limit_ns) == 64 && sizeof(RrtPlan) == 80,
+              "rrt_load_plan reads the block as five 16-byte words");
+__device__ __forceinline__ void rrt_load_plan(RrtArgs &a)
+{
+    const int4 *p = reinterpret_cast<const int4 *>(a.ws.plan);
+    const int4 h0 = __ldcg(p), h1 = __ldcg(p + 1), h2 = __ldcg(p + 2), h3 = __ldcg(p + 3), h4 = __ldcg(p + 4);
+    a.round = (unsigned)h0.x; a.robot[0] = h0.y; a.robot[1] = h0.z; a.n_cons = h0.w;
+    a.cons_total = h1.x; a.max_T = h1.y; a.max_iterations = h1.z;
+    a.goal[0] = __int_as_float(h2.x); a.goal[1] = __int_as_float(h2.y); a.goal[2] = __int_as_float(h2.z); a.goal[3] = __int_as_float(h2.w);
+    a.goal_radius = __int_as_float(h3.x); a.goal_bias = __int_as_float(h3.y);
+    a.seed = (unsigned long long)(unsigned)h3.z | ((unsigned long long)(unsigned)h3.w << 32);
+    a.limit_ns = (unsigned long long)(unsigned)h4.x | ((unsigned long long)(unsigned)h4.y << 32);
+    a.t_start = (unsigned long long)(unsigned)h4.z | ((unsigned long long)(unsigned)h4.w << 32);
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // Every kernel of an iteration starts with this test: once a goal node exists the remaining iterations already queued
 // on the stream do nothing, so the outcome is that of the first iteration that found one -- however far the host ran ahead.
@@ -148,11 +185,16 @@ constexpr int kNNChunkMax = 512;   // nodes per CTA at most (the chunk shrinks w
 
 // nodes per CTA for a tree of at most `bound` nodes and `tiles` target tiles: about 600 CTAs, multiples of 32, within
 // [32, kNNChunkMax]
-inline int nn_chunk(long long bound, int tiles)
+__host__ __device__ inline int nn_chunk(int n_nodes, int tiles)
 {
-    const long long chunks = std::max(1, 600 / std::max(tiles, 1));
-    long long c = (bound / chunks + 31) / 32 * 32;
-    return (int)std::max<long long>(32, std::min<long long>(kNNChunkMax, c));
+    const int chunks = 600 / tiles > 1 ? 600 / tiles : 1;
+    const int c = (n_nodes / chunks + 31) / 32 * 32;
+    return c < 32 ? 32 : (c > kNNChunkMax ? kNNChunkMax : c);
+}
+// chunks of the largest tree: the grid of every round (CTAs past the round's node count return at once)
+inline int nn_grid_y(int max_nodes, int tiles)
+{
+    return std::max(std::max(1, 600 / tiles), (max_nodes + kNNChunkMax - 1) / kNNChunkMax);
 }
 
 // node count of the tree at the start of `round`: counters live in a two-entry ring indexed by the round's parity, so a
@@ -191,21 +233,23 @@ __device__ __forceinline__ float nn_sqrt(float x)
     return r;
 }
 
-// grid = (ceil(n_targets / 512), chunks of the largest tree this round can have): every thread owns FOUR targets (two
+// grid = (ceil(n_targets / 512), chunks of the largest tree, nn_grid_y): every thread owns FOUR targets (two
 // packed FP32 pairs) and scans one chunk of nodes broadcast from shared memory (car 0 with every component duplicated, so
 // that a node is a packed operand as it stands; the node count is read on the device: the host does not know it).
 // Straight-line code per node -- squared L2 over (x, y, v, phi), MUFU square root, SO2 arc -- and one unsigned minimum on
 // (distance bits with the low 9 bits replaced by the node's place in the chunk): the distance is compared to 2^-14
 // relative, ties go to the smallest index, nothing diverges.
 template <int NC>
-__global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a, int chunk)
+__global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a)
 {
     constexpr int D = 5 * NC;
     static_assert(kNNChunkMax <= 512, "the node's place in the chunk takes 9 bits of the key");
     __shared__ float2 s_n[5][kNNChunkMax];             // (c, c) for c = x, y, v, phi, theta of car 0
     __shared__ float s_o[NC == 2 ? 5 : 1][kNNChunkMax];   // car 1 (merged pair only)
     if (rrt_done(a)) return;
+    rrt_load_plan(a);
     const int n_nodes = rrt_node_count(a);
+    const int chunk = nn_chunk(n_nodes, (int)gridDim.x);
     const int n0 = blockIdx.y * chunk, n1 = min(n0 + chunk, n_nodes);
     if (n0 >= n_nodes) return;
     const int B = a.n_targets, M = a.ws.max_nodes;
@@ -291,7 +335,10 @@ __device__ __forceinline__ void rrt_write_sample(const RrtArgs &a, unsigned roun
 template <int NC>
 __global__ void k_rrt_init(RrtArgs a, const float *start)
 {
+    rrt_load_plan(a);
     if (threadIdx.x == 0 && blockIdx.x == 0) {
+        a.ws.plan->round = 0;
+        a.ws.plan->t_start = global_ns();
         const int M = a.ws.max_nodes;
         for (int c = 0; c < 5 * NC; ++c) a.ws.nodes[c * M] = start[c];
         a.ws.nn_r[0] = make_float4(start[0], start[1], start[2], start[3]);
@@ -341,6 +388,7 @@ __global__ void __launch_bounds__(256) k_rrt_select(RrtArgs a)
 {
     constexpr int D = 5 * NC;
     if (rrt_done(a)) return;
+    rrt_load_plan(a);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.n_targets) return;
     const int B = a.n_targets, C = a.n_controls, n = B * C;
@@ -392,9 +440,11 @@ __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_cons
     __shared__ int s_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int B = a.n_targets, C = a.n_controls, n = B * C, M = a.ws.max_nodes;
+    rrt_load_plan(a);
     RrtProgress *slot = a.ws.d_progress + (a.round % kRrtDepth);
     if (rrt_done(a)) {   // (uniform, see rrt_done)
         if (tid == 0 && blockIdx.x == 0) {
+            if (a.in_loop) cudaGraphSetConditional(a.loop, 0u);
             slot->goal = *a.ws.goal_key;
             slot->nodes = a.ws.counters[a.round & 1u];
             slot->rounds = a.ws.counters[2];
@@ -492,11 +542,19 @@ __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_cons
     if (s_last && tid == 0) {
         __threadfence();
         const int count = min(n_nodes + tsum, M);
+        const unsigned long long goal = *(volatile unsigned long long *)a.ws.goal_key;
         a.ws.counters[(a.round + 1u) & 1u] = count;
         a.ws.counters[2] = (int)a.round + 1;
         a.ws.counters[3] = 0;
-        a.ws.counters[5] = *(volatile unsigned long long *)a.ws.goal_key != ~0ull;
-        slot->goal = *(volatile unsigned long long *)a.ws.goal_key;
+        a.ws.counters[5] = goal != ~0ull;
+        a.ws.plan->round = (int)a.round + 1;
+        if (a.in_loop) {
+            // another round?  (what the host decides between rounds when it queues them itself)
+            const bool more = goal == ~0ull && count < M && (int)a.round + 1 < a.max_iterations &&
+                              (a.limit_ns == 0 || global_ns() - a.t_start < a.limit_ns);
+            cudaGraphSetConditional(a.loop, more ? 1u : 0u);
+        }
+        slot->goal = goal;
         slot->nodes = count;
         slot->rounds = (int)a.round + 1;
     }
@@ -526,15 +584,27 @@ int dev_alloc(kcbs_ctx *ctx, T *&p, size_t n)
     return KCBS_OK;
 }
 
+// the instantiated round loops hold the workspace's pointers: they go whenever a buffer moves
+void drop_loops(RrtWorkspace &ws)
+{
+    for (auto &per_cars : ws.loop)
+        for (RrtWorkspace::Loop &l : per_cars) {
+            if (l.exec) cudaGraphExecDestroy(l.exec);
+            l = RrtWorkspace::Loop();
+        }
+}
+
 void free_workspace(RrtWorkspace &ws)
 {
-    void *d[] = {ws.nodes, ws.parent, ws.time, ws.ctrl, ws.steps, ws.targets, ws.nn, ws.s_ctrl, ws.s_steps,
+    drop_loops(ws);
+    void *d[] = {ws.plan, ws.nodes, ws.parent, ws.time, ws.ctrl, ws.steps, ws.targets, ws.nn, ws.s_ctrl, ws.s_steps,
                  ws.s_fin, ws.s_valid, ws.sel, ws.counters, ws.goal_key, ws.cons, ws.cons_states, ws.path_nodes, ws.path_ctrl,
                  ws.path_steps, ws.path_parent, ws.path_valid, ws.path_seg, ws.nn_r, ws.nn_t};
     for (void *p : d)
         if (p) cudaFree(p);
     if (ws.h_progress) cudaFreeHost(ws.h_progress);
     if (ws.h_counters) cudaFreeHost(ws.h_counters);
+    if (ws.h_plan) cudaFreeHost(ws.h_plan);
     for (cudaEvent_t e : ws.ev)
         if (e) cudaEventDestroy(e);
     ws = RrtWorkspace();
@@ -560,8 +630,9 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
             (st = dev_alloc(ctx, ws.path_ctrl, U * PC)) || (st = dev_alloc(ctx, ws.path_steps, PC)) ||
             (st = dev_alloc(ctx, ws.path_parent, PC)) || (st = dev_alloc(ctx, ws.path_valid, PC)) ||
             (st = dev_alloc(ctx, ws.path_seg, D * (size_t)KCBS_MAX_STEPS * PC)) || (st = dev_alloc(ctx, ws.nn_r, M)) ||
-            (st = dev_alloc(ctx, ws.nn_t, M)))
+            (st = dev_alloc(ctx, ws.nn_t, M)) || (st = dev_alloc(ctx, ws.plan, 1)))
             return st;
+        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_plan, sizeof(RrtPlan), cudaHostAllocDefault));
         KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_progress, sizeof(RrtProgress) * kRrtDepth, cudaHostAllocMapped));
         KCBS_CUDA(ctx, cudaHostGetDevicePointer((void **)&ws.d_progress, ws.h_progress, 0));
         KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_counters, 8 * sizeof(int), cudaHostAllocDefault));
@@ -573,6 +644,7 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
     }
     if (cons_total > ws.cons_cap) {
         KCBS_CUDA(ctx, cudaDeviceSynchronize());
+        drop_loops(ws);
         if (ws.cons_states) cudaFree(ws.cons_states);
         ws.cons_states = nullptr;
         ws.cons_cap = cons_total + cons_total / 2 + 1024;
@@ -581,6 +653,7 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
     }
     if (n_cons > ws.cons_desc_cap) {
         KCBS_CUDA(ctx, cudaDeviceSynchronize());
+        drop_loops(ws);
         if (ws.cons) cudaFree(ws.cons);
         ws.cons = nullptr;
         ws.cons_desc_cap = n_cons + 64;
@@ -588,6 +661,22 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
         if (st) return st;
     }
     return KCBS_OK;
+}
+
+// Rounds driven by the device (one graph launch per plan) unless KCBS_RRT_ROUNDS=stream asks for host-queued rounds.
+bool device_rounds()
+{
+    static const bool on = [] {
+        const char *e = std::getenv("KCBS_RRT_ROUNDS");
+        return !(e && std::strcmp(e, "stream") == 0);
+    }();
+    return on;
+}
+
+bool trace_solve()
+{
+    static const bool on = std::getenv("KCBS_TRACE_SOLVE") != nullptr;   // per-expansion and per-plan timing on stderr
+    return on;
 }
 
 double now_s()
@@ -678,41 +767,64 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
     // the start state travels through the (not yet used) target buffer
     KCBS_CUDA(ctx, cudaMemcpyAsync(ws.targets, start, sizeof(float) * D, cudaMemcpyHostToDevice, s));
 
-    RrtArgs a;
+    // what changes from plan to plan goes to the device once (RrtPlan, kernels.h); the launches below are the same for
+    // every round of every plan
+    RrtPlan &hp = *ws.h_plan;
+    std::memset(&hp, 0, sizeof(hp));
+    hp.robot[0] = robots[0]; hp.robot[1] = robots[NC - 1]; hp.n_cons = n_cons; hp.cons_total = cons_total; hp.max_T = max_T;
+    hp.max_iterations = p.max_iterations; hp.node_cap = p.max_nodes;
+    for (int c = 0; c < 2 * NC; ++c) hp.goal[c] = goal_xy[c];
+    hp.goal_radius = NC == 1 ? p.goal_radius : KCBS_PAIR_GOAL_RADIUS;
+    hp.goal_bias = p.goal_bias;
+    hp.seed = p.seed;
+    hp.limit_ns = p.time_limit_s > 0 ? (unsigned long long)(p.time_limit_s * 1e9) : 0ull;
+    KCBS_CUDA(ctx, cudaMemcpyAsync(ws.plan, ws.h_plan, sizeof(RrtPlan), cudaMemcpyHostToDevice, s));
+
+    RrtArgs a = {};
     a.ws = ws;
-    for (int c = 0; c < 2 * NC; ++c) a.goal[c] = goal_xy[c];
-    for (int c = 2 * NC; c < 4; ++c) a.goal[c] = 0.0f;
-    a.goal_radius = NC == 1 ? p.goal_radius : KCBS_PAIR_GOAL_RADIUS;
-    a.goal_bias = p.goal_bias;
     // sampling box = the state bounds the validity test uses (thresholds are within one ulp of them)
     for (int c = 0; c < 4; ++c) { a.lo[c] = ctx->world.lo_t[c]; a.hi[c] = ctx->world.hi_t[c]; }
-    a.seed = p.seed; a.round = 0;
     a.n_targets = p.n_targets; a.n_controls = p.n_controls; a.min_steps = p.min_steps; a.max_steps = p.max_steps;
-    a.robot[0] = robots[0]; a.robot[1] = robots[NC - 1]; a.n_cons = n_cons; a.cons_total = cons_total; a.max_T = max_T;
     const int n = p.n_targets * p.n_controls;
 
+    // the round's expansion: parents = the low words of the nearest-neighbour keys (little endian), controls and durations
+    // (drawn one round ahead) = the buffers of the round's parity; robot(s) and constraint counts come from the plan block
+    // (n_cons here only picks the kernel variant)
     PropArgs pa = {};
     PairArgs qa = {};
     if (NC == 1) {
         pa.rounds = ctx->prop_rounds;
         pa.n = n; pa.n_parents = ws.max_nodes; pa.parents = ws.nodes; pa.parent_idx = reinterpret_cast<const int *>(ws.nn); pa.controls = ws.s_ctrl;
-        pa.parent_group = p.n_controls; pa.parent_stride = 2;   // the low words of the nearest-neighbour keys (little endian)
+        pa.parent_group = p.n_controls; pa.parent_stride = 2;
         pa.steps = ws.s_steps; pa.seg = nullptr; pa.fin = ws.s_fin; pa.valid_steps = ws.s_valid; pa.max_steps = p.max_steps;
         pa.robot = robots[0]; pa.parent_time = ws.time; pa.cons = ws.cons; pa.cons_states = ws.cons_states; pa.n_cons = n_cons;
         pa.cons_total = cons_total;
+        pa.plan = ws.plan; pa.parity_ctrl = (long long)2 * NC * n; pa.parity_steps = n;
     } else {
         qa.n = n; qa.n_parents = ws.max_nodes; qa.parents = ws.nodes; qa.parent_idx = reinterpret_cast<const int *>(ws.nn); qa.controls = ws.s_ctrl;
         qa.parent_group = p.n_controls; qa.parent_stride = 2;
         qa.steps = ws.s_steps; qa.seg = nullptr; qa.fin = ws.s_fin; qa.valid_steps = ws.s_valid; qa.max_steps = p.max_steps;
         qa.robot1 = robots[0]; qa.robot2 = robots[NC - 1];
-        for (int c = 0; c < 4; ++c) qa.goals[c] = a.goal[c];
+        for (int c = 0; c < 4; ++c) qa.goals[c] = hp.goal[c];
         qa.hold_radius = KCBS_PAIR_GOAL_RADIUS;   // StatePropagatorDatabase.h:170
         qa.parent_time = ws.time; qa.cons = ws.cons; qa.cons_states = ws.cons_states; qa.n_cons = n_cons; qa.cons_total = cons_total;
+        qa.plan = ws.plan; qa.parity_ctrl = (long long)2 * NC * n; qa.parity_steps = n;
     }
+    const int tiles = (p.n_targets + kNNTile - 1) / kNNTile;
+    const dim3 nn_grid((unsigned)tiles, (unsigned)nn_grid_y(ws.max_nodes, tiles));
+    auto launch_init = [&](const RrtArgs &ra) {
+        k_rrt_init<NC><<<(n + 255) / 256, 256, 0, s>>>(ra, ws.targets);
+        return cudaGetLastError();
+    };
+    auto launch_round = [&](const RrtArgs &ra) {
+        k_rrt_nearest<NC><<<nn_grid, kNNThreads, 0, s>>>(ra);
+        cudaError_t e = NC == 1 ? launch_propagate(ctx->world, pa, s) : launch_propagate_pair(ctx->world, qa, s);
+        if (e != cudaSuccess) return e;
+        k_rrt_select<NC><<<(p.n_targets * 32 + 255) / 256, 256, 0, s>>>(ra);
+        k_rrt_append<NC><<<(p.n_targets + kAppendThreads - 1) / kAppendThreads, kAppendThreads, 0, s>>>(ctx->world, ra);
+        return cudaGetLastError();
+    };
 
-    for (int q = 0; q < kRrtDepth; ++q) ws.h_progress[q] = RrtProgress{~0ull, 1, 0};
-    k_rrt_init<NC><<<(n + 255) / 256, 256, 0, s>>>(a, ws.targets);
-    ctx->launches += 1;
     int n_nodes = 1, iters = 0, queued = 0;
     unsigned long long goal = ~0ull;
     // the start itself may already satisfy the goal
@@ -721,47 +833,84 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         for (int c = 0; c < NC; ++c) {
             const float gx = start[5 * c] - goal_xy[2 * c], gy = start[5 * c + 1] - goal_xy[2 * c + 1];
             const float d = std::sqrt(gx * gx + gy * gy);
-            in = in && (NC == 1 ? d <= a.goal_radius : d < a.goal_radius);
+            in = in && (NC == 1 ? d <= hp.goal_radius : d < hp.goal_radius);
         }
         if (in) goal = 0;
     }
-    while (goal == ~0ull && queued < p.max_iterations) {
-        if (queued >= kRrtDepth) {   // outcome of the round that used this ring slot last
-            KCBS_CUDA(ctx, cudaEventSynchronize(ws.ev[queued % kRrtDepth]));
-            const RrtProgress pr = ws.h_progress[queued % kRrtDepth];
-            if (pr.goal != ~0ull || pr.nodes >= p.max_nodes) break;
+    if (goal != ~0ull) {
+        KCBS_CUDA(ctx, cudaStreamSynchronize(s));   // (the uploads above)
+    } else if (device_rounds()) {
+        // ---- the whole search is ONE graph launch: k_rrt_init, then a WHILE node whose body is the four kernels of a
+        // round and whose condition k_rrt_append sets on the device (goal found, tree full, iteration or time limit) ----
+        RrtWorkspace::Loop &L = ctx->rrt->loop[NC - 1][n_cons > 0];
+        const int key[5] = {p.n_targets, p.n_controls, p.min_steps, p.max_steps, NC == 1 ? pa.rounds : 0};
+        if (!L.exec || std::memcmp(L.key, key, sizeof(key)) != 0) {
+            if (L.exec) cudaGraphExecDestroy(L.exec);
+            L = RrtWorkspace::Loop();
+            cudaGraph_t g = nullptr;
+            KCBS_CUDA(ctx, cudaGraphCreate(&g, 0));
+            RrtArgs la = a;
+            la.in_loop = 1;
+            cudaGraphNode_t init_node = nullptr, while_node = nullptr;
+            size_t one = 1;
+            cudaGraphNodeParams wp = {};
+            cudaError_t e = cudaGraphConditionalHandleCreate(&la.loop, g, 1, cudaGraphCondAssignDefault);
+            if (e == cudaSuccess) e = cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                const cudaError_t e1 = launch_init(la);
+                cudaGraph_t same = nullptr;
+                e = cudaStreamEndCapture(s, &same);
+                if (e == cudaSuccess) e = e1;
+            }
+            if (e == cudaSuccess) e = cudaGraphGetNodes(g, &init_node, &one);
+            if (e == cudaSuccess) {
+                wp.type = cudaGraphNodeTypeConditional;
+                wp.conditional.handle = la.loop;
+                wp.conditional.type = cudaGraphCondTypeWhile;
+                wp.conditional.size = 1;
+                e = cudaGraphAddNode(&while_node, g, &init_node, 1, &wp);
+            }
+            if (e == cudaSuccess) e = cudaStreamBeginCaptureToGraph(s, wp.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+            if (e == cudaSuccess) {
+                const cudaError_t e1 = launch_round(la);
+                cudaGraph_t same = nullptr;
+                e = cudaStreamEndCapture(s, &same);
+                if (e == cudaSuccess) e = e1;
+            }
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&L.exec, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) {
+                L = RrtWorkspace::Loop();
+                return fail(ctx, KCBS_ERR_CUDA, "building the round loop graph", e);
+            }
+            std::memcpy(L.key, key, sizeof(key));
         }
-        if (p.time_limit_s > 0 && now_s() - t_begin > p.time_limit_s) break;
-        a.round = (unsigned)queued;
-        // the tree has at most 1 + round * n_targets nodes when this round starts
-        const long long bound = std::min<long long>(p.max_nodes, 1 + (long long)queued * p.n_targets);
-        const int tiles = (p.n_targets + kNNTile - 1) / kNNTile;
-        const int chunk = nn_chunk(bound, tiles);
-        dim3 g((unsigned)tiles, (unsigned)((bound + chunk - 1) / chunk));
-        k_rrt_nearest<NC><<<g, kNNThreads, 0, s>>>(a, chunk);
-        // this round's controls and durations (drawn one round ahead) sit in the buffer of the round's parity
-        pa.controls = qa.controls = ws.s_ctrl + (size_t)(queued & 1) * 2 * NC * n;
-        pa.steps = qa.steps = ws.s_steps + (size_t)(queued & 1) * n;
-        if (NC == 1)
-            KCBS_CUDA(ctx, launch_propagate(ctx->world, pa, s));
-        else
-            KCBS_CUDA(ctx, launch_propagate_pair(ctx->world, qa, s));
-        k_rrt_select<NC><<<(p.n_targets * 32 + 255) / 256, 256, 0, s>>>(a);
-        k_rrt_append<NC><<<(p.n_targets + kAppendThreads - 1) / kAppendThreads, kAppendThreads, 0, s>>>(ctx->world, a);
-        KCBS_CUDA(ctx, cudaEventRecord(ws.ev[queued % kRrtDepth], s));
-        ctx->launches += 4;
-        ++queued;
+        KCBS_CUDA(ctx, cudaGraphLaunch(L.exec, s));
+    } else {
+        // ---- rounds queued by the host (KCBS_RRT_ROUNDS=stream), kRrtDepth of them ahead of the device ----
+        for (int q = 0; q < kRrtDepth; ++q) ws.h_progress[q] = RrtProgress{~0ull, 1, 0};
+        KCBS_CUDA(ctx, launch_init(a));
+        while (queued < p.max_iterations) {
+            if (queued >= kRrtDepth) {   // outcome of the round that used this ring slot last
+                KCBS_CUDA(ctx, cudaEventSynchronize(ws.ev[queued % kRrtDepth]));
+                const RrtProgress pr = ws.h_progress[queued % kRrtDepth];
+                if (pr.goal != ~0ull || pr.nodes >= p.max_nodes) break;
+            }
+            if (p.time_limit_s > 0 && now_s() - t_begin > p.time_limit_s) break;
+            KCBS_CUDA(ctx, launch_round(a));
+            KCBS_CUDA(ctx, cudaEventRecord(ws.ev[queued % kRrtDepth], s));
+            ++queued;
+        }
     }
     if (goal == ~0ull) {
-        // drain: the final word is on the device (rounds queued after the goal was found did nothing)
+        // the final word is on the device (rounds queued after the goal was found did nothing)
         KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters, ws.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
         KCBS_CUDA(ctx, cudaMemcpyAsync(&ws.h_progress[0].goal, ws.goal_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         KCBS_CUDA(ctx, cudaStreamSynchronize(s));
         goal = ws.h_progress[0].goal;
         iters = ws.h_counters[2];
         n_nodes = std::min(ws.h_counters[iters & 1], p.max_nodes);   // the entry the next round would have read
-    } else {
-        KCBS_CUDA(ctx, cudaStreamSynchronize(s));   // `desc` and the start state were still in flight
+        ctx->launches += 1 + 4 * (device_rounds() ? iters : queued);
     }
 
     int T = 0;
@@ -780,11 +929,13 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
             if (NC == 1) {
                 PropArgs pe = pa;
                 pe.n = E; pe.parent_idx = ws.path_parent; pe.parent_group = pe.parent_stride = 1; pe.controls = ws.path_ctrl; pe.steps = ws.path_steps;
+                pe.plan = nullptr;
                 pe.seg = ws.path_seg; pe.fin = nullptr; pe.valid_steps = ws.path_valid; pe.max_steps = p.max_steps;
                 KCBS_CUDA(ctx, launch_propagate(ctx->world, pe, s));
             } else {
                 PairArgs qe = qa;
                 qe.n = E; qe.parent_idx = ws.path_parent; qe.parent_group = qe.parent_stride = 1; qe.controls = ws.path_ctrl; qe.steps = ws.path_steps;
+                qe.plan = nullptr;
                 qe.seg = ws.path_seg; qe.fin = nullptr; qe.valid_steps = ws.path_valid; qe.max_steps = p.max_steps;
                 KCBS_CUDA(ctx, launch_propagate_pair(ctx->world, qe, s));
             }
@@ -800,6 +951,9 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         }
     }
     *T_out = T;
+    if (trace_solve())
+        fprintf(stderr, "[kcbs]   plan robot %d: %.0f us, %d rounds run, %d queued, %d constraints, %d nodes, path %d\n", robots[0],
+                (now_s() - t_begin) * 1e6, iters, queued, n_cons, n_nodes, T);
     if (stats) {
         stats->solved = goal != ~0ull;
         stats->iterations = iters;
@@ -1169,6 +1323,7 @@ int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int
                 traj3[((size_t)r * 3 + 2) * Tp + k] = node->traj[r][(size_t)4 * L + k];
             }
         }
+        const double t_exp0 = now_s();
         kcbs_conflict cf;
         // time indices beyond T are never scanned: every path is padded to T, and k_hi = Tp only repeats the
         // padded states of [T, Tp), which cannot introduce an earlier conflict than the ones in [0, T).  Bodies of
@@ -1176,6 +1331,7 @@ int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int
         int st = kcbs_first_conflict_groups(ctx, 1, R, Tp, traj3.data(), lens.data(), NI < R ? group.data() : nullptr, &cf);
         if (st != KCBS_OK) return st;
         ++S.conflict_checks;
+        const double t_exp1 = now_s();
         if (cf.r1 < 0) {
             solution = node;
             return KCBS_OK;
@@ -1213,6 +1369,10 @@ int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int
                                    (unsigned long long)(S.nodes_expanded * 2 + ch) + 7919ull * (unsigned long long)S.merges, solved[ch]);
         });
         if (st != KCBS_OK) return st;
+        if (trace_solve())
+            fprintf(stderr, "[kcbs] expansion %d: validation %.0f us, two re-plans %.0f us (robots %d / %d, window %d..%d, %zu / %zu constraints)\n",
+                    S.nodes_expanded, (t_exp1 - t_exp0) * 1e6, (now_s() - t_exp1) * 1e6, cf.r1, cf.r2, cf.k_start, cf.k_end,
+                    child[0]->cons[q.ind_of[cf.r1]].size(), child[1]->cons[q.ind_of[cf.r2]].size());
         for (int ch = 0; ch < 2; ++ch) {
             S.low_level_calls += (int)q.ind[q.ind_of[pair[ch][0]]].size();
             if (!solved[ch]) {

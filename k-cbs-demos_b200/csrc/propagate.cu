@@ -380,9 +380,26 @@ __device__ __forceinline__ int block_exclusive_scan(int tid, int *s_warp, Get ge
 
 template <bool HAS_OBS, bool HAS_CONS, int MODE, int ROUNDS>
 __global__ void __launch_bounds__(kPropThreads, MODE != kDirect ? PropGeom<ROUNDS>::kCtasPerSm : KCBS_PROP_MINB)
-k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs a)
+k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs a_in)
 {
     constexpr bool STAGED = MODE != kDirect;
+    // Planner rounds (direct path only): what the launch cannot know -- it is the same launch for every round of every
+    // plan -- comes from the plan block on the device: the robot, the constraint counts, the parity of the round.
+    PropArgs a_plan;
+    if (MODE == kDirect) {
+        a_plan = a_in;
+        if (a_in.plan) {
+            const int4 h = __ldcg(reinterpret_cast<const int4 *>(a_in.plan));   // round, robot[0], robot[1], n_cons
+            a_plan.robot = h.y;
+            a_plan.controls = a_in.controls + (h.x & 1) * a_in.parity_ctrl;
+            if (a_in.steps) a_plan.steps = a_in.steps + (h.x & 1) * a_in.parity_steps;
+            if (HAS_CONS) {
+                a_plan.n_cons = h.w;
+                a_plan.cons_total = __ldcg(&a_in.plan->cons_total);
+            }
+        }
+    }
+    const PropArgs &a = MODE == kDirect ? a_plan : a_in;
     constexpr int kSamples = PropGeom<ROUNDS>::kSamples, kPer = PropGeom<ROUNDS>::kPer;
     typedef PropStage<kSamples> Stage;
     __shared__ int s_hist[KCBS_MAX_STEPS + 1], s_first[KCBS_MAX_STEPS + 1];
