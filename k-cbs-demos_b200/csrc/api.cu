@@ -335,7 +335,8 @@ int kcbs_create(const kcbs_world *world, int device, kcbs_ctx **out)
     ctx->n_robots = world->n_robots;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
-        (e = init_conflict_kernels()) != cudaSuccess || (e = init_validity_kernels()) != cudaSuccess || (e = init_propagate_kernels()) != cudaSuccess) {
+        (e = init_conflict_kernels()) != cudaSuccess || (e = init_validity_kernels()) != cudaSuccess || (e = init_propagate_kernels()) != cudaSuccess ||
+        (e = init_pair_kernels()) != cudaSuccess || (e = init_planner_kernels()) != cudaSuccess) {
         fail(nullptr, KCBS_ERR_CUDA, "context setup", e);
         kcbs_destroy(ctx);
         return KCBS_ERR_CUDA;

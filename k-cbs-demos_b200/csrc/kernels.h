@@ -25,6 +25,8 @@ struct RrtPlan {
     float goal_radius, goal_bias;
     unsigned long long seed;
     unsigned long long limit_ns, t_start;   // time limit of the device-driven loop (0 = none); start stamp (k_rrt_init)
+    float start[10];           // the root state (5 per car)
+    int pad[2];
 };
 
 struct PropArgs {
@@ -52,10 +54,10 @@ struct PropArgs {
     long long packed_cap;
     unsigned long long *scan;  // (spare workspace words behind scan_ctl)
     unsigned *scan_ctl;        // 8-byte aligned row allocator (CTAs served << 40 | rows handed out); zeroed, left zeroed
-    // planner rounds (null otherwise): robot, n_cons, cons_total come from the plan block, and controls / steps are the
-    // buffers of the round's parity: controls + (round & 1) * parity_ctrl, steps + (round & 1) * parity_steps
+    // planner rounds (null otherwise): robot, n_cons, cons_total come from the plan block, and controls / steps / parent
+    // keys are the buffers of the round's parity: controls + (round & 1) * parity_ctrl, and so on
     const RrtPlan *plan;
-    long long parity_ctrl, parity_steps;
+    long long parity_ctrl, parity_steps, parity_parent;
 };
 
 struct ValidArgs {
@@ -86,7 +88,7 @@ struct PairArgs {              // merged pair: 10-d states, 4-d controls
     int n_cons, cons_total;
     // planner rounds (null otherwise): robots, goals, n_cons, cons_total and the round's parity come from the plan block
     const RrtPlan *plan;
-    long long parity_ctrl, parity_steps;
+    long long parity_ctrl, parity_steps, parity_parent;
 };
 
 struct PairValidArgs {
@@ -144,6 +146,8 @@ cudaError_t launch_fill_keys(unsigned long long *keys, int *tickets, int n, cuda
 cudaError_t launch_fp32_probe(float *sink, int iters, cudaStream_t stream, double *flops);
 cudaError_t launch_fp32x2_probe(float *sink, int iters, cudaStream_t stream, double *flops);
 cudaError_t init_propagate_kernels();
+cudaError_t init_pair_kernels();
+cudaError_t init_planner_kernels();
 cudaError_t init_validity_kernels();
 cudaError_t init_conflict_kernels();  // per-device function attributes; call once per context
 

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(128) k_propagate_pair(const __grid_constant__ 
         for (int c = 0; c < 4; ++c) a.goals[c] = __ldcg(&p.goal[c]);
         a.controls = a_in.controls + (round & 1) * a_in.parity_ctrl;
         if (a_in.steps) a.steps = a_in.steps + (round & 1) * a_in.parity_steps;
+        if (a_in.parent_idx) a.parent_idx = a_in.parent_idx + (round & 1) * a_in.parity_parent;
     }
     const long long pi = parent_of(a, i);
     int st = a.steps ? a.steps[i] : a.max_steps;
@@ -145,6 +146,13 @@ cudaError_t launch_propagate_pair(const DevWorld &w, const PairArgs &a, cudaStre
     if (a.n <= 0) return cudaSuccess;
     k_propagate_pair<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(w, a);
     return cudaGetLastError();
+}
+
+cudaError_t init_pair_kernels()   // (loaded outside any stream capture, see planner.cu)
+{
+    cudaFuncAttributes at;
+    cudaError_t e = cudaFuncGetAttributes(&at, k_propagate_pair);
+    return e != cudaSuccess ? e : cudaFuncGetAttributes(&at, k_validity_pair);
 }
 
 cudaError_t launch_validity_pair(const DevWorld &w, const PairValidArgs &a, cudaStream_t stream)

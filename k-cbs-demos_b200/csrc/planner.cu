@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <queue>
 #include <thread>
 #include <vector>
@@ -50,8 +51,8 @@ struct RrtWorkspace {
     int *time = nullptr;           // [max_nodes] absolute time index (propagation steps from the root)
     float *ctrl = nullptr;         // [2 per car][max_nodes] control of the edge into the node
     int *steps = nullptr;          // [max_nodes] duration of the edge into the node
-    float *targets = nullptr;      // [dim][n_targets]
-    unsigned long long *nn = nullptr;  // [n_targets] packed (distance bits << 32 | node); kNNEmpty between rounds
+    float *targets = nullptr;      // [2 rounds (parity)][dim][n_targets]
+    unsigned long long *nn = nullptr;  // [2 rounds (parity)][n_targets] packed (distance bits << 32 | node); kNNEmpty when unused
     float *s_ctrl = nullptr;       // [2 rounds (parity)][2 per car][n_samples]: drawn one round ahead (k_rrt_select)
     int *s_steps = nullptr;        // [2 rounds (parity)][n_samples]
     float *s_fin = nullptr;        // [dim][n_samples]
@@ -60,7 +61,8 @@ struct RrtWorkspace {
     float4 *nn_r = nullptr;        // [max_nodes] (x, y, v, phi) of the first car: what the nearest-neighbour scan streams
     float *nn_t = nullptr;         // [max_nodes] its heading
     int *counters = nullptr;       // [0], [1] = node count (ring by round parity), [2] = rounds completed, [3] = append ticket,
-                                   // [4] = edges of the extracted path, [5] = a goal node exists (set between rounds)
+                                   // [4] = edges of the extracted path, [5] = a goal node exists (set between rounds),
+                                   // [6], [7] = round and CTA tickets of the side scan (k_rrt_nearest)
     unsigned long long *goal_key = nullptr;  // packed (time << 32 | node) of the best goal node
     ConsDesc *cons = nullptr;
     float *cons_states = nullptr;
@@ -70,13 +72,19 @@ struct RrtWorkspace {
     int *path_steps = nullptr, *path_parent = nullptr, *path_valid = nullptr;
     float *path_seg = nullptr;     // [dim][KCBS_MAX_STEPS][path_cap]
     RrtProgress *h_progress = nullptr, *d_progress = nullptr;   // [kRrtDepth] host-mapped ring
-    int *h_counters = nullptr;                                  // pinned
+    int *h_counters = nullptr;                                  // pinned: [8] counters, then the goal key (2 words)
+    float *h_path_seg = nullptr;                                // pinned: the re-expanded path [dim][max_steps][e_max]
+    int *h_path_valid = nullptr;                                // pinned [e_max]
+    size_t h_path_cap = 0;                                      // floats h_path_seg holds
     cudaEvent_t ev[kRrtDepth] = {};
     RrtPlan *plan = nullptr, *h_plan = nullptr;   // the plan block on the device (kernels.h) and its pinned staging copy
+    unsigned long long *trace = nullptr;          // (KCBS_RRT_TRACE builds) [kTraceRounds][4 kernels][start, end] globaltimer stamps
+    cudaStream_t side = nullptr;                  // second branch of a round (the scan of the old nodes for the next round)
+    cudaEvent_t fork = nullptr, join = nullptr;
     // device-driven rounds: one instantiated graph per (cars, constrained or not), rebuilt when the launch shape changes
     struct Loop {
         cudaGraphExec_t exec = nullptr;
-        int key[5] = {0, 0, 0, 0, 0};   // n_targets, n_controls, min_steps, max_steps, expansion shape
+        int key[6] = {0, 0, 0, 0, 0, 0};   // n_targets, n_controls, min_steps, max_steps, expansion shape, path edge slots
     } loop[2][2];
 };
 
@@ -123,7 +131,7 @@ struct RrtArgs {
 };
 
 static_assert(offsetof(RrtPlan, goal) == 32 && offsetof(RrtPlan, goal_radius) == 48 && offsetof(RrtPlan, seed) == 56 &&
-                  offsetof(RrtPlan, limit_ns) == 64 && sizeof(RrtPlan) == 80,
+                  offsetof(RrtPlan, limit_ns) == 64 && offsetof(RrtPlan, start) == 80 && sizeof(RrtPlan) == 128,
               "rrt_load_plan reads the block as five 16-byte words");
 __device__ __forceinline__ void rrt_load_plan(RrtArgs &a)
 {
@@ -143,6 +151,18 @@ __device__ __forceinline__ unsigned long long global_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+constexpr int kTraceRounds = 128;
+// (debug builds with -DKCBS_RRT_TRACE) first start / last end of kernel k of a round over its CTAs
+__device__ __forceinline__ void trace_stamp(const RrtArgs &a, unsigned round, int k, int end)
+{
+#ifdef KCBS_RRT_TRACE
+    if (threadIdx.x == 0 && round < (unsigned)kTraceRounds) {
+        unsigned long long *w = a.ws.trace + ((size_t)round * 4 + k) * 2 + end;
+        if (end) atomicMax(w, global_ns());
+        else atomicMin(w, global_ns());
+    }
+#endif
+}
 
 // Every kernel of an iteration starts with this test: once a goal node exists the remaining iterations already queued
 // on the stream do nothing, so the outcome is that of the first iteration that found one -- however far the host ran ahead.
@@ -160,17 +180,17 @@ __device__ __forceinline__ float car_distance(const float *a, const float *b)
     return sqrtf(fmaf(dx, dx, fmaf(dy, dy, fmaf(dv, dv, dp * dp)))) + d;
 }
 
-// Random target state of round a.round: uniform over the state bounds, or (goal bias) the goal positions with random
+// Random target state of a round: uniform over the state bounds, or (goal bias) the goal positions with random
 // v, phi, theta.  A pure function of (seed, round, t), so any kernel can recompute it.
 template <int NC>
-__device__ __forceinline__ void rrt_target(const RrtArgs &a, int t, float q[5 * NC])
+__device__ __forceinline__ void rrt_target(const RrtArgs &a, unsigned round, int t, float q[5 * NC])
 {
-    const bool to_goal = urand(a.seed, a.round, t, 5) < a.goal_bias;
+    const bool to_goal = urand(a.seed, round, t, 5) < a.goal_bias;
 #pragma unroll
     for (int car = 0; car < NC; ++car) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) q[5 * car + c] = a.lo[c] + (a.hi[c] - a.lo[c]) * urand(a.seed, a.round, t, 16 * car + c);
-        q[5 * car + 4] = -kPi + kTwoPi * urand(a.seed, a.round, t, 16 * car + 4);
+        for (int c = 0; c < 4; ++c) q[5 * car + c] = a.lo[c] + (a.hi[c] - a.lo[c]) * urand(a.seed, round, t, 16 * car + c);
+        q[5 * car + 4] = -kPi + kTwoPi * urand(a.seed, round, t, 16 * car + 4);
         if (to_goal) {
             q[5 * car + 0] = a.goal[2 * car];
             q[5 * car + 1] = a.goal[2 * car + 1];
@@ -240,18 +260,44 @@ __device__ __forceinline__ float nn_sqrt(float x)
 // (distance bits with the low 9 bits replaced by the node's place in the chunk): the distance is compared to 2^-14
 // relative, ties go to the smallest index, nothing diverges.
 template <int NC>
-__global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a)
+__global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a, int fresh)
 {
     constexpr int D = 5 * NC;
     static_assert(kNNChunkMax <= 512, "the node's place in the chunk takes 9 bits of the key");
     __shared__ float2 s_n[5][kNNChunkMax];             // (c, c) for c = x, y, v, phi, theta of car 0
     __shared__ float s_o[NC == 2 ? 5 : 1][kNNChunkMax];   // car 1 (merged pair only)
-    if (rrt_done(a)) return;
     rrt_load_plan(a);
-    const int n_nodes = rrt_node_count(a);
+    // The scan of a round is split in two.  fresh = 0: the targets of the NEXT round against the nodes the tree has when
+    // this round starts -- nothing of this round is needed for it, so it runs beside the round's other kernels.
+    // fresh = 1: the targets of THIS round against the nodes the previous round appended (a few thousand at most).
+    // Together they cover the whole tree; both write the keys / targets of their round's parity.
+    // The side scan may still be running when k_rrt_append moves the plan block to the next round, so it counts rounds
+    // for itself: counters[6], advanced by the last of its CTAs to finish (counters[7] = their tickets).
+    __shared__ int s_side_round;
+    if (!fresh) {
+        if (threadIdx.x == 0) s_side_round = *(volatile int *)(a.ws.counters + 6);
+        __syncthreads();
+        a.round = (unsigned)s_side_round;
+    }
+    trace_stamp(a, a.round, fresh ? 1 : 0, 0);
+    auto leave = [&]() {   // every CTA of the side scan, whatever it did
+        trace_stamp(a, a.round, fresh ? 1 : 0, 1);
+        if (!fresh) {
+            __syncthreads();
+            if (threadIdx.x == 0 && atomicAdd(a.ws.counters + 7, 1) == (int)(gridDim.x * gridDim.y) - 1) {
+                a.ws.counters[7] = 0;
+                *(volatile int *)(a.ws.counters + 6) = (int)a.round + 1;
+            }
+        }
+    };
+    if (rrt_done(a)) return leave();
+    const unsigned tr = fresh ? a.round : a.round + 1u;
+    const int n_now = rrt_node_count(a);
+    const int lo = fresh ? min(a.ws.counters[(a.round + 1u) & 1u], n_now) : 0;   // (ring: the other entry still holds the previous count)
+    const int n_nodes = n_now - lo;
     const int chunk = nn_chunk(n_nodes, (int)gridDim.x);
-    const int n0 = blockIdx.y * chunk, n1 = min(n0 + chunk, n_nodes);
-    if (n0 >= n_nodes) return;
+    const int n0 = lo + blockIdx.y * chunk, n1 = min(n0 + chunk, n_now);
+    if (n0 >= n_now) return leave();
     const int B = a.n_targets, M = a.ws.max_nodes;
     const int m = n1 - n0;
     for (int j = threadIdx.x; j < m; j += kNNThreads) {
@@ -271,9 +317,10 @@ __global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a)
 #pragma unroll
     for (int u = 0; u < kNNPer; ++u) {
         const int t = t0 + u * kNNThreads;
-        rrt_target<NC>(a, min(t, B - 1), q[u]);
-        if (t < B && blockIdx.y == 0)
-            for (int c = 0; c < D; ++c) a.ws.targets[c * B + t] = q[u][c];
+        rrt_target<NC>(a, tr, min(t, B - 1), q[u]);
+        // (the targets of round 0 are written by its fresh scan: no earlier round scanned for it)
+        if (t < B && blockIdx.y == 0 && (!fresh || a.round == 0u))
+            for (int c = 0; c < D; ++c) a.ws.targets[(size_t)(tr & 1u) * D * B + c * B + t] = q[u][c];
     }
     nn_f32x2 Q[2][5];
 #pragma unroll
@@ -312,8 +359,9 @@ __global__ void __launch_bounds__(kNNThreads) k_rrt_nearest(RrtArgs a)
 #pragma unroll
     for (int u = 0; u < kNNPer; ++u) {
         const int t = t0 + u * kNNThreads;
-        if (t < B) atomicMin(a.ws.nn + t, ((unsigned long long)(best[u] & 0xfffffe00u) << 32) | (unsigned)(n0 + (int)(best[u] & 0x1ffu)));
+        if (t < B) atomicMin(a.ws.nn + (size_t)(tr & 1u) * B + t, ((unsigned long long)(best[u] & 0xfffffe00u) << 32) | (unsigned)(n0 + (int)(best[u] & 0x1ffu)));
     }
+    leave();
 }
 
 // Control and duration of sample s of round `round` (sample s belongs to target s / n_controls; its parent is that
@@ -333,9 +381,10 @@ __device__ __forceinline__ void rrt_write_sample(const RrtArgs &a, unsigned roun
 }
 
 template <int NC>
-__global__ void k_rrt_init(RrtArgs a, const float *start)
+__global__ void k_rrt_init(RrtArgs a)
 {
     rrt_load_plan(a);
+    const float *start = a.ws.plan->start;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         a.ws.plan->round = 0;
         a.ws.plan->t_start = global_ns();
@@ -346,14 +395,16 @@ __global__ void k_rrt_init(RrtArgs a, const float *start)
         for (int c = 0; c < 2 * NC; ++c) a.ws.ctrl[c * M] = 0.f;
         a.ws.parent[0] = -1; a.ws.time[0] = 0; a.ws.steps[0] = 0;
         a.ws.counters[0] = 1;   // node count seen by round 0 (parity ring, see rrt_node_count)
-        a.ws.counters[1] = 1;
+        a.ws.counters[1] = 0;   // ... and "the count before": round 0's fresh scan covers the root
         a.ws.counters[2] = 0;   // rounds completed
         a.ws.counters[3] = 0;   // CTA ticket of k_rrt_append
         a.ws.counters[5] = 0;   // a goal node exists (rrt_done)
+        a.ws.counters[6] = 0;   // round of the side scan (k_rrt_nearest)
+        a.ws.counters[7] = 0;   // ... and the tickets of its CTAs
         *a.ws.goal_key = ~0ull;
     }
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < a.n_targets) a.ws.nn[t] = kNNEmpty;
+    if (t < 2 * a.n_targets) a.ws.nn[t] = kNNEmpty;   // (both parities)
     if (t < a.n_targets * a.n_controls) rrt_write_sample<NC>(a, 0u, t);   // (grid = one thread per sample)
 }
 
@@ -389,11 +440,12 @@ __global__ void __launch_bounds__(256) k_rrt_select(RrtArgs a)
     constexpr int D = 5 * NC;
     if (rrt_done(a)) return;
     rrt_load_plan(a);
+    trace_stamp(a, a.round, 2, 0);
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= a.n_targets) return;
     const int B = a.n_targets, C = a.n_controls, n = B * C;
     float q[D];
-    for (int c = 0; c < D; ++c) q[c] = a.ws.targets[c * B + warp];
+    for (int c = 0; c < D; ++c) q[c] = a.ws.targets[(size_t)(a.round & 1u) * D * B + c * B + warp];
     float best = 3.0e38f;
     int best_s = -1;
     for (int j = lane; j < C; j += 32) {
@@ -421,6 +473,7 @@ __global__ void __launch_bounds__(256) k_rrt_select(RrtArgs a)
     if (lane == 0) a.ws.sel[warp] = best_s;
     // the controls and durations of the next round's samples of this target (other parity: this round's are still needed)
     for (int j = lane; j < C; j += 32) rrt_write_sample<NC>(a, a.round + 1u, warp * C + j);
+    trace_stamp(a, a.round, 2, 1);
 }
 
 // Appends the chosen samples to the tree in TARGET ORDER, so that node indices -- and with them nearest-neighbour ties,
@@ -442,6 +495,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_cons
     const int B = a.n_targets, C = a.n_controls, n = B * C, M = a.ws.max_nodes;
     rrt_load_plan(a);
     RrtProgress *slot = a.ws.d_progress + (a.round % kRrtDepth);
+    trace_stamp(a, a.round, 3, 0);
     if (rrt_done(a)) {   // (uniform, see rrt_done)
         if (tid == 0 && blockIdx.x == 0) {
             if (a.in_loop) cudaGraphSetConditional(a.loop, 0u);
@@ -475,14 +529,15 @@ __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_cons
     // the chosen sample, while the counts are reduced
     const int s = max(s_idx, 0);
     // (the parent of a target's samples = the node index in the low word of its nearest-neighbour key)
-    const int par = t < B ? (int)(a.ws.nn[t] & 0xffffffffu) : 0, nv = a.ws.s_valid[s];
+    unsigned long long *nn = a.ws.nn + (size_t)(a.round & 1u) * B;   // this round's keys
+    const int par = t < B ? (int)(nn[t] & 0xffffffffu) : 0, nv = a.ws.s_valid[s];
     const float *ctrl = a.ws.s_ctrl + (size_t)(a.round & 1u) * U * n;
     float f[D], u[U];
 #pragma unroll
     for (int c = 0; c < D; ++c) f[c] = a.ws.s_fin[c * n + s];
 #pragma unroll
     for (int c = 0; c < U; ++c) u[c] = ctrl[c * n + s];
-    if (t < B) a.ws.nn[t] = kNNEmpty;   // clean for the next round's atomicMin
+    if (t < B) nn[t] = kNNEmpty;   // clean for the round after the next (same parity)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         before += __shfl_xor_sync(0xffffffffu, before, off);
@@ -533,6 +588,7 @@ __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_cons
         if (in_goal) atomicMin(a.ws.goal_key, ((unsigned long long)(unsigned)t_node << 32) | (unsigned)idx);
     }
     // the last CTA of the round publishes the node count and reports to the host
+    trace_stamp(a, a.round, 3, 1);
     __syncthreads();
     if (tid == 0) {
         __threadfence();
@@ -560,21 +616,27 @@ __global__ void __launch_bounds__(kAppendThreads) k_rrt_append(const __grid_cons
     }
 }
 
-// Walks goal -> root (one thread) and emits the edges root -> goal as propagation inputs.
+// Walks goal -> root (one lane: a chain of dependent loads) and emits the edges root -> goal as propagation inputs, one
+// lane per edge: [e_max] entries with planes of stride e_max, the entries past the path's edges with duration 0 (they
+// expand to nothing), so that the launch that re-expands the path is the same for every plan.  One warp.
 template <int NC>
-__global__ void k_rrt_path(RrtArgs a, int goal_node, int path_cap, int *n_edges_out)
+__global__ void k_rrt_path(RrtArgs a, int e_max)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int M = a.ws.max_nodes;
+    const int M = a.ws.max_nodes, lane = threadIdx.x;
+    const unsigned long long goal = *a.ws.goal_key;
     int n = 0;
-    for (int i = goal_node; a.ws.parent[i] >= 0 && n < path_cap; i = a.ws.parent[i]) a.ws.path_nodes[n++] = i;
-    for (int e = 0; e < n; ++e) {
-        const int i = a.ws.path_nodes[n - 1 - e];
-        a.ws.path_parent[e] = a.ws.parent[i];
-        for (int c = 0; c < 2 * NC; ++c) a.ws.path_ctrl[c * n + e] = a.ws.ctrl[c * M + i];   // planes of stride n = the edge count
-        a.ws.path_steps[e] = a.ws.steps[i];
+    if (lane == 0 && goal != ~0ull)
+        for (int i = (int)(goal & 0xffffffffu); a.ws.parent[i] >= 0 && n < e_max; i = a.ws.parent[i]) a.ws.path_nodes[n++] = i;
+    n = __shfl_sync(0xffffffffu, n, 0);
+    __syncwarp();
+    for (int e = lane; e < e_max; e += 32) {
+        const bool on = e < n;
+        const int i = on ? a.ws.path_nodes[n - 1 - e] : 0;
+        a.ws.path_parent[e] = on ? a.ws.parent[i] : 0;
+        for (int c = 0; c < 2 * NC; ++c) a.ws.path_ctrl[c * e_max + e] = on ? a.ws.ctrl[c * M + i] : 0.0f;
+        a.ws.path_steps[e] = on ? a.ws.steps[i] : 0;
     }
-    *n_edges_out = n;
+    if (lane == 0) a.ws.counters[4] = n;
 }
 
 template <class T>
@@ -582,6 +644,17 @@ int dev_alloc(kcbs_ctx *ctx, T *&p, size_t n)
 {
     KCBS_CUDA(ctx, cudaMalloc((void **)&p, sizeof(T) * (n ? n : 1)));
     return KCBS_OK;
+}
+
+template <int NC>
+cudaError_t load_planner_kernels()
+{
+    cudaFuncAttributes at;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&at, k_rrt_init<NC>)) != cudaSuccess || (e = cudaFuncGetAttributes(&at, k_rrt_nearest<NC>)) != cudaSuccess ||
+        (e = cudaFuncGetAttributes(&at, k_rrt_select<NC>)) != cudaSuccess || (e = cudaFuncGetAttributes(&at, k_rrt_append<NC>)) != cudaSuccess)
+        return e;
+    return cudaFuncGetAttributes(&at, k_rrt_path<NC>);
 }
 
 // the instantiated round loops hold the workspace's pointers: they go whenever a buffer moves
@@ -597,14 +670,19 @@ void drop_loops(RrtWorkspace &ws)
 void free_workspace(RrtWorkspace &ws)
 {
     drop_loops(ws);
-    void *d[] = {ws.plan, ws.nodes, ws.parent, ws.time, ws.ctrl, ws.steps, ws.targets, ws.nn, ws.s_ctrl, ws.s_steps,
+    void *d[] = {ws.trace, ws.plan, ws.nodes, ws.parent, ws.time, ws.ctrl, ws.steps, ws.targets, ws.nn, ws.s_ctrl, ws.s_steps,
                  ws.s_fin, ws.s_valid, ws.sel, ws.counters, ws.goal_key, ws.cons, ws.cons_states, ws.path_nodes, ws.path_ctrl,
                  ws.path_steps, ws.path_parent, ws.path_valid, ws.path_seg, ws.nn_r, ws.nn_t};
     for (void *p : d)
         if (p) cudaFree(p);
     if (ws.h_progress) cudaFreeHost(ws.h_progress);
     if (ws.h_counters) cudaFreeHost(ws.h_counters);
+    if (ws.h_path_seg) cudaFreeHost(ws.h_path_seg);
+    if (ws.h_path_valid) cudaFreeHost(ws.h_path_valid);
     if (ws.h_plan) cudaFreeHost(ws.h_plan);
+    if (ws.side) cudaStreamDestroy(ws.side);
+    if (ws.fork) cudaEventDestroy(ws.fork);
+    if (ws.join) cudaEventDestroy(ws.join);
     for (cudaEvent_t e : ws.ev)
         if (e) cudaEventDestroy(e);
     ws = RrtWorkspace();
@@ -623,8 +701,8 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
         ws.path_cap = 8192;
         const size_t PC = (size_t)ws.path_cap;
         if ((st = dev_alloc(ctx, ws.nodes, D * M)) || (st = dev_alloc(ctx, ws.parent, M)) || (st = dev_alloc(ctx, ws.time, M)) ||
-            (st = dev_alloc(ctx, ws.ctrl, U * M)) || (st = dev_alloc(ctx, ws.steps, M)) || (st = dev_alloc(ctx, ws.targets, D * B)) ||
-            (st = dev_alloc(ctx, ws.nn, B)) || (st = dev_alloc(ctx, ws.s_ctrl, 2 * U * S)) ||
+            (st = dev_alloc(ctx, ws.ctrl, U * M)) || (st = dev_alloc(ctx, ws.steps, M)) || (st = dev_alloc(ctx, ws.targets, 2 * D * B)) ||
+            (st = dev_alloc(ctx, ws.nn, 2 * B)) || (st = dev_alloc(ctx, ws.s_ctrl, 2 * U * S)) ||
             (st = dev_alloc(ctx, ws.s_steps, 2 * S)) || (st = dev_alloc(ctx, ws.s_fin, D * S)) || (st = dev_alloc(ctx, ws.s_valid, S)) || (st = dev_alloc(ctx, ws.sel, B)) ||
             (st = dev_alloc(ctx, ws.counters, 8)) || (st = dev_alloc(ctx, ws.goal_key, 1)) || (st = dev_alloc(ctx, ws.path_nodes, PC)) ||
             (st = dev_alloc(ctx, ws.path_ctrl, U * PC)) || (st = dev_alloc(ctx, ws.path_steps, PC)) ||
@@ -633,9 +711,16 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
             (st = dev_alloc(ctx, ws.nn_t, M)) || (st = dev_alloc(ctx, ws.plan, 1)))
             return st;
         KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_plan, sizeof(RrtPlan), cudaHostAllocDefault));
+#ifdef KCBS_RRT_TRACE
+        if ((st = dev_alloc(ctx, ws.trace, (size_t)kTraceRounds * 8))) return st;
+#endif
+        KCBS_CUDA(ctx, cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+        KCBS_CUDA(ctx, cudaEventCreateWithFlags(&ws.fork, cudaEventDisableTiming));
+        KCBS_CUDA(ctx, cudaEventCreateWithFlags(&ws.join, cudaEventDisableTiming));
         KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_progress, sizeof(RrtProgress) * kRrtDepth, cudaHostAllocMapped));
         KCBS_CUDA(ctx, cudaHostGetDevicePointer((void **)&ws.d_progress, ws.h_progress, 0));
-        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_counters, 8 * sizeof(int), cudaHostAllocDefault));
+        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_counters, 16 * sizeof(int), cudaHostAllocDefault));
+        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_path_valid, PC * sizeof(int), cudaHostAllocDefault));
         for (cudaEvent_t &e : ws.ev) KCBS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ws.max_nodes = p.max_nodes;
         ws.n_samples = n_samples;
@@ -695,6 +780,14 @@ int check_rrt_params(kcbs_ctx *ctx, const kcbs_rrt_params &p)
 }
 
 }  // namespace
+
+// The planner's kernels are launched from inside stream captures: they are loaded when the context is created, outside
+// any capture (a kernel's first use loads it, which a capture in progress does not always survive).
+cudaError_t init_planner_kernels()
+{
+    const cudaError_t e = load_planner_kernels<1>();
+    return e != cudaSuccess ? e : load_planner_kernels<2>();
+}
 
 void destroy_rrt_workspace(kcbs_ctx *ctx)
 {
@@ -764,8 +857,6 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         // host planes have stride cons_total; keep the same stride on the device
         KCBS_CUDA(ctx, cudaMemcpyAsync(ws.cons_states, cons_states, sizeof(float) * 3 * (size_t)cons_total, cudaMemcpyHostToDevice, s));
     }
-    // the start state travels through the (not yet used) target buffer
-    KCBS_CUDA(ctx, cudaMemcpyAsync(ws.targets, start, sizeof(float) * D, cudaMemcpyHostToDevice, s));
 
     // what changes from plan to plan goes to the device once (RrtPlan, kernels.h); the launches below are the same for
     // every round of every plan
@@ -777,6 +868,7 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
     hp.goal_radius = NC == 1 ? p.goal_radius : KCBS_PAIR_GOAL_RADIUS;
     hp.goal_bias = p.goal_bias;
     hp.seed = p.seed;
+    for (int c = 0; c < D; ++c) hp.start[c] = start[c];
     hp.limit_ns = p.time_limit_s > 0 ? (unsigned long long)(p.time_limit_s * 1e9) : 0ull;
     KCBS_CUDA(ctx, cudaMemcpyAsync(ws.plan, ws.h_plan, sizeof(RrtPlan), cudaMemcpyHostToDevice, s));
 
@@ -799,7 +891,7 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         pa.steps = ws.s_steps; pa.seg = nullptr; pa.fin = ws.s_fin; pa.valid_steps = ws.s_valid; pa.max_steps = p.max_steps;
         pa.robot = robots[0]; pa.parent_time = ws.time; pa.cons = ws.cons; pa.cons_states = ws.cons_states; pa.n_cons = n_cons;
         pa.cons_total = cons_total;
-        pa.plan = ws.plan; pa.parity_ctrl = (long long)2 * NC * n; pa.parity_steps = n;
+        pa.plan = ws.plan; pa.parity_ctrl = (long long)2 * NC * n; pa.parity_steps = n; pa.parity_parent = 2 * (long long)p.n_targets;   // (in ints: two per key)
     } else {
         qa.n = n; qa.n_parents = ws.max_nodes; qa.parents = ws.nodes; qa.parent_idx = reinterpret_cast<const int *>(ws.nn); qa.controls = ws.s_ctrl;
         qa.parent_group = p.n_controls; qa.parent_stride = 2;
@@ -808,21 +900,65 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         for (int c = 0; c < 4; ++c) qa.goals[c] = hp.goal[c];
         qa.hold_radius = KCBS_PAIR_GOAL_RADIUS;   // StatePropagatorDatabase.h:170
         qa.parent_time = ws.time; qa.cons = ws.cons; qa.cons_states = ws.cons_states; qa.n_cons = n_cons; qa.cons_total = cons_total;
-        qa.plan = ws.plan; qa.parity_ctrl = (long long)2 * NC * n; qa.parity_steps = n;
+        qa.plan = ws.plan; qa.parity_ctrl = (long long)2 * NC * n; qa.parity_steps = n; qa.parity_parent = 2 * (long long)p.n_targets;
     }
     const int tiles = (p.n_targets + kNNTile - 1) / kNNTile;
     const dim3 nn_grid((unsigned)tiles, (unsigned)nn_grid_y(ws.max_nodes, tiles));
+    const dim3 nn_fresh((unsigned)tiles, (unsigned)nn_grid_y(p.n_targets, tiles));   // a round appends n_targets nodes at most
     auto launch_init = [&](const RrtArgs &ra) {
-        k_rrt_init<NC><<<(n + 255) / 256, 256, 0, s>>>(ra, ws.targets);
+        k_rrt_init<NC><<<(std::max(n, 2 * p.n_targets) + 255) / 256, 256, 0, s>>>(ra);
         return cudaGetLastError();
     };
+    // One round.  The scan of the old nodes for the NEXT round depends on nothing this round does: it is a branch of its
+    // own (the side stream; in the graph, a parallel branch of the loop body), so the round's critical path is the scan of
+    // the few nodes the previous round appended, the expansion, the selection and the append.
     auto launch_round = [&](const RrtArgs &ra) {
-        k_rrt_nearest<NC><<<nn_grid, kNNThreads, 0, s>>>(ra);
-        cudaError_t e = NC == 1 ? launch_propagate(ctx->world, pa, s) : launch_propagate_pair(ctx->world, qa, s);
+        cudaError_t e;
+        if ((e = cudaEventRecord(ws.fork, s)) != cudaSuccess || (e = cudaStreamWaitEvent(ws.side, ws.fork, 0)) != cudaSuccess) return e;
+        k_rrt_nearest<NC><<<nn_grid, kNNThreads, 0, ws.side>>>(ra, 0);
+        if ((e = cudaEventRecord(ws.join, ws.side)) != cudaSuccess) return e;
+        k_rrt_nearest<NC><<<nn_fresh, kNNThreads, 0, s>>>(ra, 1);
+        e = NC == 1 ? launch_propagate(ctx->world, pa, s) : launch_propagate_pair(ctx->world, qa, s);
         if (e != cudaSuccess) return e;
         k_rrt_select<NC><<<(p.n_targets * 32 + 255) / 256, 256, 0, s>>>(ra);
         k_rrt_append<NC><<<(p.n_targets + kAppendThreads - 1) / kAppendThreads, kAppendThreads, 0, s>>>(ctx->world, ra);
+        if ((e = cudaStreamWaitEvent(s, ws.join, 0)) != cudaSuccess) return e;
         return cudaGetLastError();
+    };
+    // What follows the last round, whatever its outcome: the path's edges (none when there is no goal node), the states
+    // along them re-expanded by the propagation kernel (same arithmetic as the search), and everything the host wants to
+    // know in pinned memory.  Same launches for every plan: e_max edge slots, the unused ones of duration 0.
+    const int e_max = std::min(p.max_iterations, ws.path_cap);
+    const size_t seg_floats = (size_t)D * p.max_steps * e_max;
+    if (seg_floats > ws.h_path_cap) {
+        KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+        drop_loops(*ctx->rrt);   // (the loops copy into the old buffer)
+        if (ws.h_path_seg) cudaFreeHost(ws.h_path_seg);
+        ws.h_path_seg = nullptr; ws.h_path_cap = 0;
+        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_path_seg, sizeof(float) * seg_floats, cudaHostAllocDefault));
+        ws.h_path_cap = seg_floats;
+    }
+    auto launch_tail = [&](const RrtArgs &ra) {
+        cudaError_t e;
+        k_rrt_path<NC><<<1, 32, 0, s>>>(ra, e_max);
+        if (NC == 1) {
+            PropArgs pe = pa;   // (plan block: robot and constraint counts; no parity: the path has its own buffers)
+            pe.n = e_max; pe.parent_idx = ws.path_parent; pe.parent_group = pe.parent_stride = 1; pe.controls = ws.path_ctrl; pe.steps = ws.path_steps;
+            pe.parity_ctrl = pe.parity_steps = pe.parity_parent = 0; pe.rounds = 1;
+            pe.seg = ws.path_seg; pe.fin = nullptr; pe.valid_steps = ws.path_valid; pe.max_steps = p.max_steps;
+            e = launch_propagate(ctx->world, pe, s);
+        } else {
+            PairArgs qe = qa;
+            qe.n = e_max; qe.parent_idx = ws.path_parent; qe.parent_group = qe.parent_stride = 1; qe.controls = ws.path_ctrl; qe.steps = ws.path_steps;
+            qe.parity_ctrl = qe.parity_steps = qe.parity_parent = 0;
+            qe.seg = ws.path_seg; qe.fin = nullptr; qe.valid_steps = ws.path_valid; qe.max_steps = p.max_steps;
+            e = launch_propagate_pair(ctx->world, qe, s);
+        }
+        if (e != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(ws.h_counters, ws.counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(ws.h_counters + 8, ws.goal_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(ws.h_path_valid, ws.path_valid, sizeof(int) * e_max, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        return cudaMemcpyAsync(ws.h_path_seg, ws.path_seg, sizeof(float) * seg_floats, cudaMemcpyDeviceToHost, s);
     };
 
     int n_nodes = 1, iters = 0, queued = 0;
@@ -837,16 +973,27 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         }
         if (in) goal = 0;
     }
+#ifdef KCBS_RRT_TRACE
+    {
+        std::vector<unsigned long long> z((size_t)kTraceRounds * 8);
+        for (size_t q = 0; q < z.size(); ++q) z[q] = (q & 1) ? 0ull : ~0ull;
+        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.trace, z.data(), z.size() * 8, cudaMemcpyHostToDevice, s));
+        KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+#endif
     if (goal != ~0ull) {
         KCBS_CUDA(ctx, cudaStreamSynchronize(s));   // (the uploads above)
     } else if (device_rounds()) {
         // ---- the whole search is ONE graph launch: k_rrt_init, then a WHILE node whose body is the four kernels of a
         // round and whose condition k_rrt_append sets on the device (goal found, tree full, iteration or time limit) ----
         RrtWorkspace::Loop &L = ctx->rrt->loop[NC - 1][n_cons > 0];
-        const int key[5] = {p.n_targets, p.n_controls, p.min_steps, p.max_steps, NC == 1 ? pa.rounds : 0};
+        const int key[6] = {p.n_targets, p.n_controls, p.min_steps, p.max_steps, NC == 1 ? pa.rounds : 0, e_max};
         if (!L.exec || std::memcmp(L.key, key, sizeof(key)) != 0) {
             if (L.exec) cudaGraphExecDestroy(L.exec);
             L = RrtWorkspace::Loop();
+            const double t_build = now_s();
+            static std::mutex build_mutex;   // one capture at a time, process wide
+            std::lock_guard<std::mutex> build_lock(build_mutex);
             cudaGraph_t g = nullptr;
             KCBS_CUDA(ctx, cudaGraphCreate(&g, 0));
             RrtArgs la = a;
@@ -854,36 +1001,40 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
             cudaGraphNode_t init_node = nullptr, while_node = nullptr;
             size_t one = 1;
             cudaGraphNodeParams wp = {};
+            const char *step = "cudaGraphConditionalHandleCreate";
             cudaError_t e = cudaGraphConditionalHandleCreate(&la.loop, g, 1, cudaGraphCondAssignDefault);
-            if (e == cudaSuccess) e = cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
-            if (e == cudaSuccess) {
-                const cudaError_t e1 = launch_init(la);
+            // captures the launches of `what` into graph `into`, after node `dep` (if any)
+            auto capture = [&](cudaGraph_t into, cudaGraphNode_t *dep, const char *name, auto what) {
+                if (e != cudaSuccess) return;
+                step = name;
+                e = cudaStreamBeginCaptureToGraph(s, into, dep, nullptr, dep ? 1 : 0, cudaStreamCaptureModeThreadLocal);
+                if (e != cudaSuccess) return;
+                const cudaError_t e1 = what(la);
                 cudaGraph_t same = nullptr;
                 e = cudaStreamEndCapture(s, &same);
-                if (e == cudaSuccess) e = e1;
-            }
-            if (e == cudaSuccess) e = cudaGraphGetNodes(g, &init_node, &one);
+                if (e1 != cudaSuccess) e = e1;
+            };
+            capture(g, nullptr, "capture of k_rrt_init", launch_init);
+            if (e == cudaSuccess) { step = "cudaGraphGetNodes"; e = cudaGraphGetNodes(g, &init_node, &one); }
             if (e == cudaSuccess) {
+                step = "cudaGraphAddNode (while)";
                 wp.type = cudaGraphNodeTypeConditional;
                 wp.conditional.handle = la.loop;
                 wp.conditional.type = cudaGraphCondTypeWhile;
                 wp.conditional.size = 1;
                 e = cudaGraphAddNode(&while_node, g, &init_node, 1, &wp);
             }
-            if (e == cudaSuccess) e = cudaStreamBeginCaptureToGraph(s, wp.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
-            if (e == cudaSuccess) {
-                const cudaError_t e1 = launch_round(la);
-                cudaGraph_t same = nullptr;
-                e = cudaStreamEndCapture(s, &same);
-                if (e == cudaSuccess) e = e1;
-            }
-            if (e == cudaSuccess) e = cudaGraphInstantiate(&L.exec, g, 0);
+            if (e == cudaSuccess) capture(wp.conditional.phGraph_out[0], nullptr, "capture of a round", launch_round);
+            capture(g, &while_node, "capture of the path extraction", launch_tail);
+            if (e == cudaSuccess) { step = "cudaGraphInstantiate"; e = cudaGraphInstantiate(&L.exec, g, 0); }
             cudaGraphDestroy(g);
             if (e != cudaSuccess) {
                 L = RrtWorkspace::Loop();
-                return fail(ctx, KCBS_ERR_CUDA, "building the round loop graph", e);
+                cudaGetLastError();
+                return fail(ctx, KCBS_ERR_CUDA, step, e);
             }
             std::memcpy(L.key, key, sizeof(key));
+            if (trace_solve()) fprintf(stderr, "[kcbs]   round loop graph built in %.0f us\n", (now_s() - t_build) * 1e6);
         }
         KCBS_CUDA(ctx, cudaGraphLaunch(L.exec, s));
     } else {
@@ -901,56 +1052,41 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
             KCBS_CUDA(ctx, cudaEventRecord(ws.ev[queued % kRrtDepth], s));
             ++queued;
         }
+        KCBS_CUDA(ctx, launch_tail(a));
     }
+    int T = 0;
     if (goal == ~0ull) {
-        // the final word is on the device (rounds queued after the goal was found did nothing)
-        KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters, ws.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-        KCBS_CUDA(ctx, cudaMemcpyAsync(&ws.h_progress[0].goal, ws.goal_key, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         KCBS_CUDA(ctx, cudaStreamSynchronize(s));
-        goal = ws.h_progress[0].goal;
+        std::memcpy(&goal, ws.h_counters + 8, sizeof(goal));
         iters = ws.h_counters[2];
         n_nodes = std::min(ws.h_counters[iters & 1], p.max_nodes);   // the entry the next round would have read
-        ctx->launches += 1 + 4 * (device_rounds() ? iters : queued);
-    }
-
-    int T = 0;
-    if (goal != ~0ull) {
-        // states of the path: start, then every edge re-expanded by the propagation kernel (same arithmetic as the search)
-        const int goal_node = (int)(goal & 0xffffffffu);
+        ctx->launches += 1 + 5 * (device_rounds() ? iters : queued) + 2;
+        if (goal != ~0ull) {
+            const int E = ws.h_counters[4];
+            for (int c = 0; c < D; ++c) traj_out[(size_t)c * max_T] = start[c];
+            T = 1;
+            for (int e = 0; e < E; ++e)
+                for (int j = 0; j < ws.h_path_valid[e] && T < max_T; ++j, ++T)
+                    for (int c = 0; c < D; ++c) traj_out[(size_t)c * max_T + T] = ws.h_path_seg[((size_t)c * p.max_steps + j) * e_max + e];
+        }
+    } else {   // (the start is in the goal region)
         for (int c = 0; c < D; ++c) traj_out[(size_t)c * max_T] = start[c];
         T = 1;
-        if (goal_node != 0) {
-            int *d_n = ws.counters + 4;
-            // (edge count first: the control planes of the path are written with exactly that stride)
-            k_rrt_path<NC><<<1, 32, 0, s>>>(a, goal_node, ws.path_cap, d_n);
-            KCBS_CUDA(ctx, cudaMemcpyAsync(ws.h_counters + 4, d_n, sizeof(int), cudaMemcpyDeviceToHost, s));
-            KCBS_CUDA(ctx, cudaStreamSynchronize(s));
-            const int E = ws.h_counters[4];
-            if (NC == 1) {
-                PropArgs pe = pa;
-                pe.n = E; pe.parent_idx = ws.path_parent; pe.parent_group = pe.parent_stride = 1; pe.controls = ws.path_ctrl; pe.steps = ws.path_steps;
-                pe.plan = nullptr;
-                pe.seg = ws.path_seg; pe.fin = nullptr; pe.valid_steps = ws.path_valid; pe.max_steps = p.max_steps;
-                KCBS_CUDA(ctx, launch_propagate(ctx->world, pe, s));
-            } else {
-                PairArgs qe = qa;
-                qe.n = E; qe.parent_idx = ws.path_parent; qe.parent_group = qe.parent_stride = 1; qe.controls = ws.path_ctrl; qe.steps = ws.path_steps;
-                qe.plan = nullptr;
-                qe.seg = ws.path_seg; qe.fin = nullptr; qe.valid_steps = ws.path_valid; qe.max_steps = p.max_steps;
-                KCBS_CUDA(ctx, launch_propagate_pair(ctx->world, qe, s));
-            }
-            ctx->launches += 2;
-            std::vector<float> seg((size_t)D * p.max_steps * E);
-            std::vector<int> valid(E);
-            KCBS_CUDA(ctx, cudaMemcpyAsync(seg.data(), ws.path_seg, sizeof(float) * seg.size(), cudaMemcpyDeviceToHost, s));
-            KCBS_CUDA(ctx, cudaMemcpyAsync(valid.data(), ws.path_valid, sizeof(int) * E, cudaMemcpyDeviceToHost, s));
-            KCBS_CUDA(ctx, cudaStreamSynchronize(s));
-            for (int e = 0; e < E; ++e)
-                for (int j = 0; j < valid[e] && T < max_T; ++j, ++T)
-                    for (int c = 0; c < D; ++c) traj_out[(size_t)c * max_T + T] = seg[((size_t)c * p.max_steps + j) * E + e];
-        }
     }
     *T_out = T;
+#ifdef KCBS_RRT_TRACE
+    if (trace_solve()) {
+        std::vector<unsigned long long> z((size_t)kTraceRounds * 8);
+        cudaMemcpy(z.data(), ws.trace, z.size() * 8, cudaMemcpyDeviceToHost);
+        const unsigned long long t0 = z[2];   // start of round 0's fresh scan
+        for (int r = 0; r < std::min(iters, kTraceRounds); ++r) {
+            const unsigned long long *w = &z[(size_t)r * 8];
+            auto us = [&](unsigned long long t) { return (double)((long long)(t - t0)) * 1e-3; };
+            fprintf(stderr, "[kcbs]     round %2d: side scan %7.1f..%7.1f | fresh scan %7.1f..%7.1f | select %7.1f..%7.1f | append %7.1f..%7.1f us\n", r,
+                    us(w[0]), us(w[1]), us(w[2]), us(w[3]), us(w[4]), us(w[5]), us(w[6]), us(w[7]));
+        }
+    }
+#endif
     if (trace_solve())
         fprintf(stderr, "[kcbs]   plan robot %d: %.0f us, %d rounds run, %d queued, %d constraints, %d nodes, path %d\n", robots[0],
                 (now_s() - t_begin) * 1e6, iters, queued, n_cons, n_nodes, T);

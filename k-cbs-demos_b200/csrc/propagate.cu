@@ -393,6 +393,7 @@ k_propagate(const __grid_constant__ DevWorld w, const __grid_constant__ PropArgs
             a_plan.robot = h.y;
             a_plan.controls = a_in.controls + (h.x & 1) * a_in.parity_ctrl;
             if (a_in.steps) a_plan.steps = a_in.steps + (h.x & 1) * a_in.parity_steps;
+            if (a_in.parent_idx) a_plan.parent_idx = a_in.parent_idx + (h.x & 1) * a_in.parity_parent;
             if (HAS_CONS) {
                 a_plan.n_cons = h.w;
                 a_plan.cons_total = __ldcg(&a_in.plan->cons_total);
@@ -782,7 +783,14 @@ cudaError_t init_propagate_kernels()
     if ((e = for_each_variant<kDense, 1>(set1)) != cudaSuccess) return e;
     if ((e = for_each_variant<kPacked, 1>(set1)) != cudaSuccess) return e;
     if ((e = for_each_variant<kDense, 2>(set2)) != cudaSuccess) return e;
-    return for_each_variant<kPacked, 2>(set2);
+    if ((e = for_each_variant<kPacked, 2>(set2)) != cudaSuccess) return e;
+    // the direct variants are launched from inside stream captures (planner.cu): load them now, outside any capture
+    auto load = [](auto *k) {
+        cudaFuncAttributes at;
+        return cudaFuncGetAttributes(&at, k);
+    };
+    if ((e = for_each_variant<kDirect, 1>(load)) != cudaSuccess) return e;
+    return for_each_variant<kDirect, 2>(load);
 }
 
 template <int MODE, int ROUNDS>
@@ -827,7 +835,8 @@ cudaError_t launch_propagate(const DevWorld &w, const PropArgs &a, cudaStream_t 
         if (a.max_steps > kStageSteps || a.seg == nullptr || a.scan == nullptr) return cudaErrorInvalidValue;
         return rounds == 1 ? launch_mode<kPacked, 1>(w, a, stream) : launch_mode<kPacked, 2>(w, a, stream);
     }
-    if (a.seg != nullptr && a.max_steps <= kStageSteps)
+    // (planner launches -- a.plan -- take the direct path: it is the one that reads the plan block)
+    if (a.seg != nullptr && a.max_steps <= kStageSteps && a.plan == nullptr)
         return rounds == 1 ? launch_mode<kDense, 1>(w, a, stream) : launch_mode<kDense, 2>(w, a, stream);
     return rounds == 1 ? launch_mode<kDirect, 1>(w, a, stream) : launch_mode<kDirect, 2>(w, a, stream);
 }
