@@ -37,11 +37,23 @@ int fail(kcbs_ctx *ctx, int status, const char *what, cudaError_t e)
     return status;
 }
 
+std::mutex &capture_gate()
+{
+    static std::mutex gate;
+    return gate;
+}
+
+cudaError_t device_sync()
+{
+    std::lock_guard<std::mutex> lock(capture_gate());
+    return cudaDeviceSynchronize();
+}
+
 int reserve(kcbs_ctx *ctx, DevBuf &b, size_t bytes)
 {
     if (bytes <= b.cap) return KCBS_OK;
     if (b.p) {
-        KCBS_CUDA(ctx, cudaDeviceSynchronize());  // callers may still use it on their own stream
+        KCBS_CUDA(ctx, device_sync());  // callers may still use it on their own stream
         KCBS_CUDA(ctx, cudaFree(b.p));
         b.p = nullptr;
         b.cap = 0;
@@ -497,7 +509,7 @@ static int ensure_keys(kcbs_ctx *ctx, int n_plans, cudaStream_t s)
 {
     if (n_plans <= ctx->key_plans) return KCBS_OK;
     const int cap_plans = n_plans + n_plans / 4 + 64;
-    if (ctx->key_plans > 0) KCBS_CUDA(ctx, cudaDeviceSynchronize());  // earlier scans (any stream) still use the old layout
+    if (ctx->key_plans > 0) KCBS_CUDA(ctx, device_sync());  // earlier scans (any stream) still use the old layout
     int st = reserve(ctx, ctx->keys, (sizeof(uint64_t) + sizeof(int)) * (size_t)cap_plans);
     if (st != KCBS_OK) return st;
     ctx->key_plans = cap_plans;
@@ -634,7 +646,7 @@ int kcbs_peer_export(kcbs_ctx *ctx, int max_plans, kcbs_peer_handle *out)
     if (!ctx || !out) return KCBS_ERR_INVALID_ARGUMENT;
     if (max_plans < 1 || max_plans > (1 << 24)) return fail(ctx, KCBS_ERR_INVALID_ARGUMENT, "max_plans out of range");
     KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
-    KCBS_CUDA(ctx, cudaDeviceSynchronize());
+    KCBS_CUDA(ctx, device_sync());
     destroy_peers(ctx);
     PeerState &ps = ctx->peers;
     const size_t bytes = sizeof(unsigned long long) * 2 * KCBS_MAX_PEERS * (size_t)max_plans;
@@ -647,7 +659,7 @@ int kcbs_peer_export(kcbs_ctx *ctx, int max_plans, kcbs_peer_handle *out)
     KCBS_CUDA(ctx, cudaHostAlloc((void **)&ps.h_error, sizeof(int), cudaHostAllocMapped));
     *ps.h_error = 0;
     KCBS_CUDA(ctx, cudaHostGetDevicePointer((void **)&ps.d_error, ps.h_error, 0));
-    KCBS_CUDA(ctx, cudaDeviceSynchronize());
+    KCBS_CUDA(ctx, device_sync());
     ps.box_plans = max_plans;
     PeerHandleRaw h;
     std::memset(&h, 0, sizeof h);
@@ -709,7 +721,7 @@ int kcbs_peer_disconnect(kcbs_ctx *ctx)
 {
     if (!ctx) return KCBS_ERR_INVALID_ARGUMENT;
     KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
-    KCBS_CUDA(ctx, cudaDeviceSynchronize());
+    KCBS_CUDA(ctx, device_sync());
     peer_unmap(ctx);
     return KCBS_OK;
 }

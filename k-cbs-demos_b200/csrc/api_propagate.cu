@@ -87,7 +87,7 @@ static int ensure_scan(kcbs_ctx *ctx, DevBuf &buf, int &have, int ctas, cudaStre
 {
     if (ctas <= have) return KCBS_OK;
     const int want = ctas + ctas / 2 + 64;
-    if (have > 0) KCBS_CUDA(ctx, cudaDeviceSynchronize());
+    if (have > 0) KCBS_CUDA(ctx, device_sync());
     int st = reserve(ctx, buf, 16 + sizeof(unsigned long long) * (size_t)want);
     if (st != KCBS_OK) return st;
     KCBS_CUDA(ctx, cudaMemsetAsync(buf.p, 0, 16 + sizeof(unsigned long long) * (size_t)want, s));

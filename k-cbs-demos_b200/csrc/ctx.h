@@ -2,6 +2,7 @@
 // planner.cu (internal).
 #pragma once
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -63,6 +64,11 @@ struct kcbs_ctx {
 namespace kcbs {
 
 int fail(kcbs_ctx *ctx, int status, const char *what, cudaError_t e = cudaSuccess);
+// Stream captures and device-wide synchronisation exclude each other, process wide: synchronising the device while ANY of
+// its streams is capturing is invalid and kills that capture (the planner lanes capture their round loops while other
+// threads work).  The gate is held for the whole of a capture sequence and around every cudaDeviceSynchronize().
+std::mutex &capture_gate();
+cudaError_t device_sync();   // cudaDeviceSynchronize() under the gate
 int reserve(kcbs_ctx *ctx, DevBuf &b, size_t bytes);
 void destroy_rrt_workspace(kcbs_ctx *ctx);
 void destroy_peers(kcbs_ctx *ctx);

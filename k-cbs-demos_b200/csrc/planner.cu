@@ -85,6 +85,7 @@ struct RrtWorkspace {
     struct Loop {
         cudaGraphExec_t exec = nullptr;
         int key[6] = {0, 0, 0, 0, 0, 0};   // n_targets, n_controls, min_steps, max_steps, expansion shape, path edge slots
+        bool failed = false;               // the graph of this key could not be built: rounds are queued by the host instead
     } loop[2][2];
 };
 
@@ -688,13 +689,22 @@ void free_workspace(RrtWorkspace &ws)
     ws = RrtWorkspace();
 }
 
+// Everything that touches a planner workspace runs on the lane's own stream or on the workspace's side stream: waiting
+// for those two is all a re-allocation needs (never the device: other lanes are at work, or capturing, see capture_gate).
+cudaError_t sync_lane(kcbs_ctx *ctx, RrtWorkspace &ws)
+{
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    return e != cudaSuccess || !ws.side ? e : cudaStreamSynchronize(ws.side);
+}
+
 int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int cons_total, int n_cons)
 {
     if (!ctx->rrt) ctx->rrt = new RrtWorkspace();
     RrtWorkspace &ws = *ctx->rrt;
     const int n_samples = p.n_targets * p.n_controls, dim = 5 * n_cars;
     if (ws.max_nodes != p.max_nodes || ws.n_samples != n_samples || ws.n_targets != p.n_targets || ws.dim < dim) {
-        KCBS_CUDA(ctx, cudaDeviceSynchronize());
+        KCBS_CUDA(ctx, sync_lane(ctx, ws));
+        std::lock_guard<std::mutex> gate(capture_gate());   // (frees and allocations stay away from captures in progress)
         free_workspace(ws);
         int st;
         const size_t M = (size_t)p.max_nodes, S = (size_t)n_samples, B = (size_t)p.n_targets, D = (size_t)dim, U = (size_t)2 * n_cars;
@@ -728,7 +738,8 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
         ws.dim = dim;
     }
     if (cons_total > ws.cons_cap) {
-        KCBS_CUDA(ctx, cudaDeviceSynchronize());
+        KCBS_CUDA(ctx, sync_lane(ctx, ws));
+        std::lock_guard<std::mutex> gate(capture_gate());
         drop_loops(ws);
         if (ws.cons_states) cudaFree(ws.cons_states);
         ws.cons_states = nullptr;
@@ -737,7 +748,8 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
         if (st) return st;
     }
     if (n_cons > ws.cons_desc_cap) {
-        KCBS_CUDA(ctx, cudaDeviceSynchronize());
+        KCBS_CUDA(ctx, sync_lane(ctx, ws));
+        std::lock_guard<std::mutex> gate(capture_gate());
         drop_loops(ws);
         if (ws.cons) cudaFree(ws.cons);
         ws.cons = nullptr;
@@ -932,6 +944,7 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
     const size_t seg_floats = (size_t)D * p.max_steps * e_max;
     if (seg_floats > ws.h_path_cap) {
         KCBS_CUDA(ctx, cudaStreamSynchronize(s));
+        std::lock_guard<std::mutex> gate(capture_gate());
         drop_loops(*ctx->rrt);   // (the loops copy into the old buffer)
         if (ws.h_path_seg) cudaFreeHost(ws.h_path_seg);
         ws.h_path_seg = nullptr; ws.h_path_cap = 0;
@@ -981,19 +994,20 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         KCBS_CUDA(ctx, cudaStreamSynchronize(s));
     }
 #endif
-    if (goal != ~0ull) {
-        KCBS_CUDA(ctx, cudaStreamSynchronize(s));   // (the uploads above)
-    } else if (device_rounds()) {
-        // ---- the whole search is ONE graph launch: k_rrt_init, then a WHILE node whose body is the four kernels of a
-        // round and whose condition k_rrt_append sets on the device (goal found, tree full, iteration or time limit) ----
+    // ---- the whole search as ONE graph launch: k_rrt_init, then a WHILE node whose body is the kernels of a round and
+    // whose condition k_rrt_append sets on the device (goal found, tree full, iteration or time limit), then the path
+    // extraction.  Built once per launch shape; a shape whose graph cannot be built keeps host-queued rounds. ----
+    cudaGraphExec_t loop_exec = nullptr;
+    if (goal == ~0ull && device_rounds()) {
         RrtWorkspace::Loop &L = ctx->rrt->loop[NC - 1][n_cons > 0];
         const int key[6] = {p.n_targets, p.n_controls, p.min_steps, p.max_steps, NC == 1 ? pa.rounds : 0, e_max};
-        if (!L.exec || std::memcmp(L.key, key, sizeof(key)) != 0) {
+        if (std::memcmp(L.key, key, sizeof(key)) != 0 || (!L.exec && !L.failed)) {
+            const double t_build = now_s();
+            // one capture at a time, process wide, and no device-wide synchronisation meanwhile (capture_gate, ctx.h)
+            std::lock_guard<std::mutex> build_lock(capture_gate());
             if (L.exec) cudaGraphExecDestroy(L.exec);
             L = RrtWorkspace::Loop();
-            const double t_build = now_s();
-            static std::mutex build_mutex;   // one capture at a time, process wide
-            std::lock_guard<std::mutex> build_lock(build_mutex);
+            std::memcpy(L.key, key, sizeof(key));
             cudaGraph_t g = nullptr;
             KCBS_CUDA(ctx, cudaGraphCreate(&g, 0));
             RrtArgs la = a;
@@ -1002,6 +1016,7 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
             size_t one = 1;
             cudaGraphNodeParams wp = {};
             const char *step = "cudaGraphConditionalHandleCreate";
+            bool capture_broken = false;
             cudaError_t e = cudaGraphConditionalHandleCreate(&la.loop, g, 1, cudaGraphCondAssignDefault);
             // captures the launches of `what` into graph `into`, after node `dep` (if any)
             auto capture = [&](cudaGraph_t into, cudaGraphNode_t *dep, const char *name, auto what) {
@@ -1013,6 +1028,7 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
                 cudaGraph_t same = nullptr;
                 e = cudaStreamEndCapture(s, &same);
                 if (e1 != cudaSuccess) e = e1;
+                capture_broken = e != cudaSuccess;
             };
             capture(g, nullptr, "capture of k_rrt_init", launch_init);
             if (e == cudaSuccess) { step = "cudaGraphGetNodes"; e = cudaGraphGetNodes(g, &init_node, &one); }
@@ -1027,16 +1043,24 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
             if (e == cudaSuccess) capture(wp.conditional.phGraph_out[0], nullptr, "capture of a round", launch_round);
             capture(g, &while_node, "capture of the path extraction", launch_tail);
             if (e == cudaSuccess) { step = "cudaGraphInstantiate"; e = cudaGraphInstantiate(&L.exec, g, 0); }
-            cudaGraphDestroy(g);
+            // (a graph whose capture was invalidated is abandoned, not destroyed: the driver has been seen to fault on it)
+            if (!capture_broken) cudaGraphDestroy(g);
             if (e != cudaSuccess) {
-                L = RrtWorkspace::Loop();
+                L.exec = nullptr;
+                L.failed = true;
                 cudaGetLastError();
-                return fail(ctx, KCBS_ERR_CUDA, step, e);
+                fprintf(stderr, "[kcbs] round loop graph not built (%s: %s): rounds of this shape are queued by the host\n", step,
+                        cudaGetErrorString(e));
+            } else if (trace_solve()) {
+                fprintf(stderr, "[kcbs]   round loop graph built in %.0f us\n", (now_s() - t_build) * 1e6);
             }
-            std::memcpy(L.key, key, sizeof(key));
-            if (trace_solve()) fprintf(stderr, "[kcbs]   round loop graph built in %.0f us\n", (now_s() - t_build) * 1e6);
         }
-        KCBS_CUDA(ctx, cudaGraphLaunch(L.exec, s));
+        loop_exec = L.exec;
+    }
+    if (goal != ~0ull) {
+        KCBS_CUDA(ctx, cudaStreamSynchronize(s));   // (the uploads above)
+    } else if (loop_exec) {
+        KCBS_CUDA(ctx, cudaGraphLaunch(loop_exec, s));
     } else {
         // ---- rounds queued by the host (KCBS_RRT_ROUNDS=stream), kRrtDepth of them ahead of the device ----
         for (int q = 0; q < kRrtDepth; ++q) ws.h_progress[q] = RrtProgress{~0ull, 1, 0};
@@ -1060,7 +1084,7 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         std::memcpy(&goal, ws.h_counters + 8, sizeof(goal));
         iters = ws.h_counters[2];
         n_nodes = std::min(ws.h_counters[iters & 1], p.max_nodes);   // the entry the next round would have read
-        ctx->launches += 1 + 5 * (device_rounds() ? iters : queued) + 2;
+        ctx->launches += 1 + 5 * (loop_exec ? iters : queued) + 2;
         if (goal != ~0ull) {
             const int E = ws.h_counters[4];
             for (int c = 0; c < D; ++c) traj_out[(size_t)c * max_T] = start[c];
