@@ -265,9 +265,10 @@ KCBS_API int kcbs_first_conflict_groups_dev(kcbs_ctx *ctx, int n_plans, int R, i
  * built from the three kernels above plus tree bookkeeping kernels; all planning state lives in HBM. */
 
 typedef struct kcbs_rrt_params {
-    int32_t n_targets;      /* tree nodes expanded per iteration                  (default 2048)   */
+    int32_t n_targets;      /* tree nodes expanded per iteration                  (default 1024;   *
+                             * kcbs_kcbs_solve doubles it for a merged pair: 10-d joint space)     */
     int32_t n_controls;     /* sampled controls per expanded node                 (default 32)     *
-                             * n_targets * n_controls = 65,536 controls per expansion round        */
+                             * n_targets * n_controls = 32,768 controls per expansion round        */
     int32_t max_nodes;      /* tree capacity; 0 = from the workspace: 1.5 x the rounds a path across it needs,
                                32 .. 128 rounds of n_targets nodes                 (default 0)     */
     int32_t max_iterations; /*                                                    (default 512)    */

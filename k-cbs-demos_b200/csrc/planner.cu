@@ -79,6 +79,8 @@ struct RrtWorkspace {
     cudaEvent_t ev[kRrtDepth] = {};
     RrtPlan *plan = nullptr, *h_plan = nullptr;   // the plan block on the device (kernels.h) and its pinned staging copy
     unsigned long long *trace = nullptr;          // (KCBS_RRT_TRACE builds) [kTraceRounds][4 kernels][start, end] globaltimer stamps
+    void *slab = nullptr, *h_slab = nullptr;      // the one device and the one pinned (mapped) allocation everything above is carved from
+    bool own_cons_states = false, own_cons = false, own_h_path_seg = false;   // outgrew the slab: allocated on their own
     cudaStream_t side = nullptr;                  // second branch of a round (the scan of the old nodes for the next round)
     cudaEvent_t fork = nullptr, join = nullptr;
     // device-driven rounds: one instantiated graph per (cars, constrained or not), rebuilt when the launch shape changes
@@ -86,7 +88,7 @@ struct RrtWorkspace {
         cudaGraphExec_t exec = nullptr;
         int key[6] = {0, 0, 0, 0, 0, 0};   // n_targets, n_controls, min_steps, max_steps, expansion shape, path edge slots
         bool failed = false;               // the graph of this key could not be built: rounds are queued by the host instead
-    } loop[2][2];
+    } loop[2][2][3];   // [cars - 1][constrained][expansion shape]: a lane that alternates between shapes keeps both graphs
 };
 
 namespace {
@@ -662,25 +664,22 @@ cudaError_t load_planner_kernels()
 void drop_loops(RrtWorkspace &ws)
 {
     for (auto &per_cars : ws.loop)
-        for (RrtWorkspace::Loop &l : per_cars) {
-            if (l.exec) cudaGraphExecDestroy(l.exec);
-            l = RrtWorkspace::Loop();
-        }
+        for (auto &per_cons : per_cars)
+            for (RrtWorkspace::Loop &l : per_cons) {
+                if (l.exec) cudaGraphExecDestroy(l.exec);
+                l = RrtWorkspace::Loop();
+            }
 }
 
 void free_workspace(RrtWorkspace &ws)
 {
     drop_loops(ws);
-    void *d[] = {ws.trace, ws.plan, ws.nodes, ws.parent, ws.time, ws.ctrl, ws.steps, ws.targets, ws.nn, ws.s_ctrl, ws.s_steps,
-                 ws.s_fin, ws.s_valid, ws.sel, ws.counters, ws.goal_key, ws.cons, ws.cons_states, ws.path_nodes, ws.path_ctrl,
-                 ws.path_steps, ws.path_parent, ws.path_valid, ws.path_seg, ws.nn_r, ws.nn_t};
-    for (void *p : d)
-        if (p) cudaFree(p);
-    if (ws.h_progress) cudaFreeHost(ws.h_progress);
-    if (ws.h_counters) cudaFreeHost(ws.h_counters);
-    if (ws.h_path_seg) cudaFreeHost(ws.h_path_seg);
-    if (ws.h_path_valid) cudaFreeHost(ws.h_path_valid);
-    if (ws.h_plan) cudaFreeHost(ws.h_plan);
+    // one device slab and one pinned slab hold everything; what outgrew its share was allocated on its own
+    if (ws.own_cons_states && ws.cons_states) cudaFree(ws.cons_states);
+    if (ws.own_cons && ws.cons) cudaFree(ws.cons);
+    if (ws.own_h_path_seg && ws.h_path_seg) cudaFreeHost(ws.h_path_seg);
+    if (ws.slab) cudaFree(ws.slab);
+    if (ws.h_slab) cudaFreeHost(ws.h_slab);
     if (ws.side) cudaStreamDestroy(ws.side);
     if (ws.fork) cudaEventDestroy(ws.fork);
     if (ws.join) cudaEventDestroy(ws.join);
@@ -688,6 +687,19 @@ void free_workspace(RrtWorkspace &ws)
         if (e) cudaEventDestroy(e);
     ws = RrtWorkspace();
 }
+
+// Hands out 256-byte aligned pieces of a slab; with a null base it only adds up the sizes.
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base((char *)b) {}
+    template <class T>
+    void take(T *&p, size_t n)
+    {
+        p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += (sizeof(T) * (n ? n : 1) + 255) & ~(size_t)255;
+    }
+};
 
 // Everything that touches a planner workspace runs on the lane's own stream or on the workspace's side stream: waiting
 // for those two is all a re-allocation needs (never the device: other lanes are at work, or capturing, see capture_gate).
@@ -697,7 +709,9 @@ cudaError_t sync_lane(kcbs_ctx *ctx, RrtWorkspace &ws)
     return e != cudaSuccess || !ws.side ? e : cudaStreamSynchronize(ws.side);
 }
 
-int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int cons_total, int n_cons)
+// A lane's first plan used to cost 8 ms of allocation calls (28 of them, serialised by the driver over 16 lanes): the
+// workspace is ONE device allocation and ONE pinned (mapped) allocation, carved up here.
+int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int cons_total, int n_cons, size_t seg_floats)
 {
     if (!ctx->rrt) ctx->rrt = new RrtWorkspace();
     RrtWorkspace &ws = *ctx->rrt;
@@ -706,31 +720,42 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
         KCBS_CUDA(ctx, sync_lane(ctx, ws));
         std::lock_guard<std::mutex> gate(capture_gate());   // (frees and allocations stay away from captures in progress)
         free_workspace(ws);
-        int st;
         const size_t M = (size_t)p.max_nodes, S = (size_t)n_samples, B = (size_t)p.n_targets, D = (size_t)dim, U = (size_t)2 * n_cars;
         ws.path_cap = 8192;
         const size_t PC = (size_t)ws.path_cap;
-        if ((st = dev_alloc(ctx, ws.nodes, D * M)) || (st = dev_alloc(ctx, ws.parent, M)) || (st = dev_alloc(ctx, ws.time, M)) ||
-            (st = dev_alloc(ctx, ws.ctrl, U * M)) || (st = dev_alloc(ctx, ws.steps, M)) || (st = dev_alloc(ctx, ws.targets, 2 * D * B)) ||
-            (st = dev_alloc(ctx, ws.nn, 2 * B)) || (st = dev_alloc(ctx, ws.s_ctrl, 2 * U * S)) ||
-            (st = dev_alloc(ctx, ws.s_steps, 2 * S)) || (st = dev_alloc(ctx, ws.s_fin, D * S)) || (st = dev_alloc(ctx, ws.s_valid, S)) || (st = dev_alloc(ctx, ws.sel, B)) ||
-            (st = dev_alloc(ctx, ws.counters, 8)) || (st = dev_alloc(ctx, ws.goal_key, 1)) || (st = dev_alloc(ctx, ws.path_nodes, PC)) ||
-            (st = dev_alloc(ctx, ws.path_ctrl, U * PC)) || (st = dev_alloc(ctx, ws.path_steps, PC)) ||
-            (st = dev_alloc(ctx, ws.path_parent, PC)) || (st = dev_alloc(ctx, ws.path_valid, PC)) ||
-            (st = dev_alloc(ctx, ws.path_seg, D * (size_t)KCBS_MAX_STEPS * PC)) || (st = dev_alloc(ctx, ws.nn_r, M)) ||
-            (st = dev_alloc(ctx, ws.nn_t, M)) || (st = dev_alloc(ctx, ws.plan, 1)))
-            return st;
-        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_plan, sizeof(RrtPlan), cudaHostAllocDefault));
+        const int cons_cap = std::max(4096, cons_total + cons_total / 2 + 1024), cons_desc_cap = std::max(64, n_cons + 64);
+        auto device_layout = [&](Carver &c) {
+            c.take(ws.nodes, D * M); c.take(ws.parent, M); c.take(ws.time, M); c.take(ws.ctrl, U * M); c.take(ws.steps, M);
+            c.take(ws.targets, 2 * D * B); c.take(ws.nn, 2 * B); c.take(ws.s_ctrl, 2 * U * S); c.take(ws.s_steps, 2 * S);
+            c.take(ws.s_fin, D * S); c.take(ws.s_valid, S); c.take(ws.sel, B); c.take(ws.counters, 8); c.take(ws.goal_key, 1);
+            c.take(ws.path_nodes, PC); c.take(ws.path_ctrl, U * PC); c.take(ws.path_steps, PC); c.take(ws.path_parent, PC);
+            c.take(ws.path_valid, PC); c.take(ws.path_seg, D * (size_t)KCBS_MAX_STEPS * PC); c.take(ws.nn_r, M); c.take(ws.nn_t, M);
+            c.take(ws.plan, 1); c.take(ws.cons_states, 3 * (size_t)cons_cap); c.take(ws.cons, (size_t)cons_desc_cap);
 #ifdef KCBS_RRT_TRACE
-        if ((st = dev_alloc(ctx, ws.trace, (size_t)kTraceRounds * 8))) return st;
+            c.take(ws.trace, (size_t)kTraceRounds * 8);
 #endif
+        };
+        auto host_layout = [&](Carver &c) {
+            c.take(ws.h_plan, 1); c.take(ws.h_progress, kRrtDepth); c.take(ws.h_counters, 16); c.take(ws.h_path_valid, PC);
+            c.take(ws.h_path_seg, seg_floats);
+        };
+        Carver dev_size(nullptr), host_size(nullptr);
+        device_layout(dev_size);
+        host_layout(host_size);
+        KCBS_CUDA(ctx, cudaMalloc(&ws.slab, dev_size.off));
+        KCBS_CUDA(ctx, cudaHostAlloc(&ws.h_slab, host_size.off, cudaHostAllocMapped));
+        Carver dev(ws.slab), host(ws.h_slab);
+        device_layout(dev);
+        host_layout(host);
+        ws.h_path_cap = seg_floats;
+        ws.cons_cap = cons_cap;
+        ws.cons_desc_cap = cons_desc_cap;
+        char *h_slab_dev = nullptr;   // the pinned slab as the device sees it (the progress ring is written by k_rrt_append)
+        KCBS_CUDA(ctx, cudaHostGetDevicePointer((void **)&h_slab_dev, ws.h_slab, 0));
+        ws.d_progress = reinterpret_cast<RrtProgress *>(h_slab_dev + ((char *)ws.h_progress - (char *)ws.h_slab));
         KCBS_CUDA(ctx, cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
         KCBS_CUDA(ctx, cudaEventCreateWithFlags(&ws.fork, cudaEventDisableTiming));
         KCBS_CUDA(ctx, cudaEventCreateWithFlags(&ws.join, cudaEventDisableTiming));
-        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_progress, sizeof(RrtProgress) * kRrtDepth, cudaHostAllocMapped));
-        KCBS_CUDA(ctx, cudaHostGetDevicePointer((void **)&ws.d_progress, ws.h_progress, 0));
-        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_counters, 16 * sizeof(int), cudaHostAllocDefault));
-        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_path_valid, PC * sizeof(int), cudaHostAllocDefault));
         for (cudaEvent_t &e : ws.ev) KCBS_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ws.max_nodes = p.max_nodes;
         ws.n_samples = n_samples;
@@ -741,8 +766,9 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
         KCBS_CUDA(ctx, sync_lane(ctx, ws));
         std::lock_guard<std::mutex> gate(capture_gate());
         drop_loops(ws);
-        if (ws.cons_states) cudaFree(ws.cons_states);
+        if (ws.own_cons_states && ws.cons_states) cudaFree(ws.cons_states);
         ws.cons_states = nullptr;
+        ws.own_cons_states = true;
         ws.cons_cap = cons_total + cons_total / 2 + 1024;
         int st = dev_alloc(ctx, ws.cons_states, 3 * (size_t)ws.cons_cap);
         if (st) return st;
@@ -751,11 +777,23 @@ int ensure_workspace(kcbs_ctx *ctx, const kcbs_rrt_params &p, int n_cars, int co
         KCBS_CUDA(ctx, sync_lane(ctx, ws));
         std::lock_guard<std::mutex> gate(capture_gate());
         drop_loops(ws);
-        if (ws.cons) cudaFree(ws.cons);
+        if (ws.own_cons && ws.cons) cudaFree(ws.cons);
         ws.cons = nullptr;
+        ws.own_cons = true;
         ws.cons_desc_cap = n_cons + 64;
         int st = dev_alloc(ctx, ws.cons, (size_t)ws.cons_desc_cap);
         if (st) return st;
+    }
+    if (seg_floats > ws.h_path_cap) {   // (the loops copy the re-expanded path into this buffer)
+        KCBS_CUDA(ctx, sync_lane(ctx, ws));
+        std::lock_guard<std::mutex> gate(capture_gate());
+        drop_loops(ws);
+        if (ws.own_h_path_seg && ws.h_path_seg) cudaFreeHost(ws.h_path_seg);
+        ws.h_path_seg = nullptr;
+        ws.own_h_path_seg = true;
+        ws.h_path_cap = 0;
+        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_path_seg, sizeof(float) * seg_floats, cudaHostAllocDefault));
+        ws.h_path_cap = seg_floats;
     }
     return KCBS_OK;
 }
@@ -858,7 +896,9 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
         cons_total = std::max(cons_total, cons_offset[c] + std::abs(cons_len[c]));
     }
     KCBS_CUDA(ctx, cudaSetDevice(ctx->device));
-    if ((st = ensure_workspace(ctx, p, NC, cons_total, n_cons))) return st;
+    const int e_max = std::min(p.max_iterations, 8192);   // edge slots of the path extraction (= RrtWorkspace::path_cap at most)
+    const size_t seg_floats = (size_t)D * p.max_steps * e_max;
+    if ((st = ensure_workspace(ctx, p, NC, cons_total, n_cons, seg_floats))) return st;
     RrtWorkspace &ws = *ctx->rrt;
     cudaStream_t s = ctx->stream;
 
@@ -940,17 +980,6 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
     // What follows the last round, whatever its outcome: the path's edges (none when there is no goal node), the states
     // along them re-expanded by the propagation kernel (same arithmetic as the search), and everything the host wants to
     // know in pinned memory.  Same launches for every plan: e_max edge slots, the unused ones of duration 0.
-    const int e_max = std::min(p.max_iterations, ws.path_cap);
-    const size_t seg_floats = (size_t)D * p.max_steps * e_max;
-    if (seg_floats > ws.h_path_cap) {
-        KCBS_CUDA(ctx, cudaStreamSynchronize(s));
-        std::lock_guard<std::mutex> gate(capture_gate());
-        drop_loops(*ctx->rrt);   // (the loops copy into the old buffer)
-        if (ws.h_path_seg) cudaFreeHost(ws.h_path_seg);
-        ws.h_path_seg = nullptr; ws.h_path_cap = 0;
-        KCBS_CUDA(ctx, cudaHostAlloc((void **)&ws.h_path_seg, sizeof(float) * seg_floats, cudaHostAllocDefault));
-        ws.h_path_cap = seg_floats;
-    }
     auto launch_tail = [&](const RrtArgs &ra) {
         cudaError_t e;
         k_rrt_path<NC><<<1, 32, 0, s>>>(ra, e_max);
@@ -999,7 +1028,7 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
     // extraction.  Built once per launch shape; a shape whose graph cannot be built keeps host-queued rounds. ----
     cudaGraphExec_t loop_exec = nullptr;
     if (goal == ~0ull && device_rounds()) {
-        RrtWorkspace::Loop &L = ctx->rrt->loop[NC - 1][n_cons > 0];
+        RrtWorkspace::Loop &L = ctx->rrt->loop[NC - 1][n_cons > 0][NC == 1 ? std::min(std::max(pa.rounds, 0), 2) : 0];
         const int key[6] = {p.n_targets, p.n_controls, p.min_steps, p.max_steps, NC == 1 ? pa.rounds : 0, e_max};
         if (std::memcmp(L.key, key, sizeof(key)) != 0 || (!L.exec && !L.failed)) {
             const double t_build = now_s();
@@ -1133,7 +1162,7 @@ extern "C" {
 void kcbs_rrt_defaults(kcbs_rrt_params *p)
 {
     if (!p) return;
-    p->n_targets = 2048;
+    p->n_targets = 1024;   // measured over the demo scenes: 2048 costs twice the work per round for no fewer rounds
     p->n_controls = 32;
     p->max_nodes = 0;       // chosen from the workspace, see auto_max_nodes
     p->max_iterations = 512;
@@ -1409,6 +1438,8 @@ int plan_individual(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsig
     }
     const int r1 = members[0], r2 = members[1];
     solved = false;
+    // the joint space has twice the dimensions: twice the targets per round (the corridor swap needs them)
+    lp.n_targets = (int)std::min<long long>(2ll * lp.n_targets, (1ll << 26) / std::max(1, lp.n_controls));
     for (int attempt = 0; attempt < 3 && !solved; ++attempt) {
         lp.seed = q.P.low_level.seed * 1000003ull + (seed + 7ull * attempt) * 131ull + (unsigned long long)(64 * r1 + r2 + 4096);
         int len = 0;
