@@ -255,3 +255,66 @@ def test_kcbs_plans_the_merged_pair_jointly(pkg, orc, gpu_ctx_factory):
     # merged cars stop within 1.5 of their goals (the merged goal region), the others within 0.5
     within = [float(np.hypot(plan[r][0, lengths[r] - 1] - goals[r][0], plan[r][1, lengths[r] - 1] - goals[r][1])) for r in range(R)]
     assert sum(d <= 0.5 + 1e-4 for d in within) >= R - 2 * st.merges and max(within) < 1.5 + 1e-4
+
+
+def test_concurrent_solves_and_device_wide_work(pkg, gpu_ctx_factory):
+    # Host threads of one process: two K-CBS solves on two contexts (their planner lanes capture the round-loop graphs
+    # while they run) beside a thread whose plan scans keep growing -- every growth re-allocates after a device-wide
+    # synchronisation, which must never meet a capture in progress (capture_gate, csrc/ctx.h).  Results = the same calls
+    # made one after the other: a plan depends on its seed only.
+    import threading
+
+    from kcbs_b200 import workloads
+
+    scenes = ["Corridor10x10_4robots", "Empty32x32_10robots"]
+    seeds = [11, 12, 13]
+
+    def solve_all(ctx, scene):
+        starts, goals = pkg.scenes.start_states(scene), pkg.scenes.goals(scene)
+        out = []
+        for seed in seeds:
+            plan, lengths, st = ctx.kcbs_solve(starts, goals, ctx.kcbs_params(low_level=ctx.rrt_params(seed=seed), time_limit_s=60.0),
+                                               max_T=1024)
+            out.append((st.solved, lengths.copy(), plan.copy()))
+        return out
+
+    def fresh(scene):   # new contexts: the lanes, their workspaces and graphs are built while the other threads run
+        return pkg.Context(pkg.scenes.world(scene), device=0)
+
+    results, errors = {}, []
+
+    def worker(name, fn):
+        try:
+            results[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            errors.append((name, repr(e)))
+
+    def scans():
+        scene = "Empty32x32_10robots"
+        n = 0
+        with fresh(scene) as ctx:
+            for P in (1, 3, 9, 40, 130, 300, 700):
+                res = ctx.first_conflict(workloads.cell_plans(scene, P, 256, seed=P))
+                assert (res["r1"] == -1).all()
+                n += P
+        return n
+
+    ctxs = [fresh(s) for s in scenes]
+    try:
+        threads = [threading.Thread(target=worker, args=(s, lambda c=c, s=s: solve_all(c, s))) for c, s in zip(ctxs, scenes)]
+        threads.append(threading.Thread(target=worker, args=("scans", scans)))
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors
+        assert results["scans"] == 1 + 3 + 9 + 40 + 130 + 300 + 700
+    finally:
+        for c in ctxs:
+            c.close()
+    for scene in scenes:
+        with fresh(scene) as ctx:
+            alone = solve_all(ctx, scene)
+        for (s1, l1, p1), (s2, l2, p2) in zip(results[scene], alone):
+            assert s1 == 1 and s2 == 1
+            assert (l1 == l2).all() and (p1 == p2).all(), f"{scene}: a concurrent solve differs from the same solve alone"
