@@ -512,12 +512,13 @@ def main():
                 ctxs[r].propagate_batch(r, pp, pc, ps, max_steps=MAX_STEPS, out=(seg_b if kind == "dense" else None, fin_b, val_b))
 
     def e2e_run(kind):
-        step = lambda: list(pool.map(lambda r: robot_calls(r, kind), range(n_robots)))  # noqa: E731
-        step()
+        # every robot planner thread makes its calls of ALL timed steps one after the other: the planners are independent
+        # (no barrier between steps -- they only meet at the start and at the end of the timed region)
+        run = lambda k: list(pool.map(lambda r: [robot_calls(r, kind) for _ in range(k)], range(n_robots)))  # noqa: E731
+        run(1)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step()
+        run(e2e_steps)
         barrier()
         return max_over_ranks(time.perf_counter() - t0)
 

@@ -235,17 +235,45 @@ __device__ __forceinline__ bool obstacles_clear_fine(const DevWorld &w, float x,
 // constraint whose last state keeps holding for every later time index.
 struct ConsDesc {
     int other, k0, len, offset;
+    float cx, cy, r;   // a circle around the positions of all its states (filled by the host): lets a sample that cannot
+    int pad;           // come near them skip the constraint for all of its steps (cons_mask)
 };
+
+// Which of the first 32 constraints can matter to a sample at all: it starts at (x0, y0) at time index t0 and drives `steps`
+// steps at a speed of at most v_max, so it stays within reach = v_max * steps * step of its parent; a constraint whose time
+// window misses [t0 + 1, t0 + steps] or whose circle is farther away than reach + both bounding radii can never fail the
+// exact test (constraints_clear applies the same circle test to the state itself first).  Constraints past the 32nd are
+// always tested.
+__device__ __forceinline__ unsigned cons_mask(const DevWorld &w, const ConsDesc *cons, int n_cons, int t0, int steps, float x0, float y0,
+                                              float rad)
+{
+    unsigned mask = 0u;
+    const float v_max = fmaxf(fabsf(w.lo_t[2]), fabsf(w.hi_t[2]));
+    const float reach = v_max * ((float)steps * w.step) * 1.01f + 0.05f;
+    const int nq = min(n_cons, 32);
+    for (int q = 0; q < nq; ++q) {
+        const int4 h = __ldg(reinterpret_cast<const int4 *>(cons + q));
+        const float4 c = __ldg(reinterpret_cast<const float4 *>(cons + q) + 1);
+        const bool in_time = t0 + steps >= h.y && (h.z < 0 || t0 + 1 < h.y + h.z);
+        const float dx = c.x - x0, dy = c.y - y0, R = c.z + rad + w.rob_rad[h.x] + reach;
+        if (in_time && fmaf(dy, dy, dx * dx) <= R * R) mask |= 1u << q;
+    }
+    return mask;
+}
 
 // Dynamic-obstacle constraints of the K-CBS low level (the fork tests `next` against the constraining robot's
 // state at that time through areStatesValid, StateValidityCheckerDatabase.h:78-125).
 __device__ __forceinline__ bool constraints_clear(const DevWorld &w, const ConsDesc *cons, int n_cons, const float *cons_states,
-                                                  int cons_total, int k, float x, float y, float th, float hl, float hw, float rad)
+                                                  int cons_total, int k, float x, float y, float th, float hl, float hw, float rad,
+                                                  unsigned mask = 0xffffffffu)
 {
     bool ok = true, have = false;
     float c = 1.0f, s = 0.0f;
     for (int q = 0; q < n_cons; ++q) {
-        const ConsDesc d = cons[q];
+        if (q < 32 && !((mask >> q) & 1u)) continue;   // (cons_mask: out of this sample's reach, in time or in space)
+        const int4 h = __ldg(reinterpret_cast<const int4 *>(cons + q));
+        ConsDesc d;
+        d.other = h.x; d.k0 = h.y; d.len = h.z; d.offset = h.w;
         int rel = k - d.k0;
         if (rel < 0) continue;
         if (d.len < 0)

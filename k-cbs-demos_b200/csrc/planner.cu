@@ -904,7 +904,21 @@ static int rrt_plan(kcbs_ctx *ctx, const int *robots, const float *start, const 
 
     std::vector<ConsDesc> desc(n_cons);
     if (n_cons > 0) {
-        for (int c = 0; c < n_cons; ++c) desc[c] = ConsDesc{cons_robot[c], cons_k0[c], cons_len[c], cons_offset[c]};
+        for (int c = 0; c < n_cons; ++c) {
+            // circle around the constraint's positions (centre of their bounding box): the expansion kernel skips the
+            // constraint for samples that cannot come near it (cons_mask, kcbs_device.cuh)
+            const int len = std::abs(cons_len[c]);
+            const float *xs = cons_states + cons_offset[c], *ys = xs + cons_total;
+            float x_lo = xs[0], x_hi = xs[0], y_lo = ys[0], y_hi = ys[0];
+            for (int j = 1; j < len; ++j) {
+                x_lo = std::min(x_lo, xs[j]); x_hi = std::max(x_hi, xs[j]);
+                y_lo = std::min(y_lo, ys[j]); y_hi = std::max(y_hi, ys[j]);
+            }
+            const float cx = 0.5f * (x_lo + x_hi), cy = 0.5f * (y_lo + y_hi);
+            float r2 = 0.0f;
+            for (int j = 0; j < len; ++j) r2 = std::max(r2, (xs[j] - cx) * (xs[j] - cx) + (ys[j] - cy) * (ys[j] - cy));
+            desc[c] = ConsDesc{cons_robot[c], cons_k0[c], cons_len[c], cons_offset[c], cx, cy, std::sqrt(r2) * 1.0001f + 1e-4f, 0};
+        }
         KCBS_CUDA(ctx, cudaMemcpyAsync(ws.cons, desc.data(), sizeof(ConsDesc) * n_cons, cudaMemcpyHostToDevice, s));
         // host planes have stride cons_total; keep the same stride on the device
         KCBS_CUDA(ctx, cudaMemcpyAsync(ws.cons_states, cons_states, sizeof(float) * 3 * (size_t)cons_total, cudaMemcpyHostToDevice, s));

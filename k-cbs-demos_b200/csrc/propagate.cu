@@ -167,6 +167,12 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
     }
     const float hl = w.rob_hl[a.robot], hw = w.rob_hw[a.robot];
     const CarConsts2 k = car_consts2(w, ua, uw, v0);
+    unsigned cmask[2] = {0u, 0u};   // constraints that can matter to the sample at all (most samples: none)
+    if (HAS_CONS) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+            if (st[e] > 0) cmask[e] = cons_mask(w, a.cons, a.n_cons, t0[e], st[e], x0[e], y0[e], w.rob_rad[a.robot]);
+    }
 
     // tan(phi) at the parent: accurate once per sample; from then on it advances step by step with the addition formula
     CarPair2 p;
@@ -216,7 +222,9 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
                 if (ok) ok = obstacles_clear_fine(w, xn[e], yn[e], tn[e], hl, hw);
             }
             if (HAS_CONS) {
-                if (ok) ok = constraints_clear(w, a.cons, a.n_cons, a.cons_states, a.cons_total, t0[e] + j + 1, xn[e], yn[e], tn[e], hl, hw, w.rob_rad[a.robot]);
+                if (ok && (cmask[e] != 0u || a.n_cons > 32))
+                    ok = constraints_clear(w, a.cons, a.n_cons, a.cons_states, a.cons_total, t0[e] + j + 1, xn[e], yn[e], tn[e], hl, hw,
+                                           w.rob_rad[a.robot], cmask[e]);
             }
             nv[e] = ok ? j + 1 : nv[e];
             alive[e] = ok & (j + 1 < st[e]);
