@@ -96,25 +96,30 @@ def plan_replans_sharded(ctx, starts, goals, rank: int, world: int, max_T: int, 
     """Config 'per-robot replans sharded across GPUs': the R independent low-level replans of a K-CBS node are dealt
     round-robin over the ranks (kcbs_rrt_plan_many on each rank's own GPU: its jobs run concurrently), the planned trajectories are
     merged on every rank (NCCL over NVLink), and the merged plan is validated there with kcbs_first_conflict.
+    The merge is ONE upload and ONE collective: every rank lays its rows, their lengths and its count of failed plans out in one
+    host buffer (everything it does not own is zero), and a SUM all-reduce over disjoint owners gathers them (it tolerates
+    uneven row counts; lengths and counts are small integers, exact in float32).
     Returns (plan [R, 5, max_T] tensor, lengths [R] tensor, all_solved flag)."""
+    import numpy as np
+
     R = starts.shape[1]
     mine = round_robin(R, rank, world)
-    plan = torch.zeros((R, 5, max_T), dtype=torch.float32, device=device)
-    lengths = torch.zeros(R, dtype=torch.int32, device=device)
-    solved = torch.ones(1, dtype=torch.int32, device=device)
+    n_plan = R * 5 * max_T
+    host = np.zeros(n_plan + R + 1, dtype=np.float32)
+    rows = host[:n_plan].reshape(R, 5, max_T)
     if len(mine):
         # this rank's replans run concurrently on the context's planner lanes (kcbs_rrt_plan_many)
-        import numpy as np
         seeds = np.array([seed * 1000003 + r for r in mine], dtype=np.uint64)
         traj, T, stats = ctx.rrt_plan_many(mine, starts[:, mine], goals[mine], seeds=seeds, max_T=max_T)
         for j, r in enumerate(mine):
             if not stats[j].solved:
-                solved[0] = 0
+                host[n_plan + R] += 1.0
                 continue
-            plan[r, :, :T[j]] = torch.from_numpy(traj[j, :, :T[j]]).to(device)
-            lengths[r] = int(T[j])
-    merge_owned_rows(plan, mine)
-    merge_owned_rows(lengths, mine)
+            rows[r, :, :T[j]] = traj[j, :, :T[j]]
+            host[n_plan + r] = float(T[j])
+    buf = torch.from_numpy(host).to(device)
     if dist.is_initialized() and world > 1:
-        dist.all_reduce(solved, op=dist.ReduceOp.MIN)
-    return plan, lengths, bool(solved.item())
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    plan = buf[:n_plan].view(R, 5, max_T)
+    lengths = buf[n_plan:n_plan + R].to(torch.int32)
+    return plan, lengths, float(buf[n_plan + R].item()) == 0.0
