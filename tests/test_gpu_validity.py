@@ -94,3 +94,29 @@ def test_per_robot_footprint(pkg, orc, workloads, gpu_ctx_factory):
         assert (got[clear] == ref[clear]).all()
         res.append(got)
     assert (res[0] != res[1]).any()
+
+
+@pytest.mark.parametrize("n", [1 << 18, (1 << 18) + 4, (1 << 18) + 124, 300004, 1000000, (1 << 21) + 64])
+def test_vector_and_scalar_load_paths_agree(pkg, workloads, n):
+    # large 16-byte aligned batches take the 16 B loads (four states per lane); the same planes at a base that is not
+    # 16-byte aligned take scalar loads.  Same verdict bits, also in the last partial pass, and nothing written past them.
+    import torch
+
+    scene = "Congested10x10_7robots"
+    states = torch.from_numpy(workloads.validity_states(scene, n, seed=n % 97)).cuda()
+    with pkg.Context(pkg.scenes.world(scene), device=0) as ctx:
+        words = (n + 31) // 32
+        shifted = torch.empty(5 * n + 1, dtype=torch.float32, device="cuda")[1:]
+        assert shifted.data_ptr() % 16 != 0 and states.data_ptr() % 16 == 0
+        shifted.copy_(states.reshape(-1))
+        out_a = torch.full((words + 4,), 0x5a5a5a5a, dtype=torch.int32, device="cuda")
+        out_b = out_a.clone()
+        st = torch.cuda.current_stream()
+        for robot in (0, 3):
+            ctx.validity_batch_dev(robot, n, states, out_a, st)
+            ctx.validity_batch_dev(robot, n, shifted, out_b, st)
+            torch.cuda.synchronize()
+            assert torch.equal(out_a, out_b)
+            assert (out_a[words:] == 0x5a5a5a5a).all()
+            bits = ctx.unpack_mask(out_a[:words].cpu().numpy().view(np.uint32), n)
+            assert 0.05 < bits.mean() < 0.95
