@@ -7,9 +7,12 @@
 // obstacle table in shared memory once, then every warp streams passes of 128 states: one 16 B load per plane and
 // lane (4 consecutive states), the bounds test, one shared-memory code lookup per state.  "free" and "hit" cells are
 // decided by the lookup alone; the states of "maybe" cells (the band where the heading decides, ~10 % of a
-// Congested10x10 batch) are compacted into a per-warp shared-memory queue with warp prefix sums, so the exact
-// rectangle test (sincos + 4 separating axes per candidate obstacle) runs once per pass with all lanes busy instead
-// of once per state slot with a few lanes active.  Verdicts leave as one 16 B store per warp and pass.
+// Congested10x10 batch) are pushed on a per-warp shared-memory queue (position, heading, cell code, place of the
+// verdict bit) with warp prefix sums.  The queue OUTLIVES a pass: the exact rectangle test (sincos + 4 separating axes
+// per candidate obstacle) runs only when 32 entries are waiting, one per lane, and clears the verdict bit of a colliding
+// state with an atomic on the mask word the warp stored earlier -- so the most expensive code of the kernel always
+// runs with every lane busy (it used to run once per pass with ~13 of 32 lanes).  Verdicts leave as one 16 B store per
+// warp and pass.
 #include "kcbs_device.cuh"
 #include "kernels.h"
 
@@ -19,12 +22,19 @@ constexpr int kValidBlock = 512;
 constexpr int kValidWarps = kValidBlock / 32;
 constexpr int kValidPass = 128;  // states per warp and pass (4 per lane)
 
+constexpr int kValidQueue = kValidPass + 32;   // a pass adds at most 128 entries to the < 32 left over from the pass before
+
+// States whose cell needs the exact test, per warp: position, heading, cell code | bit << 16, and the word of the verdict
+// mask that holds the state's bit.  The queue outlives a pass: entries are tested 32 at a time, as soon as there are 32.
+struct ValidQueue {
+    float x[kValidQueue], y[kValidQueue], th[kValidQueue];
+    uint32_t meta[kValidQueue], word[kValidQueue];
+};
+
 struct ValidShared {
     unsigned short code[kFineRows * kFinePitch];
     float4 obs[KCBS_MAX_OBSTACLES];
-    float st[kValidWarps][3][kValidPass];    // x, y, theta of the warp's current pass (read back by the exact test)
-    uint32_t queue[kValidWarps][kValidPass]; // cell code | slot << 16 of the states that need the exact test
-    uint32_t res[kValidWarps][4];
+    ValidQueue queue[kValidWarps];
 };
 static_assert(sizeof(unsigned short) * kFineRows * kFinePitch % 16 == 0, "the grid is staged with 16 B copies");
 
@@ -32,8 +42,8 @@ static_assert(sizeof(unsigned short) * kFineRows * kFinePitch % 16 == 0, "the gr
 // cell codes; states of "maybe" cells are pushed on the warp's queue.  Branch free: a state outside the bounds looks up
 // the cell of the workspace origin and ignores the answer.  Returns the lane's four verdict bits.
 template <bool HAS_OBS, bool SYM, bool FULL>
-__device__ __forceinline__ uint32_t classify4(const DevWorld &w, const unsigned short *codes, uint32_t *queue, int lane,
-                                              unsigned lt_mask, int live, const float4 X, const float4 Y, const float4 V,
+__device__ __forceinline__ uint32_t classify4(const DevWorld &w, const unsigned short *codes, ValidQueue &queue, unsigned lt_mask,
+                                              int live, long long i0, const float4 X, const float4 Y, const float4 V,
                                               const float4 P, const float4 T, int &qn)
 {
     const float x[4] = {X.x, X.y, X.z, X.w}, y[4] = {Y.x, Y.y, Y.z, Y.w}, v[4] = {V.x, V.y, V.z, V.w};
@@ -48,15 +58,33 @@ __device__ __forceinline__ uint32_t classify4(const DevWorld &w, const unsigned 
             // in-bounds coordinates index [0, kFineDim] (the upper bound itself lands on the repeated last row / column)
             const int ix = (int)fmaf(xc, w.finvx, w.foffx), iy = (int)fmaf(yc, w.finvy, w.foffy);
             const unsigned code = codes[iy * kFinePitch + ix];
-            const bool need = ok & (code - 1u < kCellMany);  // neither free (0) nor hit
+            const bool need = ok & (code - 1u < kCellMany);  // neither free (0) nor hit: valid unless the exact test says otherwise
             ok &= code != kCellHit;
             const unsigned bal = __ballot_sync(0xffffffffu, need);
-            if (need) queue[qn + __popc(bal & lt_mask)] = code | (unsigned)(lane * 4 + u) << 16;
+            if (need) {
+                const int at = qn + __popc(bal & lt_mask);
+                const long long i = i0 + u;
+                queue.x[at] = x[u];
+                queue.y[at] = y[u];
+                queue.th[at] = t[u];
+                queue.meta[at] = code | (unsigned)(i & 31) << 16;
+                queue.word[at] = (uint32_t)(i >> 5);
+            }
             qn += __popc(bal);
         }
         nib |= (ok ? 1u : 0u) << u;
     }
     return nib;
+}
+
+// The exact rectangle test (StateValidityCheckerDatabase.h:62-73,180-205) of queue entry e; a collision clears the state's
+// bit in the verdict mask (the word was stored earlier by this warp: ordered by the __syncwarp in between).
+__device__ __forceinline__ void exact_test(const DevWorld &w, const ValidShared &sh, const ValidQueue &queue, int e, float hl, float hw,
+                                           uint32_t *bitmask)
+{
+    const unsigned meta = queue.meta[e];
+    if (!obstacles_clear_code(w, meta & 0xffffu, sh.obs, queue.x[e], queue.y[e], queue.th[e], hl, hw))
+        atomicAnd(bitmask + queue.word[e], ~(1u << (meta >> 16)));
 }
 
 template <bool HAS_OBS, bool VEC, bool SYM>
@@ -79,8 +107,8 @@ k_validity(const __grid_constant__ DevWorld w, const __grid_constant__ ValidArgs
     const float hl = w.rob_hl[a.robot], hw = w.rob_hw[a.robot];
     const long long warps_total = (long long)gridDim.x * kValidWarps;
     const float *px = a.states, *py = a.states + n, *pv = a.states + 2 * n, *pp = a.states + 3 * n, *pt = a.states + 4 * n;
-    float *sx = sh.st[wib][0], *sy = sh.st[wib][1], *sth = sh.st[wib][2];
-    uint32_t *queue = sh.queue[wib], *res = sh.res[wib];
+    ValidQueue &queue = sh.queue[wib];
+    int qn = 0;   // entries waiting for the exact test (warp uniform)
 
     for (long long pass = (long long)blockIdx.x * kValidWarps + wib; pass < n_pass; pass += warps_total) {
         const long long i0 = pass * kValidPass + lane * 4;  // this lane's four consecutive states
@@ -110,37 +138,27 @@ k_validity(const __grid_constant__ DevWorld w, const __grid_constant__ ValidArgs
             P = make_float4(e[3][0], e[3][1], e[3][2], e[3][3]);
             T = make_float4(e[4][0], e[4][1], e[4][2], e[4][3]);
         }
-        if (HAS_OBS) {
-            reinterpret_cast<float4 *>(sx)[lane] = X;
-            reinterpret_cast<float4 *>(sy)[lane] = Y;
-            reinterpret_cast<float4 *>(sth)[lane] = T;
-        }
-        int qn = 0;
-        const uint32_t nib = full ? classify4<HAS_OBS, SYM, true>(w, sh.code, queue, lane, lt_mask, live, X, Y, V, P, T, qn)
-                                  : classify4<HAS_OBS, SYM, false>(w, sh.code, queue, lane, lt_mask, live, X, Y, V, P, T, qn);
+        const uint32_t nib = full ? classify4<HAS_OBS, SYM, true>(w, sh.code, queue, lt_mask, live, i0, X, Y, V, P, T, qn)
+                                  : classify4<HAS_OBS, SYM, false>(w, sh.code, queue, lt_mask, live, i0, X, Y, V, P, T, qn);
         // lanes 8k .. 8k+7 hold the 32 verdicts of mask word k
         uint32_t word = nib << (4 * (lane & 7));
         word |= __shfl_xor_sync(0xffffffffu, word, 1);
         word |= __shfl_xor_sync(0xffffffffu, word, 2);
         word |= __shfl_xor_sync(0xffffffffu, word, 4);
-        uint32_t out;
-        if (HAS_OBS && qn > 0) {
-            if ((lane & 7) == 0) res[lane >> 3] = word;
+        const uint32_t out = __shfl_sync(0xffffffffu, word, (lane & 3) * 8);
+        if (lane < 4 && (pass * 4 + lane) * 32 < n) a.bitmask[pass * 4 + lane] = out;
+        if (HAS_OBS) {
+            // the exact test runs with every lane busy: 32 entries at a time, taken from the end of the queue (the rest
+            // waits for the next pass; a Congested10x10 pass adds ~13)
             __syncwarp();
-#pragma unroll 1
-            for (int q = lane; q < qn; q += 32) {
-                const unsigned tag = queue[q], slot = tag >> 16;
-                if (!obstacles_clear_code(w, tag & 0xffffu, sh.obs, sx[slot], sy[slot], sth[slot], hl, hw))
-                    atomicAnd(&res[slot >> 5], ~(1u << (slot & 31)));
+            while (qn >= 32) {
+                qn -= 32;
+                exact_test(w, sh, queue, qn + lane, hl, hw, a.bitmask);
             }
             __syncwarp();
-            out = res[lane & 3];
-            __syncwarp();
-        } else {
-            out = __shfl_sync(0xffffffffu, word, (lane & 3) * 8);
         }
-        if (lane < 4 && (pass * 4 + lane) * 32 < n) a.bitmask[pass * 4 + lane] = out;
     }
+    if (HAS_OBS && lane < qn) exact_test(w, sh, queue, lane, hl, hw, a.bitmask);
 }
 
 template <bool HAS_OBS>
