@@ -209,6 +209,7 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
         upk(fma2(CP, p.offx, X0), xn[0], xn[1]);
         upk(fma2(CP, p.offy, Y0), yn[0], yn[1]);
         upk(ang, tn[0], tn[1]);
+        bool oks[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             // straight-line code with predicated commits, so that the two halves interleave; a half that has failed keeps
@@ -216,11 +217,35 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
             tn[e] = tn[e] >= kPi ? tn[e] - kTwoPi : tn[e];     // wrap_angle for |theta| < 3 pi
             tn[e] = tn[e] < -kPi ? tn[e] + kTwoPi : tn[e];
             // v and phi of every step below st were tested when st was derived (same expressions): x, y, theta remain
-            bool ok = alive[e] & (xn[e] >= w.lo_t[0]) & (xn[e] <= w.hi_t[0]) & (yn[e] >= w.lo_t[1]) & (yn[e] <= w.hi_t[1]) &
-                      (tn[e] >= w.th_lo_t) & (tn[e] <= w.th_hi_t);
-            if (HAS_OBS) {
-                if (ok) ok = obstacles_clear_fine(w, xn[e], yn[e], tn[e], hl, hw);
+            oks[e] = alive[e] & (xn[e] >= w.lo_t[0]) & (xn[e] <= w.hi_t[0]) & (yn[e] >= w.lo_t[1]) & (yn[e] <= w.hi_t[1]) &
+                     (tn[e] >= w.th_lo_t) & (tn[e] <= w.th_hi_t);
+        }
+        if (HAS_OBS) {
+            // Both samples' cell codes are looked up together (two independent loads), free and hit cells are decided by
+            // them; the exact rectangle test of the "maybe" cells is ONE divergent region for both samples: its first
+            // pass serves every lane's first candidate, a second pass only the lanes whose both samples need it (in an
+            // obstacle scene some lane of a warp needs the test at nearly every step, so two separate regions both ran).
+            unsigned code[2];
+            bool need[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) code[e] = oks[e] ? (unsigned)__ldg(w.fine + fine_cell(w, xn[e], yn[e])) : 0u;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                oks[e] &= code[e] != kCellHit;
+                need[e] = oks[e] & (code[e] != 0u);
             }
+            if (need[0] | need[1]) {
+                const bool first = need[0];   // which sample the first pass tests in this lane
+                const bool clear = obstacles_clear_code(w, first ? code[0] : code[1], w.obs4, first ? xn[0] : xn[1], first ? yn[0] : yn[1],
+                                                        first ? tn[0] : tn[1], hl, hw);
+                oks[0] &= clear | !first;
+                oks[1] &= clear | first;
+                if (need[0] & need[1]) oks[1] &= obstacles_clear_code(w, code[1], w.obs4, xn[1], yn[1], tn[1], hl, hw);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            bool ok = oks[e];
             if (HAS_CONS) {
                 if (ok && (cmask[e] != 0u || a.n_cons > 32))
                     ok = constraints_clear(w, a.cons, a.n_cons, a.cons_states, a.cons_total, t0[e] + j + 1, xn[e], yn[e], tn[e], hl, hw,
