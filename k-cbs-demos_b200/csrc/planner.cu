@@ -9,16 +9,24 @@
 // (StateSpaceDatabase.h:45-46: L2 over (x, y, v, phi) + SO2 arc, weights 1), goal = disc of 0.5 around the goal
 // position (GoalRegionDatabase.h:48-55), conflicts = kcbs_first_conflict.
 //
-// Low level, per round (all state in HBM, one stream, four launches):
-//   k_rrt_targets   n_targets random states (goal biased), packed (distance, index) keys reset
+// Low level: ONE CUDA graph launch per plan -- k_rrt_init, a WHILE node over the round below (its condition is set on the
+// device by k_rrt_append: goal found, tree full, iteration or time limit), then the path extraction, the re-expansion of
+// the path's edges and the copies of the results into pinned memory.  What differs from plan to plan is read by the
+// kernels from a 128-byte plan block (RrtPlan), so a lane re-uses its instantiated graph for every plan of the same
+// launch shape.  KCBS_RRT_ROUNDS=stream queues the same kernels round by round from the host instead (also the fallback
+// when a graph cannot be built).  A round (all state in HBM; targets are a pure function of (seed, round, index)):
 //   k_rrt_nearest   tiled all-pairs nearest tree node per target (four targets per thread in packed FP32 pairs, nodes
-//                   broadcast from shared memory), 64-bit atomicMin on (distance bits, index)
+//                   broadcast from shared memory), 64-bit atomicMin on (distance bits, index).  Two launches: the nodes
+//                   that existed before the previous round are scanned for the NEXT round's targets on a parallel
+//                   branch, the nodes the previous round appended are scanned on the critical path
 //   k_propagate     the K1 expansion kernel with dynamic-obstacle constraints and per-parent time indices; the parent of a
 //                   sample is its target's nearest node (the keys of k_rrt_nearest as they stand), its control and
 //                   duration were drawn one round ahead
 //   k_rrt_select    per target the sample that ends closest to it is chosen; the next round's controls and durations
-//   k_rrt_append    the chosen samples become tree nodes in target order (goal test, report to the host)
+//   k_rrt_append    the chosen samples become tree nodes in target order (goal test; decides whether the loop goes on)
 // A found path is re-expanded edge by edge with k_propagate (identical arithmetic) to emit every 0.1 s state.
+// Independent plans run on planner lanes (host thread + stream + workspace + graphs each); stream captures and device-wide
+// synchronisation exclude each other process wide (capture_gate, ctx.h).
 #include <algorithm>
 #include <atomic>
 #include <chrono>
