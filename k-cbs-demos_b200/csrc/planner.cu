@@ -864,10 +864,11 @@ void destroy_rrt_workspace(kcbs_ctx *ctx)
 }
 
 // The low-level planner proper for NC cars planned as one system (NC = 1: a robot; NC = 2: a merged pair, the 10-d
-// system of SystemMergerDatabase.h:108-156).  Host orchestration only; every arithmetic step is a kernel.  The host
-// queues iterations without waiting for them: each round reports (goal, node count) into a host-mapped ring, the host
-// looks at round i - kRrtDepth before it queues round i, and rounds queued after the goal was found cancel themselves on
-// the device.  start = 5 NC reals, goal_xy = 2 NC, traj_out = [5 NC][max_T].
+// system of SystemMergerDatabase.h:108-156).  Host orchestration only; every arithmetic step is a kernel.  By default the
+// whole search is one graph launch (the rounds are driven by the device, see the top of this file).  With host-queued
+// rounds the host queues iterations without waiting for them: each round reports (goal, node count) into a host-mapped
+// ring, the host looks at round i - kRrtDepth before it queues round i, and rounds queued after the goal was found cancel
+// themselves on the device.  start = 5 NC reals, goal_xy = 2 NC, traj_out = [5 NC][max_T].
 // Tree capacity when the caller leaves it to the planner (max_nodes = 0): the rounds a path across the workspace needs at
 // full speed (one round extends the tree by at most max_steps * step seconds of driving) with 50 % slack, between 32 and
 // 128 rounds.  A re-plan that cannot succeed -- K-CBS produces them: a constraint can park another robot on the goal --
@@ -1285,8 +1286,8 @@ kcbs_ctx *planner_lane(kcbs_ctx *ctx, int i)
 }
 
 // Runs job(lane context, j) for j in [0, n_jobs) on up to max_lanes host threads, each driving its own stream and
-// planner workspace, so that independent low-level plans overlap on the GPU (every plan is a chain of small launches
-// with a host read-back per RRT iteration).  Returns the first non-OK status.
+// planner workspace, so that independent low-level plans overlap on the GPU (a plan is a chain of small dependent
+// kernels that leaves most of the GPU idle).  Returns the first non-OK status.
 template <class Job>
 int run_planner_jobs(kcbs_ctx *ctx, int n_jobs, int max_lanes, Job job)
 {
