@@ -318,3 +318,44 @@ def test_concurrent_solves_and_device_wide_work(pkg, gpu_ctx_factory):
         for (s1, l1, p1), (s2, l2, p2) in zip(results[scene], alone):
             assert s1 == 1 and s2 == 1
             assert (l1 == l2).all() and (p1 == p2).all(), f"{scene}: a concurrent solve differs from the same solve alone"
+
+
+def test_rrt_many_constraints_and_equivalent_splits(pkg, orc, gpu_ctx_factory):
+    # (a) more constraints than the 32 the expansion kernel's per-sample mask covers: a wall of 40 parked robots across the
+    # straight line, each present for its own time window, with a gap that opens late; every state of the plan respects
+    # every constraint.  (b) one long constraint and the same states cut into 7 pieces are the same constraint set: the
+    # mask (bounding circle and time window per piece) must not change the plan.
+    scene = "Empty32x32_10robots"
+    ctx = gpu_ctx_factory(scene)
+    oracle = orc.Oracle(pkg.scenes.world(scene))
+    start = np.array([4.0, 16.0, 0, 0, 0], np.float32)
+    goal = np.array([14.0, 16.0], np.float32)
+    K = 400
+    cons = []
+    for q in range(40):
+        y = 6.0 + 0.5 * q                       # a wall at x = 9 from y = 6 to 25.5
+        k0 = 3 * q
+        block = np.zeros((3, K - k0), np.float32)
+        block[0], block[1], block[2] = 9.0, y, 0.0
+        if 19 <= q <= 21:                       # the part in front of the robot goes away at step 150
+            block = block[:, :150 - k0]
+        cons.append((1 + q % 9, k0, block))
+    traj, st = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=8), constraints=cons, max_T=1024)
+    assert st.solved == 1
+    check_path(oracle, traj, start, goal)
+    for k in range(traj.shape[1]):
+        for other, k0, block in cons:
+            if k0 <= k < k0 + block.shape[1]:
+                ok, _ = oracle.pair_valid(0, traj[[0, 1, 4], k], other, block[:, k - k0])
+                assert ok, f"constraint of robot {other} from step {k0} violated at step {k}"
+    # (b)
+    long = np.zeros((3, 300), np.float32)
+    long[0] = np.linspace(6.0, 12.0, 300)
+    long[1] = 16.0 + 0.8 * np.sin(np.linspace(0, 6, 300))
+    long[2] = 0.2
+    whole, st1 = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=9), constraints=[(2, 20, long)], max_T=1024)
+    cuts = [0, 11, 50, 51, 140, 200, 299, 300]
+    pieces = [(2, 20 + a, long[:, a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    split, st2 = ctx.rrt_plan(0, start, goal, ctx.rrt_params(seed=9), constraints=pieces, max_T=1024)
+    assert st1.solved == 1 and st2.solved == 1
+    assert whole.shape == split.shape and (whole == split).all()
