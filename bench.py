@@ -655,6 +655,37 @@ def run_secondary(pkg, workloads, dev, hbm_peak, peak_src, max_over_ranks, sum_o
                                      if has_traffic else None,
                                      "algorithmic_bytes_per_launch": VALIDITY_BYTES_PER_STATE * n}}
             del sets, mask
+    # ---- the expansion kernel on the obstacle scenes (configs 1 and 3 of BASELINE.json: Corridor10x10, Congested10x10):
+    # the headline workload has no obstacles; here every step also looks its cell up and runs the exact rectangle test in
+    # "maybe" cells.  655,360 samples per launch (own parents), packed segments, units = min(steps, valid + 1).
+    prop_obs = {}
+    n_s = 655360
+    for scene in ("Corridor10x10_4robots", "Congested10x10_7robots"):
+        with pkg.Context(pkg.scenes.world(scene), device=dev) as ctx:
+            p, c, s = workloads.expansion_batch(scene, n_s, seed=3 + rank, interior=1.5)
+            dp, dc, ds = torch.from_numpy(p).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(s).cuda()
+            seg = torch.empty((5, 10 * n_s), device="cuda")
+            fin = torch.empty((5, n_s), device="cuda")
+            val = torch.zeros(n_s, dtype=torch.int32, device="cuda")
+            off = torch.zeros(n_s + 1, dtype=torch.int32, device="cuda")
+            st = torch.cuda.current_stream()
+            for _ in range(3):
+                ctx.propagate_packed_dev(0, n_s, n_s, dp, dc, ds, None, 10, seg, 10 * n_s, off, fin, val, st)
+            barrier()
+            reps = 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                ctx.propagate_packed_dev(0, n_s, n_s, dp, dc, ds, None, 10, seg, 10 * n_s, off, fin, val, st)
+            e1.record()
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            units = float(torch.minimum(ds, val + 1).sum().item())
+            prop_obs[scene] = {"value": sum_over_ranks(units) * reps / (ms * 1e-3), "unit": "states/s", "samples": n_s,
+                               "us_per_launch": 1e3 * ms / reps, "algorithmic_tflops": units * reps * FLOPS_PER_STATE / (ms * 1e-3) * 1e-12}
+            del dp, dc, ds, seg, fin, val, off
+    out["propagate_obstacle_scenes"] = dict(prop_obs, metric="propagated states/s (scenes with obstacles)",
+                                            note="same kernel with the fused obstacle test; not the headline workload")
     # ---- conflict scan: Empty32x32 30 robots, 435 pairs x 10K steps, 256 plans (config 5) --------------
     # N > 1: every rank scans its own 256-plan batch (weak); one batch sharded by plan is reported as well (strong).
     from kcbs_b200 import sharding
