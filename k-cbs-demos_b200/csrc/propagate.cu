@@ -228,10 +228,15 @@ __device__ __forceinline__ void propagate_two(const DevWorld &w, const PropArgs 
             unsigned code[2];
             bool need[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) code[e] = oks[e] ? (unsigned)__ldg(w.fine + fine_cell(w, xn[e], yn[e])) : 0u;
+            for (int e = 0; e < 2; ++e) {
+                // (a state inside the bounds indexes [0, kFineDim]: the table repeats its last row and column, no clamps)
+                const float xc = oks[e] ? xn[e] : w.gx0, yc = oks[e] ? yn[e] : w.gy0;
+                const int ix = (int)fmaf(xc, w.finvx, w.foffx), iy = (int)fmaf(yc, w.finvy, w.foffy);
+                code[e] = __ldg(w.fine + iy * kFinePitch + ix);
+            }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                oks[e] &= code[e] != kCellHit;
+                oks[e] &= code[e] != kCellHit;   // (a state outside the bounds looked the origin's cell up: oks stays false)
                 need[e] = oks[e] & (code[e] != 0u);
             }
             if (need[0] | need[1]) {
