@@ -816,6 +816,17 @@ bool device_rounds()
     return on;
 }
 
+// Steps of the parent's path a child's re-plan gives up before the newest constraint begins (KCBS_REPLAN_BACK; 0 = every
+// re-plan starts from the robot's start state).
+int replan_back()
+{
+    static const int v = [] {
+        const char *e = std::getenv("KCBS_REPLAN_BACK");
+        return e ? std::max(0, std::atoi(e)) : 40;
+    }();
+    return v;
+}
+
 bool trace_solve()
 {
     static const bool on = std::getenv("KCBS_TRACE_SOLVE") != nullptr;   // per-expansion and per-plan timing on stderr
@@ -1330,43 +1341,68 @@ constexpr int kPlannerLanes = 16;
 }  // extern "C++"
 
 // flat constraint arrays of the C ABI from the constraint objects of a tree node
+// (shift > 0: the plan starts at absolute time index `shift`; constraint times are taken relative to it, what lies before
+// it is cut off, and of a persistent constraint that ended earlier the parked state remains)
 struct FlatConstraints {
     std::vector<int32_t> robot, k0, ln, off;
     std::vector<float> states;
-    explicit FlatConstraints(const std::vector<std::shared_ptr<Constraint>> &cons)
+    explicit FlatConstraints(const std::vector<std::shared_ptr<Constraint>> &cons, int shift = 0)
     {
+        std::vector<int> first;   // first state of every kept constraint
+        std::vector<const Constraint *> kept;
         int total = 0;
         for (const auto &c : cons) {
-            robot.push_back(c->other); k0.push_back(c->k0); off.push_back(total);
-            ln.push_back(c->persistent ? -(int)c->x.size() : (int)c->x.size());
-            total += (int)c->x.size();
+            const int n = (int)c->x.size(), ks = c->k0 - shift;
+            int f = std::max(0, -ks);
+            if (f >= n) {
+                if (!c->persistent) continue;   // over before the plan starts
+                f = n - 1;
+            }
+            kept.push_back(c.get()); first.push_back(f);
+            robot.push_back(c->other); k0.push_back(std::max(ks, 0)); off.push_back(total);
+            ln.push_back(c->persistent ? -(n - f) : n - f);
+            total += n - f;
         }
         states.assign((size_t)3 * std::max(total, 1), 0.0f);
-        for (size_t q = 0; q < cons.size(); ++q)
-            for (size_t j = 0; j < cons[q]->x.size(); ++j) {
-                states[off[q] + j] = cons[q]->x[j];
-                states[(size_t)total + off[q] + j] = cons[q]->y[j];
-                states[(size_t)2 * total + off[q] + j] = cons[q]->th[j];
+        for (size_t q = 0; q < kept.size(); ++q)
+            for (size_t j = (size_t)first[q]; j < kept[q]->x.size(); ++j) {
+                const size_t at = (size_t)off[q] + j - (size_t)first[q];
+                states[at] = kept[q]->x[j];
+                states[(size_t)total + at] = kept[q]->y[j];
+                states[(size_t)2 * total + at] = kept[q]->th[j];
             }
     }
 };
 
+// Low-level plan of robot r under `cons`.  k_split = 0: from the robot's start state.  k_split > 0 (a re-plan of a child
+// node): the path `traj` of the parent node is kept up to time index k_split -- it satisfies the older constraints, and the
+// new one begins later -- and only the rest is planned, from the state the old path has there; the tree then needs the
+// rounds of the remaining way, not of the whole way.
 int plan_robot(kcbs_ctx *ctx, int r, const float *starts, const float *goals, int R, const kcbs_rrt_params &p,
                const std::vector<std::shared_ptr<Constraint>> &cons, int max_T, std::vector<float> &traj, int &len,
-               kcbs_rrt_stats &rs)
+               kcbs_rrt_stats &rs, int k_split = 0)
 {
     float start[5];
-    for (int c = 0; c < 5; ++c) start[c] = starts[(size_t)c * R + r];
-    FlatConstraints fc(cons);
-    std::vector<float> out((size_t)5 * max_T);
+    const int L0 = len;
+    if (k_split <= 0 || k_split >= L0 || k_split >= max_T - 1) k_split = 0;
+    for (int c = 0; c < 5; ++c) start[c] = k_split > 0 ? traj[(size_t)c * L0 + k_split] : starts[(size_t)c * R + r];
+    FlatConstraints fc(cons, k_split);
+    const int sub_T = max_T - k_split;
+    std::vector<float> out((size_t)5 * sub_T);
     int32_t T = 0;
-    const int st = kcbs_rrt_plan(ctx, r, start, goals + 2 * r, &p, (int)cons.size(), fc.robot.data(), fc.k0.data(), fc.ln.data(),
-                                 fc.off.data(), fc.states.data(), max_T, out.data(), &T, &rs);
+    const int st = kcbs_rrt_plan(ctx, r, start, goals + 2 * r, &p, (int)fc.robot.size(), fc.robot.data(), fc.k0.data(), fc.ln.data(),
+                                 fc.off.data(), fc.states.data(), sub_T, out.data(), &T, &rs);
     if (st != KCBS_OK) return st;
-    len = T;
-    traj.assign((size_t)5 * std::max(T, 1), 0.0f);
-    for (int c = 0; c < 5; ++c)
-        for (int k = 0; k < T; ++k) traj[(size_t)c * T + k] = out[(size_t)c * max_T + k];
+    if (k_split > 0 && !rs.solved) return KCBS_OK;   // (the caller plans from the start instead; traj / len untouched)
+    std::vector<float> joined((size_t)5 * std::max(k_split + T, 1), 0.0f);
+    const int L = k_split + T;
+    for (int c = 0; c < 5; ++c) {
+        for (int k = 0; k < k_split; ++k) joined[(size_t)c * L + k] = traj[(size_t)c * L0 + k];
+        for (int k = 0; k < T; ++k) joined[(size_t)c * L + k_split + k] = out[(size_t)c * sub_T + k];
+    }
+    traj.swap(joined);
+    len = L;
+    rs.path_steps = L > 0 ? L - 1 : 0;
     return KCBS_OK;
 }
 
@@ -1455,7 +1491,15 @@ int plan_individual(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsig
     if (members.size() == 1) {
         const int r = members[0];
         lp.seed = q.P.low_level.seed * 1000003ull + seed * 131ull + (unsigned long long)r;  // seed = salt of this plan
-        const int st = plan_robot(lane, r, q.starts, q.goals, q.R, lp, node.cons[I], q.max_T, node.traj[r], node.len[r], rs);
+        // a child node's re-plan keeps the parent's path until replan_back() steps before the newest constraint begins
+        // (or before the old path ends, when the robot is already parked by then); when that cannot be completed the
+        // robot is planned from its start state, as the root does
+        int k_split = 0;
+        if (node.len[r] > 1 && !node.cons[I].empty() && replan_back() > 0)
+            k_split = std::max(0, std::min(node.cons[I].back()->k0, node.len[r] - 1) - replan_back());
+        int st = plan_robot(lane, r, q.starts, q.goals, q.R, lp, node.cons[I], q.max_T, node.traj[r], node.len[r], rs, k_split);
+        if (st == KCBS_OK && k_split > 0 && !rs.solved)
+            st = plan_robot(lane, r, q.starts, q.goals, q.R, lp, node.cons[I], q.max_T, node.traj[r], node.len[r], rs, 0);
         solved = st == KCBS_OK && rs.solved;
         return st;
     }
