@@ -1337,7 +1337,10 @@ int run_planner_jobs(kcbs_ctx *ctx, int n_jobs, int max_lanes, Job job)
     return KCBS_OK;
 }
 
-constexpr int kPlannerLanes = 16;
+#ifndef KCBS_PLANNER_LANES
+#define KCBS_PLANNER_LANES 16
+#endif
+constexpr int kPlannerLanes = KCBS_PLANNER_LANES;
 }  // extern "C++"
 
 // flat constraint arrays of the C ABI from the constraint objects of a tree node
