@@ -601,6 +601,7 @@ def main():
             "conflict_strong_P2048_speedup_vs_one_gpu": cs.get("P2048", {}).get("speedup_vs_one_gpu"),
             "replans20_s": secondary.get("replans", {}).get("median_s"),
             "e2e_states_per_s": e2e["value"],
+            "kcbs_solve_30robots_median_s": secondary.get("kcbs_solve", {}).get("scenes", {}).get("Benchmark_Empty32x32_30robots", {}).get("median_s"),
         }
         line = {
             "metric": "propagated states/s", "value": value, "unit": "states/s", "n_gpus": world_size,
