@@ -351,8 +351,9 @@ KCBS_API int kcbs_rrt_plan_many(kcbs_ctx *ctx, int n_jobs, const int32_t *robots
 
 /* K-CBS over the R robots of the world: root = independent low-level plans; best-first search over the
  * constraint tree with kcbs_first_conflict as the plan validator; every conflict spawns two children that
- * re-plan one robot each against the other's colliding states (a re-plan keeps the parent node's path until 4 s before
- * its newest constraint begins and plans the rest from there; from the start state when that fails).
+ * re-plan one robot each against the other's colliding states (after a pair's first conflict a re-plan keeps the parent
+ * node's path until 4 s before its newest constraint begins and plans the rest from there; from the start state when
+ * that fails and for every later conflict of the pair).
  * starts = [5][R] planes, goals = [R][2];
  * plan_out = [R][5][max_T], lengths_out = [R].  A pair with more than merge_bound conflicts is merged (the role of
  * SystemMerger::merge, SystemMergerDatabase.h:55-168) and the search restarts with it as one individual, placed last,

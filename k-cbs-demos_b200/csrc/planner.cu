@@ -816,6 +816,11 @@ bool device_rounds()
     return on;
 }
 
+#ifndef KCBS_LOCAL_REPAIRS
+#define KCBS_LOCAL_REPAIRS 1
+#endif
+constexpr int kLocalRepairs = KCBS_LOCAL_REPAIRS;   // conflicts of one pair that are answered by re-plans from the split
+
 // Steps of the parent's path a child's re-plan gives up before the newest constraint begins (KCBS_REPLAN_BACK; 0 = every
 // re-plan starts from the robot's start state).
 int replan_back()
@@ -1486,7 +1491,8 @@ struct Search {
 
 // Low-level plan of one individual into `node`: a single robot through the 5-d RRT, a merged pair through the joint 10-d
 // RRT (a few seeds are tried before a merged pair is given up: the joint space is large).  Returns KCBS_OK and sets `solved`.
-int plan_individual(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsigned long long seed, bool &solved)
+int plan_individual(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsigned long long seed, bool &solved,
+                    bool keep_prefix = true)
 {
     const std::vector<int> &members = q.ind[I];
     kcbs_rrt_params lp = q.P.low_level;
@@ -1498,7 +1504,7 @@ int plan_individual(kcbs_ctx *lane, const Search &q, CbsNode &node, int I, unsig
         // (or before the old path ends, when the robot is already parked by then); when that cannot be completed the
         // robot is planned from its start state, as the root does
         int k_split = 0;
-        if (node.len[r] > 1 && !node.cons[I].empty() && replan_back() > 0)
+        if (keep_prefix && node.len[r] > 1 && !node.cons[I].empty() && replan_back() > 0)
             k_split = std::max(0, std::min(node.cons[I].back()->k0, node.len[r] - 1) - replan_back());
         int st = plan_robot(lane, r, q.starts, q.goals, q.R, lp, node.cons[I], q.max_T, node.traj[r], node.len[r], rs, k_split);
         if (st == KCBS_OK && k_split > 0 && !rs.solved)
@@ -1626,8 +1632,11 @@ int search_tree(Search &q, std::shared_ptr<CbsNode> &solution, int &merge_a, int
             child[ch] = std::make_shared<CbsNode>(*node);
             child[ch]->cons[me].push_back(c);
             // the seed depends on the expansion and the branch only, so both branches can run at once
+            // a pair that keeps colliding is not helped by repairs near the conflict (two cars that must pass each other in a
+            // corridor): from its kLocalRepairs-th conflict on, its re-plans start from the robots' start states again
             return plan_individual(lane, q, *child[ch], me,
-                                   (unsigned long long)(S.nodes_expanded * 2 + ch) + 7919ull * (unsigned long long)S.merges, solved[ch]);
+                                   (unsigned long long)(S.nodes_expanded * 2 + ch) + 7919ull * (unsigned long long)S.merges, solved[ch],
+                                   n_conf <= kLocalRepairs);
         });
         if (st != KCBS_OK) return st;
         if (trace_solve())
